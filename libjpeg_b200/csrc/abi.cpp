@@ -1,0 +1,682 @@
+// abi.cpp -- implementation of the C ABI declared in include/b200jpg.h (compiled by nvcc as host C++).
+//
+// Host side of the decode path: parses the codestreams (parse.cpp), groups scans that share geometry and
+// tables into launch classes, lays the batch out in HBM (see internal.hpp) and drives the two CUDA stages.
+// There is no CPU decode path in here: without a CUDA device every decode entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <array>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "internal.hpp"
+
+using namespace b200jpg;
+
+namespace {
+
+thread_local std::string g_tls_error;
+thread_local int g_tls_code = 0;
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct b200jpg_ctx {
+    int device = 0;
+    std::string error;
+    int code = 0;
+    int fail(int c, const std::string &m) {
+        code = c;
+        error = m;
+        return c;
+    }
+    int fail_cuda(cudaError_t e, const char *what) {
+        return fail(B200JPG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    }
+};
+
+namespace {
+
+struct ScanClass {
+    ScanClassParams p{};
+    int table_set = 0;
+    std::vector<ClassScan> scans;
+    std::vector<uint64_t> interval_off;  // absolute offsets into the packed byte buffer
+    // offsets (bytes) of the device copies inside the input buffer
+    uint64_t dev_scans = 0, dev_intervals = 0;
+};
+
+struct ReconGroup {
+    uint32_t ncomp = 0, subx = 1, suby = 1;
+    std::vector<FrameRecon> frames;
+    uint32_t max_bw0 = 0, max_bh0 = 0, max_bwc = 0, max_bhc = 0;
+    uint64_t dev_frames = 0;
+};
+
+struct ClassKey {
+    int v[40];
+    bool operator<(const ClassKey &o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+
+}  // namespace
+
+struct b200jpg_batch {
+    b200jpg_ctx *ctx = nullptr;
+    int n = 0;
+    std::vector<ParsedFrame> frames;
+    std::vector<int> parse_status;
+    std::vector<uint64_t> out_off, out_bytes;
+    uint64_t out_total = 0;
+    std::vector<TableSet> table_sets;
+    std::vector<uint64_t> dev_tables;  // offset of each table blob inside the input buffer
+    std::vector<ScanClass> classes;
+    std::vector<ReconGroup> groups;
+    uint64_t ecs_bytes = 0, stored_blocks = 0;
+
+    // staging / device memory
+    uint8_t *h_input = nullptr;  // pinned
+    uint64_t input_bytes = 0;    // codestream bytes + descriptors
+    uint64_t bytes_region = 0;   // size of the codestream region at the start of the input buffer
+    uint8_t *d_input = nullptr;
+    int16_t *d_coef = nullptr;
+    uint64_t coef_elems = 0;
+    int32_t *d_samples = nullptr;
+    uint64_t sample_elems = 0;
+    uint32_t *d_status = nullptr;
+    std::vector<uint32_t> h_status;
+    bool status_fetched = false;
+    bool uploaded = false;
+
+    int last_launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+};
+
+extern "C" {
+
+int b200jpg_parse(const uint8_t *data, size_t len, b200jpg_frame_info *info) {
+    ParsedFrame pf;
+    std::string err;
+    int rc = parse_codestream(data, len, pf, err);
+    g_tls_code = rc;
+    g_tls_error = err;
+    if (info) *info = pf.info;
+    return rc;
+}
+
+int b200jpg_create(int device, b200jpg_ctx **out) {
+    if (!out) return B200JPG_ERR_INVALID_PARAMETER;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_tls_code = B200JPG_ERR_NO_DEVICE;
+        g_tls_error = "no CUDA device available: the B200 JPEG decode path has no CPU fallback";
+        return B200JPG_ERR_NO_DEVICE;
+    }
+    if (device < 0) {
+        e = cudaGetDevice(&device);
+        if (e != cudaSuccess) device = 0;
+    }
+    if (device >= count) {
+        g_tls_code = B200JPG_ERR_INVALID_PARAMETER;
+        g_tls_error = "CUDA device ordinal out of range";
+        return B200JPG_ERR_INVALID_PARAMETER;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess || prop.major < 10) {
+        g_tls_code = B200JPG_ERR_NO_DEVICE;
+        g_tls_error = "device is not a Blackwell (sm_100a) GPU: the kernels are built for sm_100a only";
+        return B200JPG_ERR_NO_DEVICE;
+    }
+    auto *c = new b200jpg_ctx();
+    c->device = device;
+    *out = c;
+    return B200JPG_OK;
+}
+
+void b200jpg_destroy(b200jpg_ctx *ctx) { delete ctx; }
+
+int b200jpg_last_error(b200jpg_ctx *ctx, const char **message) {
+    if (ctx) {
+        if (message) *message = ctx->error.c_str();
+        return ctx->code;
+    }
+    if (message) *message = g_tls_error.c_str();
+    return g_tls_code;
+}
+
+void b200jpg_batch_destroy(b200jpg_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    if (b->h_input) cudaFreeHost(b->h_input);
+    if (b->d_input) cudaFree(b->d_input);
+    if (b->d_coef) cudaFree(b->d_coef);
+    if (b->d_samples) cudaFree(b->d_samples);
+    if (b->d_status) cudaFree(b->d_status);
+    for (auto &e : b->ev)
+        if (e) cudaEventDestroy(e);
+    delete b;
+}
+
+int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad,
+                         b200jpg_batch **out) {
+    if (!ctx) return B200JPG_ERR_INVALID_PARAMETER;
+    if (!out || !frames || !lens || n <= 0) return ctx->fail(B200JPG_ERR_INVALID_PARAMETER, "invalid batch arguments");
+    *out = nullptr;
+    cudaError_t ce = cudaSetDevice(ctx->device);
+    if (ce != cudaSuccess) return ctx->fail_cuda(ce, "cudaSetDevice");
+
+    std::unique_ptr<b200jpg_batch, void (*)(b200jpg_batch *)> bp(new b200jpg_batch(), b200jpg_batch_destroy);
+    b200jpg_batch *b = bp.get();
+    b->ctx = ctx;
+    b->n = n;
+    b->frames.resize(n);
+    b->parse_status.assign(n, 0);
+    std::vector<std::string> errs(n);
+
+    // ---- parse (host threads: the marker scan is a memchr over every entropy coded byte)
+    {
+        unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        nt = std::min<unsigned>(nt, (unsigned)n);
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++)
+            pool.emplace_back([&, t]() {
+                for (int i = (int)t; i < n; i += (int)nt)
+                    b->parse_status[i] = parse_codestream(frames[i], lens[i], b->frames[i], errs[i]);
+            });
+        for (auto &th : pool) th.join();
+    }
+    for (int i = 0; i < n; i++) {
+        ParsedFrame &pf = b->frames[i];
+        int &st = b->parse_status[i];
+        if (st == 0) {  // what the kernels cover
+            const b200jpg_frame_info &fi = pf.info;
+            if (fi.ncomp != 1 && fi.ncomp != 3) {
+                st = B200JPG_ERR_NOT_IMPLEMENTED;
+                errs[i] = "only one and three component frames are supported by the B200 path";
+            } else if (fi.subx[0] != 1 || fi.suby[0] != 1) {
+                st = B200JPG_ERR_NOT_IMPLEMENTED;
+                errs[i] = "a subsampled first component is not supported by the B200 path";
+            } else if (fi.ncomp == 3 && (fi.subx[1] != fi.subx[2] || fi.suby[1] != fi.suby[2] || fi.subx[1] > 2 || fi.suby[1] > 2)) {
+                st = B200JPG_ERR_NOT_IMPLEMENTED;
+                errs[i] = "only 1x1, 2x1, 1x2 and 2x2 chroma subsampling (equal for both chroma components) is supported";
+            } else {
+                // every component must be covered by exactly one scan
+                int seen[4] = {0, 0, 0, 0};
+                for (auto &sc : pf.scans)
+                    for (int k = 0; k < sc.ns; k++) seen[sc.comp[k]]++;
+                for (int c = 0; c < fi.ncomp; c++)
+                    if (seen[c] != 1) {
+                        st = B200JPG_ERR_MALFORMED_STREAM;
+                        errs[i] = "sequential frame does not code every component exactly once";
+                    }
+            }
+        }
+        if (st != 0 && !tolerate_bad) return ctx->fail(st, "frame " + std::to_string(i) + ": " + errs[i]);
+    }
+
+    // ---- layout of the packed input buffer: [codestreams][table blobs][per class: scans, intervals][per group: frames]
+    std::vector<uint64_t> byte_off(n, 0);
+    uint64_t cur = 0;
+    for (int i = 0; i < n; i++) {
+        byte_off[i] = cur;
+        if (b->parse_status[i] == 0) cur = align_up(cur + lens[i] + 32, 16);
+    }
+    b->bytes_region = align_up(cur + 64, 256);
+
+    // coefficient / sample / output layout
+    b->out_off.assign(n, 0);
+    b->out_bytes.assign(n, 0);
+    std::vector<std::array<uint64_t, 4>> coef_base(n), sample_base(n);
+    uint64_t coef_cur = 0, sample_cur = 0, out_cur = 0;
+    for (int i = 0; i < n; i++) {
+        if (b->parse_status[i] != 0) continue;
+        const b200jpg_frame_info &fi = b->frames[i].info;
+        for (int c = 0; c < fi.ncomp; c++) {
+            coef_base[i][c] = coef_cur;
+            coef_cur += (uint64_t)fi.blocks_w[c] * fi.blocks_h[c] * 64;
+            if (c > 0) {
+                sample_base[i][c] = sample_cur;
+                sample_cur += (uint64_t)fi.blocks_w[c] * fi.blocks_h[c] * 64;
+            }
+        }
+        b->out_off[i] = out_cur;
+        b->out_bytes[i] = (uint64_t)fi.width * fi.height * fi.ncomp;
+        out_cur = align_up(out_cur + b->out_bytes[i], 256);
+        b->ecs_bytes += fi.ecs_bytes;
+        b->stored_blocks += fi.stored_blocks;
+    }
+    b->out_total = out_cur;
+    b->coef_elems = coef_cur;
+    b->sample_elems = sample_cur;
+
+    // ---- table sets (deduplicated by content) and scan classes
+    std::map<std::vector<uint8_t>, int> table_index;
+    std::map<ClassKey, int> class_index;
+    for (int i = 0; i < n; i++) {
+        if (b->parse_status[i] != 0) continue;
+        ParsedFrame &pf = b->frames[i];
+        const b200jpg_frame_info &fi = pf.info;
+        for (auto &sc : pf.scans) {
+            TableSet ts;
+            std::string err;
+            int rc = build_table_set(sc, ts, err);
+            if (rc != 0) {
+                b->parse_status[i] = rc;
+                if (!tolerate_bad) return ctx->fail(rc, "frame " + std::to_string(i) + ": " + err);
+                break;
+            }
+            int ti;
+            auto it = table_index.find(ts.blob);
+            if (it == table_index.end()) {
+                ti = (int)b->table_sets.size();
+                table_index.emplace(ts.blob, ti);
+                b->table_sets.push_back(std::move(ts));
+            } else {
+                ti = it->second;
+            }
+            ScanClassParams p{};
+            p.ns = sc.ns;
+            for (int k = 0; k < sc.ns; k++) {
+                int ci = sc.comp[k];
+                p.mw[k] = (sc.ns > 1) ? fi.hs[ci] : 1;
+                p.mh[k] = (sc.ns > 1) ? fi.vs[ci] : 1;
+                p.bw[k] = (int)fi.blocks_w[ci];
+                p.dc_slot[k] = sc.td[k];
+                p.ac_slot[k] = sc.ta[k];
+                p.q_slot[k] = fi.tq[ci];
+            }
+            p.mcu_cols = sc.mcu_cols;
+            p.total_mcus = sc.mcu_cols * sc.mcu_rows;
+            p.dri = sc.dri ? sc.dri : p.total_mcus;
+            p.intervals_per_scan = (uint32_t)sc.interval_off.size();
+            p.lut_words = b->table_sets[ti].lut_words();
+            ClassKey key{};
+            int kk = 0;
+            key.v[kk++] = p.ns;
+            for (int k = 0; k < 4; k++) {
+                key.v[kk++] = p.mw[k];
+                key.v[kk++] = p.mh[k];
+                key.v[kk++] = p.bw[k];
+                key.v[kk++] = p.dc_slot[k];
+                key.v[kk++] = p.ac_slot[k];
+                key.v[kk++] = p.q_slot[k];
+            }
+            key.v[kk++] = (int)p.mcu_cols;
+            key.v[kk++] = (int)p.total_mcus;
+            key.v[kk++] = (int)p.dri;
+            key.v[kk++] = (int)p.intervals_per_scan;
+            key.v[kk++] = ti;
+            int cidx;
+            auto cit = class_index.find(key);
+            if (cit == class_index.end()) {
+                cidx = (int)b->classes.size();
+                class_index.emplace(key, cidx);
+                ScanClass cl;
+                cl.p = p;
+                cl.table_set = ti;
+                b->classes.push_back(std::move(cl));
+            } else {
+                cidx = cit->second;
+            }
+            ScanClass &cl = b->classes[cidx];
+            ClassScan cs{};
+            for (int k = 0; k < sc.ns; k++) cs.coef_base[k] = coef_base[i][sc.comp[k]];
+            cs.frame = (uint32_t)i;
+            cl.scans.push_back(cs);
+            for (size_t off : sc.interval_off) cl.interval_off.push_back(off == SIZE_MAX ? ~0ull : byte_off[i] + (uint64_t)off);
+        }
+    }
+    for (auto &cl : b->classes) cl.p.n_scans = (uint32_t)cl.scans.size();
+
+    // ---- reconstruction groups
+    for (int i = 0; i < n; i++) {
+        if (b->parse_status[i] != 0) continue;
+        const b200jpg_frame_info &fi = b->frames[i].info;
+        uint32_t sx = fi.ncomp > 1 ? fi.subx[1] : 1, sy = fi.ncomp > 1 ? fi.suby[1] : 1;
+        ReconGroup *g = nullptr;
+        for (auto &gg : b->groups)
+            if (gg.ncomp == fi.ncomp && gg.subx == sx && gg.suby == sy) g = &gg;
+        if (!g) {
+            b->groups.emplace_back();
+            g = &b->groups.back();
+            g->ncomp = fi.ncomp;
+            g->subx = sx;
+            g->suby = sy;
+        }
+        FrameRecon fr{};
+        for (int c = 0; c < fi.ncomp; c++) {
+            fr.coef_base[c] = coef_base[i][c];
+            fr.sample_base[c] = sample_base[i][c];
+            fr.bw[c] = fi.blocks_w[c];
+            fr.bh[c] = fi.blocks_h[c];
+        }
+        fr.out_base = b->out_off[i];
+        fr.width = fi.width;
+        fr.height = fi.height;
+        fr.ncomp = fi.ncomp;
+        fr.ycbcr = fi.ycbcr;
+        fr.subx = sx;
+        fr.suby = sy;
+        fr.cw = (fi.width + sx - 1) / sx;
+        fr.ch = (fi.height + sy - 1) / sy;
+        fr.status_idx = (uint32_t)i;
+        g->frames.push_back(fr);
+        g->max_bw0 = std::max(g->max_bw0, (fi.width + 7) / 8);
+        g->max_bh0 = std::max(g->max_bh0, (fi.height + 7) / 8);
+        if (fi.ncomp > 1) {
+            g->max_bwc = std::max(g->max_bwc, fi.blocks_w[1]);
+            g->max_bhc = std::max(g->max_bhc, fi.blocks_h[1]);
+        }
+    }
+
+    // ---- descriptor region
+    cur = b->bytes_region;
+    b->dev_tables.resize(b->table_sets.size());
+    for (size_t t = 0; t < b->table_sets.size(); t++) {
+        b->dev_tables[t] = cur;
+        cur = align_up(cur + b->table_sets[t].blob.size(), 256);
+    }
+    for (auto &cl : b->classes) {
+        cl.dev_scans = cur;
+        cur = align_up(cur + cl.scans.size() * sizeof(ClassScan), 256);
+        cl.dev_intervals = cur;
+        cur = align_up(cur + cl.interval_off.size() * sizeof(uint64_t), 256);
+    }
+    for (auto &g : b->groups) {
+        g.dev_frames = cur;
+        cur = align_up(cur + g.frames.size() * sizeof(FrameRecon), 256);
+    }
+    b->input_bytes = cur;
+
+    // ---- pinned staging + device memory
+    ce = cudaHostAlloc((void **)&b->h_input, b->input_bytes, cudaHostAllocDefault);
+    if (ce != cudaSuccess) return ctx->fail(B200JPG_ERR_OUT_OF_MEMORY, std::string("pinned staging allocation failed: ") + cudaGetErrorString(ce));
+    {
+        unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+        nt = std::min<unsigned>(nt, (unsigned)n);
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++)
+            pool.emplace_back([&, t]() {
+                for (int i = (int)t; i < n; i += (int)nt) {
+                    if (b->parse_status[i] != 0) continue;
+                    uint8_t *dst = b->h_input + byte_off[i];
+                    memcpy(dst, frames[i], lens[i]);
+                    // sentinel: a damaged segment must still meet a marker before it leaves its codestream
+                    uint64_t pad_end = align_up(byte_off[i] + lens[i] + 32, 16);
+                    memset(dst + lens[i], 0, pad_end - (byte_off[i] + lens[i]));
+                    dst[lens[i]] = 0xff;
+                    dst[lens[i] + 1] = 0xd9;
+                }
+            });
+        for (auto &th : pool) th.join();
+    }
+    // tail of the codestream region (after the last frame) is zero + a final sentinel
+    {
+        uint64_t last_end = 0;
+        for (int i = 0; i < n; i++)
+            if (b->parse_status[i] == 0) last_end = align_up(byte_off[i] + lens[i] + 32, 16);
+        memset(b->h_input + last_end, 0, b->bytes_region - last_end);
+        b->h_input[last_end] = 0xff;
+        b->h_input[last_end + 1] = 0xd9;
+    }
+    for (size_t t = 0; t < b->table_sets.size(); t++)
+        memcpy(b->h_input + b->dev_tables[t], b->table_sets[t].blob.data(), b->table_sets[t].blob.size());
+    for (auto &cl : b->classes) {
+        memcpy(b->h_input + cl.dev_scans, cl.scans.data(), cl.scans.size() * sizeof(ClassScan));
+        memcpy(b->h_input + cl.dev_intervals, cl.interval_off.data(), cl.interval_off.size() * sizeof(uint64_t));
+    }
+    for (auto &g : b->groups) memcpy(b->h_input + g.dev_frames, g.frames.data(), g.frames.size() * sizeof(FrameRecon));
+
+    ce = cudaMalloc((void **)&b->d_input, b->input_bytes);
+    if (ce == cudaSuccess && b->coef_elems) ce = cudaMalloc((void **)&b->d_coef, b->coef_elems * sizeof(int16_t));
+    if (ce == cudaSuccess && b->sample_elems) ce = cudaMalloc((void **)&b->d_samples, b->sample_elems * sizeof(int32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&b->d_status, sizeof(uint32_t) * (size_t)n);
+    if (ce != cudaSuccess) return ctx->fail(B200JPG_ERR_OUT_OF_MEMORY, std::string("device allocation failed: ") + cudaGetErrorString(ce));
+    b->h_status.assign(n, 0);
+    *out = bp.release();
+    return B200JPG_OK;
+}
+
+int b200jpg_batch_frame_info(const b200jpg_batch *b, int i, b200jpg_frame_info *info) {
+    if (!b || i < 0 || i >= b->n || !info) return B200JPG_ERR_INVALID_PARAMETER;
+    *info = b->frames[i].info;
+    return b->parse_status[i];
+}
+
+uint64_t b200jpg_batch_out_offset(const b200jpg_batch *b, int i) { return (b && i >= 0 && i < b->n) ? b->out_off[i] : 0; }
+uint64_t b200jpg_batch_out_bytes(const b200jpg_batch *b, int i) {
+    if (!b) return 0;
+    if (i < 0) return b->out_total;
+    return i < b->n ? b->out_bytes[i] : 0;
+}
+uint64_t b200jpg_batch_ecs_bytes(const b200jpg_batch *b) { return b ? b->ecs_bytes : 0; }
+uint64_t b200jpg_batch_stored_blocks(const b200jpg_batch *b) { return b ? b->stored_blocks : 0; }
+uint64_t b200jpg_batch_h2d_bytes(const b200jpg_batch *b) { return b ? b->input_bytes : 0; }
+
+uint64_t b200jpg_batch_export_tables(const b200jpg_batch *b, uint8_t *dst, uint64_t capacity) {
+    if (!b || b->table_sets.size() != 1) return 0;
+    const auto &blob = b->table_sets[0].blob;
+    if (dst && capacity >= blob.size()) memcpy(dst, blob.data(), blob.size());
+    return blob.size();
+}
+
+int b200jpg_batch_import_tables(b200jpg_batch *b, const uint8_t *src, uint64_t size) {
+    if (!b || !src) return B200JPG_ERR_INVALID_PARAMETER;
+    if (b->table_sets.size() != 1) return b->ctx->fail(B200JPG_ERR_INVALID_PARAMETER, "table import needs a batch with exactly one table set");
+    auto &blob = b->table_sets[0].blob;
+    uint32_t hdr[4];
+    if (size < 16) return b->ctx->fail(B200JPG_ERR_INVALID_PARAMETER, "table blob too small");
+    memcpy(hdr, src, 16);
+    if (hdr[0] != kTableMagic || hdr[1] != size || size != blob.size())
+        return b->ctx->fail(B200JPG_ERR_INVALID_PARAMETER, "table blob does not match this batch (different table geometry)");
+    memcpy(blob.data(), src, size);
+    memcpy(b->h_input + b->dev_tables[0], src, size);
+    b->uploaded = false;
+    return B200JPG_OK;
+}
+
+int b200jpg_batch_upload(b200jpg_batch *b, void *stream) {
+    if (!b) return B200JPG_ERR_INVALID_PARAMETER;
+    cudaSetDevice(b->ctx->device);
+    cudaError_t e = cudaMemcpyAsync(b->d_input, b->h_input, b->input_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) return b->ctx->fail_cuda(e, "upload");
+    b->uploaded = true;
+    return B200JPG_OK;
+}
+
+static int run_entropy(b200jpg_batch *b, void *stream) {
+    cudaError_t e = cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * (size_t)b->n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return b->ctx->fail_cuda(e, "status reset");
+    for (auto &cl : b->classes) {
+        EntropyLaunch l{};
+        l.p = cl.p;
+        l.bytes = b->d_input;
+        l.interval_off = reinterpret_cast<const uint64_t *>(b->d_input + cl.dev_intervals);
+        l.scans = reinterpret_cast<const ClassScan *>(b->d_input + cl.dev_scans);
+        l.tables = b->d_input + b->dev_tables[cl.table_set];
+        l.coef = b->d_coef;
+        l.frame_status = b->d_status;
+        int rc = launch_entropy(l, stream);
+        if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "entropy kernel launch");
+        b->last_launches++;
+    }
+    return B200JPG_OK;
+}
+
+static int run_recon(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
+    for (auto &g : b->groups) {
+        ReconLaunch l{};
+        l.frames = reinterpret_cast<const FrameRecon *>(b->d_input + g.dev_frames);
+        l.n_frames = (uint32_t)g.frames.size();
+        l.max_bw0 = g.max_bw0;
+        l.max_bh0 = g.max_bh0;
+        l.max_bwc = g.max_bwc;
+        l.max_bhc = g.max_bhc;
+        l.ncomp = g.ncomp;
+        l.subx = g.subx;
+        l.suby = g.suby;
+        l.coef = b->d_coef;
+        l.samples = b->d_samples;
+        l.out = out_dev;
+        int launches = 0;
+        // grid.y carries the frame index: at most 65535 frames per launch
+        for (uint32_t first = 0; first < l.n_frames; first += 65535u) {
+            ReconLaunch part = l;
+            part.frames = l.frames + first;
+            part.n_frames = std::min<uint32_t>(65535u, l.n_frames - first);
+            int rc = launch_recon(part, stream, &launches);
+            if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "reconstruction kernel launch");
+            b->last_launches += launches;
+        }
+    }
+    return B200JPG_OK;
+}
+
+static int ensure_events(b200jpg_batch *b) {
+    for (auto &e : b->ev)
+        if (!e && cudaEventCreate(&e) != cudaSuccess) return b->ctx->fail(B200JPG_ERR_CUDA, "cudaEventCreate failed");
+    return 0;
+}
+
+int b200jpg_batch_decode(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
+    if (!b || !out_dev) return B200JPG_ERR_INVALID_PARAMETER;
+    if (!b->uploaded) return b->ctx->fail(B200JPG_ERR_OBJECT_DOESNT_EXIST, "batch has not been uploaded");
+    cudaSetDevice(b->ctx->device);
+    b->last_launches = 0;
+    b->status_fetched = false;
+    if (b->timing) {
+        if (ensure_events(b)) return B200JPG_ERR_CUDA;
+        cudaEventRecord(b->ev[0], (cudaStream_t)stream);
+    }
+    int rc = run_entropy(b, stream);
+    if (rc) return rc;
+    if (b->timing) cudaEventRecord(b->ev[1], (cudaStream_t)stream);
+    rc = run_recon(b, out_dev, stream);
+    if (rc) return rc;
+    if (b->timing) cudaEventRecord(b->ev[2], (cudaStream_t)stream);
+    return B200JPG_OK;
+}
+
+int b200jpg_batch_decode_entropy(b200jpg_batch *b, void *stream) {
+    if (!b) return B200JPG_ERR_INVALID_PARAMETER;
+    if (!b->uploaded) return b->ctx->fail(B200JPG_ERR_OBJECT_DOESNT_EXIST, "batch has not been uploaded");
+    cudaSetDevice(b->ctx->device);
+    b->last_launches = 0;
+    b->status_fetched = false;
+    return run_entropy(b, stream);
+}
+
+int b200jpg_batch_reconstruct(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
+    if (!b || !out_dev) return B200JPG_ERR_INVALID_PARAMETER;
+    if (!b->uploaded) return b->ctx->fail(B200JPG_ERR_OBJECT_DOESNT_EXIST, "batch has not been uploaded");
+    cudaSetDevice(b->ctx->device);
+    b->last_launches = 0;
+    return run_recon(b, out_dev, stream);
+}
+
+int b200jpg_batch_frame_status(b200jpg_batch *b, int i) {
+    if (!b || i < 0 || i >= b->n) return B200JPG_ERR_INVALID_PARAMETER;
+    if (b->parse_status[i] != 0) return b->parse_status[i];
+    if (!b->status_fetched) {
+        cudaSetDevice(b->ctx->device);
+        cudaError_t e = cudaMemcpy(b->h_status.data(), b->d_status, sizeof(uint32_t) * (size_t)b->n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return b->ctx->fail_cuda(e, "status download");
+        b->status_fetched = true;
+    }
+    return -(int)b->h_status[i];
+}
+
+int b200jpg_batch_read_coefficients(b200jpg_batch *b, int i, int c, int16_t *dst, uint64_t capacity) {
+    if (!b || i < 0 || i >= b->n || !dst) return B200JPG_ERR_INVALID_PARAMETER;
+    if (b->parse_status[i] != 0) return b->parse_status[i];
+    const b200jpg_frame_info &fi = b->frames[i].info;
+    if (c < 0 || c >= fi.ncomp) return B200JPG_ERR_INVALID_PARAMETER;
+    uint64_t elems = (uint64_t)fi.blocks_w[c] * fi.blocks_h[c] * 64;
+    if (capacity < elems) return B200JPG_ERR_INVALID_PARAMETER;
+    // recompute the plane base exactly as batch_create did
+    uint64_t base = 0;
+    for (int k = 0; k < b->n; k++) {
+        if (b->parse_status[k] != 0) continue;
+        const b200jpg_frame_info &fk = b->frames[k].info;
+        for (int cc = 0; cc < fk.ncomp; cc++) {
+            if (k == i && cc == c) goto found;
+            base += (uint64_t)fk.blocks_w[cc] * fk.blocks_h[cc] * 64;
+        }
+    }
+found:
+    cudaSetDevice(b->ctx->device);
+    cudaError_t e = cudaMemcpy(dst, b->d_coef + base, elems * sizeof(int16_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return b->ctx->fail_cuda(e, "coefficient download");
+    return B200JPG_OK;
+}
+
+int b200jpg_batch_last_launch_count(const b200jpg_batch *b) { return b ? b->last_launches : 0; }
+
+void b200jpg_batch_enable_timing(b200jpg_batch *b, int on) {
+    if (b) b->timing = on != 0;
+}
+
+int b200jpg_batch_last_timing(b200jpg_batch *b, float *entropy_ms, float *reconstruct_ms) {
+    if (!b || !b->ev[0]) return B200JPG_ERR_INVALID_PARAMETER;
+    float a = 0, c = 0;
+    if (cudaEventElapsedTime(&a, b->ev[0], b->ev[1]) != cudaSuccess) return B200JPG_ERR_CUDA;
+    if (cudaEventElapsedTime(&c, b->ev[1], b->ev[2]) != cudaSuccess) return B200JPG_ERR_CUDA;
+    if (entropy_ms) *entropy_ms = a;
+    if (reconstruct_ms) *reconstruct_ms = c;
+    return B200JPG_OK;
+}
+
+int b200jpg_decode_to_host(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, uint8_t *out_host,
+                           uint64_t out_capacity) {
+    if (!ctx) return B200JPG_ERR_INVALID_PARAMETER;
+    b200jpg_batch *b = nullptr;
+    int rc = b200jpg_batch_create(ctx, frames, lens, n, 0, &b);
+    if (rc) return rc;
+    uint8_t *d_out = nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (out_capacity < b->out_total) {
+        rc = ctx->fail(B200JPG_ERR_INVALID_PARAMETER, "output buffer too small");
+        goto done;
+    }
+    e = cudaMalloc((void **)&d_out, b->out_total);
+    if (e != cudaSuccess) {
+        rc = ctx->fail(B200JPG_ERR_OUT_OF_MEMORY, "device allocation of the output failed");
+        goto done;
+    }
+    e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        rc = ctx->fail_cuda(e, "cudaStreamCreate");
+        goto done;
+    }
+    rc = b200jpg_batch_upload(b, s);
+    if (!rc) rc = b200jpg_batch_decode(b, d_out, s);
+    if (!rc) {
+        e = cudaMemcpyAsync(out_host, d_out, b->out_total, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = ctx->fail_cuda(e, "download");
+    }
+    if (!rc) {
+        for (int i = 0; i < n && !rc; i++) {
+            int st = b200jpg_batch_frame_status(b, i);
+            if (st) rc = ctx->fail(st, "frame " + std::to_string(i) + ": invalid stream, found invalid huffman code in entropy coded segment");
+        }
+    }
+done:
+    if (s) cudaStreamDestroy(s);
+    if (d_out) cudaFree(d_out);
+    b200jpg_batch_destroy(b);
+    return rc;
+}
+
+}  // extern "C"

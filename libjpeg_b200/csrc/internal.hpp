@@ -1,0 +1,129 @@
+// internal.hpp -- shared declarations of the B200 baseline-JPEG decode path (host parser <-> CUDA stages).
+//
+// Data layout in HBM (one "batch" = n codestreams decoded by the same launches):
+//   bytes      : the codestreams, each copied whole at a 16-byte aligned offset and followed by FF D9 + zero
+//                padding, so a bit reader that runs off a damaged segment always meets a marker.
+//   coef       : int16, one 128-byte block per 8x8 DCT block, DEQUANTISED (coefficient * delta, the << 4
+//                preshift of dct/idct.cpp:105 is applied by the reconstruction kernels), raster order inside
+//                the block; per component a plane [blocks_h][blocks_w] over the MCU-padded grid.
+//   samples    : int32, IDCT output (4 fractional bits, level shifted) of the SUBSAMPLED components only,
+//                plane [8*blocks_h][8*blocks_w] -- the role of the reference's upsampler line buffers
+//                (upsampling/upsamplerbase.cpp:300-327), whole-frame instead of a sliding window.
+//   out        : interleaved 8-bit pixels, caller-provided.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "b200jpg.h"
+
+namespace b200jpg {
+
+// ---- host-side parse results -------------------------------------------------------------------------
+struct HuffSpec {  // DHT payload, coding/huffmantemplate.cpp:878-904
+    bool defined = false;
+    uint8_t bits[16] = {0};
+    uint8_t vals[256] = {0};
+    int nvals = 0;
+};
+
+struct ScanInfo {  // one SOS + its entropy coded segment
+    int ns = 0;
+    int comp[4] = {0, 0, 0, 0};  // frame component index, SOS order
+    int td[4] = {0, 0, 0, 0}, ta[4] = {0, 0, 0, 0};
+    int lowbit = 0;
+    uint32_t dri = 0;            // MCUs per restart interval, 0 = none
+    size_t ecs_off = 0, ecs_end = 0;
+    uint32_t mcu_cols = 0, mcu_rows = 0;
+    // byte offset (within the codestream) of the first ECS byte of every restart interval;
+    // SIZE_MAX marks an interval the stream does not contain (zero-filled like an invalid segment,
+    // codestream/sequentialscan.cpp:415-419)
+    std::vector<size_t> interval_off;
+    HuffSpec dc[4], ac[4];       // tables in effect at this SOS
+    uint16_t quant[4][64];       // zig-zag order as transmitted, in effect at this SOS
+    bool quant_defined[4] = {false, false, false, false};
+};
+
+struct ParsedFrame {
+    b200jpg_frame_info info{};
+    std::vector<ScanInfo> scans;
+};
+
+// Returns 0 or a negative reference error code; `err` receives a message.
+int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::string &err);
+
+extern const uint8_t kZigZagToRaster[64];  // dct/dct.cpp:57-73
+
+// ---- table sets: what the entropy kernel needs besides the bytes ------------------------------------
+// Serialised, device independent (this blob is what rank 0 broadcasts over NCCL):
+//   uint32 magic, uint32 total_bytes, uint32 lut_words, uint32 flags
+//   uint16 lut_off[8]      word offset of the level-1 LUT of DC0..3, AC0..3 (0xFFFF = undefined)
+//   uint32 qz[4][64]       per quantisation table, index = zig-zag k: (delta << lowbit) << 8 | raster position
+//   uint16 lut[lut_words]  per table: 256 level-1 entries then 256 per level-2 sub-table
+// LUT entry: (len << 8) | symbol, len 1..16; level-1 entries with len == 0 hold the 1-based index of the
+// level-2 sub-table in the low byte; len == 0xFF marks an unused code (coding/huffmandecoder.hpp:87).
+constexpr uint32_t kTableMagic = 0x4a54424cu;  // "LBTJ"
+constexpr int kTableHeaderBytes = 16 + 16 + 4 * 64 * 4;
+
+struct TableSet {
+    std::vector<uint8_t> blob;
+    uint32_t lut_words() const;
+};
+
+// Builds the blob for one scan (two-level decoder tables, coding/huffmantemplate.cpp:802-874).
+int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err);
+
+// ---- device-side descriptors -------------------------------------------------------------------------
+struct ClassScan {        // one scan of one frame inside a scan class
+    uint64_t coef_base[4];  // element (int16) offset of the plane of scan component c
+    uint32_t frame;         // index into the batch
+    uint32_t pad;
+};
+
+struct ScanClassParams {  // uniform over a launch of the entropy kernel
+    int ns;
+    int mw[4], mh[4];       // blocks per MCU of scan component c (1,1 for single component scans)
+    int bw[4];              // plane pitch in blocks of scan component c
+    int dc_slot[4], ac_slot[4], q_slot[4];
+    uint32_t mcu_cols, total_mcus, dri /* MCUs per interval, >= 1 */, intervals_per_scan;
+    uint32_t n_scans;       // scans in this class
+    uint32_t lut_words;
+};
+
+struct FrameRecon {       // per frame, for the reconstruction kernels
+    uint64_t coef_base[4];    // int16 element offsets
+    uint64_t sample_base[4];  // int32 element offsets (subsampled components only)
+    uint64_t out_base;        // byte offset into the output buffer
+    uint32_t width, height;
+    uint32_t bw[4], bh[4];
+    uint32_t ncomp, ycbcr, subx, suby;  // subx/suby of the subsampled (chroma) components
+    uint32_t cw, ch;                    // true subsampled size ceil(W/subx), ceil(H/suby)
+    uint32_t status_idx, pad;
+};
+
+// kernel launchers (huffman_sm100.cu, recon_sm100.cu). All asynchronous on `stream`.
+struct EntropyLaunch {
+    ScanClassParams p;
+    const uint8_t *bytes;
+    const uint64_t *interval_off;   // [n_scans * intervals_per_scan], ~0ull = absent
+    const ClassScan *scans;         // [n_scans]
+    const uint8_t *tables;          // device copy of the table-set blob
+    int16_t *coef;
+    uint32_t *frame_status;         // [n_frames]
+};
+int launch_entropy(const EntropyLaunch &l, void *stream);
+
+struct ReconLaunch {
+    const FrameRecon *frames;  // device
+    uint32_t n_frames;
+    uint32_t max_bw0, max_bh0;     // largest luma block grid in the group
+    uint32_t max_bwc, max_bhc;     // largest chroma block grid in the group
+    uint32_t ncomp, subx, suby;    // uniform over the group
+    const int16_t *coef;
+    int32_t *samples;
+    uint8_t *out;
+};
+int launch_recon(const ReconLaunch &l, void *stream, int *launches);
+
+}  // namespace b200jpg

@@ -1,0 +1,338 @@
+// parse.cpp -- host-side marker parser, restart-interval index and decoder-table builder.
+//
+// Restates, over a flat in-memory byte view, what the reference does incrementally through its ByteStream:
+//   SOI / marker walk          codestream/decoder.cpp:77, codestream/tables.cpp:1003-1420
+//   DQT                        marker/quantization.cpp:474-537
+//   DHT                        marker/huffmantable.cpp:127-169, coding/huffmantemplate.cpp:878-904
+//   DRI                        marker/restartintervalmarker.cpp:80-102
+//   SOF0/SOF1                  marker/frame.cpp:111-214, marker/component.cpp:86-111, component.hpp:99-106
+//   SOS                        marker/scan.cpp:163-315
+//   RSTn sequence              codestream/entropyparser.cpp:117-136, entropyparser.hpp:147-160
+//   two-level Huffman decoder  coding/huffmantemplate.cpp:802-874, coding/huffmandecoder.hpp:64-124
+// The validation rules and error codes follow those files so that LastError reports what a client of the
+// reference would see.
+#include <cstring>
+
+#include "internal.hpp"
+
+namespace b200jpg {
+
+const uint8_t kZigZagToRaster[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
+                                     12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                                     35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+                                     58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+namespace {
+
+struct Cursor {
+    const uint8_t *d;
+    size_t n;
+    int u8(size_t p) const { return p < n ? d[p] : -1; }
+    int u16(size_t p) const { return p + 1 < n ? (d[p] << 8) | d[p + 1] : -1; }
+};
+
+#define FAIL(code, msg) \
+    do {                \
+        err = msg;      \
+        return code;    \
+    } while (0)
+
+// Walks one entropy coded segment, recording where every restart interval begins.
+// Returns the offset of the first marker that is neither RSTn nor a fill byte (or n).
+size_t index_ecs(const Cursor &c, size_t pos, std::vector<size_t> &rst_at, std::vector<uint8_t> &rst_id) {
+    const uint8_t *d = c.d;
+    size_t n = c.n;
+    while (pos < n) {
+        const void *q = memchr(d + pos, 0xff, n - pos);
+        if (!q) return n;
+        pos = (size_t)((const uint8_t *)q - d);
+        if (pos + 1 >= n) return n;
+        uint8_t m = d[pos + 1];
+        if (m == 0x00) {
+            pos += 2;  // stuffed byte
+        } else if (m == 0xff) {
+            pos += 1;  // fill byte in front of a marker (entropyparser.cpp:121-125)
+        } else if (m >= 0xd0 && m <= 0xd7) {
+            rst_at.push_back(pos);
+            rst_id.push_back(m);
+            pos += 2;
+        } else {
+            return pos;
+        }
+    }
+    return n;
+}
+
+}  // namespace
+
+int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::string &err) {
+    Cursor c{data, len};
+    b200jpg_frame_info &fi = out.info;
+    memset(&fi, 0, sizeof(fi));
+    out.scans.clear();
+    if (!data || len < 4) FAIL(B200JPG_ERR_UNEXPECTED_EOF, "stream is too short to be a JPEG codestream");
+    if (c.u16(0) != 0xffd8) FAIL(B200JPG_ERR_MALFORMED_STREAM, "stream does not start with SOI, not a JPEG codestream");
+
+    HuffSpec dc[4], ac[4];
+    uint16_t quant[4][64];
+    bool quant_defined[4] = {false, false, false, false};
+    uint32_t dri = 0;
+    bool have_sof = false, adobe_none = false;
+    int hmax = 0, vmax = 0;
+    size_t pos = 2;
+
+    for (;;) {
+        if (pos + 1 >= len) FAIL(B200JPG_ERR_UNEXPECTED_EOF, "run out of data while looking for the next marker");
+        if (data[pos] != 0xff) FAIL(B200JPG_ERR_MALFORMED_STREAM, "expected a marker segment");
+        while (pos + 1 < len && data[pos + 1] == 0xff) pos++;  // filler, tables.cpp:1371-1373
+        if (pos + 1 >= len) FAIL(B200JPG_ERR_UNEXPECTED_EOF, "run out of data while looking for the next marker");
+        int m = data[pos + 1];
+        pos += 2;
+        if (m == 0xd9) break;  // EOI
+        if (m >= 0xd0 && m <= 0xd7) continue;
+        int seglen = c.u16(pos);
+        if (seglen < 2 || pos + (size_t)seglen > len) FAIL(B200JPG_ERR_UNEXPECTED_EOF, "marker segment runs past the end of the stream");
+        const uint8_t *s = data + pos + 2;
+        int rem = seglen - 2;
+
+        switch (m) {
+        case 0xdb:  // DQT
+            while (rem > 2) {
+                int type = s[0] >> 4, target = s[0] & 15;
+                s++, rem--;
+                if (type > 1) FAIL(B200JPG_ERR_MALFORMED_STREAM, "DQT marker entry type must be either 0 or 1");
+                if (target > 3) FAIL(B200JPG_ERR_MALFORMED_STREAM, "DQT marker target table must be between 0 and 3");
+                int need = 64 * (type + 1);
+                if (rem < need) FAIL(B200JPG_ERR_MALFORMED_STREAM, "DQT marker contains insufficient data");
+                for (int i = 0; i < 64; i++) quant[target][i] = type ? (uint16_t)((s[2 * i] << 8) | s[2 * i + 1]) : s[i];
+                quant_defined[target] = true;
+                s += need, rem -= need;
+            }
+            if (rem != 0) FAIL(B200JPG_ERR_MALFORMED_STREAM, "DQT marker size corrupt");
+            break;
+        case 0xc4:  // DHT
+            while (rem > 0) {
+                int t = s[0];
+                s++, rem--;
+                if ((t >> 4) > 1) FAIL(B200JPG_ERR_MALFORMED_STREAM, "undefined Huffman table type");
+                if ((t & 15) > 3) FAIL(B200JPG_ERR_MALFORMED_STREAM, "invalid Huffman table destination, must be between 0 and 3");
+                if (rem < 16) FAIL(B200JPG_ERR_MALFORMED_STREAM, "Huffman table marker run out of data");
+                int total = 0;
+                for (int i = 0; i < 16; i++) total += s[i];
+                if (rem < 16 + total) FAIL(B200JPG_ERR_MALFORMED_STREAM, "Huffman table marker run out of data");
+                if (total > 256) FAIL(B200JPG_ERR_MALFORMED_STREAM, "Huffman table defines more than 256 symbols");
+                HuffSpec &h = (t >> 4) ? ac[t & 3] : dc[t & 3];
+                h.defined = true;
+                memcpy(h.bits, s, 16);
+                memcpy(h.vals, s + 16, (size_t)total);
+                h.nvals = total;
+                s += 16 + total, rem -= 16 + total;
+            }
+            break;
+        case 0xdd:  // DRI
+            if (seglen != 4) FAIL(B200JPG_ERR_MALFORMED_STREAM, "DRI restart interval definition marker size is invalid");
+            dri = (uint32_t)c.u16(pos + 2);
+            break;
+        case 0xee:  // APP14: Adobe colour information (tables.cpp:2023-2025)
+            if (rem >= 12 && memcmp(s, "Adobe", 5) == 0) adobe_none = (s[11] == 0);
+            break;
+        case 0xc0:
+        case 0xc1: {
+            if (have_sof) FAIL(B200JPG_ERR_MALFORMED_STREAM, "found a second frame header, hierarchical JPEG is not supported");
+            if (seglen < 8) FAIL(B200JPG_ERR_MALFORMED_STREAM, "start of frame marker size invalid");
+            fi.frame_type = (m == 0xc1);
+            fi.precision = s[0];
+            if (m == 0xc0 && fi.precision != 8) FAIL(B200JPG_ERR_MALFORMED_STREAM, "frame precision in baseline mode must be 8");
+            if (fi.precision != 8 && fi.precision != 12) FAIL(B200JPG_ERR_MALFORMED_STREAM, "frame precision in lossy mode must be 8 or 12");
+            if (fi.precision != 8) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "12 bit extended sequential frames are not supported by the B200 path");
+            fi.height = (uint32_t)((s[1] << 8) | s[2]);
+            fi.width = (uint32_t)((s[3] << 8) | s[4]);
+            if (fi.width == 0) FAIL(B200JPG_ERR_MALFORMED_STREAM, "image width must not be zero");
+            if (fi.height == 0) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "frame height defined by a DNL marker is not supported by the B200 path");
+            int nc = s[5];
+            if (nc < 1) FAIL(B200JPG_ERR_MALFORMED_STREAM, "number of components must be between 1 and 255");
+            if (seglen - 8 != 3 * nc) FAIL(B200JPG_ERR_MALFORMED_STREAM, "frame header marker size is invalid");
+            if (nc > B200JPG_MAX_COMPONENTS) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "more than four components are not supported by the B200 path");
+            fi.ncomp = (uint8_t)nc;
+            for (int i = 0; i < nc; i++) {
+                fi.comp_id[i] = s[6 + 3 * i];
+                fi.hs[i] = s[7 + 3 * i] >> 4;
+                fi.vs[i] = s[7 + 3 * i] & 15;
+                fi.tq[i] = s[8 + 3 * i];
+                if (fi.hs[i] == 0 || fi.vs[i] == 0) FAIL(B200JPG_ERR_MALFORMED_STREAM, "frame marker corrupt, MCU size cannot be 0");
+                if (fi.tq[i] > 3) FAIL(B200JPG_ERR_MALFORMED_STREAM, "quantization table identifier corrupt, must be >= 0 and <= 3");
+                if (fi.hs[i] > hmax) hmax = fi.hs[i];
+                if (fi.vs[i] > vmax) vmax = fi.vs[i];
+            }
+            fi.mcu_cols = (fi.width + 8 * hmax - 1) / (8 * hmax);
+            fi.mcu_rows = (fi.height + 8 * vmax - 1) / (8 * vmax);
+            fi.stored_blocks = 0;
+            for (int i = 0; i < nc; i++) {
+                if (hmax % fi.hs[i] || vmax % fi.vs[i])
+                    FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "subsampling factors are not integer, this is not supported");  // component.hpp:99-106
+                fi.subx[i] = (uint8_t)(hmax / fi.hs[i]);
+                fi.suby[i] = (uint8_t)(vmax / fi.vs[i]);
+                fi.blocks_w[i] = fi.mcu_cols * fi.hs[i];
+                fi.blocks_h[i] = fi.mcu_rows * fi.vs[i];
+                uint32_t cw = (fi.width + fi.subx[i] - 1) / fi.subx[i], ch = (fi.height + fi.suby[i] - 1) / fi.suby[i];
+                fi.stored_blocks += (uint64_t)((cw + 7) >> 3) * ((ch + 7) >> 3);
+            }
+            have_sof = true;
+            break;
+        }
+        case 0xda: {
+            if (!have_sof) FAIL(B200JPG_ERR_MALFORMED_STREAM, "found a start of scan before the frame header");
+            if (out.scans.size() >= B200JPG_MAX_SCANS) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "too many scans for the B200 path");
+            if (seglen < 8) FAIL(B200JPG_ERR_MALFORMED_STREAM, "marker length of the SOS marker invalid, must be at least 8 bytes long");
+            ScanInfo sc;
+            sc.ns = s[0];
+            if (sc.ns < 1 || sc.ns > 4) FAIL(B200JPG_ERR_MALFORMED_STREAM, "number of components in scan is invalid, must be between 1 and 4");
+            if (seglen != 2 * sc.ns + 6) FAIL(B200JPG_ERR_MALFORMED_STREAM, "length of the SOS marker is invalid");
+            for (int i = 0; i < sc.ns; i++) {
+                int id = s[1 + 2 * i], sel = s[2 + 2 * i], found = -1;
+                for (int j = 0; j < fi.ncomp; j++)
+                    if (fi.comp_id[j] == id) found = j;
+                if (found < 0) FAIL(B200JPG_ERR_MALFORMED_STREAM, "SOS marker references a component that is not part of the frame");
+                for (int j = 0; j < i; j++)
+                    if (sc.comp[j] == found) FAIL(B200JPG_ERR_MALFORMED_STREAM, "SOS includes the same component twice");
+                sc.comp[i] = found;
+                sc.td[i] = sel >> 4;
+                sc.ta[i] = sel & 15;
+                if (sc.td[i] > 3) FAIL(B200JPG_ERR_MALFORMED_STREAM, "DC table index in SOS marker is out of range, must be at most 4");
+                if (sc.ta[i] > 3) FAIL(B200JPG_ERR_MALFORMED_STREAM, "AC table index in SOS marker is out of range, must be at most 4");
+            }
+            const uint8_t *t = s + 1 + 2 * sc.ns;
+            if (t[0] != 0 || t[1] != 63)
+                FAIL(B200JPG_ERR_MALFORMED_STREAM, "scan start must be zero and scan stop must be 63 for the sequential operating modes");
+            if ((t[2] >> 4) != 0)
+                FAIL(B200JPG_ERR_MALFORMED_STREAM, "successive approximation parameters must be zero for the sequential operating modes");
+            sc.lowbit = t[2] & 15;
+            sc.dri = dri;
+            sc.ecs_off = pos + (size_t)seglen;
+            if (sc.ns > 1) {
+                sc.mcu_cols = fi.mcu_cols;
+                sc.mcu_rows = fi.mcu_rows;
+            } else {  // sequentialscan.cpp:393-394: a single component scan walks that component's own block grid
+                int ci = sc.comp[0];
+                uint32_t cw = (fi.width + fi.subx[ci] - 1) / fi.subx[ci], ch = (fi.height + fi.suby[ci] - 1) / fi.suby[ci];
+                sc.mcu_cols = (cw + 7) >> 3;
+                sc.mcu_rows = (ch + 7) >> 3;
+            }
+            for (int i = 0; i < 4; i++) {
+                sc.dc[i] = dc[i];
+                sc.ac[i] = ac[i];
+                memcpy(sc.quant[i], quant[i], sizeof(quant[i]));
+                sc.quant_defined[i] = quant_defined[i];
+            }
+            for (int i = 0; i < sc.ns; i++) {
+                if (!dc[sc.td[i]].defined || !ac[sc.ta[i]].defined)
+                    FAIL(B200JPG_ERR_MALFORMED_STREAM, "Huffman decoder not specified for all components included in scan");  // sequentialscan.cpp:117-129
+                if (!quant_defined[fi.tq[sc.comp[i]]])
+                    FAIL(B200JPG_ERR_MALFORMED_STREAM, "quantization table for a component of the scan is not defined");
+            }
+            // restart-interval index
+            std::vector<size_t> rst_at;
+            std::vector<uint8_t> rst_id;
+            sc.ecs_end = index_ecs(c, sc.ecs_off, rst_at, rst_id);
+            uint64_t total = (uint64_t)sc.mcu_cols * sc.mcu_rows;
+            uint64_t per = sc.dri ? sc.dri : total;
+            uint64_t nint = (total + per - 1) / per;
+            sc.interval_off.assign((size_t)nint, SIZE_MAX);
+            sc.interval_off[0] = sc.ecs_off;
+            for (size_t k = 0; k + 1 < nint; k++) {
+                if (k >= rst_at.size()) break;  // stream ends early: remaining intervals stay absent (zero-filled)
+                if (rst_id[k] != 0xd0 + (k & 7))
+                    FAIL(B200JPG_ERR_MALFORMED_STREAM, "restart markers are out of sequence, resynchronisation is not supported by the B200 path");
+                sc.interval_off[k + 1] = rst_at[k] + 2;
+            }
+            fi.n_intervals += (uint32_t)nint;
+            fi.ecs_bytes += sc.ecs_end - sc.ecs_off;
+            if (out.scans.empty()) fi.restart_interval = dri;
+            pos = sc.ecs_end;
+            out.scans.push_back(std::move(sc));
+            continue;
+        }
+        default:
+            if (m == 0xc2 || m == 0xc3 || (m >= 0xc5 && m <= 0xcf && m != 0xc8 && m != 0xcc))
+                FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "only baseline / extended sequential Huffman frames are supported by the B200 path");
+            break;  // APPn, COM, JPG extensions: skipped by length (tables.cpp:1057-1072,1385-1399)
+        }
+        pos += (size_t)seglen;
+    }
+    if (!have_sof) FAIL(B200JPG_ERR_MALFORMED_STREAM, "codestream contains no frame header");
+    if (out.scans.empty()) FAIL(B200JPG_ERR_MALFORMED_STREAM, "codestream contains no scan");
+    fi.nscans = (uint32_t)out.scans.size();
+    fi.ycbcr = (fi.ncomp == 3 && !adobe_none) ? 1 : 0;  // tables.cpp:2023-2030
+    return B200JPG_OK;
+}
+
+uint32_t TableSet::lut_words() const {
+    uint32_t v;
+    memcpy(&v, blob.data() + 8, 4);
+    return v;
+}
+
+int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
+    std::vector<uint16_t> lut;
+    uint16_t lut_off[8];
+    for (int t = 0; t < 8; t++) {
+        const HuffSpec &h = (t < 4) ? scan.dc[t] : scan.ac[t - 4];
+        lut_off[t] = 0xffff;
+        if (!h.defined) continue;
+        bool used = false;
+        for (int i = 0; i < scan.ns; i++) used |= (t < 4) ? (scan.td[i] == t) : (scan.ta[i] == t - 4);
+        if (!used) continue;
+        size_t base = lut.size();
+        if (base > 0xfff0) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "Huffman tables too large for the B200 decoder tables");
+        lut_off[t] = (uint16_t)base;
+        lut.resize(base + 256, 0xff00);
+        int sub_of[256];
+        for (int i = 0; i < 256; i++) sub_of[i] = 0;
+        int nsub = 0;
+        uint32_t code = 0;  // left aligned in 16 bits
+        int v = 0;
+        for (int i = 0; i < 16; i++) {
+            for (int j = 0; j < h.bits[i]; j++) {
+                if (v >= h.nvals) FAIL(B200JPG_ERR_MALFORMED_STREAM, "Huffman table marker depends on undefined data");
+                uint8_t sym = h.vals[v++];
+                uint32_t last = code + (1u << (15 - i));
+                if (last > 0x10000u)
+                    FAIL(B200JPG_ERR_MALFORMED_STREAM, "Huffman table corrupt - entry depends on more bits than available for the bit length");
+                uint32_t q = code >> 8, qlast = last >> 8;
+                if (i < 8) {
+                    do {
+                        lut[base + q] = (uint16_t)(((i + 1) << 8) | sym);
+                    } while (++q < qlast);
+                    code = last;
+                } else {
+                    if (!sub_of[q]) {
+                        sub_of[q] = ++nsub;
+                        lut.resize(base + 256 + 256 * (size_t)nsub, 0xff00);
+                        lut[base + q] = (uint16_t)sub_of[q];  // len 0 -> level 2
+                    }
+                    size_t sb = base + 256 * (size_t)sub_of[q];
+                    do {
+                        lut[sb + (code & 0xff)] = (uint16_t)(((i + 1) << 8) | sym);
+                    } while (++code < last);
+                }
+            }
+        }
+    }
+    if (lut.size() > 0xffff + 256u * 256u) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "Huffman tables too large for the B200 decoder tables");
+    size_t total = kTableHeaderBytes + lut.size() * 2;
+    total = (total + 15) & ~(size_t)15;
+    out.blob.assign(total, 0);
+    uint32_t hdr[4] = {kTableMagic, (uint32_t)total, (uint32_t)lut.size(), 0};
+    memcpy(out.blob.data(), hdr, 16);
+    memcpy(out.blob.data() + 16, lut_off, 16);
+    uint32_t *qz = (uint32_t *)(out.blob.data() + 32);
+    for (int t = 0; t < 4; t++)
+        for (int k = 0; k < 64; k++) {
+            uint32_t delta = scan.quant_defined[t] ? scan.quant[t][k] : 0;
+            qz[t * 64 + k] = ((delta << scan.lowbit) << 8) | kZigZagToRaster[k];
+        }
+    memcpy(out.blob.data() + kTableHeaderBytes, lut.data(), lut.size() * 2);
+    return B200JPG_OK;
+}
+
+}  // namespace b200jpg

@@ -1,0 +1,98 @@
+"""ctypes binding of oracle/_ref/libjpgoracle.so (the plain-C restatement of the reference). TEST-ONLY."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "_ref", "libjpgoracle.so")
+REF_HARNESS = os.path.join(ORACLE_DIR, "_ref", "refharness")
+REF_CLI = os.path.join(ORACLE_DIR, "_ref", "jpeg")
+
+
+class ScanStruct(ctypes.Structure):
+    _fields_ = [("ns", ctypes.c_int), ("comp", ctypes.c_int * 4), ("td", ctypes.c_int * 4), ("ta", ctypes.c_int * 4),
+                ("restart_interval", ctypes.c_int), ("ecs_offset", ctypes.c_size_t), ("ecs_end", ctypes.c_size_t),
+                ("mcu_cols", ctypes.c_int), ("mcu_rows", ctypes.c_int)]
+
+
+class InfoStruct(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("ncomp", ctypes.c_int), ("precision", ctypes.c_int),
+                ("frame_type", ctypes.c_int), ("cid", ctypes.c_int * 4), ("hs", ctypes.c_int * 4), ("vs", ctypes.c_int * 4),
+                ("tq", ctypes.c_int * 4), ("hmax", ctypes.c_int), ("vmax", ctypes.c_int), ("subx", ctypes.c_int * 4),
+                ("suby", ctypes.c_int * 4), ("mcu_cols", ctypes.c_int), ("mcu_rows", ctypes.c_int), ("bw", ctypes.c_int * 4),
+                ("bh", ctypes.c_int * 4), ("sbw", ctypes.c_int * 4), ("sbh", ctypes.c_int * 4), ("ycbcr", ctypes.c_int),
+                ("nscans", ctypes.c_int), ("scan", ScanStruct * 8), ("quant", (ctypes.c_uint16 * 64) * 4),
+                ("quant_defined", ctypes.c_int * 4)]
+
+
+class Oracle:
+    def __init__(self, lib):
+        self.lib = lib
+        lib.jpgo_read_info.restype = ctypes.c_int
+        lib.jpgo_read_info.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(InfoStruct)]
+        lib.jpgo_decode.restype = ctypes.c_int
+        lib.jpgo_decode.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(InfoStruct)]
+        lib.jpgo_decode_coefficients.restype = ctypes.c_int
+        lib.jpgo_decode_coefficients.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(InfoStruct), ctypes.POINTER(ctypes.c_void_p)]
+        lib.jpgo_idct_block.restype = None
+        lib.jpgo_idct_block.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+
+    def info(self, data):
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        s = InfoStruct()
+        rc = self.lib.jpgo_read_info(data.ctypes.data, data.size, ctypes.byref(s))
+        return rc, s
+
+    def decode(self, data):
+        """-> (rc, pixels [H,W,C] uint8 or None)"""
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        rc, s = self.info(data)
+        if rc != 0:
+            return rc, None
+        out = np.zeros((s.height, s.width, s.ncomp), dtype=np.uint8)
+        rc = self.lib.jpgo_decode(data.ctypes.data, data.size, out.ctypes.data, out.size, ctypes.byref(s))
+        return rc, (out if rc == 0 else None)
+
+    def coefficients(self, data):
+        """-> (rc, info, [per component int32 [bh,bw,8,8] QUANTIZED raster-order coefficients])"""
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        rc, s = self.info(data)
+        if rc != 0:
+            return rc, s, None
+        planes = [np.zeros((s.bh[c], s.bw[c], 8, 8), dtype=np.int32) for c in range(s.ncomp)]
+        ptrs = (ctypes.c_void_p * 4)(*[p.ctypes.data for p in planes] + [None] * (4 - s.ncomp))
+        rc = self.lib.jpgo_decode_coefficients(data.ctypes.data, data.size, ctypes.byref(s), ptrs)
+        return rc, s, planes
+
+    def idct(self, block_raster_int32, delta_raster_u16, dcoffset=128):
+        src = np.ascontiguousarray(block_raster_int32, dtype=np.int32)
+        q = np.ascontiguousarray(delta_raster_u16, dtype=np.uint16)
+        out = np.zeros(64, dtype=np.int32)
+        self.lib.jpgo_idct_block(out.ctypes.data, src.ctypes.data, q.ctypes.data, dcoffset)
+        return out.reshape(8, 8)
+
+
+def build():
+    """Compiles the C restatement (always) and, where /root/reference exists, the reference itself."""
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "all"], check=True)
+
+
+def load():
+    if not os.path.exists(LIB):
+        build()
+    return Oracle(ctypes.CDLL(LIB))
+
+
+def have_reference():
+    return os.path.exists(REF_HARNESS) and os.path.exists(REF_CLI)
+
+
+def reference_decode(jpg_path, tmp_raw):
+    r = subprocess.run([REF_HARNESS, "decode", jpg_path, tmp_raw], capture_output=True, text=True)
+    if r.returncode != 0:
+        return None
+    w, h, d = map(int, r.stdout.split())
+    return np.fromfile(tmp_raw, dtype=np.uint8).reshape(h, w, d)

@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library loads, exports every symbol include/b200jpg.h declares, and its host-side parser
+agrees with the oracle's on the golden vectors.  No compute calls (there is no GPU here)."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.jpg")))
+
+
+def test_library_exports_every_declared_symbol(built):
+    header = open(os.path.join(ROOT, "include", "b200jpg.h")).read()
+    declared = sorted(set(re.findall(r"B200JPG_API\s+[\w\s\*]+?\b(b200jpg_\w+)\s*\(", header)))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(built.library_path())
+    for name in declared:
+        assert hasattr(lib, name), "missing export " + name
+    from libjpeg_b200 import native
+    assert sorted(native.ABI_SYMBOLS) == declared
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_parser_agrees_with_oracle(built, oracle, name):
+    data = open(os.path.join(GOLDEN, name + ".jpg"), "rb").read()
+    fi = built.parse(data)
+    rc, s = oracle.info(data)
+    assert rc == 0
+    assert (fi.width, fi.height, fi.ncomp) == (s.width, s.height, s.ncomp)
+    assert list(fi.subx) == list(s.subx[:s.ncomp]) and list(fi.suby) == list(s.suby[:s.ncomp])
+    assert list(fi.blocks_w) == list(s.bw[:s.ncomp]) and list(fi.blocks_h) == list(s.bh[:s.ncomp])
+    assert fi.nscans == s.nscans and fi.restart_interval == s.scan[0].restart_interval
+    assert fi.ecs_bytes == sum(s.scan[k].ecs_end - s.scan[k].ecs_offset for k in range(s.nscans))
+    assert fi.stored_blocks == sum(s.sbw[c] * s.sbh[c] for c in range(s.ncomp))
+    assert bool(fi.ycbcr) == bool(s.ycbcr)
+
+
+def test_parser_error_codes(built):
+    from libjpeg_b200 import NativeError
+    data = bytearray(open(os.path.join(GOLDEN, NAMES[0] + ".jpg"), "rb").read())
+    with pytest.raises(NativeError) as e:
+        built.parse(b"\x00\x01\x02\x03\x04")
+    assert e.value.code == -1038
+    prog = bytearray(data)
+    prog[prog.find(b"\xff\xc0") + 1] = 0xC2
+    with pytest.raises(NativeError) as e:
+        built.parse(bytes(prog))
+    assert e.value.code == -1034
+    with pytest.raises(NativeError) as e:
+        built.parse(bytes(data[:200]))
+    assert e.value.code in (-1025, -1038)
+
+
+def test_decode_fails_loudly_without_gpu(built):
+    """No CPU fallback: creating a decode context without a CUDA device is an error, never a silent detour."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from libjpeg_b200 import NativeError
+    from libjpeg_b200.decoder import Context
+    with pytest.raises(NativeError) as e:
+        Context()
+    assert e.value.code == -8193
+
+
+def test_synthetic_generator_roundtrip_through_oracle(built, oracle):
+    from libjpeg_b200 import synth
+    img = synth.source_image(64, 48, 3)
+    data = synth.encode(img, 90, (2, 2), 4)
+    rc, px = oracle.decode(data.tobytes())
+    assert rc == 0 and px.shape == img.shape
+    assert np.abs(px.astype(int) - img.astype(int)).mean() < 12  # a lossy codec, not garbage

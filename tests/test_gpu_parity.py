@@ -1,0 +1,128 @@
+"""GPU: the CUDA path (through the C ABI) against the golden vectors, the oracle, and size-independent
+properties at the benchmark's frame sizes."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.jpg")))
+
+
+def gpu_decode(built, frames, **kw):
+    import torch
+    dec = built.BatchDecoder(frames, **kw)
+    out = dec.new_output()
+    out.fill_(0x5A)
+    dec.upload()
+    dec.decode(out)
+    torch.cuda.synchronize()
+    return dec, out
+
+
+@pytest.fixture(scope="module")
+def golden_pixels():
+    return np.load(os.path.join(GOLDEN, "golden_pixels.npz"))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_vector_bit_exact(built, golden_pixels, name):
+    data = open(os.path.join(GOLDEN, name + ".jpg"), "rb").read()
+    dec, out = gpu_decode(built, [data])
+    assert dec.status(0) == 0
+    px = dec.frame_view(out, 0).cpu().numpy()
+    ref = golden_pixels[name]
+    assert px.shape == ref.shape
+    assert np.array_equal(px, ref), "%d differing bytes" % int((px != ref).sum())
+
+
+def test_golden_vectors_as_one_heterogeneous_batch(built, golden_pixels):
+    """All fixtures in ONE batch: different geometries, samplings and tables -> several launch classes."""
+    datas = [open(os.path.join(GOLDEN, n + ".jpg"), "rb").read() for n in NAMES]
+    dec, out = gpu_decode(built, datas)
+    for i, n in enumerate(NAMES):
+        assert dec.status(i) == 0
+        assert np.array_equal(dec.frame_view(out, i).cpu().numpy(), golden_pixels[n]), n
+
+
+@pytest.mark.parametrize("name", ["c420_96x80_z6_q75", "c444_64x64_z16_q90", "c420_130x70_z9_q98", "g_40x24_z2_q75"])
+def test_coefficients_match_oracle(built, oracle, name):
+    """Stage (a) alone: dequantised int16 coefficients == oracle's quantised coefficients * delta."""
+    import torch
+    data = open(os.path.join(GOLDEN, name + ".jpg"), "rb").read()
+    dec = built.BatchDecoder([data])
+    dec.upload()
+    dec.decode_entropy()
+    torch.cuda.synchronize()
+    assert dec.status(0) == 0
+    rc, s, planes = oracle.coefficients(data)
+    assert rc == 0
+    for c in range(s.ncomp):
+        q = np.array(s.quant[s.tq[c]], dtype=np.int32).reshape(8, 8)
+        want = planes[c] * q
+        got = dec.coefficients(0, c).astype(np.int32)
+        assert np.array_equal(got, want), "component %d" % c
+
+
+@pytest.mark.parametrize("w,h,sub,z,q", [(1920, 1080, (2, 2), 120, 75), (3840, 2160, (2, 2), 240, 75), (512, 512, (1, 1), 256, 90),
+                                          (641, 479, (2, 2), 13, 75), (333, 200, (2, 1), 0, 60)])
+def test_synthetic_frames_match_oracle(built, oracle, w, h, sub, z, q):
+    """Benchmark-sized frames (cfg2/cfg3 geometry) from the in-repo generator: GPU pixels == oracle pixels."""
+    from libjpeg_b200 import synth
+    data = synth.encode(synth.source_image(w, h, 11), q, sub, z)
+    dec, out = gpu_decode(built, [data])
+    assert dec.status(0) == 0
+    rc, ref = oracle.decode(data.tobytes())
+    assert rc == 0
+    assert np.array_equal(dec.frame_view(out, 0).cpu().numpy(), ref)
+
+
+def test_batch_of_identical_geometry_is_frame_independent(built, oracle):
+    """Checksum-of-checksums property at batch scale: every copy of a frame decodes to the same bytes, and
+    distinct frames to their own oracle result, whatever their position in the batch."""
+    import torch
+    from libjpeg_b200 import synth
+    base = [synth.encode(synth.source_image(320, 176, s), 75, (2, 2), 20) for s in (1, 2, 3)]
+    frames = [base[i % 3] for i in range(96)]
+    dec, out = gpu_decode(built, frames)
+    refs = [oracle.decode(b.tobytes())[1] for b in base]
+    for i in range(96):
+        assert dec.status(i) == 0
+        assert np.array_equal(dec.frame_view(out, i).cpu().numpy(), refs[i % 3]), i
+    # and decode is idempotent: a second run over the same batch gives the same buffer
+    out2 = dec.new_output()
+    dec.decode(out2)
+    torch.cuda.synchronize()
+    for i in range(96):
+        assert torch.equal(dec.frame_view(out, i), dec.frame_view(out2, i))
+
+
+def test_corrupt_stream_is_reported_not_crashing(built):
+    from libjpeg_b200 import synth
+    good = synth.encode(synth.source_image(128, 64, 5), 75, (2, 2), 8)
+    bad = bytearray(good.tobytes())
+    i = bad.find(b"\xff\xda") + 14
+    for k in range(i + 40, i + 400):
+        if bad[k] != 0xFF and bad[k - 1] != 0xFF:
+            bad[k] = 0xF7  # mostly-ones bytes: runs the decoder into invalid / overlong codes
+    dec, out = gpu_decode(built, [good.tobytes(), bytes(bad)])
+    assert dec.status(0) == 0
+    assert dec.status(1) in (0, -1038, -1025)  # reported per frame; the good frame is untouched
+
+
+def test_truncated_stream_zero_fills_missing_intervals(built, oracle):
+    """A stream that ends early: intervals the file does not contain decode as zero blocks (the reference
+    greys out an invalid segment, sequentialscan.cpp:415-419) and the intervals before stay bit-exact."""
+    from libjpeg_b200 import synth
+    good = synth.encode(synth.source_image(128, 128, 9), 75, (2, 2), 8).tobytes()
+    rc, ref = oracle.decode(good)
+    cut = good.rfind(b"\xff\xd3")  # drop everything from the 4th restart marker on
+    trunc = good[:cut] + b"\xff\xd9"
+    dec, out = gpu_decode(built, [trunc])
+    assert dec.status(0) == 0
+    px = dec.frame_view(out, 0).cpu().numpy()
+    assert np.array_equal(px[:48], ref[:48])  # 4 intervals of one 16-row MCU row each, minus the filter halo row

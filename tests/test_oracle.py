@@ -1,0 +1,68 @@
+"""CPU: pins the oracle (oracle/jpeg_oracle.c) -- against the committed golden vectors that the unmodified
+reference produced (tests/golden/make_golden.py) and, where the reference build is present, against the
+reference itself on fresh streams."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from tests import oracle_binding
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.jpg")))
+
+
+@pytest.fixture(scope="module")
+def golden_pixels():
+    return np.load(os.path.join(GOLDEN, "golden_pixels.npz"))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_matches_golden(oracle, golden_pixels, name):
+    data = open(os.path.join(GOLDEN, name + ".jpg"), "rb").read()
+    rc, px = oracle.decode(data)
+    assert rc == 0
+    ref = golden_pixels[name]
+    assert px.shape == ref.shape
+    assert np.array_equal(px, ref), "oracle differs from the reference's pixels in %d bytes" % int((px != ref).sum())
+
+
+def test_golden_covers_all_vectors(golden_pixels):
+    assert sorted(golden_pixels.files) == NAMES and len(NAMES) >= 12
+
+
+@pytest.mark.skipif(not oracle_binding.have_reference(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("w,h,sub,z,q", [(72, 40, (2, 2), 3, 60), (31, 47, (2, 2), 0, 85), (64, 32, (1, 1), 8, 92),
+                                          (90, 33, (2, 1), 2, 70), (45, 90, (1, 2), 6, 70)])
+def test_oracle_matches_reference_on_synthetic_streams(oracle, built, tmp_path, w, h, sub, z, q):
+    """Streams from the repo's own generator, decoded by the real reference and by the oracle."""
+    from libjpeg_b200 import synth
+    data = synth.encode(synth.source_image(w, h, 7 * w + h), q, sub, z)
+    jpg = tmp_path / "s.jpg"
+    jpg.write_bytes(data.tobytes())
+    ref = oracle_binding.reference_decode(str(jpg), str(tmp_path / "s.raw"))
+    assert ref is not None
+    rc, px = oracle.decode(data.tobytes())
+    assert rc == 0 and np.array_equal(px, ref)
+
+
+def test_oracle_idct_dc_only(oracle):
+    """DC-only block: every sample = ((dc*q*16 + 128*128) * 512 + 256 >> 9) * 512 + 2048 >> 12 (idct.cpp:233-334)."""
+    blk = np.zeros(64, dtype=np.int32)
+    blk[0] = 5
+    q = np.full(64, 16, dtype=np.uint16)
+    out = oracle.idct(blk, q)
+    t = 5 * 16 * 16 + 128 * 128
+    p1 = (t * 512 + 256) >> 9
+    assert np.all(out == ((p1 * 512 + 2048) >> 12))
+
+
+def test_oracle_rejects_progressive_and_garbage(oracle):
+    data = bytearray(open(os.path.join(GOLDEN, NAMES[0] + ".jpg"), "rb").read())
+    i = data.find(b"\xff\xc0")
+    data[i + 1] = 0xC2
+    rc, _ = oracle.decode(bytes(data))
+    assert rc == -1034  # NOT_IMPLEMENTED
+    rc, _ = oracle.decode(b"\x00\x01\x02\x03")
+    assert rc == -1038  # MALFORMED_STREAM
