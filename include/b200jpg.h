@@ -133,6 +133,10 @@ B200JPG_API int b200jpg_batch_last_launch_count(const b200jpg_batch *batch);
 B200JPG_API void b200jpg_batch_enable_timing(b200jpg_batch *batch, int on);
 B200JPG_API int b200jpg_batch_last_timing(b200jpg_batch *batch, float *entropy_ms, float *reconstruct_ms);
 
+/* Measured int32 issue rate of the device in Gop/s (integer multiply-add counted as 2 ops):
+ * multiply-add only, add/logic only, and a 1:1 mix. Denominator of the reconstruction kernel's roofline. */
+B200JPG_API int b200jpg_microbench_int32(int device, float *imad_gops, float *alu_gops, float *mix_gops);
+
 /* One-call convenience used by the C++ JPEG shim: host codestreams in, HOST pixels out (upload, decode,
  * download, synchronise).  `out_host` receives b200jpg_batch_out_bytes(batch,-1) bytes. */
 B200JPG_API int b200jpg_decode_to_host(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, uint8_t *out_host,

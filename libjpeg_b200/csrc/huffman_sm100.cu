@@ -9,8 +9,10 @@
 //
 // Mapping.  The restart interval is the unit of work (each one restarts the bit reader byte-aligned and
 // resets the DC predictors, so intervals are independent).  A warp decodes 32 restart intervals, one per
-// lane, in lock step block by block: every lane owns its private bit window (64-bit register pair fed by
-// 32-bit read-only loads through L1), the Huffman tables of the scan live in shared memory, and each lane
+// lane, in lock step block by block: every lane owns its private bit window (64-bit register pair) fed from a
+// 64-byte shared-memory ring that cp.async (LDGSTS, 16 bytes at a time, three chunks ahead of the reader)
+// keeps filled, so HBM latency never sits on the decode chain; the Huffman tables of the scan live in shared
+// memory as combined (total bits | code length | symbol) entries, and each lane
 // scatters its coefficients de-zigzagged and dequantised into a private 128-byte shared-memory block that is
 // flushed to HBM as eight 16-byte vector stores -- explicit zeros included, so the coefficient store needs
 // no memset and every 128-byte block line is written exactly once.  Warp votes keep the per-symbol loop
@@ -34,21 +36,59 @@ constexpr uint32_t kErrUnexpectedEof = 1025u;  // -(-1025)
 
 struct BitWindow {
     const uint8_t *base;
-    uint64_t pos;   // next unread byte
-    uint64_t w;     // MSB-aligned window
-    int n;          // bits in w (real + virtual)
-    int vbits;      // virtual zero bits appended after a marker was met (io/bitstream.cpp:96-101)
+    uint32_t *ring;     // this lane's 16-word (64-byte) ring in shared memory: word (pos >> 2) & 15
+    uint64_t pos;       // next unread byte
+    uint64_t w;         // MSB-aligned window
+    uint32_t chunk;     // 16-byte chunk index the reader is in; chunks chunk .. chunk+3 are requested
+    int n;              // bits in w (real + virtual)
+    int vbits;          // virtual zero bits appended after a marker was met (io/bitstream.cpp:96-101)
     bool stopped;
 };
 
-__device__ __forceinline__ uint32_t ld_u8(const uint8_t *p) { return (uint32_t)__ldg(p); }
+__device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint8_t *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void ring_request(BitWindow &b, uint32_t chunk) {
+    cp_async16(b.ring + ((chunk & 3u) << 2), b.base + ((uint64_t)chunk << 4));
+    cp_async_commit();
+}
+
+// Opens the window at byte offset `off`: four chunks in flight, the first two landed.
+__device__ __forceinline__ void open_window(BitWindow &b, uint64_t off) {
+    b.pos = off;
+    b.chunk = (uint32_t)(off >> 4);
+    b.w = 0;
+    b.n = 0;
+    b.vbits = 0;
+    b.stopped = false;
+#pragma unroll
+    for (uint32_t i = 0; i < 4; i++) ring_request(b, b.chunk + i);
+    cp_async_wait<2>();
+}
+
+__device__ __forceinline__ uint32_t ring_byte(const BitWindow &b, uint64_t pos) {
+    return (b.ring[(uint32_t)(pos >> 2) & 15u] >> ((uint32_t)(pos & 3) * 8u)) & 0xffu;
+}
 
 // Guarantees n >= 32 (a Huffman code of <= 16 bits plus <= 15 value bits always fits).
 __device__ __forceinline__ void refill(BitWindow &b) {
     if (b.n > 32) return;
     if (!b.stopped) {
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(b.base + (b.pos & ~3ull));
-        uint32_t lo = __ldg(wp), hi = __ldg(wp + 1);
+        uint32_t c = (uint32_t)(b.pos >> 4);
+        if (c != b.chunk) {  // entered the next chunk: request the one three ahead, chunks c and c+1 must have landed
+            b.chunk = c;
+            ring_request(b, c + 3);
+            cp_async_wait<2>();
+        }
+        uint32_t wq = (uint32_t)(b.pos >> 2);
+        uint32_t lo = b.ring[wq & 15u], hi = b.ring[(wq + 1) & 15u];
         uint32_t raw = __funnelshift_r(lo, hi, (uint32_t)(b.pos & 3) * 8u);  // bytes pos..pos+3, little endian
         uint32_t ff = ((~raw) - 0x01010101u) & raw & 0x80808080u;             // any byte == 0xFF ?
         if (ff == 0) {
@@ -61,9 +101,9 @@ __device__ __forceinline__ void refill(BitWindow &b) {
         // rare: a 0xFF among the next four bytes -> byte stuffing or a marker (io/bitstream.cpp:63-101)
 #pragma unroll 1
         for (int i = 0; i < 4; i++) {
-            uint32_t v = ld_u8(b.base + b.pos);
+            uint32_t v = ring_byte(b, b.pos);
             if (v == 0xffu) {
-                if (ld_u8(b.base + b.pos + 1) != 0u) {
+                if (ring_byte(b, b.pos + 1) != 0u) {
                     b.stopped = true;  // marker: stay in front of it, feed zeros from now on
                     break;
                 }
@@ -88,17 +128,18 @@ __device__ __forceinline__ void consume(BitWindow &b, int bits) {
 }
 
 template <bool kLutShared>
-__device__ __forceinline__ uint32_t lut_at(const uint16_t *lut, uint32_t idx) {
+__device__ __forceinline__ uint32_t lut_at(const uint32_t *lut, uint32_t idx) {
     if (kLutShared) return lut[idx];
-    return (uint32_t)__ldg(lut + idx);
+    return __ldg(lut + idx);
 }
 
-// Huffman symbol at the head of the window: returns (len << 8) | symbol, len == 0xff for an unused code.
+// Huffman symbol at the head of the window: returns (total bits << 16) | (len << 8) | symbol, len == 0xff for
+// an unused code; total = code length + value bits that follow.
 template <bool kLutShared>
-__device__ __forceinline__ uint32_t huff_peek(const uint16_t *lut, uint32_t off, const BitWindow &b) {
+__device__ __forceinline__ uint32_t huff_peek(const uint32_t *lut, uint32_t off, const BitWindow &b) {
     uint32_t peek = (uint32_t)(b.w >> 48);
     uint32_t e = lut_at<kLutShared>(lut, off + (peek >> 8));
-    if ((e >> 8) == 0) e = lut_at<kLutShared>(lut, off + 256u * (e & 0xffu) + (peek & 0xffu));
+    if ((e & 0xff00u) == 0) e = lut_at<kLutShared>(lut, off + 256u * (e & 0xffu) + (peek & 0xffu));
     return e;
 }
 
@@ -116,18 +157,17 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ bytes, cons
                       const ClassScan *__restrict__ scans, const uint8_t *__restrict__ tables, int16_t *__restrict__ coef,
                       uint32_t *__restrict__ frame_status) {
     extern __shared__ __align__(16) uint8_t smem[];
-    // layout: [stage: kThreads * kStageStride int16][qz: 4*64 uint32][lut: lut_words uint16 (if shared)]
+    // layout: [stage: kThreads * kStageStride int16][ring: kThreads * 16 uint32][qz: 4*64 uint32][lut: lut_words uint32 (if shared)]
     int16_t *stage_all = reinterpret_cast<int16_t *>(smem);
-    uint32_t *qz = reinterpret_cast<uint32_t *>(smem + kThreads * kStageStride * 2);
-    uint16_t *lut_s = reinterpret_cast<uint16_t *>(smem + kThreads * kStageStride * 2 + 4 * 64 * 4);
+    uint32_t *ring_all = reinterpret_cast<uint32_t *>(smem + kThreads * kStageStride * 2);
+    uint32_t *qz = ring_all + kThreads * 16;
+    uint32_t *lut_s = qz + 4 * 64;
 
     const uint32_t *g_qz = reinterpret_cast<const uint32_t *>(tables + 32);
-    const uint16_t *g_lut = reinterpret_cast<const uint16_t *>(tables + kTableHeaderBytes);
+    const uint32_t *g_lut = reinterpret_cast<const uint32_t *>(tables + kTableHeaderBytes);
     for (int i = threadIdx.x; i < 4 * 64; i += kThreads) qz[i] = g_qz[i];
     if (kLutShared) {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(g_lut);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(lut_s);
-        for (uint32_t i = threadIdx.x; i < (p.lut_words + 1) / 2; i += kThreads) dst[i] = src[i];
+        for (uint32_t i = threadIdx.x; i < p.lut_words; i += kThreads) lut_s[i] = g_lut[i];
     }
     {
         uint4 z = make_uint4(0, 0, 0, 0);
@@ -136,7 +176,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ bytes, cons
         for (int i = 0; i < 8; i++) st[i] = z;
     }
     __syncthreads();
-    const uint16_t *lut = kLutShared ? lut_s : g_lut;
+    const uint32_t *lut = kLutShared ? lut_s : g_lut;
     const uint16_t *lut_off = reinterpret_cast<const uint16_t *>(tables + 16);
 
     int16_t *stage = stage_all + threadIdx.x * kStageStride;
@@ -167,11 +207,14 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ bytes, cons
 
     BitWindow b;
     b.base = bytes;
-    b.pos = (off == ~0ull) ? 0 : off;
+    b.ring = ring_all + threadIdx.x * 16;
+    b.pos = 0;
+    b.chunk = 0;
     b.w = 0;
     b.n = 0;
     b.vbits = 0;
     b.stopped = false;
+    if (lane_valid && off != ~0ull) open_window(b, off);
     bool decoding = lane_valid && off != ~0ull;  // absent interval: blocks stay zero (sequentialscan.cpp:415-419)
     uint32_t err = 0;
     int pred[4] = {0, 0, 0, 0};
@@ -198,14 +241,14 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ bytes, cons
                     if (busy) {
                         refill(b);
                         uint32_t e = huff_peek<kLutShared>(lut, dc_off[c], b);
-                        int len = (int)(e >> 8), s = (int)(e & 0xffu);
+                        int len = (int)((e >> 8) & 0xffu), s = (int)(e & 0xffu);
                         if (len > 16 || s > 15) {
                             err = kErrMalformed;
                             busy = false;
                             decoding = false;
                         } else {
                             int diff = value_bits(b, len, s);
-                            consume(b, len + s);
+                            consume(b, (int)(e >> 16));
                             pred[c] += diff;
                             int v = pred[c] * (int)(qz[q_off[c]] >> 8);
                             if (v != (int)(int16_t)v) err = kErrMalformed;  // does not fit the int16 store
@@ -217,7 +260,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ bytes, cons
                         if (busy) {
                             refill(b);
                             uint32_t e = huff_peek<kLutShared>(lut, ac_off[c], b);
-                            int len = (int)(e >> 8), rs = (int)(e & 0xffu);
+                            int len = (int)((e >> 8) & 0xffu), rs = (int)(e & 0xffu);
                             int r = rs >> 4, s = rs & 15;
                             if (len > 16) {
                                 err = kErrMalformed;
@@ -238,7 +281,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ bytes, cons
                             } else {
                                 k += r;
                                 int diff = value_bits(b, len, s);
-                                consume(b, len + s);
+                                consume(b, (int)(e >> 16));
                                 if (k >= 64) {
                                     err = kErrMalformed;  // :764-766
                                     busy = false;
@@ -286,8 +329,8 @@ int launch_entropy(const EntropyLaunch &l, void *stream) {
     const uint64_t total = (uint64_t)l.p.n_scans * l.p.intervals_per_scan;
     if (total == 0) return 0;
     const uint32_t grid = (uint32_t)((total + kThreads - 1) / kThreads);
-    size_t base_smem = (size_t)kThreads * kStageStride * 2 + 4 * 64 * 4;
-    size_t lut_bytes = ((size_t)l.p.lut_words * 2 + 3) & ~(size_t)3;
+    size_t base_smem = (size_t)kThreads * kStageStride * 2 + (size_t)kThreads * 64 + 4 * 64 * 4;
+    size_t lut_bytes = (size_t)l.p.lut_words * 4;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
     if (base_smem + lut_bytes <= 160 * 1024) {

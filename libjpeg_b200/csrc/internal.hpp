@@ -60,9 +60,10 @@ extern const uint8_t kZigZagToRaster[64];  // dct/dct.cpp:57-73
 //   uint32 magic, uint32 total_bytes, uint32 lut_words, uint32 flags
 //   uint16 lut_off[8]      word offset of the level-1 LUT of DC0..3, AC0..3 (0xFFFF = undefined)
 //   uint32 qz[4][64]       per quantisation table, index = zig-zag k: (delta << lowbit) << 8 | raster position
-//   uint16 lut[lut_words]  per table: 256 level-1 entries then 256 per level-2 sub-table
-// LUT entry: (len << 8) | symbol, len 1..16; level-1 entries with len == 0 hold the 1-based index of the
-// level-2 sub-table in the low byte; len == 0xFF marks an unused code (coding/huffmandecoder.hpp:87).
+//   uint32 lut[lut_words]  per table: 256 level-1 entries then 256 per level-2 sub-table
+// LUT entry: (total << 16) | (len << 8) | symbol, len 1..16 the code length, total = len + number of value bits
+// that follow the code; level-1 entries with len == 0 hold the 1-based index of the level-2 sub-table in the
+// low byte; len == 0xFF marks an unused code (coding/huffmandecoder.hpp:87).
 constexpr uint32_t kTableMagic = 0x4a54424cu;  // "LBTJ"
 constexpr int kTableHeaderBytes = 16 + 16 + 4 * 64 * 4;
 

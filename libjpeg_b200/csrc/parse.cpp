@@ -273,19 +273,21 @@ uint32_t TableSet::lut_words() const {
 }
 
 int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
-    std::vector<uint16_t> lut;
+    std::vector<uint32_t> lut;
     uint16_t lut_off[8];
+    const uint32_t kUnused = 0x0000ff00u;
     for (int t = 0; t < 8; t++) {
         const HuffSpec &h = (t < 4) ? scan.dc[t] : scan.ac[t - 4];
+        const bool is_ac = t >= 4;
         lut_off[t] = 0xffff;
         if (!h.defined) continue;
         bool used = false;
-        for (int i = 0; i < scan.ns; i++) used |= (t < 4) ? (scan.td[i] == t) : (scan.ta[i] == t - 4);
+        for (int i = 0; i < scan.ns; i++) used |= is_ac ? (scan.ta[i] == t - 4) : (scan.td[i] == t);
         if (!used) continue;
         size_t base = lut.size();
         if (base > 0xfff0) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "Huffman tables too large for the B200 decoder tables");
         lut_off[t] = (uint16_t)base;
-        lut.resize(base + 256, 0xff00);
+        lut.resize(base + 256, kUnused);
         int sub_of[256];
         for (int i = 0; i < 256; i++) sub_of[i] = 0;
         int nsub = 0;
@@ -298,28 +300,31 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
                 uint32_t last = code + (1u << (15 - i));
                 if (last > 0x10000u)
                     FAIL(B200JPG_ERR_MALFORMED_STREAM, "Huffman table corrupt - entry depends on more bits than available for the bit length");
+                // value bits that follow the code: DC: the symbol (<= 15 valid), AC: low nibble
+                uint32_t vbits = is_ac ? (sym & 15u) : (sym <= 15 ? sym : 0u);
+                uint32_t entry = ((uint32_t)(i + 1) + vbits) << 16 | (uint32_t)(i + 1) << 8 | sym;
                 uint32_t q = code >> 8, qlast = last >> 8;
                 if (i < 8) {
                     do {
-                        lut[base + q] = (uint16_t)(((i + 1) << 8) | sym);
+                        lut[base + q] = entry;
                     } while (++q < qlast);
                     code = last;
                 } else {
                     if (!sub_of[q]) {
                         sub_of[q] = ++nsub;
-                        lut.resize(base + 256 + 256 * (size_t)nsub, 0xff00);
-                        lut[base + q] = (uint16_t)sub_of[q];  // len 0 -> level 2
+                        lut.resize(base + 256 + 256 * (size_t)nsub, kUnused);
+                        lut[base + q] = (uint32_t)sub_of[q];  // len 0 -> level 2
                     }
                     size_t sb = base + 256 * (size_t)sub_of[q];
                     do {
-                        lut[sb + (code & 0xff)] = (uint16_t)(((i + 1) << 8) | sym);
+                        lut[sb + (code & 0xff)] = entry;
                     } while (++code < last);
                 }
             }
         }
     }
-    if (lut.size() > 0xffff + 256u * 256u) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "Huffman tables too large for the B200 decoder tables");
-    size_t total = kTableHeaderBytes + lut.size() * 2;
+    if (lut.size() > 0xffffu) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "Huffman tables too large for the B200 decoder tables");
+    size_t total = kTableHeaderBytes + lut.size() * 4;
     total = (total + 15) & ~(size_t)15;
     out.blob.assign(total, 0);
     uint32_t hdr[4] = {kTableMagic, (uint32_t)total, (uint32_t)lut.size(), 0};
@@ -329,9 +334,11 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
     for (int t = 0; t < 4; t++)
         for (int k = 0; k < 64; k++) {
             uint32_t delta = scan.quant_defined[t] ? scan.quant[t][k] : 0;
+            if (((uint64_t)delta << scan.lowbit) >= (1u << 24))
+                FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "quantisation step times point transform too large for the B200 path");
             qz[t * 64 + k] = ((delta << scan.lowbit) << 8) | kZigZagToRaster[k];
         }
-    memcpy(out.blob.data() + kTableHeaderBytes, lut.data(), lut.size() * 2);
+    memcpy(out.blob.data() + kTableHeaderBytes, lut.data(), lut.size() * 4);
     return B200JPG_OK;
 }
 
