@@ -49,8 +49,11 @@ struct ScanClass {
     int table_set = 0;
     std::vector<ClassScan> scans;
     std::vector<uint64_t> interval_off;  // absolute offsets into the packed byte buffer
+    std::vector<uint64_t> interval_end;
+    std::vector<uint64_t> clean_off;     // offsets into the unstuffed buffer
+    uint64_t interval_base = 0;          // index of this class's first interval in d_interval_len
     // offsets (bytes) of the device copies inside the input buffer
-    uint64_t dev_scans = 0, dev_intervals = 0;
+    uint64_t dev_scans = 0, dev_intervals = 0, dev_interval_end = 0, dev_clean_off = 0;
 };
 
 struct ReconGroup {
@@ -89,6 +92,10 @@ struct b200jpg_batch {
     uint64_t coef_elems = 0;
     int32_t *d_samples = nullptr;
     uint64_t sample_elems = 0;
+    uint8_t *d_clean = nullptr;
+    uint64_t clean_bytes = 0;
+    uint32_t *d_interval_len = nullptr;
+    uint64_t n_intervals = 0;
     uint32_t *d_status = nullptr;
     std::vector<uint32_t> h_status;
     bool status_fetched = false;
@@ -161,6 +168,8 @@ void b200jpg_batch_destroy(b200jpg_batch *b) {
     if (b->d_input) cudaFree(b->d_input);
     if (b->d_coef) cudaFree(b->d_coef);
     if (b->d_samples) cudaFree(b->d_samples);
+    if (b->d_clean) cudaFree(b->d_clean);
+    if (b->d_interval_len) cudaFree(b->d_interval_len);
     if (b->d_status) cudaFree(b->d_status);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
@@ -333,10 +342,30 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
             for (int k = 0; k < sc.ns; k++) cs.coef_base[k] = coef_base[i][sc.comp[k]];
             cs.frame = (uint32_t)i;
             cl.scans.push_back(cs);
-            for (size_t off : sc.interval_off) cl.interval_off.push_back(off == SIZE_MAX ? ~0ull : byte_off[i] + (uint64_t)off);
+            for (size_t k = 0; k < sc.interval_off.size(); k++) {
+                size_t off = sc.interval_off[k], end = sc.interval_end[k];
+                cl.interval_off.push_back(off == SIZE_MAX ? ~0ull : byte_off[i] + (uint64_t)off);
+                cl.interval_end.push_back(off == SIZE_MAX ? 0ull : byte_off[i] + (uint64_t)end);
+            }
         }
     }
-    for (auto &cl : b->classes) cl.p.n_scans = (uint32_t)cl.scans.size();
+    // unstuffed-buffer layout: every interval gets its source length rounded up to 16 bytes + 48 bytes of zero tail
+    {
+        uint64_t ccur = 0, ibase = 0;
+        for (auto &cl : b->classes) {
+            cl.p.n_scans = (uint32_t)cl.scans.size();
+            cl.interval_base = ibase;
+            cl.clean_off.resize(cl.interval_off.size());
+            for (size_t k = 0; k < cl.interval_off.size(); k++) {
+                cl.clean_off[k] = ccur;
+                uint64_t len = cl.interval_off[k] == ~0ull ? 0 : cl.interval_end[k] - cl.interval_off[k];
+                ccur += align_up(len, 16) + 48;
+            }
+            ibase += cl.interval_off.size();
+        }
+        b->clean_bytes = ccur + 512;  // slack: the ring prefetch runs up to 64 bytes ahead of the reader
+        b->n_intervals = ibase;
+    }
 
     // ---- reconstruction groups
     for (int i = 0; i < n; i++) {
@@ -391,6 +420,10 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
         cur = align_up(cur + cl.scans.size() * sizeof(ClassScan), 256);
         cl.dev_intervals = cur;
         cur = align_up(cur + cl.interval_off.size() * sizeof(uint64_t), 256);
+        cl.dev_interval_end = cur;
+        cur = align_up(cur + cl.interval_end.size() * sizeof(uint64_t), 256);
+        cl.dev_clean_off = cur;
+        cur = align_up(cur + cl.clean_off.size() * sizeof(uint64_t), 256);
     }
     for (auto &g : b->groups) {
         g.dev_frames = cur;
@@ -434,13 +467,17 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
     for (auto &cl : b->classes) {
         memcpy(b->h_input + cl.dev_scans, cl.scans.data(), cl.scans.size() * sizeof(ClassScan));
         memcpy(b->h_input + cl.dev_intervals, cl.interval_off.data(), cl.interval_off.size() * sizeof(uint64_t));
+        memcpy(b->h_input + cl.dev_interval_end, cl.interval_end.data(), cl.interval_end.size() * sizeof(uint64_t));
+        memcpy(b->h_input + cl.dev_clean_off, cl.clean_off.data(), cl.clean_off.size() * sizeof(uint64_t));
     }
     for (auto &g : b->groups) memcpy(b->h_input + g.dev_frames, g.frames.data(), g.frames.size() * sizeof(FrameRecon));
 
     ce = cudaMalloc((void **)&b->d_input, b->input_bytes);
     if (ce == cudaSuccess && b->coef_elems) ce = cudaMalloc((void **)&b->d_coef, b->coef_elems * sizeof(int16_t));
     if (ce == cudaSuccess && b->sample_elems) ce = cudaMalloc((void **)&b->d_samples, b->sample_elems * sizeof(int32_t));
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&b->d_status, sizeof(uint32_t) * (size_t)n);
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&b->d_clean, b->clean_bytes);
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&b->d_interval_len, sizeof(uint32_t) * (size_t)std::max<uint64_t>(b->n_intervals, 1));
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&b->d_status, sizeof(uint32_t) * 2 * (size_t)n);  // status words + wide flags
     if (ce != cudaSuccess) return ctx->fail(B200JPG_ERR_OUT_OF_MEMORY, std::string("device allocation failed: ") + cudaGetErrorString(ce));
     b->h_status.assign(n, 0);
     *out = bp.release();
@@ -497,23 +534,31 @@ int b200jpg_batch_upload(b200jpg_batch *b, void *stream) {
 static int run_entropy(b200jpg_batch *b, void *stream) {
     cudaError_t e = cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * (size_t)b->n, (cudaStream_t)stream);
     if (e != cudaSuccess) return b->ctx->fail_cuda(e, "status reset");
-    for (auto &cl : b->classes) {
-        EntropyLaunch l{};
-        l.p = cl.p;
-        l.bytes = b->d_input;
-        l.interval_off = reinterpret_cast<const uint64_t *>(b->d_input + cl.dev_intervals);
-        l.scans = reinterpret_cast<const ClassScan *>(b->d_input + cl.dev_scans);
-        l.tables = b->d_input + b->dev_tables[cl.table_set];
-        l.coef = b->d_coef;
-        l.frame_status = b->d_status;
-        int rc = launch_entropy(l, stream);
-        if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "entropy kernel launch");
-        b->last_launches++;
+    for (int pass = 0; pass < 2; pass++) {  // a0 for every class, then a1 for every class
+        for (auto &cl : b->classes) {
+            EntropyLaunch l{};
+            l.p = cl.p;
+            l.bytes = b->d_input;
+            l.interval_off = reinterpret_cast<const uint64_t *>(b->d_input + cl.dev_intervals);
+            l.interval_end = reinterpret_cast<const uint64_t *>(b->d_input + cl.dev_interval_end);
+            l.clean_off = reinterpret_cast<const uint64_t *>(b->d_input + cl.dev_clean_off);
+            l.clean = b->d_clean;
+            l.interval_len = b->d_interval_len + cl.interval_base;
+            l.scans = reinterpret_cast<const ClassScan *>(b->d_input + cl.dev_scans);
+            l.tables = b->d_input + b->dev_tables[cl.table_set];
+            l.coef = b->d_coef;
+            l.frame_status = b->d_status;
+            int rc = pass == 0 ? launch_unstuff(l, stream) : launch_entropy(l, stream);
+            if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, pass == 0 ? "unstuff kernel launch" : "entropy kernel launch");
+            b->last_launches++;
+        }
     }
     return B200JPG_OK;
 }
 
 static int run_recon(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
+    cudaError_t me = cudaMemsetAsync(b->d_status + b->n, 0, sizeof(uint32_t) * (size_t)b->n, (cudaStream_t)stream);
+    if (me != cudaSuccess) return b->ctx->fail_cuda(me, "flag reset");
     for (auto &g : b->groups) {
         ReconLaunch l{};
         l.frames = reinterpret_cast<const FrameRecon *>(b->d_input + g.dev_frames);
@@ -527,6 +572,7 @@ static int run_recon(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
         l.suby = g.suby;
         l.coef = b->d_coef;
         l.samples = b->d_samples;
+        l.wide_flags = b->d_status + b->n;
         l.out = out_dev;
         int launches = 0;
         // grid.y carries the frame index: at most 65535 frames per launch

@@ -7,16 +7,24 @@
 //   BitStream<false>::Fill / Get / PeekWord / SkipBits io/bitstream.cpp:56-118, io/bitstream.hpp:168-208
 //   dequantisation multiplier                          dct/idct.cpp:98-108 (the << 4 is left to stage b)
 //
-// Mapping.  The restart interval is the unit of work (each one restarts the bit reader byte-aligned and
-// resets the DC predictors, so intervals are independent).  A warp decodes 32 restart intervals, one per
-// lane, in lock step block by block: every lane owns its private bit window (64-bit register pair) fed from a
-// 64-byte shared-memory ring that cp.async (LDGSTS, 16 bytes at a time, three chunks ahead of the reader)
-// keeps filled, so HBM latency never sits on the decode chain; the Huffman tables of the scan live in shared
-// memory as combined (total bits | code length | symbol) entries, and each lane
-// scatters its coefficients de-zigzagged and dequantised into a private 128-byte shared-memory block that is
-// flushed to HBM as eight 16-byte vector stores -- explicit zeros included, so the coefficient store needs
-// no memset and every 128-byte block line is written exactly once.  Warp votes keep the per-symbol loop
-// convergent.  All intervals of all frames that share scan geometry and tables form one launch.
+// The restart interval is the unit of work: each one restarts the bit reader byte-aligned and resets the DC
+// predictors (sequentialscan.cpp:266-274), so intervals are independent.  Two kernels:
+//
+// a0  unstuff_kernel -- ONE WARP PER RESTART INTERVAL.  Streams the interval's entropy coded bytes (coalesced
+//     32-bit loads), finds stuffed zeros (FF 00 -> FF) and the terminating marker with byte tests, resolves every
+//     kept byte's destination with warp ballots + population-count prefix sums, stages the compacted bytes in shared
+//     memory and writes them out as big-endian 32-bit words (coalesced).  What the reference's Fill() does byte by
+//     byte (io/bitstream.cpp:56-118) is done here once, in parallel, so the decoder's refill is branch-free.
+//
+// a1  entropy_decode_kernel -- a warp decodes 32 restart intervals, one per lane, in lock step block by block.
+//     Every lane owns a 64-bit bit window (two registers) fed from a 64-byte shared-memory ring that cp.async
+//     (LDGSTS, 16-byte chunks, topped up at block boundaries, two to four chunks ahead of the reader) keeps filled,
+//     so HBM latency never sits on the decode chain.  The scan's Huffman tables live in shared memory as combined
+//     (total bits | code length | symbol) entries; each coefficient is de-zigzagged and dequantised with one more
+//     shared-memory lookup and scattered into the lane's private 128-byte shared-memory block, which is flushed to
+//     HBM as eight 16-byte vector stores -- explicit zeros included, so the coefficient store needs no memset and
+//     every 128-byte block line is written exactly once.  Warp votes keep the per-symbol loop convergent.
+//     All intervals of all frames that share scan geometry and tables form one launch.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -27,170 +35,184 @@ namespace b200jpg {
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kStageStride = 72;  // int16 per lane: 64 + 8 pad -> 144-byte stride, conflict-free 16-byte accesses
+constexpr int kStageStride = 144;  // bytes per lane: 128 + 16 pad -> conflict-free 16-byte accesses
 constexpr unsigned kFull = 0xffffffffu;
 
 // error codes written to frame_status (reference's numeric values, interface/parameters.hpp:1156-1228)
-constexpr uint32_t kErrMalformed = 1038u;      // -(-1038)
-constexpr uint32_t kErrUnexpectedEof = 1025u;  // -(-1025)
+constexpr uint32_t kErrMalformed = 1038u;      // -(-1038) MALFORMED_STREAM
+constexpr uint32_t kErrUnexpectedEof = 1025u;  // -(-1025) UNEXPECTED_EOF
 
-struct BitWindow {
-    const uint8_t *base;
-    uint32_t *ring;     // this lane's 16-word (64-byte) ring in shared memory: word (pos >> 2) & 15
-    uint64_t pos;       // next unread byte
-    uint64_t w;         // MSB-aligned window
-    uint32_t chunk;     // 16-byte chunk index the reader is in; chunks chunk .. chunk+3 are requested
-    int n;              // bits in w (real + virtual)
-    int vbits;          // virtual zero bits appended after a marker was met (io/bitstream.cpp:96-101)
-    bool stopped;
-};
-
-__device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint8_t *gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+// ---- shared-memory accessors on 32-bit shared-space addresses (keeps the compiler away from generic pointers)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {  // read-only tables: may be scheduled freely
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u32_v(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v4_zero(uint32_t a) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const uint8_t *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__device__ __forceinline__ void ring_request(BitWindow &b, uint32_t chunk) {
-    cp_async16(b.ring + ((chunk & 3u) << 2), b.base + ((uint64_t)chunk << 4));
-    cp_async_commit();
-}
+// =====================================================================================================
+// a0: byte unstuffing, one warp per restart interval
+// =====================================================================================================
+constexpr int kUnstuffWarps = 4;
 
-// Opens the window at byte offset `off`: four chunks in flight, the first two landed.
-__device__ __forceinline__ void open_window(BitWindow &b, uint64_t off) {
-    b.pos = off;
-    b.chunk = (uint32_t)(off >> 4);
-    b.w = 0;
-    b.n = 0;
-    b.vbits = 0;
-    b.stopped = false;
-#pragma unroll
-    for (uint32_t i = 0; i < 4; i++) ring_request(b, b.chunk + i);
-    cp_async_wait<2>();
-}
-
-__device__ __forceinline__ uint32_t ring_byte(const BitWindow &b, uint64_t pos) {
-    return (b.ring[(uint32_t)(pos >> 2) & 15u] >> ((uint32_t)(pos & 3) * 8u)) & 0xffu;
-}
-
-// Guarantees n >= 32 (a Huffman code of <= 16 bits plus <= 15 value bits always fits).
-__device__ __forceinline__ void refill(BitWindow &b) {
-    if (b.n > 32) return;
-    if (!b.stopped) {
-        uint32_t c = (uint32_t)(b.pos >> 4);
-        if (c != b.chunk) {  // entered the next chunk: request the one three ahead, chunks c and c+1 must have landed
-            b.chunk = c;
-            ring_request(b, c + 3);
-            cp_async_wait<2>();
-        }
-        uint32_t wq = (uint32_t)(b.pos >> 2);
-        uint32_t lo = b.ring[wq & 15u], hi = b.ring[(wq + 1) & 15u];
-        uint32_t raw = __funnelshift_r(lo, hi, (uint32_t)(b.pos & 3) * 8u);  // bytes pos..pos+3, little endian
-        uint32_t ff = ((~raw) - 0x01010101u) & raw & 0x80808080u;             // any byte == 0xFF ?
-        if (ff == 0) {
-            uint32_t be = __byte_perm(raw, 0, 0x0123);
-            b.w |= (uint64_t)be << (32 - b.n);
-            b.n += 32;
-            b.pos += 4;
-            return;
-        }
-        // rare: a 0xFF among the next four bytes -> byte stuffing or a marker (io/bitstream.cpp:63-101)
-#pragma unroll 1
-        for (int i = 0; i < 4; i++) {
-            uint32_t v = ring_byte(b, b.pos);
-            if (v == 0xffu) {
-                if (ring_byte(b, b.pos + 1) != 0u) {
-                    b.stopped = true;  // marker: stay in front of it, feed zeros from now on
-                    break;
-                }
-                b.pos += 2;
-            } else {
-                b.pos += 1;
-            }
-            b.w |= (uint64_t)v << (56 - b.n);
-            b.n += 8;
-        }
-        if (!b.stopped || b.n > 32) return;
+__global__ void __launch_bounds__(kUnstuffWarps * 32)
+unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ interval_off,
+               const uint64_t *__restrict__ interval_end, const uint64_t *__restrict__ clean_off, uint8_t *__restrict__ clean,
+               uint32_t *__restrict__ interval_len) {
+    __shared__ __align__(16) uint8_t sbuf[kUnstuffWarps][256];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.x * kUnstuffWarps + wib;
+    if (g >= n_intervals) return;  // whole warp
+    const uint64_t src0 = interval_off[g];
+    if (src0 == ~0ull) {  // interval not present in the stream
+        if (lane == 0) interval_len[g] = 0;
+        return;
     }
-    // in front of a marker: the reference appends zero bits (io/bitstream.cpp:96-101); count them so the
-    // end-of-interval check can tell whether any of them was actually consumed
-    b.n += 32;
-    b.vbits += 32;
+    const uint64_t src1 = interval_end[g];  // offset of the marker that ends the interval
+    uint32_t *dst = reinterpret_cast<uint32_t *>(clean + clean_off[g]);
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(&sbuf[wib][0]);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    uint32_t fill = 0;     // bytes waiting in sbuf (< 128 between steps)
+    uint32_t written = 0;  // words already written to dst
+    uint32_t total = 0;    // clean bytes so far
+    uint32_t carry_ff = 0; // the last byte of the previous step was a data 0xFF
+    bool done = false;
+    // the source is read in aligned 32-bit words; bytes in front of src0 are masked out
+    for (uint64_t base = src0 & ~3ull; base < src1 && !done; base += 128) {
+        const uint64_t wo = base + 4ull * lane;
+        uint32_t cur = 0, nxt = 0;
+        if (wo < src1) cur = __ldg(reinterpret_cast<const uint32_t *>(bytes + wo));
+        if (wo + 4 < src1 + 2) nxt = __ldg(reinterpret_cast<const uint32_t *>(bytes + wo + 4));  // reaches the marker bytes
+        // byte in front of this lane's word: the previous lane's last byte (lane 0: carried from the last step)
+        uint32_t prev_word = __shfl_up_sync(kFull, cur, 1);
+        uint32_t pb = (lane == 0) ? (carry_ff ? 0xffu : 0u) : ((wo - 1 >= src0) ? (prev_word >> 24) : 0u);
+        uint32_t keep[4];
+        uint32_t mk = 4;  // index of the first marker byte in this word, 4 = none
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint64_t q = wo + k;
+            const uint32_t v = (cur >> (8 * k)) & 0xffu;
+            const uint32_t nb = (k < 3) ? ((cur >> (8 * k + 8)) & 0xffu) : (nxt & 0xffu);
+            const bool in = (q >= src0) && (q < src1);
+            const bool stuffed = (v == 0u) && (pb == 0xffu);      // the 00 of FF 00 (io/bitstream.cpp:87-95)
+            const bool marker = in && (v == 0xffu) && (nb != 0u);  // FF followed by non-zero (:96-101)
+            if (marker && mk == 4) mk = k;
+            keep[k] = (in && !stuffed) ? 1u : 0u;
+            pb = in ? v : 0u;
+        }
+        // the first lane that holds a marker byte ends the interval: nothing at or after it is data
+        const uint32_t mmask = __ballot_sync(kFull, mk < 4);
+        const uint32_t first = mmask ? (uint32_t)(__ffs(mmask) - 1) : 32u;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (lane > first || (lane == first && k >= (int)mk)) keep[k] = 0;
+        // destination of every kept byte: one ballot per byte column + population-count prefix sums
+        const uint32_t b0 = __ballot_sync(kFull, keep[0]), b1 = __ballot_sync(kFull, keep[1]);
+        const uint32_t b2 = __ballot_sync(kFull, keep[2]), b3 = __ballot_sync(kFull, keep[3]);
+        const uint32_t before = __popc(b0 & lt_mask) + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
+        const uint32_t step_total = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+        uint32_t o = fill + before;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (keep[k]) {
+                sts_u8(sb + (o ^ 3u), (cur >> (8 * k)) & 0xffu);  // ^3: big-endian inside each 32-bit word
+                o++;
+            }
+        }
+        carry_ff = __shfl_sync(kFull, ((cur >> 24) == 0xffu && keep[3]) ? 1u : 0u, 31);
+        fill += step_total;
+        total += step_total;
+        done = (first < 32);
+        __syncwarp();
+        if (fill >= 128) {  // flush 32 complete words, move the rest down
+            const uint32_t w = lds_u32_v(sb + 4 * lane);
+            const uint32_t w2 = lds_u32_v(sb + 128 + 4 * lane);
+            dst[written + lane] = w;
+            __syncwarp();
+            sts_u32(sb + 4 * lane, w2);
+            written += 32;
+            fill -= 128;
+            __syncwarp();
+        }
+    }
+    // tail: remaining bytes, zero padded to 16 bytes, plus 32 zero bytes so that the decoder reads zeros past the
+    // end (the reference feeds zero bits once it stands in front of a marker, io/bitstream.cpp:96-101)
+    __syncwarp();
+    {
+        uint32_t w = lds_u32_v(sb + 4 * lane);
+        const uint32_t nbytes = fill, wi = 4 * lane;
+        if (wi >= nbytes) w = 0;
+        else if (wi + 4 > nbytes) w &= ~0u << (8 * (wi + 4 - nbytes));  // big-endian word: keep the leading bytes
+        const uint32_t nwords = (nbytes + 3) / 4;
+        const uint32_t padded = ((nwords + 3) & ~3u) + 8;
+        if (lane < padded) dst[written + lane] = w;
+        if (lane + 32 < padded) dst[written + 32 + lane] = 0;
+    }
+    if (lane == 0) interval_len[g] = total;
 }
 
-__device__ __forceinline__ void consume(BitWindow &b, int bits) {
-    b.w <<= bits;
-    b.n -= bits;
-}
-
-template <bool kLutShared>
-__device__ __forceinline__ uint32_t lut_at(const uint32_t *lut, uint32_t idx) {
-    if (kLutShared) return lut[idx];
-    return __ldg(lut + idx);
-}
-
-// Huffman symbol at the head of the window: returns (total bits << 16) | (len << 8) | symbol, len == 0xff for
-// an unused code; total = code length + value bits that follow.
-template <bool kLutShared>
-__device__ __forceinline__ uint32_t huff_peek(const uint32_t *lut, uint32_t off, const BitWindow &b) {
-    uint32_t peek = (uint32_t)(b.w >> 48);
-    uint32_t e = lut_at<kLutShared>(lut, off + (peek >> 8));
-    if ((e & 0xff00u) == 0) e = lut_at<kLutShared>(lut, off + 256u * (e & 0xffu) + (peek & 0xffu));
-    return e;
-}
-
-// `s` value bits that follow a code of `len` bits, sign-extended as in sequentialscan.cpp:692-696 / 757-762
-__device__ __forceinline__ int value_bits(const BitWindow &b, int len, int s) {
-    uint32_t hi = (uint32_t)(b.w >> 32);
-    uint32_t v = ((hi << len) >> 1) >> (31 - s);  // s == 0 -> 0
-    uint32_t thresh = (1u << s) >> 1;
-    return (int)v - ((v < thresh) ? (int)((1u << s) - 1u) : 0);
-}
-
+// =====================================================================================================
+// a1: Huffman decode, one restart interval per lane
+// =====================================================================================================
 template <bool kLutShared>
 __global__ void __launch_bounds__(kThreads)
-entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ interval_off,
-                      const ClassScan *__restrict__ scans, const uint8_t *__restrict__ tables, int16_t *__restrict__ coef,
-                      uint32_t *__restrict__ frame_status) {
+entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uint64_t *__restrict__ clean_off,
+                      const uint32_t *__restrict__ interval_len, const ClassScan *__restrict__ scans,
+                      const uint8_t *__restrict__ tables, int16_t *__restrict__ coef, uint32_t *__restrict__ frame_status) {
     extern __shared__ __align__(16) uint8_t smem[];
-    // layout: [stage: kThreads * kStageStride int16][ring: kThreads * 16 uint32][qz: 4*64 uint32][lut: lut_words uint32 (if shared)]
-    int16_t *stage_all = reinterpret_cast<int16_t *>(smem);
-    uint32_t *ring_all = reinterpret_cast<uint32_t *>(smem + kThreads * kStageStride * 2);
-    uint32_t *qz = ring_all + kThreads * 16;
-    uint32_t *lut_s = qz + 4 * 64;
-
-    const uint32_t *g_qz = reinterpret_cast<const uint32_t *>(tables + 32);
+    // layout (bytes): [stage: kThreads*144][ring: kThreads*64][qz: 4*64*4][lut: lut_words*4 (if shared)]
+    uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("" : "+r"(s_base));  // opaque: keeps the base in a register instead of re-deriving it (S2UR) at every use
+    const uint32_t s_stage = s_base + threadIdx.x * kStageStride;
+    const uint32_t s_ring = s_base + kThreads * kStageStride + threadIdx.x * 64;
+    const uint32_t s_qz = s_base + kThreads * kStageStride + kThreads * 64;
+    const uint32_t s_lut = s_qz + 4 * 64 * 4;
     const uint32_t *g_lut = reinterpret_cast<const uint32_t *>(tables + kTableHeaderBytes);
-    for (int i = threadIdx.x; i < 4 * 64; i += kThreads) qz[i] = g_qz[i];
-    if (kLutShared) {
-        for (uint32_t i = threadIdx.x; i < p.lut_words; i += kThreads) lut_s[i] = g_lut[i];
-    }
     {
-        uint4 z = make_uint4(0, 0, 0, 0);
-        uint4 *st = reinterpret_cast<uint4 *>(stage_all + threadIdx.x * kStageStride);
+        const uint32_t *g_qz = reinterpret_cast<const uint32_t *>(tables + 32);
+        for (uint32_t i = threadIdx.x; i < 4 * 64; i += kThreads) sts_u32(s_qz + 4 * i, g_qz[i]);
+        if (kLutShared)
+            for (uint32_t i = threadIdx.x; i < p.lut_words; i += kThreads) sts_u32(s_lut + 4 * i, g_lut[i]);
 #pragma unroll
-        for (int i = 0; i < 8; i++) st[i] = z;
+        for (int i = 0; i < 8; i++) sts_v4_zero(s_stage + 16 * i);
     }
     __syncthreads();
-    const uint32_t *lut = kLutShared ? lut_s : g_lut;
     const uint16_t *lut_off = reinterpret_cast<const uint16_t *>(tables + 16);
 
-    int16_t *stage = stage_all + threadIdx.x * kStageStride;
     const uint64_t total_intervals = (uint64_t)p.n_scans * p.intervals_per_scan;
     const uint64_t g = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool lane_valid = g < total_intervals;
-
-    // per-lane interval
     uint32_t j = 0, iv = 0;
     if (lane_valid) {
         j = (uint32_t)(g / p.intervals_per_scan);
         iv = (uint32_t)(g % p.intervals_per_scan);
     }
-    uint64_t off = lane_valid ? interval_off[g] : ~0ull;
+    const uint32_t len_bytes = lane_valid ? interval_len[g] : 0u;
+    const uint8_t *src = clean + (lane_valid ? clean_off[g] : 0ull);
     const uint32_t mcu0 = iv * p.dri;
     uint32_t nmcu = 0;
     if (lane_valid) nmcu = (p.total_mcus - mcu0 < p.dri) ? (p.total_mcus - mcu0) : p.dri;
@@ -205,21 +227,23 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ bytes, cons
         frame = cs.frame;
     }
 
-    BitWindow b;
-    b.base = bytes;
-    b.ring = ring_all + threadIdx.x * 16;
-    b.pos = 0;
-    b.chunk = 0;
-    b.w = 0;
-    b.n = 0;
-    b.vbits = 0;
-    b.stopped = false;
-    if (lane_valid && off != ~0ull) open_window(b, off);
-    bool decoding = lane_valid && off != ~0ull;  // absent interval: blocks stay zero (sequentialscan.cpp:415-419)
+    // an interval the stream does not contain keeps its blocks zero (sequentialscan.cpp:415-419)
+    bool decoding = lane_valid && len_bytes != 0u;
+    // bit window: MSB-aligned 64 bits in (hi, lo), n valid bits; wpos = 32-bit words taken from the stream;
+    // req = 16-byte chunks requested from HBM so far, safe = chunks known to have landed in the ring
+    uint32_t hi = 0, lo = 0, wpos = 0, req = 0, safe = 0;
+    int n = 0;
+    if (decoding) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) cp_async16(s_ring + 16 * i, src + 16 * i);
+        req = 4;
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    safe = req;
+
     uint32_t err = 0;
     int pred[4] = {0, 0, 0, 0};
-
-    // table offsets (uniform)
     uint32_t dc_off[4], ac_off[4], q_off[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
@@ -228,6 +252,48 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ bytes, cons
         q_off[c] = (c < p.ns) ? 64u * p.q_slot[c] : 0;
     }
 
+    // next 32 stream bits into the window (callers guarantee n <= 32)
+    auto refill = [&]() {
+        const uint32_t ch = wpos >> 2;
+        if (ch >= safe) {  // rare: ran past what the block-boundary top-up guarantees
+            while (req <= ch) {
+                cp_async16(s_ring + ((req & 3u) << 4), src + ((uint64_t)req << 4));
+                req++;
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            safe = req;
+        }
+        const uint32_t x = lds_u32_v(s_ring + ((wpos & 15u) << 2));
+        wpos++;
+        hi |= __funnelshift_rc(x, 0u, (uint32_t)n);  // x >> n          (0 for n == 32)
+        lo |= __funnelshift_rc(0u, x, (uint32_t)n);  // x << (32 - n)   (0 for n == 0)
+        n += 32;
+    };
+    auto lookup = [&](uint32_t off) -> uint32_t {
+        uint32_t e;
+        if (kLutShared) {
+            e = lds_u32(s_lut + ((off + (hi >> 24)) << 2));
+            if ((e & 0xff00u) == 0) e = lds_u32(s_lut + ((off + ((e & 0xffu) << 8) + ((hi >> 16) & 0xffu)) << 2));
+        } else {
+            e = __ldg(g_lut + off + (hi >> 24));
+            if ((e & 0xff00u) == 0) e = __ldg(g_lut + off + ((e & 0xffu) << 8) + ((hi >> 16) & 0xffu));
+        }
+        return e;
+    };
+    // s value bits after a code of len bits, sign-extended as sequentialscan.cpp:692-696 / 757-762
+    auto value_bits = [&](uint32_t len, uint32_t s) -> int {
+        const uint32_t t = hi << len;
+        const uint32_t v = __funnelshift_rc(t, 0u, 32u - s);  // t >> (32 - s), 0 for s == 0
+        const int ext = ((int)t < 0) ? 0 : (int)(1u - (1u << s));
+        return (int)v + (s ? ext : 0);
+    };
+    auto consume = [&](uint32_t t) {
+        hi = __funnelshift_l(lo, hi, t);
+        lo <<= t;
+        n -= (int)t;
+    };
+
     for (uint32_t mi = 0; mi < p.dri; mi++) {
         const bool has_mcu = mi < nmcu;
 #pragma unroll
@@ -235,78 +301,91 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ bytes, cons
             if (c >= p.ns) break;
             for (int y = 0; y < p.mh[c]; y++) {
                 for (int x = 0; x < p.mw[c]; x++) {
+                    // ---- convergent ring top-up: keep the reader two to four 16-byte chunks ahead
+                    {
+                        const uint32_t ch = wpos >> 2;
+                        const uint32_t landed = req;  // requested before this point: lands at the wait below
+#pragma unroll
+                        for (int t = 0; t < 2; t++) {
+                            if (decoding && req < ch + 4u) {
+                                cp_async16(s_ring + ((req & 3u) << 4), src + ((uint64_t)req << 4));
+                                req++;
+                            }
+                            cp_async_commit();
+                        }
+                        cp_async_wait<2>();
+                        safe = landed;
+                    }
                     bool busy = has_mcu && decoding;
                     int k = 1;
                     // ---- DC: sequentialscan.cpp:682-701
                     if (busy) {
-                        refill(b);
-                        uint32_t e = huff_peek<kLutShared>(lut, dc_off[c], b);
-                        int len = (int)((e >> 8) & 0xffu), s = (int)(e & 0xffu);
-                        if (len > 16 || s > 15) {
+                        if (n <= 32) refill();
+                        const uint32_t e = lookup(dc_off[c]);
+                        const uint32_t len = (e >> 8) & 0xffu, s = e & 0xffu;
+                        if (len > 16u || s > 15u) {
                             err = kErrMalformed;
                             busy = false;
                             decoding = false;
                         } else {
-                            int diff = value_bits(b, len, s);
-                            consume(b, (int)(e >> 16));
+                            const int diff = value_bits(len, s);
+                            consume(e >> 16);
                             pred[c] += diff;
-                            int v = pred[c] * (int)(qz[q_off[c]] >> 8);
-                            if (v != (int)(int16_t)v) err = kErrMalformed;  // does not fit the int16 store
-                            stage[0] = (int16_t)v;
+                            const int v = pred[c] * (int)(lds_u32(s_qz + (q_off[c] << 2)) >> 8);
+                            if (v != (int)(short)v) err = kErrMalformed;  // does not fit the int16 store
+                            sts_u16(s_stage, v);
                         }
                     }
                     // ---- AC: sequentialscan.cpp:704-771, one symbol per warp-convergent iteration
                     while (__any_sync(kFull, busy)) {
                         if (busy) {
-                            refill(b);
-                            uint32_t e = huff_peek<kLutShared>(lut, ac_off[c], b);
-                            int len = (int)((e >> 8) & 0xffu), rs = (int)(e & 0xffu);
-                            int r = rs >> 4, s = rs & 15;
-                            if (len > 16) {
+                            if (n <= 32) refill();
+                            const uint32_t e = lookup(ac_off[c]);
+                            const uint32_t len = (e >> 8) & 0xffu, r = (e >> 4) & 15u, s = e & 15u;
+                            if (len > 16u) {
                                 err = kErrMalformed;
                                 busy = false;
                                 decoding = false;
-                            } else if (s == 0) {
-                                consume(b, len);
-                                if (r == 15) {
-                                    k += 16;  // ZRL; the reference re-tests k <= 63 and silently ends the block
-                                    busy = (k <= 63);
-                                } else if (r == 0) {
-                                    busy = false;  // EOB
-                                } else {
-                                    err = kErrMalformed;  // sequentialscan.cpp:750-752
-                                    busy = false;
-                                    decoding = false;
-                                }
                             } else {
-                                k += r;
-                                int diff = value_bits(b, len, s);
-                                consume(b, (int)(e >> 16));
-                                if (k >= 64) {
-                                    err = kErrMalformed;  // :764-766
-                                    busy = false;
-                                    decoding = false;
+                                const int diff = value_bits(len, s);
+                                consume(e >> 16);
+                                if (s == 0u) {
+                                    if (r == 15u) {
+                                        k += 16;  // ZRL; the reference re-tests k <= 63 and silently ends the block
+                                        busy = (k <= 63);
+                                    } else {
+                                        busy = false;  // EOB (r == 0); any other code is an error (:750-752)
+                                        if (r != 0u) {
+                                            err = kErrMalformed;
+                                            decoding = false;
+                                        }
+                                    }
                                 } else {
-                                    uint32_t qe = qz[q_off[c] + k];
-                                    int v = diff * (int)(qe >> 8);
-                                    if (v != (int)(int16_t)v) err = kErrMalformed;
-                                    stage[qe & 0xffu] = (int16_t)v;
-                                    k++;
-                                    busy = (k <= 63);
+                                    k += (int)r;
+                                    if (k >= 64) {
+                                        err = kErrMalformed;  // :764-766
+                                        busy = false;
+                                        decoding = false;
+                                    } else {
+                                        const uint32_t qe = lds_u32(s_qz + ((q_off[c] + (uint32_t)k) << 2));
+                                        const int v = diff * (int)(qe >> 8);
+                                        if (v != (int)(short)v) err = kErrMalformed;
+                                        sts_u16(s_stage + ((qe & 0xffu) << 1), v);
+                                        k++;
+                                        busy = (k <= 63);
+                                    }
                                 }
                             }
                         }
                     }
                     // ---- flush the block (zeros included) and clear the staging block
                     if (has_mcu) {
-                        uint32_t bx = mx * p.mw[c] + x, by = my * p.mh[c] + y;
+                        const uint32_t bx = mx * p.mw[c] + x, by = my * p.mh[c] + y;
                         uint4 *dst = reinterpret_cast<uint4 *>(coef + plane[c] + ((uint64_t)by * p.bw[c] + bx) * 64u);
-                        uint4 *st = reinterpret_cast<uint4 *>(stage);
-                        uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
-                            uint4 v = st[i];
-                            st[i] = z;
+                            const uint4 v = lds_v4(s_stage + 16 * i);
+                            sts_v4_zero(s_stage + 16 * i);
                             dst[i] = v;
                         }
                     }
@@ -319,29 +398,42 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ bytes, cons
         }
     }
     // a valid stream never consumes bits beyond the marker that ends its interval
-    if (decoding && err == 0 && b.vbits > b.n) err = kErrUnexpectedEof;
+    if (decoding && err == 0) {
+        const uint64_t consumed = (uint64_t)wpos * 32u - (uint64_t)n;
+        if (consumed > (uint64_t)len_bytes * 8u) err = kErrUnexpectedEof;
+    }
     if (err) atomicMax(frame_status + frame, err);
 }
 
 }  // namespace
 
+int launch_unstuff(const EntropyLaunch &l, void *stream) {
+    const uint64_t total = (uint64_t)l.p.n_scans * l.p.intervals_per_scan;
+    if (total == 0) return 0;
+    const uint32_t grid = (uint32_t)((total + kUnstuffWarps - 1) / kUnstuffWarps);
+    unstuff_kernel<<<grid, kUnstuffWarps * 32, 0, (cudaStream_t)stream>>>((uint32_t)total, l.bytes, l.interval_off, l.interval_end, l.clean_off,
+                                                                           l.clean, l.interval_len);
+    return (int)cudaGetLastError();
+}
+
 int launch_entropy(const EntropyLaunch &l, void *stream) {
     const uint64_t total = (uint64_t)l.p.n_scans * l.p.intervals_per_scan;
     if (total == 0) return 0;
     const uint32_t grid = (uint32_t)((total + kThreads - 1) / kThreads);
-    size_t base_smem = (size_t)kThreads * kStageStride * 2 + (size_t)kThreads * 64 + 4 * 64 * 4;
-    size_t lut_bytes = (size_t)l.p.lut_words * 4;
+    const size_t base_smem = (size_t)kThreads * kStageStride + (size_t)kThreads * 64 + 4 * 64 * 4;
+    const size_t lut_bytes = (size_t)l.p.lut_words * 4;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
     if (base_smem + lut_bytes <= 160 * 1024) {
-        size_t smem = base_smem + lut_bytes;
+        const size_t smem = base_smem + lut_bytes;
         if (smem > 48 * 1024) {
             e = cudaFuncSetAttribute(entropy_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
         }
-        entropy_decode_kernel<true><<<grid, kThreads, smem, s>>>(l.p, l.bytes, l.interval_off, l.scans, l.tables, l.coef, l.frame_status);
+        entropy_decode_kernel<true><<<grid, kThreads, smem, s>>>(l.p, l.clean, l.clean_off, l.interval_len, l.scans, l.tables, l.coef, l.frame_status);
     } else {
-        entropy_decode_kernel<false><<<grid, kThreads, base_smem, s>>>(l.p, l.bytes, l.interval_off, l.scans, l.tables, l.coef, l.frame_status);
+        entropy_decode_kernel<false><<<grid, kThreads, base_smem, s>>>(l.p, l.clean, l.clean_off, l.interval_len, l.scans, l.tables, l.coef,
+                                                                       l.frame_status);
     }
     e = cudaGetLastError();
     return (int)e;

@@ -3,6 +3,8 @@
 // Data layout in HBM (one "batch" = n codestreams decoded by the same launches):
 //   bytes      : the codestreams, each copied whole at a 16-byte aligned offset and followed by FF D9 + zero
 //                padding, so a bit reader that runs off a damaged segment always meets a marker.
+//   clean      : the entropy coded segments with byte stuffing removed, one 16-byte aligned run per restart
+//                interval, stored as big-endian 32-bit words and followed by >= 32 zero bytes (stage a0 output).
 //   coef       : int16, one 128-byte block per 8x8 DCT block, DEQUANTISED (coefficient * delta, the << 4
 //                preshift of dct/idct.cpp:105 is applied by the reconstruction kernels), raster order inside
 //                the block; per component a plane [blocks_h][blocks_w] over the MCU-padded grid.
@@ -40,6 +42,7 @@ struct ScanInfo {  // one SOS + its entropy coded segment
     // SIZE_MAX marks an interval the stream does not contain (zero-filled like an invalid segment,
     // codestream/sequentialscan.cpp:415-419)
     std::vector<size_t> interval_off;
+    std::vector<size_t> interval_end;  // offset of the marker (or end of data) that terminates the interval
     HuffSpec dc[4], ac[4];       // tables in effect at this SOS
     uint16_t quant[4][64];       // zig-zag order as transmitted, in effect at this SOS
     bool quant_defined[4] = {false, false, false, false};
@@ -106,13 +109,18 @@ struct FrameRecon {       // per frame, for the reconstruction kernels
 // kernel launchers (huffman_sm100.cu, recon_sm100.cu). All asynchronous on `stream`.
 struct EntropyLaunch {
     ScanClassParams p;
-    const uint8_t *bytes;
-    const uint64_t *interval_off;   // [n_scans * intervals_per_scan], ~0ull = absent
+    const uint8_t *bytes;           // packed codestreams
+    const uint64_t *interval_off;   // [n_scans * intervals_per_scan] first ECS byte, ~0ull = absent
+    const uint64_t *interval_end;   // [..] offset of the marker that ends the interval
+    const uint64_t *clean_off;      // [..] 16-byte aligned offset of the interval's unstuffed bytes in `clean`
+    uint8_t *clean;                 // unstuffed, big-endian-word entropy coded data (written by a0, read by a1)
+    uint32_t *interval_len;         // [..] unstuffed length in bytes (written by a0)
     const ClassScan *scans;         // [n_scans]
     const uint8_t *tables;          // device copy of the table-set blob
     int16_t *coef;
     uint32_t *frame_status;         // [n_frames]
 };
+int launch_unstuff(const EntropyLaunch &l, void *stream);
 int launch_entropy(const EntropyLaunch &l, void *stream);
 
 struct ReconLaunch {
@@ -123,6 +131,7 @@ struct ReconLaunch {
     uint32_t ncomp, subx, suby;    // uniform over the group
     const int16_t *coef;
     int32_t *samples;
+    uint32_t *wide_flags;          // [n_frames in batch], zeroed per decode: set when a sample leaves the 32-bit colour range
     uint8_t *out;
 };
 int launch_recon(const ReconLaunch &l, void *stream, int *launches);

@@ -238,13 +238,16 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
             uint64_t per = sc.dri ? sc.dri : total;
             uint64_t nint = (total + per - 1) / per;
             sc.interval_off.assign((size_t)nint, SIZE_MAX);
+            sc.interval_end.assign((size_t)nint, sc.ecs_end);
             sc.interval_off[0] = sc.ecs_off;
             for (size_t k = 0; k + 1 < nint; k++) {
                 if (k >= rst_at.size()) break;  // stream ends early: remaining intervals stay absent (zero-filled)
                 if (rst_id[k] != 0xd0 + (k & 7))
                     FAIL(B200JPG_ERR_MALFORMED_STREAM, "restart markers are out of sequence, resynchronisation is not supported by the B200 path");
+                sc.interval_end[k] = rst_at[k];
                 sc.interval_off[k + 1] = rst_at[k] + 2;
             }
+            if (nint - 1 < rst_at.size()) sc.interval_end[nint - 1] = rst_at[nint - 1];  // surplus RSTn: stop there
             fi.n_intervals += (uint32_t)nint;
             fi.ecs_bytes += sc.ecs_end - sc.ecs_off;
             if (out.scans.empty()) fi.restart_interval = dri;

@@ -10,12 +10,17 @@
 //                                                     read-after-write of out[1], :301-302, which is part of the contract)
 //   YCbCrTrafo<UBYTE,3,ClampFlag,YCbCr,Zero>::YCbCr2RGB colortrafo/ycbcrtrafo.cpp:679-1008 (:842-850, :922-935)
 //
-// Mapping.  One thread owns one 8x8 block: the 64 coefficients live in registers through both 1-D passes, so the
-// transform needs no shared memory, no shuffles and no synchronisation.  Kernel b1 transforms the blocks of the
-// non-luma components into int32 sample planes (the whole-frame equivalent of the reference's upsampler line
-// buffers).  Kernel b2 transforms one luma block per thread, pulls the matching chroma window from the planes
-// (clamped addressing = the reference's edge replication at the true subsampled size), runs the vertical and
-// horizontal filter cores and the colour transform in registers and stores 8 x 24 bytes of interleaved RGB.
+// Mapping.  One thread owns one 8x8 block.
+//  b1 idct_planes_kernel: blocks of the non-luma components -> int32 sample planes (the whole-frame equivalent of
+//     the reference's upsampler line buffers); both 1-D passes in registers.
+//  b2 reconstruct_kernel: a warp owns 32 horizontally adjacent luma blocks (256 x 8 pixels), a CTA four such rows.
+//     The row pass and the column pass of the luma IDCT run as two compact loops over a shared-memory tile laid out
+//     [coefficient][thread] (bank-conflict free, thread-private columns, so no barrier is needed); a third loop walks
+//     the eight output lines: chroma window from the planes (clamped addressing = the reference's edge replication at
+//     the true subsampled size), vertical + horizontal filter cores, colour transform, and the line's 768 bytes of
+//     interleaved RGB are staged per warp in shared memory and leave as 16-byte vector stores.  Small loop bodies keep
+//     the kernel inside the instruction cache and at ~100 registers (the fully unrolled register-resident version
+//     stalled on instruction fetch).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -26,6 +31,7 @@ namespace b200jpg {
 namespace {
 
 constexpr int kThreadsB = 128;
+constexpr int kWide = 65535;  // |sample| above this may overflow the 32-bit colour arithmetic -> 64-bit path
 
 #define WMUL(a, k) ((int)((unsigned)(a) * (unsigned)(int)(k)))
 #define WADD(a, b) ((int)((unsigned)(a) + (unsigned)(b)))
@@ -67,33 +73,22 @@ __device__ __forceinline__ void idct8(int &v0, int &v1, int &v2, int &v3, int &v
     v4 = WADD(WSUB(tmp13, t0), kRound) >> kShift;
 }
 
-// Loads one dequantised int16 block (128 bytes) and leaves the 64 reconstructed samples (4 fractional bits,
-// level shift included) in s[row][col].
-__device__ __forceinline__ void idct_block(const int16_t *__restrict__ blk, int (&s)[8][8]) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(blk);
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        uint4 q = __ldg(src + r);
-        // coefficient * delta is stored; the multiplier of dct/idct.cpp:105 is delta << 4
-        s[r][0] = (int)(short)(q.x & 0xffffu) << 4;
-        s[r][1] = (int)(short)(q.x >> 16) << 4;
-        s[r][2] = (int)(short)(q.y & 0xffffu) << 4;
-        s[r][3] = (int)(short)(q.y >> 16) << 4;
-        s[r][4] = (int)(short)(q.z & 0xffffu) << 4;
-        s[r][5] = (int)(short)(q.z >> 16) << 4;
-        s[r][6] = (int)(short)(q.w & 0xffffu) << 4;
-        s[r][7] = (int)(short)(q.w >> 16) << 4;
-    }
-    s[0][0] = WADD(s[0][0], 128 << 7);  // dcoffset << (preshift + 3), idct.cpp:233,244
-#pragma unroll
-    for (int r = 0; r < 8; r++) idct8<256, 9>(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7]);
-#pragma unroll
-    for (int c = 0; c < 8; c++) idct8<2048, 12>(s[0][c], s[1][c], s[2][c], s[3][c], s[4][c], s[5][c], s[6][c], s[7][c]);
+// eight dequantised int16 coefficients (one block row) -> ints carrying the << 4 preshift of dct/idct.cpp:105
+__device__ __forceinline__ void unpack_row(const uint4 q, int (&v)[8]) {
+    v[0] = (int)(short)(q.x & 0xffffu) << 4;
+    v[1] = (int)(short)(q.x >> 16) << 4;
+    v[2] = (int)(short)(q.y & 0xffffu) << 4;
+    v[3] = (int)(short)(q.y >> 16) << 4;
+    v[4] = (int)(short)(q.z & 0xffffu) << 4;
+    v[5] = (int)(short)(q.z >> 16) << 4;
+    v[6] = (int)(short)(q.w & 0xffffu) << 4;
+    v[7] = (int)(short)(q.w >> 16) << 4;
 }
 
 // ---- b1: non-luma components -> sample planes ---------------------------------------------------------
 __global__ void __launch_bounds__(kThreadsB)
-idct_planes_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, int32_t *__restrict__ samples) {
+idct_planes_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, int32_t *__restrict__ samples,
+                   uint32_t *__restrict__ wide_flags) {
     const FrameRecon &f = frames[blockIdx.y];
     const int c = 1 + blockIdx.z;
     if (c >= (int)f.ncomp) return;
@@ -102,7 +97,23 @@ idct_planes_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
     if (t >= bw * bh) return;
     const uint32_t bx = t % bw, by = t / bw;
     int s[8][8];
-    idct_block(coef + f.coef_base[c] + (uint64_t)t * 64u, s);
+    const uint4 *src = reinterpret_cast<const uint4 *>(coef + f.coef_base[c] + (uint64_t)t * 64u);
+#pragma unroll
+    for (int r = 0; r < 8; r++) unpack_row(__ldg(src + r), s[r]);
+    s[0][0] = WADD(s[0][0], 128 << 7);  // dcoffset << (preshift + 3), idct.cpp:233,244
+#pragma unroll
+    for (int r = 0; r < 8; r++) idct8<256, 9>(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7]);
+    int mx = 0, mn = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        idct8<2048, 12>(s[0][k], s[1][k], s[2][k], s[3][k], s[4][k], s[5][k], s[6][k], s[7][k]);
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) {
+            mx = __vimax3_s32(mx, s[r][k], s[r + 1][k]);
+            mn = __vimin3_s32(mn, s[r][k], s[r + 1][k]);
+        }
+    }
+    if (mx > kWide || mn < -kWide) atomicOr(wide_flags + f.status_idx, 1u);  // damaged stream: colour needs 64 bits
     const uint32_t pitch = 8u * bw;
     int32_t *dst = samples + f.sample_base[c] + (uint64_t)(8u * by) * pitch + 8u * bx;
 #pragma unroll
@@ -116,13 +127,21 @@ idct_planes_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
 // ---- b2 ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// Window of the sample plane of one component for an 8x8 output block: NW columns starting at column x0
-// (clamped to [0, cw-1]: dest[-1] = dest[0], dest[width] = dest[width-1], upsamplerbase.cpp:322-323).
+// NW samples of line y of a sample plane starting at column x0. Away from the frame edge this is a plain run;
+// at the edge the clamped addressing reproduces dest[-1] = dest[0], dest[width] = dest[width-1]
+// (upsamplerbase.cpp:322-323) and the duplicated first / last line (upsampler.cpp:100-106).
 template <int NW>
-__device__ __forceinline__ void load_row(const int32_t *__restrict__ plane, uint32_t pitch, int y, int x0, int cw, int ch, int (&v)[NW]) {
-    const int32_t *row = plane + (uint64_t)clampi(y, 0, ch - 1) * pitch;
+__device__ __forceinline__ void load_row(const int32_t *__restrict__ plane, uint32_t pitch, int y, int x0, int cw, int ch, bool interior,
+                                         int (&v)[NW]) {
+    if (interior) {
+        const int32_t *row = plane + (uint64_t)y * pitch + x0;
 #pragma unroll
-    for (int j = 0; j < NW; j++) v[j] = __ldg(row + clampi(x0 + j, 0, cw - 1));
+        for (int j = 0; j < NW; j++) v[j] = __ldg(row + j);
+    } else {
+        const int32_t *row = plane + (uint64_t)clampi(y, 0, ch - 1) * pitch;
+#pragma unroll
+        for (int j = 0; j < NW; j++) v[j] = __ldg(row + clampi(x0 + j, 0, cw - 1));
+    }
 }
 
 // HorizontalFilterCore<2> on a window w[0..5] (w[j] = sample at subsampled x0 - 1 + j): upsampler.cpp:283-307.
@@ -137,41 +156,79 @@ __device__ __forceinline__ void hfilter2(const int (&w)[6], int (&o)[8]) {
     o[0] = WADD(WADD(w[0], WMUL(3, w[1])), 2) >> 2;
 }
 
-__device__ __forceinline__ uint32_t clamp255(int v) { return (uint32_t)min(max(v, 0), 255); }
-__device__ __forceinline__ uint32_t clamp255_64(long long v) { return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+__device__ __forceinline__ uint32_t sat_u8(int v) {  // CLAMP(255, v), ycbcrtrafo.cpp:61
+    uint32_t d;
+    asm("cvt.sat.u8.s32 %0, %1;" : "=r"(d) : "r"(v));
+    return d;
+}
+__device__ __forceinline__ uint32_t sat_u8_64(long long v) { return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 
 // ycbcrtrafo.cpp:842-850 with the matrix of colortransformerfactory.cpp:136-138 (13 fractional bits) and
-// FIX_COLOR_TO_INT (tools/numerics.hpp:65); the reference multiplies in 64 bits, which only matters for samples
-// far outside the 8-bit range (damaged streams): those take the 64-bit branch.
-__device__ __forceinline__ void ycc_to_rgb(int y, int cbv, int crv, uint32_t &r, uint32_t &g, uint32_t &b) {
-    int cb = WSUB(cbv, 128 << 4), cr = WSUB(crv, 128 << 4);
-    if ((((unsigned)(y + 32768) | (unsigned)(cb + 32768) | (unsigned)(cr + 32768)) >> 16) == 0) {
-        int yy = y * 8192 + 65536;
-        r = clamp255((yy + cr * 11485) >> 17);
-        g = clamp255((yy - cb * 2819 - cr * 5850) >> 17);
-        b = clamp255((yy + cb * 14516) >> 17);
+// FIX_COLOR_TO_INT (tools/numerics.hpp:65).  The reference multiplies in 64 bits; 32 bits give the same result
+// while |y|, |cb|, |cr| <= 65535 -- blocks that violate that (damaged streams only) are flagged `wide`.
+__device__ __forceinline__ void ycc_to_rgb(int y, int cbv, int crv, bool wide, uint32_t &r, uint32_t &g, uint32_t &b) {
+    const int cb = WSUB(cbv, 128 << 4), cr = WSUB(crv, 128 << 4);
+    if (!wide) {
+        const int yy = y * 8192 + 65536;
+        r = sat_u8((yy + cr * 11485) >> 17);
+        g = sat_u8((yy - cb * 2819 - cr * 5850) >> 17);
+        b = sat_u8((yy + cb * 14516) >> 17);
     } else {
-        long long Y = y, CB = (long long)cbv - (128 << 4), CR = (long long)crv - (128 << 4);
-        r = clamp255_64((Y * 8192 + CR * 11485 + 65536) >> 17);
-        g = clamp255_64((Y * 8192 - CB * 2819 - CR * 5850 + 65536) >> 17);
-        b = clamp255_64((Y * 8192 + CB * 14516 + 65536) >> 17);
+        const long long Y = y, CB = cb, CR = cr;
+        r = sat_u8_64((Y * 8192 + CR * 11485 + 65536) >> 17);
+        g = sat_u8_64((Y * 8192 - CB * 2819 - CR * 5850 + 65536) >> 17);
+        b = sat_u8_64((Y * 8192 + CB * 14516 + 65536) >> 17);
     }
 }
 
 template <int NC, int SX, int SY>
 __global__ void __launch_bounds__(kThreadsB)
 reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, const int32_t *__restrict__ samples,
-                   uint8_t *__restrict__ out) {
-    const FrameRecon &f = frames[blockIdx.y];
+                   const uint32_t *__restrict__ wide_flags, uint8_t *__restrict__ out) {
+    __shared__ int ys[64 * kThreadsB];                                   // [coefficient][thread]
+    __shared__ __align__(16) uint32_t stage[kThreadsB / 32][32 * 6];     // one RGB line of 32 blocks per warp
+
+    const FrameRecon &f = frames[blockIdx.z];
     const uint32_t W = f.width, H = f.height;
     const uint32_t vbw = (W + 7) >> 3, vbh = (H + 7) >> 3;  // blocks that carry visible pixels
-    const uint32_t t = blockIdx.x * kThreadsB + threadIdx.x;
-    if (t >= vbw * vbh) return;
-    const uint32_t bx = t % vbw, by = t / vbw;
-    const int X = 8 * bx, Y = 8 * by;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bx0 = blockIdx.x * 32, bx = bx0 + lane, by = blockIdx.y * (kThreadsB / 32) + warp;
+    if (by >= vbh) return;  // whole warp
+    const bool valid = bx < vbw;
+    const int X = 8 * (int)bx, Y = 8 * (int)by;
+    int *my = ys + threadIdx.x;
 
-    int s[8][8];
-    idct_block(coef + f.coef_base[0] + ((uint64_t)by * f.bw[0] + bx) * 64u, s);
+    // ---- luma IDCT, row pass (dct/idct.cpp:237-287): one 16-byte load per block row, next row in flight
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(coef + f.coef_base[0] + ((uint64_t)by * f.bw[0] + (valid ? bx : 0)) * 64u);
+        uint4 q = __ldg(src);
+#pragma unroll 1
+        for (int r = 0; r < 8; r++) {
+            const uint4 qn = __ldg(src + ((r < 7) ? r + 1 : r));
+            int v[8];
+            unpack_row(q, v);
+            if (r == 0) v[0] = WADD(v[0], 128 << 7);  // dcoffset << (preshift + 3), idct.cpp:233,244
+            idct8<256, 9>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) my[(8 * r + k) * kThreadsB] = v[k];
+            q = qn;
+        }
+    }
+    // ---- column pass (:291-334) + range guard for the 32-bit colour arithmetic
+    int mx = 0, mn = 0;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        int v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = my[(8 * r + k) * kThreadsB];
+        idct8<2048, 12>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int r = 0; r < 8; r++) my[(8 * r + k) * kThreadsB] = v[r];
+        mx = __vimax3_s32(__vimax3_s32(mx, v[0], v[1]), v[2], v[3]);
+        mx = __vimax3_s32(__vimax3_s32(mx, v[4], v[5]), v[6], v[7]);
+        mn = __vimin3_s32(__vimin3_s32(mn, v[0], v[1]), v[2], v[3]);
+        mn = __vimin3_s32(__vimin3_s32(mn, v[4], v[5]), v[6], v[7]);
+    }
 
     const int xmax = (X + 7 < (int)W) ? 7 : (int)((W - 1) & 7);
     const int ymax = (Y + 7 < (int)H) ? 7 : (int)((H - 1) & 7);
@@ -179,13 +236,21 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
     uint8_t *obase = out + f.out_base + (uint64_t)Y * opitch + (uint64_t)X * NC;
 
     if (NC == 1) {  // identity, COLOR_TO_INT (numerics.hpp:69) + clamp
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            if (r > ymax) break;
+        if (!valid) return;
+#pragma unroll 1
+        for (int r = 0; r <= ymax; r++) {
             uint8_t *o = obase + (uint64_t)r * opitch;
+            uint32_t px[8];
 #pragma unroll
-            for (int x = 0; x < 8; x++)
-                if (x <= xmax) o[x] = (uint8_t)clamp255(WADD(s[r][x], 8) >> 4);
+            for (int x = 0; x < 8; x++) px[x] = sat_u8(WADD(my[(8 * r + x) * kThreadsB], 8) >> 4);
+            if (xmax == 7 && ((reinterpret_cast<uintptr_t>(o) & 7u) == 0)) {
+                *reinterpret_cast<uint2 *>(o) = make_uint2(px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24),
+                                                           px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24));
+            } else {
+#pragma unroll
+                for (int x = 0; x < 8; x++)
+                    if (x <= xmax) o[x] = (uint8_t)px[x];
+            }
         }
         return;
     }
@@ -198,85 +263,100 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
     const int cx0 = X / SX - ((SX == 2) ? 1 : 0);  // window column 0 (upsampler.cpp:87,108-109)
     const int cy0 = Y / SY;
     const bool ycbcr = f.ycbcr != 0;
+    const bool wide = (wide_flags[f.status_idx] != 0u) || mx > kWide || mn < -kWide;
+    // the whole window lies inside the plane: no clamping needed
+    const bool interior = valid && cx0 >= 0 && cx0 + NW <= cw && cy0 - 1 >= 0 && cy0 + ((SY == 2) ? 5 : 8) <= ch;
+    // a full line of the warp leaves as 48 aligned 16-byte stores
+    const bool vec_line = (bx0 + 32 <= vbw) && ((W & 7u) == 0) && (((f.out_base | opitch) & 15u) == 0);
+    uint32_t *wstage = stage[warp];
+    uint8_t *wrow = out + f.out_base + (uint64_t)Y * opitch + (uint64_t)bx0 * 8u * NC;  // first byte of the warp's line 0
 
-    // rolling rows: SY == 2 keeps top/cur/bot (upsampler.cpp:92-106), SY == 1 only cur
+    // rolling lines: SY == 2 keeps top/cur/bot (upsampler.cpp:92-106), SY == 1 only cur
     int top1[NW], cur1[NW], bot1[NW], top2[NW], cur2[NW], bot2[NW];
-    if (SY == 2) {
-        load_row<NW>(p1, cpitch, cy0 - 1, cx0, cw, ch, top1);
-        load_row<NW>(p2, cpitch, cy0 - 1, cx0, cw, ch, top2);
-        load_row<NW>(p1, cpitch, cy0 + 1, cx0, cw, ch, bot1);
-        load_row<NW>(p2, cpitch, cy0 + 1, cx0, cw, ch, bot2);
+    if (valid) {
+        if (SY == 2) {
+            load_row<NW>(p1, cpitch, cy0 - 1, cx0, cw, ch, interior, top1);
+            load_row<NW>(p2, cpitch, cy0 - 1, cx0, cw, ch, interior, top2);
+            load_row<NW>(p1, cpitch, cy0 + 1, cx0, cw, ch, interior, bot1);
+            load_row<NW>(p2, cpitch, cy0 + 1, cx0, cw, ch, interior, bot2);
+        }
+        load_row<NW>(p1, cpitch, cy0, cx0, cw, ch, interior, cur1);
+        load_row<NW>(p2, cpitch, cy0, cx0, cw, ch, interior, cur2);
     }
-    load_row<NW>(p1, cpitch, cy0, cx0, cw, ch, cur1);
-    load_row<NW>(p2, cpitch, cy0, cx0, cw, ch, cur2);
 
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < 8; r++) {
-        int v1[NW], v2[NW];
-        if (SY == 2) {  // VerticalFilterCore<2>, upsampler.cpp:136-168
-            if ((r & 1) == 0) {
-#pragma unroll
-                for (int j = 0; j < NW; j++) {
-                    v1[j] = WADD(WADD(top1[j], WMUL(3, cur1[j])), (j & 1) ? 1 : 2) >> 2;
-                    v2[j] = WADD(WADD(top2[j], WMUL(3, cur2[j])), (j & 1) ? 1 : 2) >> 2;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < NW; j++) {
-                    v1[j] = WADD(WADD(bot1[j], WMUL(3, cur1[j])), (j & 1) ? 2 : 1) >> 2;
-                    v2[j] = WADD(WADD(bot2[j], WMUL(3, cur2[j])), (j & 1) ? 2 : 1) >> 2;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NW; j++) {
-                v1[j] = cur1[j];
-                v2[j] = cur2[j];
-            }
-        }
-        int c1[8], c2[8];
-        if (SX == 2) {
-            int w1[6], w2[6];
-#pragma unroll
-            for (int j = 0; j < 6; j++) {
-                w1[j] = v1[j];
-                w2[j] = v2[j];
-            }
-            hfilter2(w1, c1);
-            hfilter2(w2, c2);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                c1[j] = v1[j];
-                c2[j] = v2[j];
-            }
-        }
-        // colour + store of output row r
+        if (r > ymax) break;  // uniform over the warp (same block row)
         uint32_t px[24];
+        if (valid) {
+            int v1[NW], v2[NW];
+            if (SY == 2) {  // VerticalFilterCore<2>, upsampler.cpp:136-168: even lines lean on top, odd lines on bot
+                const bool odd = (r & 1) != 0;
+                const int ra = odd ? 1 : 2, rb = odd ? 2 : 1;  // rounding of even / odd window columns
 #pragma unroll
-        for (int x = 0; x < 8; x++) {
-            uint32_t R, G, B;
-            if (ycbcr) {
-                ycc_to_rgb(s[r][x], c1[x], c2[x], R, G, B);
+                for (int j = 0; j < NW; j++) {
+                    const int n1 = odd ? bot1[j] : top1[j], n2 = odd ? bot2[j] : top2[j];
+                    v1[j] = WADD(WADD(n1, WMUL(3, cur1[j])), (j & 1) ? rb : ra) >> 2;
+                    v2[j] = WADD(WADD(n2, WMUL(3, cur2[j])), (j & 1) ? rb : ra) >> 2;
+                }
             } else {
-                R = clamp255(WADD(s[r][x], 8) >> 4);
-                G = clamp255(WADD(c1[x], 8) >> 4);
-                B = clamp255(WADD(c2[x], 8) >> 4);
+#pragma unroll
+                for (int j = 0; j < NW; j++) {
+                    v1[j] = cur1[j];
+                    v2[j] = cur2[j];
+                }
             }
-            px[3 * x] = R;
-            px[3 * x + 1] = G;
-            px[3 * x + 2] = B;
+            int c1[8], c2[8];
+            if (SX == 2) {
+                int w1[6], w2[6];
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    w1[j] = v1[j];
+                    w2[j] = v2[j];
+                }
+                hfilter2(w1, c1);
+                hfilter2(w2, c2);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    c1[j] = v1[j];
+                    c2[j] = v2[j];
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                const int yv = my[(8 * r + x) * kThreadsB];
+                uint32_t R, G, B;
+                if (ycbcr) {
+                    ycc_to_rgb(yv, c1[x], c2[x], wide, R, G, B);
+                } else {
+                    R = sat_u8(WADD(yv, 8) >> 4);
+                    G = sat_u8(WADD(c1[x], 8) >> 4);
+                    B = sat_u8(WADD(c2[x], 8) >> 4);
+                }
+                px[3 * x] = R;
+                px[3 * x + 1] = G;
+                px[3 * x + 2] = B;
+            }
         }
-        if (r <= ymax) {
+        if (vec_line) {
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                wstage[lane * 6 + k] = px[4 * k] | (px[4 * k + 1] << 8) | (px[4 * k + 2] << 16) | (px[4 * k + 3] << 24);
+            __syncwarp();
+            uint4 *dst = reinterpret_cast<uint4 *>(wrow + (uint64_t)r * opitch);
+            const uint4 *sv = reinterpret_cast<const uint4 *>(wstage);
+            dst[lane] = sv[lane];
+            if (lane < 16) dst[32 + lane] = sv[32 + lane];
+            __syncwarp();
+        } else if (valid) {
             uint8_t *o = obase + (uint64_t)r * opitch;
             if (xmax == 7 && ((reinterpret_cast<uintptr_t>(o) & 7u) == 0)) {
                 uint2 *o2 = reinterpret_cast<uint2 *>(o);
 #pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    uint32_t lo = px[8 * k] | (px[8 * k + 1] << 8) | (px[8 * k + 2] << 16) | (px[8 * k + 3] << 24);
-                    uint32_t hi = px[8 * k + 4] | (px[8 * k + 5] << 8) | (px[8 * k + 6] << 16) | (px[8 * k + 7] << 24);
-                    o2[k] = make_uint2(lo, hi);
-                }
+                for (int k = 0; k < 3; k++)
+                    o2[k] = make_uint2(px[8 * k] | (px[8 * k + 1] << 8) | (px[8 * k + 2] << 16) | (px[8 * k + 3] << 24),
+                                       px[8 * k + 4] | (px[8 * k + 5] << 8) | (px[8 * k + 6] << 16) | (px[8 * k + 7] << 24));
             } else {
 #pragma unroll
                 for (int x = 0; x < 8; x++) {
@@ -289,23 +369,25 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
             }
         }
         // advance the line window after every odd output line (upsampler.cpp:160-165) / every line for SY == 1
-        if (SY == 2) {
-            if (r & 1) {
+        if (valid) {
+            if (SY == 2) {
+                if (r & 1) {
 #pragma unroll
-                for (int j = 0; j < NW; j++) {
-                    top1[j] = cur1[j];
-                    cur1[j] = bot1[j];
-                    top2[j] = cur2[j];
-                    cur2[j] = bot2[j];
+                    for (int j = 0; j < NW; j++) {
+                        top1[j] = cur1[j];
+                        cur1[j] = bot1[j];
+                        top2[j] = cur2[j];
+                        cur2[j] = bot2[j];
+                    }
+                    if (r < 7) {
+                        load_row<NW>(p1, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, interior, bot1);
+                        load_row<NW>(p2, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, interior, bot2);
+                    }
                 }
-                if (r < 7) {
-                    load_row<NW>(p1, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, bot1);
-                    load_row<NW>(p2, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, bot2);
-                }
+            } else if (r < 7) {
+                load_row<NW>(p1, cpitch, cy0 + r + 1, cx0, cw, ch, interior, cur1);
+                load_row<NW>(p2, cpitch, cy0 + r + 1, cx0, cw, ch, interior, cur2);
             }
-        } else if (r < 7) {
-            load_row<NW>(p1, cpitch, cy0 + r + 1, cx0, cw, ch, cur1);
-            load_row<NW>(p2, cpitch, cy0 + r + 1, cx0, cw, ch, cur2);
         }
     }
 }
@@ -318,21 +400,20 @@ int launch_recon(const ReconLaunch &l, void *stream, int *launches) {
     if (l.ncomp > 1) {
         uint32_t blocks = l.max_bwc * l.max_bhc;
         dim3 grid((blocks + kThreadsB - 1) / kThreadsB, l.n_frames, l.ncomp - 1);
-        idct_planes_kernel<<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples);
+        idct_planes_kernel<<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags);
         n++;
     }
-    uint32_t vblocks = l.max_bw0 * l.max_bh0;
-    dim3 grid((vblocks + kThreadsB - 1) / kThreadsB, l.n_frames, 1);
+    dim3 grid((l.max_bw0 + 31) / 32, (l.max_bh0 + kThreadsB / 32 - 1) / (kThreadsB / 32), l.n_frames);
     if (l.ncomp == 1) {
-        reconstruct_kernel<1, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.out);
+        reconstruct_kernel<1, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else if (l.subx == 2 && l.suby == 2) {
-        reconstruct_kernel<3, 2, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.out);
+        reconstruct_kernel<3, 2, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else if (l.subx == 2 && l.suby == 1) {
-        reconstruct_kernel<3, 2, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.out);
+        reconstruct_kernel<3, 2, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else if (l.subx == 1 && l.suby == 2) {
-        reconstruct_kernel<3, 1, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.out);
+        reconstruct_kernel<3, 1, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else {
-        reconstruct_kernel<3, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.out);
+        reconstruct_kernel<3, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     }
     n++;
     if (launches) *launches = n;

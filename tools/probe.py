@@ -6,7 +6,7 @@ from libjpeg_b200 import synth
 t0=time.time()
 base=[synth.frame(3840,2160,s) for s in range(1,5)]
 print('gen 4 frames', time.time()-t0, 'bytes', [len(b) for b in base], flush=True)
-for nf in (16, 128):
+for nf in (128, 512):
     frames=[base[i%4] for i in range(nf)]
     t0=time.time(); dec=libjpeg_b200.BatchDecoder(frames); print('batch_create', nf, time.time()-t0, flush=True)
     out=dec.new_output(); dec.upload(); dec.enable_timing(True)
