@@ -178,27 +178,29 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
 // =====================================================================================================
 // a1: Huffman decode, one restart interval per lane
 // =====================================================================================================
+constexpr int kQzBytes = 4 * 128 * 8;  // four quantisation tables x 128 (q, offset) pairs
+
 template <bool kLutShared>
 __global__ void __launch_bounds__(kThreads)
 entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uint64_t *__restrict__ clean_off,
                       const uint32_t *__restrict__ interval_len, const ClassScan *__restrict__ scans,
                       const uint8_t *__restrict__ tables, int16_t *__restrict__ coef, uint32_t *__restrict__ frame_status) {
     extern __shared__ __align__(16) uint8_t smem[];
-    // layout (bytes): [stage: kThreads*144][ring: kThreads*64][qz: 4*64*4][lut: lut_words*4 (if shared)]
+    // layout (bytes): [stage: kThreads*144][ring: kThreads*64][qz: 4*128*8][lut: lut_words*4 (if shared)]
     uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("" : "+r"(s_base));  // opaque: keeps the base in a register instead of re-deriving it (S2UR) at every use
     const uint32_t s_stage = s_base + threadIdx.x * kStageStride;
     const uint32_t s_ring = s_base + kThreads * kStageStride + threadIdx.x * 64;
     const uint32_t s_qz = s_base + kThreads * kStageStride + kThreads * 64;
-    const uint32_t s_lut = s_qz + 4 * 64 * 4;
+    const uint32_t s_lut = s_qz + kQzBytes;
     const uint32_t *g_lut = reinterpret_cast<const uint32_t *>(tables + kTableHeaderBytes);
     {
         const uint32_t *g_qz = reinterpret_cast<const uint32_t *>(tables + 32);
-        for (uint32_t i = threadIdx.x; i < 4 * 64; i += kThreads) sts_u32(s_qz + 4 * i, g_qz[i]);
+        for (uint32_t i = threadIdx.x; i < kQzBytes / 4; i += kThreads) sts_u32(s_qz + 4 * i, g_qz[i]);
         if (kLutShared)
             for (uint32_t i = threadIdx.x; i < p.lut_words; i += kThreads) sts_u32(s_lut + 4 * i, g_lut[i]);
 #pragma unroll
-        for (int i = 0; i < 8; i++) sts_v4_zero(s_stage + 16 * i);
+        for (int i = 0; i < 9; i++) sts_v4_zero(s_stage + 16 * i);
     }
     __syncthreads();
     const uint16_t *lut_off = reinterpret_cast<const uint16_t *>(tables + 16);
@@ -213,6 +215,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
     }
     const uint32_t len_bytes = lane_valid ? interval_len[g] : 0u;
     const uint8_t *src = clean + (lane_valid ? clean_off[g] : 0ull);
+    const uint32_t max_chunks = (len_bytes + 15u) / 16u + 2u;  // data + the 32 zero bytes a0 appended
     const uint32_t mcu0 = iv * p.dri;
     uint32_t nmcu = 0;
     if (lane_valid) nmcu = (p.total_mcus - mcu0 < p.dri) ? (p.total_mcus - mcu0) : p.dri;
@@ -228,38 +231,42 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
     }
 
     // an interval the stream does not contain keeps its blocks zero (sequentialscan.cpp:415-419)
-    bool decoding = lane_valid && len_bytes != 0u;
+    const bool decoding = lane_valid && len_bytes != 0u;
     // bit window: MSB-aligned 64 bits in (hi, lo), n valid bits; wpos = 32-bit words taken from the stream;
     // req = 16-byte chunks requested from HBM so far, safe = chunks known to have landed in the ring
     uint32_t hi = 0, lo = 0, wpos = 0, req = 0, safe = 0;
     int n = 0;
+    // chunk `c` of the interval into its ring slot; past the end of the interval the reader sees zeros, exactly what
+    // the reference's bit reader hands out once it stands in front of a marker (io/bitstream.cpp:96-101)
+    auto request = [&](uint32_t c) {
+        if (c < max_chunks) cp_async16(s_ring + ((c & 3u) << 4), src + ((uint64_t)c << 4));
+        else sts_v4_zero(s_ring + ((c & 3u) << 4));
+    };
     if (decoding) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) cp_async16(s_ring + 16 * i, src + 16 * i);
+        for (uint32_t i = 0; i < 4; i++) request(i);
         req = 4;
     }
     cp_async_commit();
     cp_async_wait<0>();
     safe = req;
 
-    uint32_t err = 0;
+    uint32_t errbits = 0;  // bit 31: an entry that must not be decoded was decoded
+    uint32_t ovf = 0;      // | (v + 32768): bits 16.. set when a dequantised coefficient left the int16 range
     int pred[4] = {0, 0, 0, 0};
-    uint32_t dc_off[4], ac_off[4], q_off[4];
+    uint32_t dc_off[4], ac_off[4], q_addr[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        dc_off[c] = (c < p.ns) ? lut_off[p.dc_slot[c]] : 0;
-        ac_off[c] = (c < p.ns) ? lut_off[4 + p.ac_slot[c]] : 0;
-        q_off[c] = (c < p.ns) ? 64u * p.q_slot[c] : 0;
+        dc_off[c] = (c < p.ns) ? s_lut + 4u * lut_off[p.dc_slot[c]] : 0;
+        ac_off[c] = (c < p.ns) ? s_lut + 4u * lut_off[4 + p.ac_slot[c]] : 0;
+        q_addr[c] = s_qz + ((c < p.ns) ? 1024u * p.q_slot[c] : 0u);
     }
 
     // next 32 stream bits into the window (callers guarantee n <= 32)
     auto refill = [&]() {
         const uint32_t ch = wpos >> 2;
         if (ch >= safe) {  // rare: ran past what the block-boundary top-up guarantees
-            while (req <= ch) {
-                cp_async16(s_ring + ((req & 3u) << 4), src + ((uint64_t)req << 4));
-                req++;
-            }
+            while (req <= ch) request(req++);
             cp_async_commit();
             cp_async_wait<0>();
             safe = req;
@@ -270,28 +277,35 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         lo |= __funnelshift_rc(0u, x, (uint32_t)n);  // x << (32 - n)   (0 for n == 0)
         n += 32;
     };
-    auto lookup = [&](uint32_t off) -> uint32_t {
+    // two-level lookup; `tab` is the shared-space address of the table (kLutShared) or its word offset (global)
+    auto lookup = [&](uint32_t tab) -> uint32_t {
         uint32_t e;
         if (kLutShared) {
-            e = lds_u32(s_lut + ((off + (hi >> 24)) << 2));
-            if ((e & 0xff00u) == 0) e = lds_u32(s_lut + ((off + ((e & 0xffu) << 8) + ((hi >> 16) & 0xffu)) << 2));
+            e = lds_u32(tab + ((hi >> (32 - kLutL1Bits)) << 2));
+            if ((e & (31u << 5)) == 0)
+                e = lds_u32(tab + (((1u << kLutL1Bits) + ((e >> 22) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u))) << 2));
         } else {
-            e = __ldg(g_lut + off + (hi >> 24));
-            if ((e & 0xff00u) == 0) e = __ldg(g_lut + off + ((e & 0xffu) << 8) + ((hi >> 16) & 0xffu));
+            const uint32_t *t = g_lut + ((tab - s_lut) >> 2);
+            e = __ldg(t + (hi >> (32 - kLutL1Bits)));
+            if ((e & (31u << 5)) == 0)
+                e = __ldg(t + (1u << kLutL1Bits) + ((e >> 22) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u)));
         }
         return e;
     };
-    // s value bits after a code of len bits, sign-extended as sequentialscan.cpp:692-696 / 757-762
-    auto value_bits = [&](uint32_t len, uint32_t s) -> int {
-        const uint32_t t = hi << len;
-        const uint32_t v = __funnelshift_rc(t, 0u, 32u - s);  // t >> (32 - s), 0 for s == 0
-        const int ext = ((int)t < 0) ? 0 : (int)(1u - (1u << s));
-        return (int)v + (s ? ext : 0);
+    // value bits of entry e, sign-extended as sequentialscan.cpp:692-696 / 757-762. All shifts are funnel shifts in
+    // wrap mode, which use only the low five bits of the count: the fields of e need no masking.
+    auto value_of = [&](uint32_t e) -> int {
+        const uint32_t t = __funnelshift_l(0u, hi, e >> 5);     // hi << len
+        const uint32_t u = __funnelshift_l(t, 0u, e);           // t >> (32 - s), 0 for s == 0
+        const uint32_t m = (uint32_t)((int)t >> 31);            // all ones: first value bit set = non-negative
+        const uint32_t ext = (1u - __funnelshift_l(0u, 1u, e)) & ~m;  // (-1 << s) + 1 for negative values
+        return (int)(u + ext);
     };
-    auto consume = [&](uint32_t t) {
+    auto consume = [&](uint32_t e) {
+        const uint32_t t = e >> 16;  // total bits (< 32); error entries carry garbage here and stop the lane anyway
         hi = __funnelshift_l(lo, hi, t);
-        lo <<= t;
-        n -= (int)t;
+        lo = __funnelshift_l(0u, lo, t);
+        n -= (int)(t & 63u);
     };
 
     for (uint32_t mi = 0; mi < p.dri; mi++) {
@@ -307,33 +321,28 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                         const uint32_t landed = req;  // requested before this point: lands at the wait below
 #pragma unroll
                         for (int t = 0; t < 2; t++) {
-                            if (decoding && req < ch + 4u) {
-                                cp_async16(s_ring + ((req & 3u) << 4), src + ((uint64_t)req << 4));
-                                req++;
-                            }
+                            if (decoding && req < ch + 4u) request(req++);
                             cp_async_commit();
                         }
                         cp_async_wait<2>();
                         safe = landed;
                     }
-                    bool busy = has_mcu && decoding;
+                    // a lane that met an error keeps its blocks zero from there on
+                    bool busy = has_mcu && decoding && (int)errbits >= 0;
                     int k = 1;
                     // ---- DC: sequentialscan.cpp:682-701
                     if (busy) {
                         if (n <= 32) refill();
                         const uint32_t e = lookup(dc_off[c]);
-                        const uint32_t len = (e >> 8) & 0xffu, s = e & 0xffu;
-                        if (len > 16u || s > 15u) {
-                            err = kErrMalformed;
-                            busy = false;
-                            decoding = false;
-                        } else {
-                            const int diff = value_bits(len, s);
-                            consume(e >> 16);
-                            pred[c] += diff;
-                            const int v = pred[c] * (int)(lds_u32(s_qz + (q_off[c] << 2)) >> 8);
-                            if (v != (int)(short)v) err = kErrMalformed;  // does not fit the int16 store
+                        errbits |= e;
+                        if ((int)e >= 0) {
+                            pred[c] += value_of(e);
+                            consume(e);
+                            const int v = pred[c] * (int)lds_u32(q_addr[c]);
+                            ovf |= (uint32_t)(v + 32768);
                             sts_u16(s_stage, v);
+                        } else {
+                            busy = false;
                         }
                     }
                     // ---- AC: sequentialscan.cpp:704-771, one symbol per warp-convergent iteration
@@ -341,40 +350,24 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                         if (busy) {
                             if (n <= 32) refill();
                             const uint32_t e = lookup(ac_off[c]);
-                            const uint32_t len = (e >> 8) & 0xffu, r = (e >> 4) & 15u, s = e & 15u;
-                            if (len > 16u) {
-                                err = kErrMalformed;
-                                busy = false;
-                                decoding = false;
+                            errbits |= e;
+                            const int diff = value_of(e);
+                            consume(e);
+                            if ((e & 31u) == 0u) {
+                                // EOB, ZRL (the reference re-tests k <= 63 and silently ends the block, :717-719),
+                                // or an error entry (bit 31, zero fields): the block ends
+                                k += 16;
+                                busy = (((e >> 10) & 15u) == 15u) && (k <= 63);
                             } else {
-                                const int diff = value_bits(len, s);
-                                consume(e >> 16);
-                                if (s == 0u) {
-                                    if (r == 15u) {
-                                        k += 16;  // ZRL; the reference re-tests k <= 63 and silently ends the block
-                                        busy = (k <= 63);
-                                    } else {
-                                        busy = false;  // EOB (r == 0); any other code is an error (:750-752)
-                                        if (r != 0u) {
-                                            err = kErrMalformed;
-                                            decoding = false;
-                                        }
-                                    }
-                                } else {
-                                    k += (int)r;
-                                    if (k >= 64) {
-                                        err = kErrMalformed;  // :764-766
-                                        busy = false;
-                                        decoding = false;
-                                    } else {
-                                        const uint32_t qe = lds_u32(s_qz + ((q_off[c] + (uint32_t)k) << 2));
-                                        const int v = diff * (int)(qe >> 8);
-                                        if (v != (int)(short)v) err = kErrMalformed;
-                                        sts_u16(s_stage + ((qe & 0xffu) << 1), v);
-                                        k++;
-                                        busy = (k <= 63);
-                                    }
-                                }
+                                k += (int)((e >> 10) & 15u);
+                                uint2 q;  // {delta (bit 31: k >= 64, :764-766), byte offset of the raster position}
+                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(q.x), "=r"(q.y) : "r"(q_addr[c] + ((uint32_t)k << 3)));
+                                errbits |= q.x;
+                                const int v = diff * (int)q.x;
+                                ovf |= (uint32_t)(v + 32768);
+                                sts_u16(s_stage + q.y, v);
+                                k++;
+                                busy = (k <= 63);
                             }
                         }
                     }
@@ -397,8 +390,11 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
             my++;
         }
     }
-    // a valid stream never consumes bits beyond the marker that ends its interval
-    if (decoding && err == 0) {
+    uint32_t err = 0;
+    if ((int)errbits < 0 || (ovf >> 16) != 0u) {
+        err = kErrMalformed;  // invalid code / out-of-sync coefficient index / coefficient beyond the int16 store
+    } else if (decoding) {
+        // a valid stream never consumes bits beyond the marker that ends its interval
         const uint64_t consumed = (uint64_t)wpos * 32u - (uint64_t)n;
         if (consumed > (uint64_t)len_bytes * 8u) err = kErrUnexpectedEof;
     }
@@ -420,7 +416,7 @@ int launch_entropy(const EntropyLaunch &l, void *stream) {
     const uint64_t total = (uint64_t)l.p.n_scans * l.p.intervals_per_scan;
     if (total == 0) return 0;
     const uint32_t grid = (uint32_t)((total + kThreads - 1) / kThreads);
-    const size_t base_smem = (size_t)kThreads * kStageStride + (size_t)kThreads * 64 + 4 * 64 * 4;
+    const size_t base_smem = (size_t)kThreads * kStageStride + (size_t)kThreads * 64 + kQzBytes;
     const size_t lut_bytes = (size_t)l.p.lut_words * 4;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;

@@ -61,14 +61,17 @@ extern const uint8_t kZigZagToRaster[64];  // dct/dct.cpp:57-73
 // ---- table sets: what the entropy kernel needs besides the bytes ------------------------------------
 // Serialised, device independent (this blob is what rank 0 broadcasts over NCCL):
 //   uint32 magic, uint32 total_bytes, uint32 lut_words, uint32 flags
-//   uint16 lut_off[8]      word offset of the level-1 LUT of DC0..3, AC0..3 (0xFFFF = undefined)
-//   uint32 qz[4][64]       per quantisation table, index = zig-zag k: (delta << lowbit) << 8 | raster position
-//   uint32 lut[lut_words]  per table: 256 level-1 entries then 256 per level-2 sub-table
-// LUT entry: (total << 16) | (len << 8) | symbol, len 1..16 the code length, total = len + number of value bits
-// that follow the code; level-1 entries with len == 0 hold the 1-based index of the level-2 sub-table in the
-// low byte; len == 0xFF marks an unused code (coding/huffmandecoder.hpp:87).
-constexpr uint32_t kTableMagic = 0x4a54424cu;  // "LBTJ"
-constexpr int kTableHeaderBytes = 16 + 16 + 4 * 64 * 4;
+//   uint16 lut_off[8]        word offset of the first-level LUT of DC0..3, AC0..3 (0xFFFF = undefined)
+//   uint32 qz[4][128][2]     per quantisation table, index = zig-zag position k: {delta << lowbit, byte offset of the
+//                            raster position inside a block}; k >= 64 entries carry bit 31 (out-of-sync error) and
+//                            point at the staging block's pad slot
+//   uint32 lut[lut_words]    per table: 2^kLutL1Bits first-level entries, then 2^(16-kLutL1Bits) per second-level table
+// LUT entry: [4:0] s = value bits that follow the code, [9:5] code length (0: pointer to second-level table
+// [29:22]; 31: unused code, coding/huffmandecoder.hpp:87), [13:10] zero run, [21:16] total = length + s,
+// [31] decoding this entry is an error (unused code, DC category > 15, AC symbol that baseline does not define).
+constexpr uint32_t kTableMagic = 0x4a54424du;  // "MBTJ"
+constexpr int kLutL1Bits = 10;
+constexpr int kTableHeaderBytes = 16 + 16 + 4 * 128 * 2 * 4;
 
 struct TableSet {
     std::vector<uint8_t> blob;

@@ -276,9 +276,13 @@ uint32_t TableSet::lut_words() const {
 }
 
 int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
+    // LUT entry (see internal.hpp): [4:0] value bits s, [9:5] code length (0 = pointer to a second-level table,
+    // 31 = unused code), [13:10] zero run r, [21:16] total bits = length + s, [29:22] second-level table index,
+    // [31] "decoding this entry is an error".  First level: top kLutL1Bits bits of the 16-bit window.
     std::vector<uint32_t> lut;
     uint16_t lut_off[8];
-    const uint32_t kUnused = 0x0000ff00u;
+    const uint32_t kUnused = 0x80000000u | (31u << 5);
+    const int L1 = kLutL1Bits, L2 = 16 - kLutL1Bits;
     for (int t = 0; t < 8; t++) {
         const HuffSpec &h = (t < 4) ? scan.dc[t] : scan.ac[t - 4];
         const bool is_ac = t >= 4;
@@ -288,45 +292,56 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
         for (int i = 0; i < scan.ns; i++) used |= is_ac ? (scan.ta[i] == t - 4) : (scan.td[i] == t);
         if (!used) continue;
         size_t base = lut.size();
-        if (base > 0xfff0) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "Huffman tables too large for the B200 decoder tables");
+        if (base > 0xf000) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "Huffman tables too large for the B200 decoder tables");
         lut_off[t] = (uint16_t)base;
-        lut.resize(base + 256, kUnused);
-        int sub_of[256];
-        for (int i = 0; i < 256; i++) sub_of[i] = 0;
+        lut.resize(base + ((size_t)1 << L1), kUnused);
+        std::vector<int> sub_of((size_t)1 << L1, 0);
         int nsub = 0;
-        uint32_t code = 0;  // left aligned in 16 bits
+        uint32_t code = 0;  // left aligned in 16 bits (coding/huffmantemplate.cpp:823-826)
         int v = 0;
         for (int i = 0; i < 16; i++) {
             for (int j = 0; j < h.bits[i]; j++) {
                 if (v >= h.nvals) FAIL(B200JPG_ERR_MALFORMED_STREAM, "Huffman table marker depends on undefined data");
-                uint8_t sym = h.vals[v++];
-                uint32_t last = code + (1u << (15 - i));
+                const uint8_t sym = h.vals[v++];
+                const uint32_t last = code + (1u << (15 - i));
                 if (last > 0x10000u)
                     FAIL(B200JPG_ERR_MALFORMED_STREAM, "Huffman table corrupt - entry depends on more bits than available for the bit length");
-                // value bits that follow the code: DC: the symbol (<= 15 valid), AC: low nibble
-                uint32_t vbits = is_ac ? (sym & 15u) : (sym <= 15 ? sym : 0u);
-                uint32_t entry = ((uint32_t)(i + 1) + vbits) << 16 | (uint32_t)(i + 1) << 8 | sym;
-                uint32_t q = code >> 8, qlast = last >> 8;
-                if (i < 8) {
-                    do {
-                        lut[base + q] = entry;
-                    } while (++q < qlast);
-                    code = last;
+                const uint32_t len = (uint32_t)i + 1;
+                uint32_t s, r, bad = 0;
+                if (is_ac) {
+                    s = sym & 15u;
+                    r = sym >> 4;
+                    if (s == 0 && r != 0 && r != 15) bad = 1;  // sequentialscan.cpp:750-752: not a baseline symbol
                 } else {
-                    if (!sub_of[q]) {
-                        sub_of[q] = ++nsub;
-                        lut.resize(base + 256 + 256 * (size_t)nsub, kUnused);
-                        lut[base + q] = (uint32_t)sub_of[q];  // len 0 -> level 2
+                    s = sym;
+                    r = 0;
+                    if (sym > 15) {  // sequentialscan.cpp:688-690
+                        bad = 1;
+                        s = 0;
                     }
-                    size_t sb = base + 256 * (size_t)sub_of[q];
-                    do {
-                        lut[sb + (code & 0xff)] = entry;
-                    } while (++code < last);
                 }
+                const uint32_t entry = (bad << 31) | ((len + s) << 16) | (r << 10) | (len << 5) | s;
+                if ((int)len <= L1) {
+                    for (uint32_t q = code >> L2, qlast = last >> L2; q < qlast; q++) lut[base + q] = entry;
+                } else {
+                    for (uint32_t c16 = code; c16 < last; c16++) {
+                        const uint32_t q = c16 >> L2;
+                        if (!sub_of[q]) {
+                            sub_of[q] = ++nsub;
+                            if (nsub > 255) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "Huffman tables too large for the B200 decoder tables");
+                            lut.resize(base + ((size_t)1 << L1) + ((size_t)nsub << L2), kUnused);
+                            lut[base + q] = (uint32_t)(sub_of[q] - 1) << 22;  // len field 0 -> second level
+                        }
+                        lut[base + ((size_t)1 << L1) + ((size_t)(sub_of[q] - 1) << L2) + (c16 & ((1u << L2) - 1))] = entry;
+                    }
+                }
+                code = last;
             }
         }
     }
     if (lut.size() > 0xffffu) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "Huffman tables too large for the B200 decoder tables");
+    // quantisation + de-zigzag: per table 128 (q, byte offset) pairs indexed by the zig-zag position k; k >= 64 is
+    // the "AC coefficient decoding out of sync" case of sequentialscan.cpp:764-766: flagged, parked in the pad slot
     size_t total = kTableHeaderBytes + lut.size() * 4;
     total = (total + 15) & ~(size_t)15;
     out.blob.assign(total, 0);
@@ -335,11 +350,20 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
     memcpy(out.blob.data() + 16, lut_off, 16);
     uint32_t *qz = (uint32_t *)(out.blob.data() + 32);
     for (int t = 0; t < 4; t++)
-        for (int k = 0; k < 64; k++) {
-            uint32_t delta = scan.quant_defined[t] ? scan.quant[t][k] : 0;
-            if (((uint64_t)delta << scan.lowbit) >= (1u << 24))
-                FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "quantisation step times point transform too large for the B200 path");
-            qz[t * 64 + k] = ((delta << scan.lowbit) << 8) | kZigZagToRaster[k];
+        for (int k = 0; k < 128; k++) {
+            uint32_t q, off;
+            if (k < 64) {
+                uint32_t delta = scan.quant_defined[t] ? scan.quant[t][k] : 0;
+                if (((uint64_t)delta << scan.lowbit) >= (1u << 24))
+                    FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "quantisation step times point transform too large for the B200 path");
+                q = delta << scan.lowbit;
+                off = 2u * kZigZagToRaster[k];
+            } else {
+                q = 0x80000000u;
+                off = 128;  // first pad halfword of the lane's staging block
+            }
+            qz[(t * 128 + k) * 2] = q;
+            qz[(t * 128 + k) * 2 + 1] = off;
         }
     memcpy(out.blob.data() + kTableHeaderBytes, lut.data(), lut.size() * 4);
     return B200JPG_OK;

@@ -182,7 +182,7 @@ __device__ __forceinline__ void ycc_to_rgb(int y, int cbv, int crv, bool wide, u
 }
 
 template <int NC, int SX, int SY>
-__global__ void __launch_bounds__(kThreadsB)
+__global__ void __launch_bounds__(kThreadsB, 4)
 reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, const int32_t *__restrict__ samples,
                    const uint32_t *__restrict__ wide_flags, uint8_t *__restrict__ out) {
     __shared__ int ys[64 * kThreadsB];                                   // [coefficient][thread]
