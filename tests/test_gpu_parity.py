@@ -126,3 +126,27 @@ def test_truncated_stream_zero_fills_missing_intervals(built, oracle):
     assert dec.status(0) == 0
     px = dec.frame_view(out, 0).cpu().numpy()
     assert np.array_equal(px[:48], ref[:48])  # 4 intervals of one 16-row MCU row each, minus the filter halo row
+
+
+def test_dropin_client_through_cpp_interface(built, golden_pixels, tmp_path):
+    """The reference-style stripe client (tests/client/stripe_client.cpp), compiled against include/interface and
+    linked to libb200jpg.so: JPEG::Read / GetInformation / DisplayRectangle in 8-row stripes via the BitMapHook."""
+    import subprocess
+    lib_dir = os.path.join(ROOT, "libjpeg_b200")
+    exe = str(tmp_path / "stripe_b200")
+    subprocess.run(["g++", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "client", "stripe_client.cpp"),
+                    "-L" + lib_dir, "-lb200jpg", "-Wl,-rpath," + lib_dir, "-o", exe], check=True)
+    for name in NAMES:
+        if name.startswith("cfg1"):
+            continue
+        out = str(tmp_path / (name + ".pnm"))
+        r = subprocess.run([exe, os.path.join(GOLDEN, name + ".jpg"), out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        data = open(out, "rb").read()
+        magic, dims, maxv, rest = data.split(b"\n", 3)
+        w, h = map(int, dims.split())
+        px = np.frombuffer(rest, dtype=np.uint8).reshape(h, w, 3 if magic == b"P6" else 1)
+        assert np.array_equal(px, golden_pixels[name]), name
+        depth = px.shape[2]
+        stripes = (h + 7) // 8
+        assert "requests=%d releases=%d" % (stripes * depth, stripes * depth) in r.stdout
