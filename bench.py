@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--distinct", type=int, default=64)
     ap.add_argument("--e2e-chunk", type=int, default=32)
+    ap.add_argument("--streams", type=int, default=2, help="batches in flight per GPU (each on its own CUDA stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -168,7 +169,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ncpu = os.cpu_count() or 8
     config = {"workload": "cfg3: 3840x2160 4:2:0 q75 baseline, DRI=240 (one restart interval per MCU row), Annex-K tables",
-              "frames_per_gpu": args.frames_per_gpu, "global_batch": args.frames_per_gpu * max(world, 1),
+              "frames_per_gpu": args.frames_per_gpu, "global_batch": args.frames_per_gpu * max(world, 1), "steps_in_flight": args.streams,
               "distinct_frames": args.distinct, "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
               "l2": "inputs larger than L2 (no flush needed): >= 0.6 GB codestreams + 12.7 GB coefficients per step vs 126 MB L2"}
 
@@ -216,17 +217,25 @@ def main():
     frames = [base[(first + i) % len(base)] for i in range(nf)]
     mean_bytes = sum(len(b) for b in base) / len(base)
 
-    dec = libjpeg_b200.BatchDecoder(frames, device=local_rank)
+    # `--streams` batches in flight per GPU: step k runs on stream k % streams with its own coefficient / sample /
+    # output buffers, so the latency-bound entropy kernel of one step overlaps the issue-bound reconstruction of another
+    nstreams = max(1, min(args.streams, max(args.steps, 1)))
+    decs = [libjpeg_b200.BatchDecoder(frames, device=local_rank) for _ in range(nstreams)]
+    dec = decs[0]
     # ---- the ONE collective of the path: rank 0 broadcasts the shared Huffman/quantisation table blob (NCCL)
     blob = torch.from_numpy(dec.export_tables()).cuda()
     if dist is not None:
         mine = blob.clone()
         dist.broadcast(blob, src=0)
         assert torch.equal(mine, blob), "frames of this rank use tables different from rank 0's"
-        dec.import_tables(blob.cpu().numpy())
-    out = dec.new_output()
-    stream = torch.cuda.current_stream()
-    dec.upload(stream)
+        for d in decs:
+            d.import_tables(blob.cpu().numpy())
+    outs = [d.new_output() for d in decs]
+    out = outs[0]
+    streams = [torch.cuda.Stream() for _ in range(nstreams)]
+    stream = streams[0]
+    for d, st in zip(decs, streams):
+        d.upload(st)
     torch.cuda.synchronize()
     dec.enable_timing(True)
 
@@ -236,30 +245,36 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        dec.decode(out, stream)
+        for d, o, st in zip(decs, outs, streams):
+            d.decode(o, st)
     torch.cuda.synchronize()
-    bad = [i for i in range(nf) if dec.status(i) != 0]
-    assert not bad, "decode reported errors for frames %s" % bad[:8]
+    for d in decs:
+        bad = [i for i in range(nf) if d.status(i) != 0]
+        assert not bad, "decode reported errors for frames %s" % bad[:8]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    dec.enable_timing(False)
 
     # ---- value: K steps, device-timed
     sampler = ClockSampler(local_rank)
-    ent_ms, rec_ms = [], []
+    ent_ms, rec_ms, uns_ms = [], [], []
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    e0.record(streams[0])
+    for st in streams[1:]:
+        st.wait_event(e0)
     launches = 0
-    for _ in range(args.steps):
-        dec.decode(out, stream)
-        launches += dec.launches
-    e1.record(stream)
+    for k in range(args.steps):
+        d = decs[k % nstreams]
+        d.decode(outs[k % nstreams], streams[k % nstreams])
+        launches += d.launches
+    for st in streams[1:]:
+        streams[0].wait_stream(st)
+    e1.record(streams[0])
     barrier()
     clocks = sampler.stop()
     total_ms = e0.elapsed_time(e1)
-    # per-stage durations of the LAST step (events recorded by the library on the same stream)
-    a, b = dec.last_timing()
-    ent_ms.append(a)
-    rec_ms.append(b)
     t = torch.tensor([total_ms], device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -267,19 +282,23 @@ def main():
     ms_per_step = total_ms / args.steps
     value = nf * world * args.steps / (total_ms * 1e-3)
 
-    # stage split averaged over a few extra timed steps (each synchronised, so the events are per step)
+    # per-stage durations for the rooflines: single stream, one step at a time, CUDA events recorded by the library
+    # on the launching stream around each stage
+    dec.enable_timing(True)
     for _ in range(3):
         dec.decode(out, stream)
         torch.cuda.synchronize()
         a, b = dec.last_timing()
         ent_ms.append(a)
         rec_ms.append(b)
+        uns_ms.append(dec.last_unstuff_ms())
     ent = statistics.mean(ent_ms)
     rec = statistics.mean(rec_ms)
+    uns = statistics.mean(uns_ms)
 
     peaks, peak_kind = measured_peaks()
     algo_bytes = dec.ecs_bytes + 128 * dec.stored_blocks
-    roof = {"bound": "hbm", "kernel": "entropy_decode_kernel", "achieved": algo_bytes / (ent * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+    roof = {"bound": "hbm", "kernel": "stage a = unstuff_kernel + entropy_decode_kernel", "ms_unstuff": uns, "ms_decode": ent - uns, "achieved": algo_bytes / (ent * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
             "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s", "traffic": None,
             "algorithmic_bytes_per_launch": algo_bytes, "ms_per_launch": ent, "share_of_step": ent / (ent + rec)}
     roof["frac"] = roof["achieved"] / roof["peak"]
@@ -353,7 +372,7 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic", "config": dict(config, mean_codestream_bytes=mean_bytes),
                 "clocks": clocks, "gpu_launches": launches, "roofline": roof, "roofline_recon": roof_recon,
-                "stage_ms": {"entropy": ent, "reconstruction": rec}}
+                "stage_ms": {"entropy": ent, "entropy_unstuff_share": uns, "reconstruction": rec}}
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:

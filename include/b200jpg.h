@@ -132,6 +132,8 @@ B200JPG_API int b200jpg_batch_last_launch_count(const b200jpg_batch *batch);
  * the call record events on `stream`, it does not synchronise. Read after synchronising. */
 B200JPG_API void b200jpg_batch_enable_timing(b200jpg_batch *batch, int on);
 B200JPG_API int b200jpg_batch_last_timing(b200jpg_batch *batch, float *entropy_ms, float *reconstruct_ms);
+/* Share of entropy_ms spent in the unstuffing pre-pass (stage a0), ms; negative when not available. */
+B200JPG_API float b200jpg_batch_last_unstuff_ms(b200jpg_batch *batch);
 
 /* Measured int32 issue rate of the device in Gop/s (integer multiply-add counted as 2 ops):
  * multiply-add only, add/logic only, and a 1:1 mix. Denominator of the reconstruction kernel's roofline. */

@@ -103,7 +103,7 @@ struct b200jpg_batch {
 
     int last_launches = 0;
     bool timing = false;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, after a0, after a1, after b
 };
 
 extern "C" {
@@ -535,6 +535,7 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
     cudaError_t e = cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * (size_t)b->n, (cudaStream_t)stream);
     if (e != cudaSuccess) return b->ctx->fail_cuda(e, "status reset");
     for (int pass = 0; pass < 2; pass++) {  // a0 for every class, then a1 for every class
+        if (pass == 1 && b->timing && b->ev[3]) cudaEventRecord(b->ev[3], (cudaStream_t)stream);
         for (auto &cl : b->classes) {
             EntropyLaunch l{};
             l.p = cl.p;
@@ -670,6 +671,13 @@ int b200jpg_batch_last_launch_count(const b200jpg_batch *b) { return b ? b->last
 
 void b200jpg_batch_enable_timing(b200jpg_batch *b, int on) {
     if (b) b->timing = on != 0;
+}
+
+float b200jpg_batch_last_unstuff_ms(b200jpg_batch *b) {
+    float a = 0;
+    if (!b || !b->ev[0] || !b->ev[3]) return -1.f;
+    if (cudaEventElapsedTime(&a, b->ev[0], b->ev[3]) != cudaSuccess) return -1.f;
+    return a;
 }
 
 int b200jpg_batch_last_timing(b200jpg_batch *b, float *entropy_ms, float *reconstruct_ms) {

@@ -189,6 +189,9 @@ class BatchDecoder:
         native.check(lib.b200jpg_batch_last_timing(self.handle, ctypes.byref(a), ctypes.byref(b)), self.ctx.handle)
         return a.value, b.value
 
+    def last_unstuff_ms(self):
+        return lib.b200jpg_batch_last_unstuff_ms(self.handle)
+
     def frame_view(self, out, i):
         """Frame i of a decoded output tensor as [H, W, C]."""
         fi = self.info(i)
