@@ -71,6 +71,11 @@ typedef struct b200jpg_frame_info {
 /* Parses the marker segments of one codestream. Returns B200JPG_OK or a negative error code. */
 B200JPG_API int b200jpg_parse(const uint8_t *data, size_t len, b200jpg_frame_info *info);
 
+/* Builds the device-independent Huffman / quantisation table blob of scan `scan` of one codestream on the host
+ * (replaces HuffmanTemplate::BuildDecoder coding/huffmantemplate.cpp:802-874 and IDCT::DefineQuant dct/idct.cpp:98-108).
+ * Returns the blob size (also when dst is NULL or too small), 0 on error. This blob is what rank 0 broadcasts. */
+B200JPG_API uint64_t b200jpg_build_tables(const uint8_t *data, size_t len, int scan, uint8_t *dst, uint64_t capacity);
+
 /* --- device context -------------------------------------------------------------------------------- */
 typedef struct b200jpg_ctx b200jpg_ctx;
 

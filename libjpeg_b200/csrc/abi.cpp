@@ -118,6 +118,23 @@ int b200jpg_parse(const uint8_t *data, size_t len, b200jpg_frame_info *info) {
     return rc;
 }
 
+uint64_t b200jpg_build_tables(const uint8_t *data, size_t len, int scan, uint8_t *dst, uint64_t capacity) {
+    ParsedFrame pf;
+    std::string err;
+    int rc = parse_codestream(data, len, pf, err);
+    if (rc == 0 && (scan < 0 || scan >= (int)pf.scans.size())) {
+        rc = B200JPG_ERR_INVALID_PARAMETER;
+        err = "scan index out of range";
+    }
+    TableSet ts;
+    if (rc == 0) rc = build_table_set(pf.scans[scan], ts, err);
+    g_tls_code = rc;
+    g_tls_error = err;
+    if (rc) return 0;
+    if (dst && capacity >= ts.blob.size()) memcpy(dst, ts.blob.data(), ts.blob.size());
+    return ts.blob.size();
+}
+
 int b200jpg_create(int device, b200jpg_ctx **out) {
     if (!out) return B200JPG_ERR_INVALID_PARAMETER;
     *out = nullptr;

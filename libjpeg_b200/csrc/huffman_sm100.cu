@@ -262,8 +262,10 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         q_addr[c] = s_qz + ((c < p.ns) ? 1024u * p.q_slot[c] : 0u);
     }
 
-    // next 32 stream bits into the window (callers guarantee n <= 32)
-    auto refill = [&]() {
+    // `nxt` always holds the stream word at wpos, loaded one refill ahead so that the shared-memory latency of the
+    // ring never sits on the decode chain
+    uint32_t nxt = 0;
+    auto preload = [&]() {
         const uint32_t ch = wpos >> 2;
         if (ch >= safe) {  // rare: ran past what the block-boundary top-up guarantees
             while (req <= ch) request(req++);
@@ -271,8 +273,14 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
             cp_async_wait<0>();
             safe = req;
         }
-        const uint32_t x = lds_u32_v(s_ring + ((wpos & 15u) << 2));
+        nxt = lds_u32_v(s_ring + ((wpos & 15u) << 2));
+    };
+    if (decoding) preload();
+    // next 32 stream bits into the window (callers guarantee n <= 32)
+    auto refill = [&]() {
+        const uint32_t x = nxt;
         wpos++;
+        preload();
         hi |= __funnelshift_rc(x, 0u, (uint32_t)n);  // x >> n          (0 for n == 32)
         lo |= __funnelshift_rc(0u, x, (uint32_t)n);  // x << (32 - n)   (0 for n == 0)
         n += 32;
@@ -330,6 +338,17 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                     // a lane that met an error keeps its blocks zero from there on
                     bool busy = has_mcu && decoding && (int)errbits >= 0;
                     int k = 1;
+                    // The dequantise + store of a coefficient is deferred by one symbol: its table pair (pq) is loaded
+                    // when the symbol is decoded and consumed after the NEXT symbol's table lookup has been issued, so
+                    // neither shared-memory latency is exposed. {0, 128} parks a "nothing pending" store in the pad slot.
+                    uint2 pq = make_uint2(0u, 128u);
+                    int pd = 0;
+                    auto drain = [&]() {
+                        const int v = pd * (int)pq.x;
+                        errbits |= pq.x;                 // bit 31: coefficient index >= 64 (:764-766)
+                        ovf |= (uint32_t)(v + 32768);
+                        sts_u16(s_stage + pq.y, v);
+                    };
                     // ---- DC: sequentialscan.cpp:682-701
                     if (busy) {
                         if (n <= 32) refill();
@@ -338,9 +357,8 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                         if ((int)e >= 0) {
                             pred[c] += value_of(e);
                             consume(e);
-                            const int v = pred[c] * (int)lds_u32(q_addr[c]);
-                            ovf |= (uint32_t)(v + 32768);
-                            sts_u16(s_stage, v);
+                            pd = pred[c];
+                            asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c]));
                         } else {
                             busy = false;
                         }
@@ -350,6 +368,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                         if (busy) {
                             if (n <= 32) refill();
                             const uint32_t e = lookup(ac_off[c]);
+                            drain();
                             errbits |= e;
                             const int diff = value_of(e);
                             consume(e);
@@ -358,19 +377,19 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                                 // or an error entry (bit 31, zero fields): the block ends
                                 k += 16;
                                 busy = (((e >> 10) & 15u) == 15u) && (k <= 63);
+                                pq = make_uint2(0u, 128u);
+                                pd = 0;
                             } else {
                                 k += (int)((e >> 10) & 15u);
-                                uint2 q;  // {delta (bit 31: k >= 64, :764-766), byte offset of the raster position}
-                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(q.x), "=r"(q.y) : "r"(q_addr[c] + ((uint32_t)k << 3)));
-                                errbits |= q.x;
-                                const int v = diff * (int)q.x;
-                                ovf |= (uint32_t)(v + 32768);
-                                sts_u16(s_stage + q.y, v);
+                                // {delta (bit 31: k >= 64), byte offset of the raster position}
+                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c] + ((uint32_t)k << 3)));
+                                pd = diff;
                                 k++;
                                 busy = (k <= 63);
                             }
                         }
                     }
+                    drain();
                     // ---- flush the block (zeros included) and clear the staging block
                     if (has_mcu) {
                         const uint32_t bx = mx * p.mw[c] + x, by = my * p.mh[c] + y;

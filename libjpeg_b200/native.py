@@ -39,6 +39,7 @@ def _load():
     vp, u8p, u64, i32 = ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_uint64, ctypes.c_int
     sig = {
         "b200jpg_parse": (i32, [vp, ctypes.c_size_t, ctypes.POINTER(FrameInfoStruct)]),
+        "b200jpg_build_tables": (u64, [vp, ctypes.c_size_t, i32, vp, u64]),
         "b200jpg_create": (i32, [i32, ctypes.POINTER(vp)]),
         "b200jpg_destroy": (None, [vp]),
         "b200jpg_last_error": (i32, [vp, ctypes.POINTER(ctypes.c_char_p)]),
@@ -74,7 +75,7 @@ def _load():
 
 lib = _load()
 ABI_SYMBOLS = [
-    "b200jpg_parse", "b200jpg_create", "b200jpg_destroy", "b200jpg_last_error", "b200jpg_batch_create",
+    "b200jpg_parse", "b200jpg_build_tables", "b200jpg_create", "b200jpg_destroy", "b200jpg_last_error", "b200jpg_batch_create",
     "b200jpg_batch_destroy", "b200jpg_batch_frame_info", "b200jpg_batch_out_offset", "b200jpg_batch_out_bytes",
     "b200jpg_batch_ecs_bytes", "b200jpg_batch_stored_blocks", "b200jpg_batch_h2d_bytes", "b200jpg_batch_export_tables",
     "b200jpg_batch_import_tables", "b200jpg_batch_upload", "b200jpg_batch_decode", "b200jpg_batch_decode_entropy",
