@@ -255,6 +255,7 @@ def main():
     ev_a = [torch.cuda.Event() for _ in range(nstreams)]
     ev_b = [torch.cuda.Event() for _ in range(nstreams)]
     launch_count = [0]
+    trace = []  # (event at start of a, end of a, start of b, end of b) of every timed step, for the overlap diagnosis
 
     def run_steps(k0, count):
         """steps k0 .. k0+count-1: entropy of step k on s_a, reconstruction on s_b; batch k % nstreams is reused only
@@ -264,13 +265,19 @@ def main():
             d = decs[i]
             if k >= nstreams:
                 s_a.wait_event(ev_b[i])
+            t = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            t[0].record(s_a)
             d.decode_entropy(s_a)
             launch_count[0] += d.launches
+            t[1].record(s_a)
             ev_a[i].record(s_a)
             s_b.wait_event(ev_a[i])
+            t[2].record(s_b)
             d.reconstruct(outs[i], s_b)
             launch_count[0] += d.launches
+            t[3].record(s_b)
             ev_b[i].record(s_b)
+            trace.append(t)
 
     run_steps(0, max(args.warmup, 3))
     torch.cuda.synchronize()
@@ -296,6 +303,11 @@ def main():
     launches = launch_count[0]
     clocks = sampler.stop()
     total_ms = e0.elapsed_time(e1)
+    timed = trace[-args.steps:]
+    overlap = {"entropy_ms_in_pipeline": statistics.mean(t[0].elapsed_time(t[1]) for t in timed),
+               "reconstruction_ms_in_pipeline": statistics.mean(t[2].elapsed_time(t[3]) for t in timed),
+               "a_start_offsets_ms": [round(e0.elapsed_time(t[0]), 2) for t in timed[:6]],
+               "b_start_offsets_ms": [round(e0.elapsed_time(t[2]), 2) for t in timed[:6]]}
     t = torch.tensor([total_ms], device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -393,7 +405,7 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic", "config": dict(config, mean_codestream_bytes=mean_bytes),
                 "clocks": clocks, "gpu_launches": launches, "roofline": roof, "roofline_recon": roof_recon,
-                "stage_ms": {"entropy": ent, "entropy_unstuff_share": uns, "reconstruction": rec}}
+                "stage_ms": {"entropy": ent, "entropy_unstuff_share": uns, "reconstruction": rec}, "pipeline": overlap}
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
