@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "internal.hpp"
 
@@ -166,9 +167,16 @@ __device__ __forceinline__ uint32_t sat_u8_64(long long v) { return (uint32_t)(v
 // ycbcrtrafo.cpp:842-850 with the matrix of colortransformerfactory.cpp:136-138 (13 fractional bits) and
 // FIX_COLOR_TO_INT (tools/numerics.hpp:65).  The reference multiplies in 64 bits; 32 bits give the same result
 // while |y|, |cb|, |cr| <= 65535 -- blocks that violate that (damaged streams only) are flagged `wide`.
-__device__ __forceinline__ void ycc_to_rgb(int y, int cbv, int crv, bool wide, uint32_t &r, uint32_t &g, uint32_t &b) {
+template <int MODE>  // 0: 32-bit YCbCr, 1: 64-bit YCbCr (samples outside the guarded range), 2: identity
+__device__ __forceinline__ void to_rgb(int y, int cbv, int crv, uint32_t &r, uint32_t &g, uint32_t &b) {
+    if (MODE == 2) {  // COLOR_TO_INT (tools/numerics.hpp:69) + clamp
+        r = sat_u8(WADD(y, 8) >> 4);
+        g = sat_u8(WADD(cbv, 8) >> 4);
+        b = sat_u8(WADD(crv, 8) >> 4);
+        return;
+    }
     const int cb = WSUB(cbv, 128 << 4), cr = WSUB(crv, 128 << 4);
-    if (!wide) {
+    if (MODE == 0) {
         const int yy = y * 8192 + 65536;
         r = sat_u8((yy + cr * 11485) >> 17);
         g = sat_u8((yy - cb * 2819 - cr * 5850) >> 17);
@@ -284,9 +292,11 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
         load_row<NW>(p2, cpitch, cy0, cx0, cw, ch, interior, cur2);
     }
 
+    auto lines = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll 1
-    for (int r = 0; r < 8; r++) {
-        if (r > ymax) break;  // uniform over the warp (same block row)
+        for (int r = 0; r < 8; r++) {
+            if (r > ymax) break;  // uniform over the warp (same block row)
         uint32_t px[24];
         if (valid) {
             int v1[NW], v2[NW];
@@ -327,13 +337,7 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
             for (int x = 0; x < 8; x++) {
                 const int yv = my[(8 * r + x) * kThreadsB];
                 uint32_t R, G, B;
-                if (ycbcr) {
-                    ycc_to_rgb(yv, c1[x], c2[x], wide, R, G, B);
-                } else {
-                    R = sat_u8(WADD(yv, 8) >> 4);
-                    G = sat_u8(WADD(c1[x], 8) >> 4);
-                    B = sat_u8(WADD(c2[x], 8) >> 4);
-                }
+                to_rgb<MODE>(yv, c1[x], c2[x], R, G, B);
                 px[3 * x] = R;
                 px[3 * x + 1] = G;
                 px[3 * x + 2] = B;
@@ -390,6 +394,11 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
             }
         }
     }
+    };
+    // one instantiation per colour mode keeps every per-pixel branch out of the line loop
+    if (!ycbcr) lines(std::integral_constant<int, 2>());
+    else if (wide) lines(std::integral_constant<int, 1>());
+    else lines(std::integral_constant<int, 0>());
 }
 
 }  // namespace
