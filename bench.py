@@ -140,6 +140,19 @@ def run_reference(frames, procs, iters):
     return {"frames": procs * iters, "procs": procs, "wall_s": wall, "fps": procs * iters / wall, "kind": "port"}
 
 
+def best_reference_config(frames, ncpu):
+    """The reference is single threaded and allocation heavy: beyond a few dozen processes this box's memory system, not
+    its cores, limits it. Scan the process count (short samples) and keep the fastest: that is the CPU arm's best case."""
+    cands = sorted(set(max(1, c) for c in (ncpu, ncpu // 2, ncpu // 4, ncpu // 8, 3 * ncpu // 8)))
+    best, scan = None, {}
+    for procs in cands:
+        d = run_reference(frames, procs, max(2, 128 // procs))
+        scan[procs] = round(d["fps"], 1)
+        if best is None or d["fps"] > best[1]:
+            best = (procs, d["fps"])
+    return best[0], scan
+
+
 def _oracle_worker(args):
     frames, iters, p = args
     from tests import oracle_binding
@@ -177,10 +190,8 @@ def main():
         if rank != 0:
             return 0
         frames = make_frames(8, min(8, ncpu))
-        procs = ncpu
-        iters = 8
-        for _ in range(max(args.warmup, 0) and 1):
-            run_reference(frames, procs, 1)
+        procs, scan = best_reference_config(frames, ncpu)  # doubles as the warm-up
+        iters = max(8, 512 // procs)
         vals, last = [], None
         t0 = time.time()
         for _ in range(args.steps):
@@ -192,8 +203,9 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "frames/s", "cores": procs, "kind": last["kind"],
-                                 "sample": "%d frames per step (8 distinct cfg3 frames cycled), one process per hardware thread, "
-                                           "Read + 8-row-striped DisplayRectangle through the reference's public API" % (procs * iters),
+                                 "sample": "%d frames per step (8 distinct cfg3 frames cycled), %d worker processes = the fastest of the "
+                                           "process counts scanned on this %d-thread host (%s fps), "
+                                           "Read + 8-row-striped DisplayRectangle through the reference's public API" % (procs * iters, procs, ncpu, scan),
                                  "read_ms_per_frame": last.get("read_ms_per_frame"), "display_ms_per_frame": last.get("display_ms_per_frame")},
                 "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
@@ -409,10 +421,12 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
-            cb = run_reference(base, ncpu, 16)
+            procs, scan = best_reference_config(base, ncpu)
+            cb = run_reference(base, procs, max(16, 1024 // procs))
             line["cpu_baseline"] = {"value": cb["fps"], "unit": "frames/s", "cores": cb["procs"], "kind": cb["kind"],
-                                    "sample": "%d frames (8 distinct cfg3 frames cycled), one process per hardware thread (%d), "
-                                              "Read + 8-row-striped DisplayRectangle via the reference's public API" % (cb["frames"], cb["procs"]),
+                                    "sample": "%d frames (8 distinct cfg3 frames cycled), %d worker processes = the fastest of the process "
+                                              "counts scanned on this %d-thread host (%s fps), Read + 8-row-striped DisplayRectangle via the "
+                                              "reference's public API" % (cb["frames"], cb["procs"], ncpu, scan),
                                     "read_ms_per_frame": cb.get("read_ms_per_frame"), "display_ms_per_frame": cb.get("display_ms_per_frame")}
         print(json.dumps(line))
     if dist is not None:
