@@ -107,6 +107,29 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
         uint32_t cur = 0, nxt = 0;
         if (wo < src1) cur = __ldg(reinterpret_cast<const uint32_t *>(bytes + wo));
         if (wo + 4 < src1 + 2) nxt = __ldg(reinterpret_cast<const uint32_t *>(bytes + wo + 4));  // reaches the marker bytes
+        // fast path (about 60 % of the steps): no 0xFF anywhere in these 128 bytes and all of them inside the interval:
+        // nothing to remove, nothing ends -- the bytes just move
+        if (base >= src0 && base + 128 <= src1 && carry_ff == 0 && !__any_sync(kFull, __vcmpeq4(cur, 0xffffffffu) != 0u)) {
+            const uint32_t o = fill + 4 * lane;
+            if ((fill & 3u) == 0u) {
+                sts_u32(sb + o, __byte_perm(cur, 0, 0x0123));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) sts_u8(sb + ((o + k) ^ 3u), (cur >> (8 * k)) & 0xffu);
+            }
+            fill += 128;
+            total += 128;
+            __syncwarp();
+            const uint32_t w = lds_u32_v(sb + 4 * lane);
+            const uint32_t w2 = lds_u32_v(sb + 128 + 4 * lane);
+            dst[written + lane] = w;
+            __syncwarp();
+            sts_u32(sb + 4 * lane, w2);
+            written += 32;
+            fill -= 128;
+            __syncwarp();
+            continue;
+        }
         // byte in front of this lane's word: the previous lane's last byte (lane 0: carried from the last step)
         uint32_t prev_word = __shfl_up_sync(kFull, cur, 1);
         uint32_t pb = (lane == 0) ? (carry_ff ? 0xffu : 0u) : ((wo - 1 >= src0) ? (prev_word >> 24) : 0u);
