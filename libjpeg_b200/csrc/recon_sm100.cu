@@ -32,7 +32,6 @@ namespace b200jpg {
 namespace {
 
 constexpr int kThreadsB = 128;
-constexpr int kSmemB2 = 64 * kThreadsB * 4 + (kThreadsB / 32) * 32 * 144;  // sample tile + coefficient / RGB staging
 constexpr int kWide = 65535;  // |sample| above this may overflow the 32-bit colour arithmetic -> 64-bit path
 
 #define WMUL(a, k) ((int)((unsigned)(a) * (unsigned)(int)(k)))
@@ -129,40 +128,18 @@ idct_planes_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
 // ---- b2 ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// NW samples of line y of a sample plane starting at column x0.  Three ways to get them:
-//  * `wfast` (uniform over the warp: all 32 blocks valid and their samples inside the true plane width): every lane loads
-//    the aligned 16-byte group(s) it owns -- 512 coalesced bytes per warp -- and, for SX == 2, takes the sample left of
-//    its group from lane-1 and the one right of it from lane+1 by shuffle (the two end lanes load theirs, clamped);
-//  * `interior`: plain run of scalar loads;
-//  * otherwise clamped addressing, which reproduces dest[-1] = dest[0], dest[width] = dest[width-1]
-//    (upsamplerbase.cpp:322-323).  The line index is always clamped: duplicated first / last line (upsampler.cpp:100-106).
+// NW samples of line y of a sample plane starting at column x0. Away from the frame edge this is a plain run;
+// at the edge the clamped addressing reproduces dest[-1] = dest[0], dest[width] = dest[width-1]
+// (upsamplerbase.cpp:322-323) and the duplicated first / last line (upsampler.cpp:100-106).
 template <int NW>
 __device__ __forceinline__ void load_row(const int32_t *__restrict__ plane, uint32_t pitch, int y, int x0, int cw, int ch, bool interior,
-                                         bool wfast, uint32_t lane, int (&v)[NW]) {
-    const int32_t *row = plane + (uint64_t)clampi(y, 0, ch - 1) * pitch;
-    if (wfast) {
-        if (NW == 6) {  // window = x0 .. x0+5 with x0 = 4*bx - 1: own group is x0+1 .. x0+4
-            const int4 q = __ldg(reinterpret_cast<const int4 *>(row + x0 + 1));
-            int left = __shfl_up_sync(0xffffffffu, q.w, 1);
-            int right = __shfl_down_sync(0xffffffffu, q.x, 1);
-            if (lane == 0) left = __ldg(row + (x0 < 0 ? 0 : x0));
-            if (lane == 31) right = __ldg(row + (x0 + 5 > cw - 1 ? cw - 1 : x0 + 5));
-            v[0] = left;
-            v[1] = q.x;
-            v[2] = q.y;
-            v[3] = q.z;
-            v[4] = q.w;
-            v[5] = right;
-        } else {  // window = 8*bx .. 8*bx+7
-            const int4 a = __ldg(reinterpret_cast<const int4 *>(row + x0));
-            const int4 b = __ldg(reinterpret_cast<const int4 *>(row + x0 + 4));
-            v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
-            v[NW - 4] = b.x, v[NW - 3] = b.y, v[NW - 2] = b.z, v[NW - 1] = b.w;
-        }
-    } else if (interior) {
+                                         int (&v)[NW]) {
+    if (interior) {
+        const int32_t *row = plane + (uint64_t)y * pitch + x0;
 #pragma unroll
-        for (int j = 0; j < NW; j++) v[j] = __ldg(row + x0 + j);
+        for (int j = 0; j < NW; j++) v[j] = __ldg(row + j);
     } else {
+        const int32_t *row = plane + (uint64_t)clampi(y, 0, ch - 1) * pitch;
 #pragma unroll
         for (int j = 0; j < NW; j++) v[j] = __ldg(row + clampi(x0 + j, 0, cw - 1));
     }
@@ -216,10 +193,8 @@ template <int NC, int SX, int SY>
 __global__ void __launch_bounds__(kThreadsB, 4)
 reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, const int32_t *__restrict__ samples,
                    const uint32_t *__restrict__ wide_flags, uint8_t *__restrict__ out) {
-    extern __shared__ __align__(16) uint8_t b2_smem[];
-    int *ys = reinterpret_cast<int *>(b2_smem);                                             // [coefficient][thread], 32 KB
-    uint8_t(*cstage)[32 * 144] = reinterpret_cast<uint8_t(*)[32 * 144]>(b2_smem + 64 * kThreadsB * 4);  // per warp: its 32 coefficient blocks
-    // one RGB line of 32 blocks per warp; lives in the coefficient staging area, which is dead after the row pass
+    __shared__ int ys[64 * kThreadsB];                                   // [coefficient][thread]
+    __shared__ __align__(16) uint32_t stage[kThreadsB / 32][32 * 6];     // one RGB line of 32 blocks per warp
 
     const FrameRecon &f = frames[blockIdx.z];
     const uint32_t W = f.width, H = f.height;
@@ -231,33 +206,21 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
     const int X = 8 * (int)bx, Y = 8 * (int)by;
     int *my = ys + threadIdx.x;
 
-    // ---- the warp's 32 coefficient blocks are contiguous in HBM (4 KB): read them as 8 x 512 coalesced bytes and
-    // re-deal them through shared memory (144-byte pitch: conflict free) so that each lane ends up with its own block
+    // ---- luma IDCT, row pass (dct/idct.cpp:237-287): one 16-byte load per block row, next row in flight
     {
-        const int16_t *wsrc = coef + f.coef_base[0] + ((uint64_t)by * f.bw[0] + bx0) * 64u;
-        const uint32_t nblk = (f.bw[0] - bx0 < 32u) ? (f.bw[0] - bx0) : 32u;  // blocks of this row that exist in the plane
-        uint8_t *cs = cstage[warp];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t c = i * 32 + lane;  // 16-byte chunk index inside the 4 KB span
-            if ((c >> 3) < nblk) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(wsrc) + c);
-                *reinterpret_cast<uint4 *>(cs + (c >> 3) * 144 + (c & 7) * 16) = v;
-            }
-        }
-        __syncwarp();
-        // ---- luma IDCT, row pass (dct/idct.cpp:237-287)
-        const uint4 *mine = reinterpret_cast<const uint4 *>(cs + lane * 144);
+        const uint4 *src = reinterpret_cast<const uint4 *>(coef + f.coef_base[0] + ((uint64_t)by * f.bw[0] + (valid ? bx : 0)) * 64u);
+        uint4 q = __ldg(src);
 #pragma unroll 1
         for (int r = 0; r < 8; r++) {
+            const uint4 qn = __ldg(src + ((r < 7) ? r + 1 : r));
             int v[8];
-            unpack_row(mine[r], v);
+            unpack_row(q, v);
             if (r == 0) v[0] = WADD(v[0], 128 << 7);  // dcoffset << (preshift + 3), idct.cpp:233,244
             idct8<256, 9>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
 #pragma unroll
             for (int k = 0; k < 8; k++) my[(8 * r + k) * kThreadsB] = v[k];
+            q = qn;
         }
-        __syncwarp();  // the staging area is reused for the RGB lines below
     }
     // ---- column pass (:291-334) + range guard for the 32-bit colour arithmetic
     int mx = 0, mn = 0;
@@ -310,25 +273,23 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
     const bool ycbcr = f.ycbcr != 0;
     const bool wide = (wide_flags[f.status_idx] != 0u) || mx > kWide || mn < -kWide;
     // the whole window lies inside the plane: no clamping needed
-    const bool interior = valid && cx0 >= 0 && cx0 + NW <= cw;
-    // all 32 blocks of the warp exist and none of their chroma groups reaches past the true plane width
-    const bool wfast = (bx0 + 32 <= vbw) && ((int)(bx0 + 31) * (8 / SX) + (8 / SX) - 1 <= cw - 1);
+    const bool interior = valid && cx0 >= 0 && cx0 + NW <= cw && cy0 - 1 >= 0 && cy0 + ((SY == 2) ? 5 : 8) <= ch;
     // a full line of the warp leaves as 48 aligned 16-byte stores
     const bool vec_line = (bx0 + 32 <= vbw) && ((W & 7u) == 0) && (((f.out_base | opitch) & 15u) == 0);
-    uint32_t *wstage = reinterpret_cast<uint32_t *>(cstage[warp]);
+    uint32_t *wstage = stage[warp];
     uint8_t *wrow = out + f.out_base + (uint64_t)Y * opitch + (uint64_t)bx0 * 8u * NC;  // first byte of the warp's line 0
 
     // rolling lines: SY == 2 keeps top/cur/bot (upsampler.cpp:92-106), SY == 1 only cur
     int top1[NW], cur1[NW], bot1[NW], top2[NW], cur2[NW], bot2[NW];
     if (valid) {
         if (SY == 2) {
-            load_row<NW>(p1, cpitch, cy0 - 1, cx0, cw, ch, interior, wfast, lane, top1);
-            load_row<NW>(p2, cpitch, cy0 - 1, cx0, cw, ch, interior, wfast, lane, top2);
-            load_row<NW>(p1, cpitch, cy0 + 1, cx0, cw, ch, interior, wfast, lane, bot1);
-            load_row<NW>(p2, cpitch, cy0 + 1, cx0, cw, ch, interior, wfast, lane, bot2);
+            load_row<NW>(p1, cpitch, cy0 - 1, cx0, cw, ch, interior, top1);
+            load_row<NW>(p2, cpitch, cy0 - 1, cx0, cw, ch, interior, top2);
+            load_row<NW>(p1, cpitch, cy0 + 1, cx0, cw, ch, interior, bot1);
+            load_row<NW>(p2, cpitch, cy0 + 1, cx0, cw, ch, interior, bot2);
         }
-        load_row<NW>(p1, cpitch, cy0, cx0, cw, ch, interior, wfast, lane, cur1);
-        load_row<NW>(p2, cpitch, cy0, cx0, cw, ch, interior, wfast, lane, cur2);
+        load_row<NW>(p1, cpitch, cy0, cx0, cw, ch, interior, cur1);
+        load_row<NW>(p2, cpitch, cy0, cx0, cw, ch, interior, cur2);
     }
 
     auto lines = [&](auto mode_tag) {
@@ -423,13 +384,13 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
                         cur2[j] = bot2[j];
                     }
                     if (r < 7) {
-                        load_row<NW>(p1, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, interior, wfast, lane, bot1);
-                        load_row<NW>(p2, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, interior, wfast, lane, bot2);
+                        load_row<NW>(p1, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, interior, bot1);
+                        load_row<NW>(p2, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, interior, bot2);
                     }
                 }
             } else if (r < 7) {
-                load_row<NW>(p1, cpitch, cy0 + r + 1, cx0, cw, ch, interior, wfast, lane, cur1);
-                load_row<NW>(p2, cpitch, cy0 + r + 1, cx0, cw, ch, interior, wfast, lane, cur2);
+                load_row<NW>(p1, cpitch, cy0 + r + 1, cx0, cw, ch, interior, cur1);
+                load_row<NW>(p2, cpitch, cy0 + r + 1, cx0, cw, ch, interior, cur2);
             }
         }
     }
@@ -452,23 +413,17 @@ int launch_recon(const ReconLaunch &l, void *stream, int *launches) {
         n++;
     }
     dim3 grid((l.max_bw0 + 31) / 32, (l.max_bh0 + kThreadsB / 32 - 1) / (kThreadsB / 32), l.n_frames);
-    auto go = [&](auto kernel) -> cudaError_t {
-        static bool configured = false;  // one flag per instantiation (the lambda body is instantiated per kernel type)
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemB2);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
-        kernel<<<grid, kThreadsB, kSmemB2, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
-        return cudaSuccess;
-    };
-    cudaError_t ge;
-    if (l.ncomp == 1) ge = go(reconstruct_kernel<1, 1, 1>);
-    else if (l.subx == 2 && l.suby == 2) ge = go(reconstruct_kernel<3, 2, 2>);
-    else if (l.subx == 2 && l.suby == 1) ge = go(reconstruct_kernel<3, 2, 1>);
-    else if (l.subx == 1 && l.suby == 2) ge = go(reconstruct_kernel<3, 1, 2>);
-    else ge = go(reconstruct_kernel<3, 1, 1>);
-    if (ge != cudaSuccess) return (int)ge;
+    if (l.ncomp == 1) {
+        reconstruct_kernel<1, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+    } else if (l.subx == 2 && l.suby == 2) {
+        reconstruct_kernel<3, 2, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+    } else if (l.subx == 2 && l.suby == 1) {
+        reconstruct_kernel<3, 2, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+    } else if (l.subx == 1 && l.suby == 2) {
+        reconstruct_kernel<3, 1, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+    } else {
+        reconstruct_kernel<3, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+    }
     n++;
     if (launches) *launches = n;
     return (int)cudaGetLastError();
