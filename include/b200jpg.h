@@ -97,6 +97,8 @@ typedef struct b200jpg_batch b200jpg_batch;
  * skipped and reported through b200jpg_batch_frame_status. */
 B200JPG_API int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad,
                          b200jpg_batch **batch);
+/* Waits for the work last enqueued for this batch (its buffers return to the context's pool for reuse by the
+ * next batch; b200jpg_destroy frees the pool). The caller must have consumed `out_dev` before reusing it. */
 B200JPG_API void b200jpg_batch_destroy(b200jpg_batch *batch);
 
 B200JPG_API int b200jpg_batch_frame_info(const b200jpg_batch *batch, int i, b200jpg_frame_info *info);

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -28,10 +29,58 @@ inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+// Device / pinned-host buffers are recycled through the context: a streaming caller creates and destroys one batch per
+// chunk of frames, and cudaMalloc / cudaHostAlloc per chunk would dominate the host side of the pipeline.
+struct PoolBuf {
+    void *p;
+    size_t bytes;
+    int kind;  // 0 = pinned host, 1 = device
+};
+
 struct b200jpg_ctx {
     int device = 0;
     std::string error;
     int code = 0;
+    std::mutex pool_mutex;
+    std::vector<PoolBuf> pool;
+    void *get(int kind, size_t bytes, cudaError_t *err) {
+        *err = cudaSuccess;
+        if (bytes == 0) bytes = 256;
+        {
+            std::lock_guard<std::mutex> lock(pool_mutex);
+            int best = -1;
+            for (size_t i = 0; i < pool.size(); i++)
+                if (pool[i].kind == kind && pool[i].bytes >= bytes && pool[i].bytes <= bytes + bytes / 2 + (1u << 20) &&
+                    (best < 0 || pool[i].bytes < pool[(size_t)best].bytes))
+                    best = (int)i;
+            if (best >= 0) {
+                void *p = pool[(size_t)best].p;
+                pool.erase(pool.begin() + best);
+                return p;
+            }
+        }
+        void *p = nullptr;
+        *err = kind ? cudaMalloc(&p, bytes) : cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        if (*err != cudaSuccess) {  // make room and retry once
+            trim();
+            *err = kind ? cudaMalloc(&p, bytes) : cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        }
+        return *err == cudaSuccess ? p : nullptr;
+    }
+    void put(int kind, void *p, size_t bytes) {
+        if (!p) return;
+        if (bytes == 0) bytes = 256;
+        std::lock_guard<std::mutex> lock(pool_mutex);
+        pool.push_back(PoolBuf{p, bytes, kind});
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lock(pool_mutex);
+        for (auto &b : pool) {
+            if (b.kind) cudaFree(b.p);
+            else cudaFreeHost(b.p);
+        }
+        pool.clear();
+    }
     int fail(int c, const std::string &m) {
         code = c;
         error = m;
@@ -101,6 +150,8 @@ struct b200jpg_batch {
     bool status_fetched = false;
     bool uploaded = false;
 
+    size_t sz_status = 0, sz_ilen = 0;
+    cudaEvent_t ev_last = nullptr;  // recorded after the last work enqueued for this batch: destroy waits for it
     int last_launches = 0;
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, after a0, after a1, after b
@@ -167,7 +218,12 @@ int b200jpg_create(int device, b200jpg_ctx **out) {
     return B200JPG_OK;
 }
 
-void b200jpg_destroy(b200jpg_ctx *ctx) { delete ctx; }
+void b200jpg_destroy(b200jpg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->trim();
+    delete ctx;
+}
 
 int b200jpg_last_error(b200jpg_ctx *ctx, const char **message) {
     if (ctx) {
@@ -181,13 +237,17 @@ int b200jpg_last_error(b200jpg_ctx *ctx, const char **message) {
 void b200jpg_batch_destroy(b200jpg_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
-    if (b->h_input) cudaFreeHost(b->h_input);
-    if (b->d_input) cudaFree(b->d_input);
-    if (b->d_coef) cudaFree(b->d_coef);
-    if (b->d_samples) cudaFree(b->d_samples);
-    if (b->d_clean) cudaFree(b->d_clean);
-    if (b->d_interval_len) cudaFree(b->d_interval_len);
-    if (b->d_status) cudaFree(b->d_status);
+    if (b->ev_last) {  // buffers go back to the pool: nothing of this batch may still be in flight
+        cudaEventSynchronize(b->ev_last);
+        cudaEventDestroy(b->ev_last);
+    }
+    b->ctx->put(0, b->h_input, b->input_bytes);
+    b->ctx->put(1, b->d_input, b->input_bytes);
+    b->ctx->put(1, b->d_coef, b->coef_elems * sizeof(int16_t));
+    b->ctx->put(1, b->d_samples, b->sample_elems * sizeof(int32_t));
+    b->ctx->put(1, b->d_clean, b->clean_bytes);
+    b->ctx->put(1, b->d_interval_len, b->sz_ilen);
+    b->ctx->put(1, b->d_status, b->sz_status);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
     delete b;
@@ -449,7 +509,7 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
     b->input_bytes = cur;
 
     // ---- pinned staging + device memory
-    ce = cudaHostAlloc((void **)&b->h_input, b->input_bytes, cudaHostAllocDefault);
+    b->h_input = (uint8_t *)ctx->get(0, b->input_bytes, &ce);
     if (ce != cudaSuccess) return ctx->fail(B200JPG_ERR_OUT_OF_MEMORY, std::string("pinned staging allocation failed: ") + cudaGetErrorString(ce));
     {
         unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
@@ -489,12 +549,15 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
     }
     for (auto &g : b->groups) memcpy(b->h_input + g.dev_frames, g.frames.data(), g.frames.size() * sizeof(FrameRecon));
 
-    ce = cudaMalloc((void **)&b->d_input, b->input_bytes);
-    if (ce == cudaSuccess && b->coef_elems) ce = cudaMalloc((void **)&b->d_coef, b->coef_elems * sizeof(int16_t));
-    if (ce == cudaSuccess && b->sample_elems) ce = cudaMalloc((void **)&b->d_samples, b->sample_elems * sizeof(int32_t));
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&b->d_clean, b->clean_bytes);
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&b->d_interval_len, sizeof(uint32_t) * (size_t)std::max<uint64_t>(b->n_intervals, 1));
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&b->d_status, sizeof(uint32_t) * 2 * (size_t)n);  // status words + wide flags
+    b->sz_ilen = sizeof(uint32_t) * (size_t)std::max<uint64_t>(b->n_intervals, 1);
+    b->sz_status = sizeof(uint32_t) * 2 * (size_t)n;  // status words + wide flags
+    b->d_input = (uint8_t *)ctx->get(1, b->input_bytes, &ce);
+    if (ce == cudaSuccess && b->coef_elems) b->d_coef = (int16_t *)ctx->get(1, b->coef_elems * sizeof(int16_t), &ce);
+    if (ce == cudaSuccess && b->sample_elems) b->d_samples = (int32_t *)ctx->get(1, b->sample_elems * sizeof(int32_t), &ce);
+    if (ce == cudaSuccess) b->d_clean = (uint8_t *)ctx->get(1, b->clean_bytes, &ce);
+    if (ce == cudaSuccess) b->d_interval_len = (uint32_t *)ctx->get(1, b->sz_ilen, &ce);
+    if (ce == cudaSuccess) b->d_status = (uint32_t *)ctx->get(1, b->sz_status, &ce);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->ev_last, cudaEventDisableTiming);
     if (ce != cudaSuccess) return ctx->fail(B200JPG_ERR_OUT_OF_MEMORY, std::string("device allocation failed: ") + cudaGetErrorString(ce));
     b->h_status.assign(n, 0);
     *out = bp.release();
@@ -544,6 +607,7 @@ int b200jpg_batch_upload(b200jpg_batch *b, void *stream) {
     cudaSetDevice(b->ctx->device);
     cudaError_t e = cudaMemcpyAsync(b->d_input, b->h_input, b->input_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
     if (e != cudaSuccess) return b->ctx->fail_cuda(e, "upload");
+    cudaEventRecord(b->ev_last, (cudaStream_t)stream);
     b->uploaded = true;
     return B200JPG_OK;
 }
@@ -571,6 +635,7 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
             b->last_launches++;
         }
     }
+    cudaEventRecord(b->ev_last, (cudaStream_t)stream);
     return B200JPG_OK;
 }
 
@@ -603,6 +668,7 @@ static int run_recon(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
             b->last_launches += launches;
         }
     }
+    cudaEventRecord(b->ev_last, (cudaStream_t)stream);
     return B200JPG_OK;
 }
 
