@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 
 #include "internal.hpp"
@@ -413,16 +414,37 @@ int launch_recon(const ReconLaunch &l, void *stream, int *launches) {
         n++;
     }
     dim3 grid((l.max_bw0 + 31) / 32, (l.max_bh0 + kThreadsB / 32 - 1) / (kThreadsB / 32), l.n_frames);
+    // Optional occupancy cap for stage b (B200JPG_RECON_CTAS_PER_SM = 1..3): b2 fills the register file with 4 CTAs per
+    // SM; capping it leaves room for the entropy CTAs of the next batch to run next to it (pipelined callers, bench.py).
+    // Implemented by padding the CTA's shared memory so that only that many fit in 227 KB.
+    static int pad_bytes = -1;
+    if (pad_bytes < 0) {
+        pad_bytes = 0;
+        const char *env = getenv("B200JPG_RECON_CTAS_PER_SM");
+        int want = env ? atoi(env) : 0;
+        if (want >= 1 && want <= 3) {
+            const int per_cta = (227 * 1024) / want - 1024;          // 1 KB per CTA is reserved by the system
+            const int stat = 64 * kThreadsB * 4 + (kThreadsB / 32) * 32 * 6 * 4;
+            pad_bytes = per_cta - stat - 2048;                        // just below the limit for `want`, above for want + 1
+            if (pad_bytes < 0) pad_bytes = 0;
+            cudaFuncSetAttribute(reconstruct_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_bytes);
+            cudaFuncSetAttribute(reconstruct_kernel<3, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_bytes);
+            cudaFuncSetAttribute(reconstruct_kernel<3, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_bytes);
+            cudaFuncSetAttribute(reconstruct_kernel<3, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_bytes);
+            cudaFuncSetAttribute(reconstruct_kernel<3, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_bytes);
+        }
+    }
+    const size_t dyn = (size_t)pad_bytes;
     if (l.ncomp == 1) {
-        reconstruct_kernel<1, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+        reconstruct_kernel<1, 1, 1><<<grid, kThreadsB, dyn, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else if (l.subx == 2 && l.suby == 2) {
-        reconstruct_kernel<3, 2, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+        reconstruct_kernel<3, 2, 2><<<grid, kThreadsB, dyn, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else if (l.subx == 2 && l.suby == 1) {
-        reconstruct_kernel<3, 2, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+        reconstruct_kernel<3, 2, 1><<<grid, kThreadsB, dyn, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else if (l.subx == 1 && l.suby == 2) {
-        reconstruct_kernel<3, 1, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+        reconstruct_kernel<3, 1, 2><<<grid, kThreadsB, dyn, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else {
-        reconstruct_kernel<3, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+        reconstruct_kernel<3, 1, 1><<<grid, kThreadsB, dyn, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     }
     n++;
     if (launches) *launches = n;
