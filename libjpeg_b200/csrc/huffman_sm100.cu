@@ -299,14 +299,19 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         nxt = lds_u32_v(s_ring + ((wpos & 15u) << 2));
     };
     if (decoding) preload();
-    // next 32 stream bits into the window (callers guarantee n <= 32)
+    // Branch-free refill: when fewer than 33 bits are left, the preloaded word enters the window and the next one is
+    // fetched; otherwise nothing changes (x = 0 ORs nothing in). Every lane executes this each iteration: cheaper than a
+    // divergent branch that some lane of the warp takes nine iterations out of ten.
     auto refill = [&]() {
-        const uint32_t x = nxt;
-        wpos++;
-        preload();
-        hi |= __funnelshift_rc(x, 0u, (uint32_t)n);  // x >> n          (0 for n == 32)
+        const bool take = n <= 32;
+        const uint32_t x = take ? nxt : 0u;
+        hi |= __funnelshift_rc(x, 0u, (uint32_t)n);  // x >> n          (0 for n == 32); n > 32 only when x == 0
         lo |= __funnelshift_rc(0u, x, (uint32_t)n);  // x << (32 - n)   (0 for n == 0)
-        n += 32;
+        if (take) {
+            n += 32;
+            wpos++;
+            preload();
+        }
     };
     // two-level lookup; `tab` is the shared-space address of the table (kLutShared) or its word offset (global)
     auto lookup = [&](uint32_t tab) -> uint32_t {
@@ -374,7 +379,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                     };
                     // ---- DC: sequentialscan.cpp:682-701
                     if (busy) {
-                        if (n <= 32) refill();
+                        refill();
                         const uint32_t e = lookup(dc_off[c]);
                         errbits |= e;
                         if ((int)e >= 0) {
@@ -389,7 +394,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                     // ---- AC: sequentialscan.cpp:704-771, one symbol per warp-convergent iteration
                     while (__any_sync(kFull, busy)) {
                         if (busy) {
-                            if (n <= 32) refill();
+                            refill();
                             const uint32_t e = lookup(ac_off[c]);
                             drain();
                             errbits |= e;
