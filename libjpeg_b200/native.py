@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libb200jpg.so")
+_LIB_PATH = os.environ.get("B200JPG_LIB") or os.path.join(_HERE, "libb200jpg.so")  # env override: kernel experiments
 
 
 class NativeError(RuntimeError):
