@@ -35,7 +35,7 @@ namespace b200jpg {
 namespace {
 
 #ifndef B200JPG_A1_THREADS
-#define B200JPG_A1_THREADS 128
+#define B200JPG_A1_THREADS 256
 #endif
 constexpr int kThreads = B200JPG_A1_THREADS;  // a1: CTA size (experiments may override at build time)
 constexpr int kStageStride = 144;  // bytes per lane: 128 + 16 pad -> conflict-free 16-byte accesses
@@ -291,17 +291,22 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
     // `nxt` always holds the stream word at wpos, loaded one refill ahead so that the shared-memory latency of the
     // ring never sits on the decode chain
     uint32_t nxt = 0;
-    auto preload = [&]() {
+    // `go` selects the lanes that really load: the load is predicated and writes the loop-carried register directly, so
+    // no move waits for it and lanes that do not refill keep their word
+    auto preload = [&](bool go) {
         const uint32_t ch = wpos >> 2;
-        if (ch >= safe) {  // rare: ran past what the block-boundary top-up guarantees
+        if (go && ch >= safe) {  // rare: ran past what the block-boundary top-up guarantees
             while (req <= ch) request(req++);
             cp_async_commit();
             cp_async_wait<0>();
             safe = req;
         }
-        nxt = lds_u32_v(s_ring + ((wpos & 15u) << 2));
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.u32 %0, [%1]; }"
+                     : "+r"(nxt)
+                     : "r"(s_ring + ((wpos & 15u) << 2)), "r"((uint32_t)go)
+                     : "memory");
     };
-    if (decoding) preload();
+    preload(decoding);
     // Branch-free refill: when fewer than 33 bits are left, the preloaded word enters the window and the next one is
     // fetched; otherwise nothing changes (x = 0 ORs nothing in). Every lane executes this each iteration: cheaper than a
     // divergent branch that some lane of the warp takes nine iterations out of ten.
@@ -310,19 +315,21 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         const uint32_t x = take ? nxt : 0u;
         hi |= __funnelshift_rc(x, 0u, (uint32_t)n);  // x >> n          (0 for n == 32); n > 32 only when x == 0
         lo |= __funnelshift_rc(0u, x, (uint32_t)n);  // x << (32 - n)   (0 for n == 0)
-        if (take) {
-            n += 32;
-            wpos++;
-            preload();
-        }
+        n += take ? 32 : 0;
+        wpos += take ? 1u : 0u;
+        preload(take);
     };
     // two-level lookup; `tab` is the shared-space address of the table (kLutShared) or its word offset (global)
     auto lookup = [&](uint32_t tab) -> uint32_t {
         uint32_t e;
         if (kLutShared) {
             e = lds_u32(tab + ((hi >> (32 - kLutL1Bits)) << 2));
-            if ((e & (31u << 5)) == 0)
-                e = lds_u32(tab + (((1u << kLutL1Bits) + ((e >> 22) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u))) << 2));
+            // codes longer than kLutL1Bits are rare: a real branch (not a predicated load) keeps the second lookup and
+            // its latency out of the iterations in which no lane of the warp needs it
+            while (__builtin_expect((e & (31u << 5)) == 0, 0)) {
+                e = lds_u32_v(tab + (((1u << kLutL1Bits) + ((e >> 22) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u))) << 2));
+                break;
+            }
         } else {
             const uint32_t *t = g_lut + ((tab - s_lut) >> 2);
             e = __ldg(t + (hi >> (32 - kLutL1Bits)));

@@ -70,7 +70,7 @@ extern const uint8_t kZigZagToRaster[64];  // dct/dct.cpp:57-73
 // [29:22]; 31: unused code, coding/huffmandecoder.hpp:87), [13:10] zero run, [21:16] total = length + s,
 // [31] decoding this entry is an error (unused code, DC category > 15, AC symbol that baseline does not define).
 constexpr uint32_t kTableMagic = 0x4a54424du;  // "MBTJ"
-constexpr int kLutL1Bits = 10;
+constexpr int kLutL1Bits = 11;  // 2 KB entries per table; at q75 fewer than 0.4 % of the AC codes are longer
 constexpr int kTableHeaderBytes = 16 + 16 + 4 * 128 * 2 * 4;
 
 struct TableSet {
