@@ -402,31 +402,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                         }
                     }
                     // ---- AC: sequentialscan.cpp:704-771, one symbol per warp-convergent iteration
-                    // two symbols per vote: the second `if (busy)` costs nothing when every lane is done
                     while (__any_sync(kFull, busy)) {
-                        if (busy) {
-                            refill();
-                            const uint32_t e = lookup(ac_off[c]);
-                            drain();
-                            errbits |= e;
-                            const int diff = value_of(e);
-                            consume(e);
-                            if ((e & 31u) == 0u) {
-                                // EOB, ZRL (the reference re-tests k <= 63 and silently ends the block, :717-719),
-                                // or an error entry (bit 31, zero fields): the block ends
-                                k += 16;
-                                busy = (((e >> 10) & 15u) == 15u) && (k <= 63);
-                                pq = make_uint2(0u, 128u);
-                                pd = 0;
-                            } else {
-                                k += (int)((e >> 10) & 15u);
-                                // {delta (bit 31: k >= 64), byte offset of the raster position}
-                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c] + ((uint32_t)k << 3)));
-                                pd = diff;
-                                k++;
-                                busy = (k <= 63);
-                            }
-                        }
                         if (busy) {
                             refill();
                             const uint32_t e = lookup(ac_off[c]);

@@ -142,8 +142,16 @@ void put16(std::vector<uint8_t> &o, int v) {
 
 }  // namespace
 
+// flags: 1 = one scan per component (non-interleaved), 2 = SOF1 (extended sequential) frame header, 4 = 16-bit DQT entries
+extern "C" __attribute__((visibility("default"))) long b200jpg_synth_encode_ex(const uint8_t *pix, int w, int h, int ncomp, int hs, int vs,
+                                                                                 int quality, int dri, int flags, uint8_t *dst, long cap);
 extern "C" __attribute__((visibility("default"))) long b200jpg_synth_encode(const uint8_t *pix, int w, int h, int ncomp, int hs, int vs,
                                                                               int quality, int dri, uint8_t *dst, long cap) {
+    return b200jpg_synth_encode_ex(pix, w, h, ncomp, hs, vs, quality, dri, 0, dst, cap);
+}
+
+extern "C" __attribute__((visibility("default"))) long b200jpg_synth_encode_ex(const uint8_t *pix, int w, int h, int ncomp, int hs, int vs,
+                                                                                 int quality, int dri, int flags, uint8_t *dst, long cap) {
     if (!pix || w <= 0 || h <= 0 || (ncomp != 1 && ncomp != 3) || hs < 1 || hs > 2 || vs < 1 || vs > 2) return -1;
     if (ncomp == 1) hs = vs = 1;
     if (quality < 1) quality = 1;
@@ -204,18 +212,22 @@ extern "C" __attribute__((visibility("default"))) long b200jpg_synth_encode(cons
     o.push_back(0xff), o.push_back(0xd8);
     const uint8_t jfif[] = {0xff, 0xe0, 0, 16, 'J', 'F', 'I', 'F', 0, 1, 2, 0, 0, 1, 0, 1, 0, 0};
     o.insert(o.end(), jfif, jfif + sizeof(jfif));
+    const bool wide_q = (flags & 4) != 0;
     o.push_back(0xff), o.push_back(0xdb);
-    put16(o, 2 + (ncomp == 3 ? 2 : 1) * 65);
+    put16(o, 2 + (ncomp == 3 ? 2 : 1) * (wide_q ? 129 : 65));
     for (int t = 0; t < (ncomp == 3 ? 2 : 1); t++) {
-        o.push_back((uint8_t)t);
-        for (int i = 0; i < 64; i++) o.push_back(q[t][kZZ[i]]);
+        o.push_back((uint8_t)(t | (wide_q ? 0x10 : 0)));
+        for (int i = 0; i < 64; i++) {
+            if (wide_q) o.push_back(0);
+            o.push_back(q[t][kZZ[i]]);
+        }
     }
     if (dri > 0) {
         o.push_back(0xff), o.push_back(0xdd);
         put16(o, 4);
         put16(o, dri);
     }
-    o.push_back(0xff), o.push_back(0xc0);
+    o.push_back(0xff), o.push_back((flags & 2) ? 0xc1 : 0xc0);
     put16(o, 8 + 3 * ncomp);
     o.push_back(8);
     put16(o, h);
@@ -242,15 +254,6 @@ extern "C" __attribute__((visibility("default"))) long b200jpg_synth_encode(cons
         tab(0x10, kAcLumBits, kAcLumVals, 162);
         if (ncomp == 3) tab(0x11, kAcChrBits, kAcChrVals, 162);
     }
-    o.push_back(0xff), o.push_back(0xda);
-    put16(o, 6 + 2 * ncomp);
-    o.push_back((uint8_t)ncomp);
-    for (int c = 0; c < ncomp; c++) {
-        o.push_back((uint8_t)c);
-        o.push_back(c == 0 ? 0x00 : 0x11);
-    }
-    o.push_back(0), o.push_back(63), o.push_back(0);
-
     HuffEnc dcl, dcc, acl, acc_;
     dcl.build(kDcLumBits, kDcVals);
     dcc.build(kDcChrBits, kDcVals);
@@ -293,26 +296,57 @@ extern "C" __attribute__((visibility("default"))) long b200jpg_synth_encode(cons
         }
         if (run) bw.put(ac.code[0], ac.len[0]);
     };
-    for (int my = 0; my < mrows; my++)
-        for (int mx = 0; mx < mcols; mx++) {
-            if (dri > 0) {
-                if (togo == 0) {
-                    bw.flush();
-                    o.push_back(0xff), o.push_back((uint8_t)(0xd0 + rst));
-                    rst = (rst + 1) & 7;
-                    pred[0] = pred[1] = pred[2] = 0;
-                    togo = dri;
-                }
-                togo--;
+    auto restart_check = [&]() {
+        if (dri > 0) {
+            if (togo == 0) {
+                bw.flush();
+                o.push_back(0xff), o.push_back((uint8_t)(0xd0 + rst));
+                rst = (rst + 1) & 7;
+                pred[0] = pred[1] = pred[2] = 0;
+                togo = dri;
             }
-            for (int y = 0; y < vs; y++)
-                for (int x = 0; x < hs; x++) encode_block(Y.data(), pw, mx * hs + x, my * vs + y, 0);
-            if (ncomp == 3) {
-                encode_block(Cb.data(), cw, mx, my, 1);
-                encode_block(Cr.data(), cw, mx, my, 2);
-            }
+            togo--;
         }
-    bw.flush();
+    };
+    auto sos = [&](int first, int count) {
+        o.push_back(0xff), o.push_back(0xda);
+        put16(o, 6 + 2 * count);
+        o.push_back((uint8_t)count);
+        for (int c = first; c < first + count; c++) {
+            o.push_back((uint8_t)c);
+            o.push_back(c == 0 ? 0x00 : 0x11);
+        }
+        o.push_back(0), o.push_back(63), o.push_back(0);
+        pred[0] = pred[1] = pred[2] = 0;
+        togo = dri;
+        rst = 0;
+    };
+    if (!(flags & 1) || ncomp == 1) {  // one interleaved scan
+        sos(0, ncomp);
+        for (int my = 0; my < mrows; my++)
+            for (int mx = 0; mx < mcols; mx++) {
+                restart_check();
+                for (int y = 0; y < vs; y++)
+                    for (int x = 0; x < hs; x++) encode_block(Y.data(), pw, mx * hs + x, my * vs + y, 0);
+                if (ncomp == 3) {
+                    encode_block(Cb.data(), cw, mx, my, 1);
+                    encode_block(Cr.data(), cw, mx, my, 2);
+                }
+            }
+        bw.flush();
+    } else {  // one scan per component: the MCU is a single block over the component's own (unpadded) block grid
+        for (int c = 0; c < 3; c++) {
+            const int compw = c ? (w + hs - 1) / hs : w, comph = c ? (h + vs - 1) / vs : h;
+            const int bwc = (compw + 7) / 8, bhc = (comph + 7) / 8;
+            sos(c, 1);
+            for (int by = 0; by < bhc; by++)
+                for (int bx = 0; bx < bwc; bx++) {
+                    restart_check();
+                    encode_block(c == 0 ? Y.data() : (c == 1 ? Cb.data() : Cr.data()), c ? cw : pw, bx, by, c);
+                }
+            bw.flush();
+        }
+    }
     o.push_back(0xff), o.push_back(0xd9);
     if ((long)o.size() > cap || !dst) return -(long)o.size();
     memcpy(dst, o.data(), o.size());

@@ -19,6 +19,9 @@ def _load():
         _lib.b200jpg_synth_encode.restype = ctypes.c_long
         _lib.b200jpg_synth_encode.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_long]
+        _lib.b200jpg_synth_encode_ex.restype = ctypes.c_long
+        _lib.b200jpg_synth_encode_ex.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_long]
     return _lib
 
 
@@ -35,16 +38,20 @@ def source_image(w, h, seed):
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
-def encode(pixels, quality=75, subsampling=(2, 2), restart_interval=0):
-    """Baseline JPEG bytes for an [H,W,3] or [H,W] uint8 image. subsampling = (hs, vs) of the luma component."""
+NON_INTERLEAVED, SOF1, DQT16 = 1, 2, 4
+
+
+def encode(pixels, quality=75, subsampling=(2, 2), restart_interval=0, flags=0):
+    """Baseline JPEG bytes for an [H,W,3] or [H,W] uint8 image. subsampling = (hs, vs) of the luma component.
+    flags: NON_INTERLEAVED (one scan per component), SOF1 (extended sequential header), DQT16 (16-bit table entries)."""
     lib = _load()
     px = np.ascontiguousarray(pixels, dtype=np.uint8)
     h, w = px.shape[:2]
     nc = 1 if px.ndim == 2 else px.shape[2]
     cap = w * h * nc * 2 + 65536
     out = np.empty(cap, dtype=np.uint8)
-    n = lib.b200jpg_synth_encode(px.ctypes.data, w, h, nc, subsampling[0], subsampling[1], quality, restart_interval,
-                                 out.ctypes.data, cap)
+    n = lib.b200jpg_synth_encode_ex(px.ctypes.data, w, h, nc, subsampling[0], subsampling[1], quality, restart_interval, flags,
+                                    out.ctypes.data, cap)
     if n <= 0:
         raise RuntimeError("synthetic encoder failed (%d)" % n)
     return out[:n].copy()

@@ -150,3 +150,17 @@ def test_dropin_client_through_cpp_interface(built, golden_pixels, tmp_path):
         depth = px.shape[2]
         stripes = (h + 7) // 8
         assert "requests=%d releases=%d" % (stripes * depth, stripes * depth) in r.stdout
+
+
+@pytest.mark.parametrize("flags,w,h,sub,z", [(1, 70, 50, (2, 2), 5), (1, 64, 48, (1, 1), 0), (2, 40, 40, (2, 2), 3), (6, 40, 40, (2, 1), 0),
+                                            (7, 33, 47, (1, 2), 4), (1, 1920, 1080, (2, 2), 40)])
+def test_stream_variants_match_oracle(built, oracle, flags, w, h, sub, z):
+    """Non-interleaved scans (each component its own scan and restart index), SOF1 headers, 16-bit quantisation tables."""
+    from libjpeg_b200 import synth
+    data = synth.encode(synth.source_image(w, h, 5), 80, sub, z, flags)
+    dec, out = gpu_decode(built, [data])
+    assert dec.status(0) == 0
+    assert dec.info(0).nscans == (3 if flags & 1 else 1)
+    rc, ref = oracle.decode(data.tobytes())
+    assert rc == 0
+    assert np.array_equal(dec.frame_view(out, 0).cpu().numpy(), ref)

@@ -66,3 +66,18 @@ def test_oracle_rejects_progressive_and_garbage(oracle):
     assert rc == -1034  # NOT_IMPLEMENTED
     rc, _ = oracle.decode(b"\x00\x01\x02\x03")
     assert rc == -1038  # MALFORMED_STREAM
+
+
+@pytest.mark.skipif(not oracle_binding.have_reference(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("flags,w,h,sub,z", [(1, 70, 50, (2, 2), 5), (1, 64, 48, (1, 1), 0), (2, 40, 40, (2, 2), 3), (6, 40, 40, (2, 1), 0),
+                                            (7, 33, 47, (1, 2), 4)])
+def test_oracle_matches_reference_on_stream_variants(oracle, built, tmp_path, flags, w, h, sub, z):
+    """One scan per component (flag 1), SOF1 header (2), 16-bit DQT (4): accepted by the reference, same pixels."""
+    from libjpeg_b200 import synth
+    data = synth.encode(synth.source_image(w, h, 5), 80, sub, z, flags)
+    jpg = tmp_path / "v.jpg"
+    jpg.write_bytes(data.tobytes())
+    ref = oracle_binding.reference_decode(str(jpg), str(tmp_path / "v.raw"))
+    assert ref is not None
+    rc, px = oracle.decode(data.tobytes())
+    assert rc == 0 and np.array_equal(px, ref)
