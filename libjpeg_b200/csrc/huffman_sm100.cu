@@ -112,19 +112,13 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
         if (wo + 4 < src1 + 2) nxt = __ldg(reinterpret_cast<const uint32_t *>(bytes + wo + 4));  // reaches the marker bytes
         // fast path (about 60 % of the steps): no 0xFF anywhere in these 128 bytes and all of them inside the interval:
         // nothing to remove, nothing ends -- the bytes just move
-        if (base >= src0 && base + 128 <= src1 && carry_ff == 0 &&
-            !__any_sync(kFull, (((cur & 0x7f7f7f7fu) + 0x01010101u) & cur & 0x80808080u) != 0u)) {
-            // output word j of this step = the last sh bytes of input word j-1 followed by the first 4-sh of word j
-            const uint32_t sh = fill & 3u, w0 = fill >> 2;
-            const uint32_t prev = __shfl_up_sync(kFull, cur, 1);
-            const uint32_t merged = sh ? __funnelshift_r(prev, cur, 8u * (4u - sh)) : cur;
-            if (sh == 0u || lane != 0u) {
-                sts_u32(sb + 4u * (w0 + lane), __byte_perm(merged, 0, 0x0123));
-            } else {  // lane 0, sh != 0: its word completes the partial word already in the buffer
-                for (uint32_t k = 0; k < 4u - sh; k++) sts_u8(sb + ((fill + k) ^ 3u), (cur >> (8u * k)) & 0xffu);
-            }
-            if (sh != 0u && lane == 31u) {  // the last sh bytes of the step open the next word
-                for (uint32_t k = 4u - sh; k < 4u; k++) sts_u8(sb + ((fill + 124u + k) ^ 3u), (cur >> (8u * k)) & 0xffu);
+        if (base >= src0 && base + 128 <= src1 && carry_ff == 0 && !__any_sync(kFull, __vcmpeq4(cur, 0xffffffffu) != 0u)) {
+            const uint32_t o = fill + 4 * lane;
+            if ((fill & 3u) == 0u) {
+                sts_u32(sb + o, __byte_perm(cur, 0, 0x0123));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) sts_u8(sb + ((o + k) ^ 3u), (cur >> (8 * k)) & 0xffu);
             }
             fill += 128;
             total += 128;
