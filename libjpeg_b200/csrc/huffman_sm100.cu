@@ -64,6 +64,12 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
     return v;
 }
+__device__ __forceinline__ void sts_u64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ uint64_t lds_u64(uint32_t a) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts_v4_zero(uint32_t a) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
 }
@@ -219,6 +225,9 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
     const uint32_t s_ring = s_base + kThreads * kStageStride + threadIdx.x * 64;
     const uint32_t s_qz = s_base + kThreads * kStageStride + kThreads * 64;
     const uint32_t s_lut = s_qz + kQzBytes;
+    // cooperative flush: in step i this lane moves bytes [16*(lane&7), +16) of the block staged by lane 4*i + (lane>>3)
+    const uint32_t s_flush_sub = (threadIdx.x & 7u) << 4;
+    const uint32_t s_flush = s_base + ((threadIdx.x & ~31u) + ((threadIdx.x & 31u) >> 3)) * kStageStride + s_flush_sub;
     const uint32_t *g_lut = reinterpret_cast<const uint32_t *>(tables + kTableHeaderBytes);
     {
         const uint32_t *g_qz = reinterpret_cast<const uint32_t *>(tables + 32);
@@ -428,16 +437,24 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                         }
                     }
                     drain();
-                    // ---- flush the block (zeros included) and clear the staging block
-                    if (has_mcu) {
+                    // ---- flush (zeros included) and clear the staging blocks, the whole warp together: every lane
+                    // publishes where its block goes (0 = nowhere) in the pad of its staging block, then each store
+                    // instruction moves four complete 128-byte blocks (eight lanes x 16 bytes per block) instead of one
+                    // 16-byte piece of 32 different blocks -- 4 instead of 32 L1 wavefronts per instruction
+                    {
                         const uint32_t bx = mx * p.mw[c] + x, by = my * p.mh[c] + y;
-                        uint4 *dst = reinterpret_cast<uint4 *>(coef + plane[c] + ((uint64_t)by * p.bw[c] + bx) * 64u);
+                        const int16_t *d = coef + plane[c] + ((uint64_t)by * p.bw[c] + bx) * 64u;
+                        sts_u64(s_stage + 136, has_mcu ? (uint64_t)d : 0ull);
+                        __syncwarp();
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
-                            const uint4 v = lds_v4(s_stage + 16 * i);
-                            sts_v4_zero(s_stage + 16 * i);
-                            dst[i] = v;
+                            const uint32_t a = s_flush + i * (4 * kStageStride);
+                            const uint64_t dst = lds_u64(a + 136 - s_flush_sub);
+                            const uint4 v = lds_v4(a);
+                            sts_v4_zero(a);
+                            if (dst) *reinterpret_cast<uint4 *>(dst + s_flush_sub) = v;
                         }
+                        __syncwarp();
                     }
                 }
             }
