@@ -35,7 +35,7 @@ namespace b200jpg {
 namespace {
 
 #ifndef B200JPG_A1_THREADS
-#define B200JPG_A1_THREADS 256
+#define B200JPG_A1_THREADS 768
 #endif
 constexpr int kThreads = B200JPG_A1_THREADS;  // a1: CTA size (experiments may override at build time)
 constexpr int kStageStride = 144;  // bytes per lane: 128 + 16 pad -> conflict-free 16-byte accesses
@@ -213,7 +213,7 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
 constexpr int kQzBytes = 4 * 128 * 8;  // four quantisation tables x 128 (q, offset) pairs
 
 template <bool kLutShared>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)
 entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uint64_t *__restrict__ clean_off,
                       const uint32_t *__restrict__ interval_len, const ClassScan *__restrict__ scans,
                       const uint8_t *__restrict__ tables, int16_t *__restrict__ coef, uint32_t *__restrict__ frame_status) {
@@ -240,239 +240,245 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
     __syncthreads();
     const uint16_t *lut_off = reinterpret_cast<const uint16_t *>(tables + 16);
 
+    // Persistent CTAs (one per SM): warp w of CTA b takes the groups of 32 consecutive restart intervals b + gridDim.x * w,
+    // then every (gridDim.x * warps per CTA)-th one after that, so any batch size spreads evenly over the SMs.
     const uint64_t total_intervals = (uint64_t)p.n_scans * p.intervals_per_scan;
-    const uint64_t g = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    const bool lane_valid = g < total_intervals;
-    uint32_t j = 0, iv = 0;
-    if (lane_valid) {
-        j = (uint32_t)(g / p.intervals_per_scan);
-        iv = (uint32_t)(g % p.intervals_per_scan);
-    }
-    const uint32_t len_bytes = lane_valid ? interval_len[g] : 0u;
-    const uint8_t *src = clean + (lane_valid ? clean_off[g] : 0ull);
-    const uint32_t max_chunks = (len_bytes + 15u) / 16u + 2u;  // data + the 32 zero bytes a0 appended
-    const uint32_t mcu0 = iv * p.dri;
-    uint32_t nmcu = 0;
-    if (lane_valid) nmcu = (p.total_mcus - mcu0 < p.dri) ? (p.total_mcus - mcu0) : p.dri;
-    uint32_t mx = mcu0 % p.mcu_cols, my = mcu0 / p.mcu_cols;
-
-    uint64_t plane[4];
-    uint32_t frame = 0;
-    {
-        const ClassScan &cs = scans[lane_valid ? j : 0];
-#pragma unroll
-        for (int c = 0; c < 4; c++) plane[c] = cs.coef_base[c];
-        frame = cs.frame;
-    }
-
-    // an interval the stream does not contain keeps its blocks zero (sequentialscan.cpp:415-419)
-    const bool decoding = lane_valid && len_bytes != 0u;
-    // bit window: MSB-aligned 64 bits in (hi, lo), n valid bits; wpos = 32-bit words taken from the stream;
-    // req = 16-byte chunks requested from HBM so far, safe = chunks known to have landed in the ring
-    uint32_t hi = 0, lo = 0, wpos = 0, req = 0, safe = 0;
-    int n = 0;
-    // chunk `c` of the interval into its ring slot; past the end of the interval the reader sees zeros, exactly what
-    // the reference's bit reader hands out once it stands in front of a marker (io/bitstream.cpp:96-101)
-    auto request = [&](uint32_t c) {
-        if (c < max_chunks) cp_async16(s_ring + ((c & 3u) << 4), src + ((uint64_t)c << 4));
-        else sts_v4_zero(s_ring + ((c & 3u) << 4));
-    };
-    if (decoding) {
-#pragma unroll
-        for (uint32_t i = 0; i < 4; i++) request(i);
-        req = 4;
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    safe = req;
-
-    uint32_t errbits = 0;  // bit 31: an entry that must not be decoded was decoded
-    uint32_t ovf = 0;      // | (v + 32768): bits 16.. set when a dequantised coefficient left the int16 range
-    int pred[4] = {0, 0, 0, 0};
-    uint32_t dc_off[4], ac_off[4], q_addr[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        dc_off[c] = (c < p.ns) ? s_lut + 4u * lut_off[p.dc_slot[c]] : 0;
-        ac_off[c] = (c < p.ns) ? s_lut + 4u * lut_off[4 + p.ac_slot[c]] : 0;
-        q_addr[c] = s_qz + ((c < p.ns) ? 1024u * p.q_slot[c] : 0u);
-    }
-
-    // `nxt` always holds the stream word at wpos, loaded one refill ahead so that the shared-memory latency of the
-    // ring never sits on the decode chain
-    uint32_t nxt = 0;
-    // `go` selects the lanes that really load: the load is predicated and writes the loop-carried register directly, so
-    // no move waits for it and lanes that do not refill keep their word
-    auto preload = [&](bool go) {
-        const uint32_t ch = wpos >> 2;
-        if (go && ch >= safe) {  // rare: ran past what the block-boundary top-up guarantees
-            while (req <= ch) request(req++);
-            cp_async_commit();
-            cp_async_wait<0>();
-            safe = req;
+    const uint64_t n_groups = (total_intervals + 31u) / 32u;
+    for (uint64_t grp = blockIdx.x + (uint64_t)gridDim.x * (threadIdx.x >> 5); grp < n_groups; grp += (uint64_t)gridDim.x * (kThreads / 32)) {
+        const uint64_t g = grp * 32u + (threadIdx.x & 31u);
+        cp_async_wait<0>();  // nothing of the previous group may still land in the ring
+        const bool lane_valid = g < total_intervals;
+        uint32_t j = 0, iv = 0;
+        if (lane_valid) {
+            j = (uint32_t)(g / p.intervals_per_scan);
+            iv = (uint32_t)(g % p.intervals_per_scan);
         }
-        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.u32 %0, [%1]; }"
-                     : "+r"(nxt)
-                     : "r"(s_ring + ((wpos & 15u) << 2)), "r"((uint32_t)go)
-                     : "memory");
-    };
-    preload(decoding);
-    // Branch-free refill: when fewer than 33 bits are left, the preloaded word enters the window and the next one is
-    // fetched; otherwise nothing changes (x = 0 ORs nothing in). Every lane executes this each iteration: cheaper than a
-    // divergent branch that some lane of the warp takes nine iterations out of ten.
-    auto refill = [&]() {
-        const bool take = n <= 32;
-        const uint32_t x = take ? nxt : 0u;
-        hi |= __funnelshift_rc(x, 0u, (uint32_t)n);  // x >> n          (0 for n == 32); n > 32 only when x == 0
-        lo |= __funnelshift_rc(0u, x, (uint32_t)n);  // x << (32 - n)   (0 for n == 0)
-        n += take ? 32 : 0;
-        wpos += take ? 1u : 0u;
-        preload(take);
-    };
-    // two-level lookup; `tab` is the shared-space address of the table (kLutShared) or its word offset (global)
-    auto lookup = [&](uint32_t tab) -> uint32_t {
-        uint32_t e;
-        if (kLutShared) {
-            e = lds_u32(tab + ((hi >> (32 - kLutL1Bits)) << 2));
-            // codes longer than kLutL1Bits are rare: a real branch (not a predicated load) keeps the second lookup and
-            // its latency out of the iterations in which no lane of the warp needs it
-            while (__builtin_expect((e & (31u << 5)) == 0, 0)) {
-                e = lds_u32_v(tab + (((1u << kLutL1Bits) + ((e >> 22) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u))) << 2));
-                break;
-            }
-        } else {
-            const uint32_t *t = g_lut + ((tab - s_lut) >> 2);
-            e = __ldg(t + (hi >> (32 - kLutL1Bits)));
-            if ((e & (31u << 5)) == 0)
-                e = __ldg(t + (1u << kLutL1Bits) + ((e >> 22) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u)));
-        }
-        return e;
-    };
-    // value bits of entry e, sign-extended as sequentialscan.cpp:692-696 / 757-762. All shifts are funnel shifts in
-    // wrap mode, which use only the low five bits of the count: the fields of e need no masking.
-    auto value_of = [&](uint32_t e) -> int {
-        const uint32_t t = __funnelshift_l(0u, hi, e >> 5);     // hi << len
-        const uint32_t u = __funnelshift_l(t, 0u, e);           // t >> (32 - s), 0 for s == 0
-        const uint32_t m = (uint32_t)((int)t >> 31);            // all ones: first value bit set = non-negative
-        const uint32_t ext = (1u - __funnelshift_l(0u, 1u, e)) & ~m;  // (-1 << s) + 1 for negative values
-        return (int)(u + ext);
-    };
-    auto consume = [&](uint32_t e) {
-        const uint32_t t = e >> 16;  // total bits (< 32); error entries carry garbage here and stop the lane anyway
-        hi = __funnelshift_l(lo, hi, t);
-        lo = __funnelshift_l(0u, lo, t);
-        n -= (int)(t & 63u);
-    };
+        const uint32_t len_bytes = lane_valid ? interval_len[g] : 0u;
+        const uint8_t *src = clean + (lane_valid ? clean_off[g] : 0ull);
+        const uint32_t max_chunks = (len_bytes + 15u) / 16u + 2u;  // data + the 32 zero bytes a0 appended
+        const uint32_t mcu0 = iv * p.dri;
+        uint32_t nmcu = 0;
+        if (lane_valid) nmcu = (p.total_mcus - mcu0 < p.dri) ? (p.total_mcus - mcu0) : p.dri;
+        uint32_t mx = mcu0 % p.mcu_cols, my = mcu0 / p.mcu_cols;
 
-    for (uint32_t mi = 0; mi < p.dri; mi++) {
-        const bool has_mcu = mi < nmcu;
-#pragma unroll
+        uint64_t plane[4];
+        uint32_t frame = 0;
+        {
+            const ClassScan &cs = scans[lane_valid ? j : 0];
+    #pragma unroll
+            for (int c = 0; c < 4; c++) plane[c] = cs.coef_base[c];
+            frame = cs.frame;
+        }
+
+        // an interval the stream does not contain keeps its blocks zero (sequentialscan.cpp:415-419)
+        const bool decoding = lane_valid && len_bytes != 0u;
+        // bit window: MSB-aligned 64 bits in (hi, lo), n valid bits; wpos = 32-bit words taken from the stream;
+        // req = 16-byte chunks requested from HBM so far, safe = chunks known to have landed in the ring
+        uint32_t hi = 0, lo = 0, wpos = 0, req = 0, safe = 0;
+        int n = 0;
+        // chunk `c` of the interval into its ring slot; past the end of the interval the reader sees zeros, exactly what
+        // the reference's bit reader hands out once it stands in front of a marker (io/bitstream.cpp:96-101)
+        auto request = [&](uint32_t c) {
+            if (c < max_chunks) cp_async16(s_ring + ((c & 3u) << 4), src + ((uint64_t)c << 4));
+            else sts_v4_zero(s_ring + ((c & 3u) << 4));
+        };
+        if (decoding) {
+    #pragma unroll
+            for (uint32_t i = 0; i < 4; i++) request(i);
+            req = 4;
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        safe = req;
+
+        uint32_t errbits = 0;  // bit 31: an entry that must not be decoded was decoded
+        uint32_t ovf = 0;      // | (v + 32768): bits 16.. set when a dequantised coefficient left the int16 range
+        int pred[4] = {0, 0, 0, 0};
+        uint32_t dc_off[4], ac_off[4], q_addr[4];
+    #pragma unroll
         for (int c = 0; c < 4; c++) {
-            if (c >= p.ns) break;
-            for (int y = 0; y < p.mh[c]; y++) {
-                for (int x = 0; x < p.mw[c]; x++) {
-                    // ---- convergent ring top-up: keep the reader two to four 16-byte chunks ahead
-                    {
-                        const uint32_t ch = wpos >> 2;
-                        const uint32_t landed = req;  // requested before this point: lands at the wait below
-#pragma unroll
-                        for (int t = 0; t < 2; t++) {
-                            if (decoding && req < ch + 4u) request(req++);
-                            cp_async_commit();
+            dc_off[c] = (c < p.ns) ? s_lut + 4u * lut_off[p.dc_slot[c]] : 0;
+            ac_off[c] = (c < p.ns) ? s_lut + 4u * lut_off[4 + p.ac_slot[c]] : 0;
+            q_addr[c] = s_qz + ((c < p.ns) ? 1024u * p.q_slot[c] : 0u);
+        }
+
+        // `nxt` always holds the stream word at wpos, loaded one refill ahead so that the shared-memory latency of the
+        // ring never sits on the decode chain
+        uint32_t nxt = 0;
+        // `go` selects the lanes that really load: the load is predicated and writes the loop-carried register directly, so
+        // no move waits for it and lanes that do not refill keep their word
+        auto preload = [&](bool go) {
+            const uint32_t ch = wpos >> 2;
+            if (go && ch >= safe) {  // rare: ran past what the block-boundary top-up guarantees
+                while (req <= ch) request(req++);
+                cp_async_commit();
+                cp_async_wait<0>();
+                safe = req;
+            }
+            asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.u32 %0, [%1]; }"
+                         : "+r"(nxt)
+                         : "r"(s_ring + ((wpos & 15u) << 2)), "r"((uint32_t)go)
+                         : "memory");
+        };
+        preload(decoding);
+        // Branch-free refill: when fewer than 33 bits are left, the preloaded word enters the window and the next one is
+        // fetched; otherwise nothing changes (x = 0 ORs nothing in). Every lane executes this each iteration: cheaper than a
+        // divergent branch that some lane of the warp takes nine iterations out of ten.
+        auto refill = [&]() {
+            const bool take = n <= 32;
+            const uint32_t x = take ? nxt : 0u;
+            hi |= __funnelshift_rc(x, 0u, (uint32_t)n);  // x >> n          (0 for n == 32); n > 32 only when x == 0
+            lo |= __funnelshift_rc(0u, x, (uint32_t)n);  // x << (32 - n)   (0 for n == 0)
+            n += take ? 32 : 0;
+            wpos += take ? 1u : 0u;
+            preload(take);
+        };
+        // two-level lookup; `tab` is the shared-space address of the table (kLutShared) or its word offset (global)
+        auto lookup = [&](uint32_t tab) -> uint32_t {
+            uint32_t e;
+            if (kLutShared) {
+                e = lds_u32(tab + ((hi >> (32 - kLutL1Bits)) << 2));
+                // codes longer than kLutL1Bits are rare: a real branch (not a predicated load) keeps the second lookup and
+                // its latency out of the iterations in which no lane of the warp needs it
+                while (__builtin_expect((e & (31u << 5)) == 0, 0)) {
+                    e = lds_u32_v(tab + (((1u << kLutL1Bits) + ((e >> 22) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u))) << 2));
+                    break;
+                }
+            } else {
+                const uint32_t *t = g_lut + ((tab - s_lut) >> 2);
+                e = __ldg(t + (hi >> (32 - kLutL1Bits)));
+                if ((e & (31u << 5)) == 0)
+                    e = __ldg(t + (1u << kLutL1Bits) + ((e >> 22) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u)));
+            }
+            return e;
+        };
+        // value bits of entry e, sign-extended as sequentialscan.cpp:692-696 / 757-762. All shifts are funnel shifts in
+        // wrap mode, which use only the low five bits of the count: the fields of e need no masking.
+        auto value_of = [&](uint32_t e) -> int {
+            const uint32_t t = __funnelshift_l(0u, hi, e >> 5);     // hi << len
+            const uint32_t u = __funnelshift_l(t, 0u, e);           // t >> (32 - s), 0 for s == 0
+            const uint32_t m = (uint32_t)((int)t >> 31);            // all ones: first value bit set = non-negative
+            const uint32_t ext = (1u - __funnelshift_l(0u, 1u, e)) & ~m;  // (-1 << s) + 1 for negative values
+            return (int)(u + ext);
+        };
+        auto consume = [&](uint32_t e) {
+            const uint32_t t = e >> 16;  // total bits (< 32); error entries carry garbage here and stop the lane anyway
+            hi = __funnelshift_l(lo, hi, t);
+            lo = __funnelshift_l(0u, lo, t);
+            n -= (int)(t & 63u);
+        };
+
+        for (uint32_t mi = 0; mi < p.dri; mi++) {
+            const bool has_mcu = mi < nmcu;
+    #pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (c >= p.ns) break;
+                for (int y = 0; y < p.mh[c]; y++) {
+                    for (int x = 0; x < p.mw[c]; x++) {
+                        // ---- convergent ring top-up: keep the reader two to four 16-byte chunks ahead
+                        {
+                            const uint32_t ch = wpos >> 2;
+                            const uint32_t landed = req;  // requested before this point: lands at the wait below
+    #pragma unroll
+                            for (int t = 0; t < 2; t++) {
+                                if (decoding && req < ch + 4u) request(req++);
+                                cp_async_commit();
+                            }
+                            cp_async_wait<2>();
+                            safe = landed;
                         }
-                        cp_async_wait<2>();
-                        safe = landed;
-                    }
-                    // a lane that met an error keeps its blocks zero from there on
-                    bool busy = has_mcu && decoding && (int)errbits >= 0;
-                    int k = 1;
-                    // The dequantise + store of a coefficient is deferred by one symbol: its table pair (pq) is loaded
-                    // when the symbol is decoded and consumed after the NEXT symbol's table lookup has been issued, so
-                    // neither shared-memory latency is exposed. {0, 128} parks a "nothing pending" store in the pad slot.
-                    uint2 pq = make_uint2(0u, 128u);
-                    int pd = 0;
-                    auto drain = [&]() {
-                        const int v = pd * (int)pq.x;
-                        errbits |= pq.x;                 // bit 31: coefficient index >= 64 (:764-766)
-                        ovf |= (uint32_t)(v + 32768);
-                        sts_u16(s_stage + pq.y, v);
-                    };
-                    // ---- DC: sequentialscan.cpp:682-701
-                    if (busy) {
-                        refill();
-                        const uint32_t e = lookup(dc_off[c]);
-                        errbits |= e;
-                        if ((int)e >= 0) {
-                            pred[c] += value_of(e);
-                            consume(e);
-                            pd = pred[c];
-                            asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c]));
-                        } else {
-                            busy = false;
-                        }
-                    }
-                    // ---- AC: sequentialscan.cpp:704-771, one symbol per warp-convergent iteration
-                    while (__any_sync(kFull, busy)) {
+                        // a lane that met an error keeps its blocks zero from there on
+                        bool busy = has_mcu && decoding && (int)errbits >= 0;
+                        int k = 1;
+                        // The dequantise + store of a coefficient is deferred by one symbol: its table pair (pq) is loaded
+                        // when the symbol is decoded and consumed after the NEXT symbol's table lookup has been issued, so
+                        // neither shared-memory latency is exposed. {0, 128} parks a "nothing pending" store in the pad slot.
+                        uint2 pq = make_uint2(0u, 128u);
+                        int pd = 0;
+                        auto drain = [&]() {
+                            const int v = pd * (int)pq.x;
+                            errbits |= pq.x;                 // bit 31: coefficient index >= 64 (:764-766)
+                            ovf |= (uint32_t)(v + 32768);
+                            sts_u16(s_stage + pq.y, v);
+                        };
+                        // ---- DC: sequentialscan.cpp:682-701
                         if (busy) {
                             refill();
-                            const uint32_t e = lookup(ac_off[c]);
-                            drain();
+                            const uint32_t e = lookup(dc_off[c]);
                             errbits |= e;
-                            const int diff = value_of(e);
-                            consume(e);
-                            if ((e & 31u) == 0u) {
-                                // EOB, ZRL (the reference re-tests k <= 63 and silently ends the block, :717-719),
-                                // or an error entry (bit 31, zero fields): the block ends
-                                k += 16;
-                                busy = (((e >> 10) & 15u) == 15u) && (k <= 63);
-                                pq = make_uint2(0u, 128u);
-                                pd = 0;
+                            if ((int)e >= 0) {
+                                pred[c] += value_of(e);
+                                consume(e);
+                                pd = pred[c];
+                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c]));
                             } else {
-                                k += (int)((e >> 10) & 15u);
-                                // {delta (bit 31: k >= 64), byte offset of the raster position}
-                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c] + ((uint32_t)k << 3)));
-                                pd = diff;
-                                k++;
-                                busy = (k <= 63);
+                                busy = false;
                             }
                         }
-                    }
-                    drain();
-                    // ---- flush (zeros included) and clear the staging blocks, the whole warp together: every lane
-                    // publishes where its block goes (0 = nowhere) in the pad of its staging block, then each store
-                    // instruction moves four complete 128-byte blocks (eight lanes x 16 bytes per block) instead of one
-                    // 16-byte piece of 32 different blocks -- 4 instead of 32 L1 wavefronts per instruction
-                    {
-                        const uint32_t bx = mx * p.mw[c] + x, by = my * p.mh[c] + y;
-                        const int16_t *d = coef + plane[c] + ((uint64_t)by * p.bw[c] + bx) * 64u;
-                        sts_u64(s_stage + 136, has_mcu ? (uint64_t)d : 0ull);
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const uint32_t a = s_flush + i * (4 * kStageStride);
-                            const uint64_t dst = lds_u64(a + 136 - s_flush_sub);
-                            const uint4 v = lds_v4(a);
-                            sts_v4_zero(a);
-                            if (dst) *reinterpret_cast<uint4 *>(dst + s_flush_sub) = v;
+                        // ---- AC: sequentialscan.cpp:704-771, one symbol per warp-convergent iteration
+                        while (__any_sync(kFull, busy)) {
+                            if (busy) {
+                                refill();
+                                const uint32_t e = lookup(ac_off[c]);
+                                drain();
+                                errbits |= e;
+                                const int diff = value_of(e);
+                                consume(e);
+                                if ((e & 31u) == 0u) {
+                                    // EOB, ZRL (the reference re-tests k <= 63 and silently ends the block, :717-719),
+                                    // or an error entry (bit 31, zero fields): the block ends
+                                    k += 16;
+                                    busy = (((e >> 10) & 15u) == 15u) && (k <= 63);
+                                    pq = make_uint2(0u, 128u);
+                                    pd = 0;
+                                } else {
+                                    k += (int)((e >> 10) & 15u);
+                                    // {delta (bit 31: k >= 64), byte offset of the raster position}
+                                    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c] + ((uint32_t)k << 3)));
+                                    pd = diff;
+                                    k++;
+                                    busy = (k <= 63);
+                                }
+                            }
                         }
-                        __syncwarp();
+                        drain();
+                        // ---- flush (zeros included) and clear the staging blocks, the whole warp together: every lane
+                        // publishes where its block goes (0 = nowhere) in the pad of its staging block, then each store
+                        // instruction moves four complete 128-byte blocks (eight lanes x 16 bytes per block) instead of one
+                        // 16-byte piece of 32 different blocks -- 4 instead of 32 L1 wavefronts per instruction
+                        {
+                            const uint32_t bx = mx * p.mw[c] + x, by = my * p.mh[c] + y;
+                            const int16_t *d = coef + plane[c] + ((uint64_t)by * p.bw[c] + bx) * 64u;
+                            sts_u64(s_stage + 136, has_mcu ? (uint64_t)d : 0ull);
+                            __syncwarp();
+    #pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const uint32_t a = s_flush + i * (4 * kStageStride);
+                                const uint64_t dst = lds_u64(a + 136 - s_flush_sub);
+                                const uint4 v = lds_v4(a);
+                                sts_v4_zero(a);
+                                if (dst) *reinterpret_cast<uint4 *>(dst + s_flush_sub) = v;
+                            }
+                            __syncwarp();
+                        }
                     }
                 }
             }
+            if (++mx == p.mcu_cols) {
+                mx = 0;
+                my++;
+            }
         }
-        if (++mx == p.mcu_cols) {
-            mx = 0;
-            my++;
+        uint32_t err = 0;
+        if ((int)errbits < 0 || (ovf >> 16) != 0u) {
+            err = kErrMalformed;  // invalid code / out-of-sync coefficient index / coefficient beyond the int16 store
+        } else if (decoding) {
+            // a valid stream never consumes bits beyond the marker that ends its interval
+            const uint64_t consumed = (uint64_t)wpos * 32u - (uint64_t)n;
+            if (consumed > (uint64_t)len_bytes * 8u) err = kErrUnexpectedEof;
         }
+        if (err) atomicMax(frame_status + frame, err);
     }
-    uint32_t err = 0;
-    if ((int)errbits < 0 || (ovf >> 16) != 0u) {
-        err = kErrMalformed;  // invalid code / out-of-sync coefficient index / coefficient beyond the int16 store
-    } else if (decoding) {
-        // a valid stream never consumes bits beyond the marker that ends its interval
-        const uint64_t consumed = (uint64_t)wpos * 32u - (uint64_t)n;
-        if (consumed > (uint64_t)len_bytes * 8u) err = kErrUnexpectedEof;
-    }
-    if (err) atomicMax(frame_status + frame, err);
 }
 
 }  // namespace
@@ -489,12 +495,16 @@ int launch_unstuff(const EntropyLaunch &l, void *stream) {
 int launch_entropy(const EntropyLaunch &l, void *stream) {
     const uint64_t total = (uint64_t)l.p.n_scans * l.p.intervals_per_scan;
     if (total == 0) return 0;
-    const uint32_t grid = (uint32_t)((total + kThreads - 1) / kThreads);
+    int dev = 0, sm_count = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return (int)cudaGetLastError();
+    const uint64_t groups = (total + 31) / 32;
+    const uint32_t grid = (uint32_t)(groups < (uint64_t)sm_count ? groups : (uint64_t)sm_count);
     const size_t base_smem = (size_t)kThreads * kStageStride + (size_t)kThreads * 64 + kQzBytes;
     const size_t lut_bytes = (size_t)l.p.lut_words * 4;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
-    if (base_smem + lut_bytes <= 160 * 1024) {
+    if (base_smem + lut_bytes <= 227 * 1024) {
         const size_t smem = base_smem + lut_bytes;
         if (smem > 48 * 1024) {
             e = cudaFuncSetAttribute(entropy_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
