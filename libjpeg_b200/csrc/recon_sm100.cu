@@ -24,7 +24,6 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
-#include <cstdlib>
 #include <type_traits>
 
 #include "internal.hpp"
@@ -158,30 +157,34 @@ __device__ __forceinline__ void hfilter2(const int (&w)[6], int (&o)[8]) {
     o[0] = WADD(WADD(w[0], WMUL(3, w[1])), 2) >> 2;
 }
 
-__device__ __forceinline__ uint32_t sat_u8(int v) {  // CLAMP(255, v), ycbcrtrafo.cpp:61
-    uint32_t d;
-    asm("cvt.sat.u8.s32 %0, %1;" : "=r"(d) : "r"(v));
-    return d;
+__device__ __forceinline__ int sat_u8_64(long long v) { return (int)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+// four values -> four bytes, each saturated to 0..255 (CLAMP(255, v)), p0 in the low byte: two I2IP instead of four
+// conversions plus the shifts and ORs
+__device__ __forceinline__ uint32_t pack_sat4(int p0, int p1, int p2, int p3) {
+    uint32_t hi, w;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(p3), "r"(p2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(p1), "r"(p0), "r"(hi));
+    return w;
 }
-__device__ __forceinline__ uint32_t sat_u8_64(long long v) { return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 
 // ycbcrtrafo.cpp:842-850 with the matrix of colortransformerfactory.cpp:136-138 (13 fractional bits) and
 // FIX_COLOR_TO_INT (tools/numerics.hpp:65).  The reference multiplies in 64 bits; 32 bits give the same result
 // while |y|, |cb|, |cr| <= 65535 -- blocks that violate that (damaged streams only) are flagged `wide`.
+// The results are NOT yet clamped (pack_sat4 does that), except in the 64-bit mode.
 template <int MODE>  // 0: 32-bit YCbCr, 1: 64-bit YCbCr (samples outside the guarded range), 2: identity
-__device__ __forceinline__ void to_rgb(int y, int cbv, int crv, uint32_t &r, uint32_t &g, uint32_t &b) {
-    if (MODE == 2) {  // COLOR_TO_INT (tools/numerics.hpp:69) + clamp
-        r = sat_u8(WADD(y, 8) >> 4);
-        g = sat_u8(WADD(cbv, 8) >> 4);
-        b = sat_u8(WADD(crv, 8) >> 4);
+__device__ __forceinline__ void to_rgb(int y, int cbv, int crv, int &r, int &g, int &b) {
+    if (MODE == 2) {  // COLOR_TO_INT (tools/numerics.hpp:69)
+        r = WADD(y, 8) >> 4;
+        g = WADD(cbv, 8) >> 4;
+        b = WADD(crv, 8) >> 4;
         return;
     }
     const int cb = WSUB(cbv, 128 << 4), cr = WSUB(crv, 128 << 4);
     if (MODE == 0) {
         const int yy = y * 8192 + 65536;
-        r = sat_u8((yy + cr * 11485) >> 17);
-        g = sat_u8((yy - cb * 2819 - cr * 5850) >> 17);
-        b = sat_u8((yy + cb * 14516) >> 17);
+        r = (yy + cr * 11485) >> 17;
+        g = (yy - cb * 2819 - cr * 5850) >> 17;
+        b = (yy + cb * 14516) >> 17;
     } else {
         const long long Y = y, CB = cb, CR = cr;
         r = sat_u8_64((Y * 8192 + CR * 11485 + 65536) >> 17);
@@ -249,16 +252,16 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
 #pragma unroll 1
         for (int r = 0; r <= ymax; r++) {
             uint8_t *o = obase + (uint64_t)r * opitch;
-            uint32_t px[8];
+            int px[8];
 #pragma unroll
-            for (int x = 0; x < 8; x++) px[x] = sat_u8(WADD(my[(8 * r + x) * kThreadsB], 8) >> 4);
+            for (int x = 0; x < 8; x++) px[x] = WADD(my[(8 * r + x) * kThreadsB], 8) >> 4;
+            const uint32_t w0 = pack_sat4(px[0], px[1], px[2], px[3]), w1 = pack_sat4(px[4], px[5], px[6], px[7]);
             if (xmax == 7 && ((reinterpret_cast<uintptr_t>(o) & 7u) == 0)) {
-                *reinterpret_cast<uint2 *>(o) = make_uint2(px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24),
-                                                           px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24));
+                *reinterpret_cast<uint2 *>(o) = make_uint2(w0, w1);
             } else {
 #pragma unroll
                 for (int x = 0; x < 8; x++)
-                    if (x <= xmax) o[x] = (uint8_t)px[x];
+                    if (x <= xmax) o[x] = (uint8_t)(((x < 4) ? w0 : w1) >> (8 * (x & 3)));
             }
         }
         return;
@@ -298,8 +301,9 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
 #pragma unroll 1
         for (int r = 0; r < 8; r++) {
             if (r > ymax) break;  // uniform over the warp (same block row)
-        uint32_t px[24];
+        uint32_t wd[6];
         if (valid) {
+            int px[24];
             int v1[NW], v2[NW];
             if (SY == 2) {  // VerticalFilterCore<2>, upsampler.cpp:136-168: even lines lean on top, odd lines on bot
                 const bool odd = (r & 1) != 0;
@@ -337,17 +341,18 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
 #pragma unroll
             for (int x = 0; x < 8; x++) {
                 const int yv = my[(8 * r + x) * kThreadsB];
-                uint32_t R, G, B;
+                int R, G, B;
                 to_rgb<MODE>(yv, c1[x], c2[x], R, G, B);
                 px[3 * x] = R;
                 px[3 * x + 1] = G;
                 px[3 * x + 2] = B;
             }
+#pragma unroll
+            for (int k = 0; k < 6; k++) wd[k] = pack_sat4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
         }
         if (vec_line) {
 #pragma unroll
-            for (int k = 0; k < 6; k++)
-                wstage[lane * 6 + k] = px[4 * k] | (px[4 * k + 1] << 8) | (px[4 * k + 2] << 16) | (px[4 * k + 3] << 24);
+            for (int k = 0; k < 6; k++) wstage[lane * 6 + k] = wd[k];
             __syncwarp();
             uint4 *dst = reinterpret_cast<uint4 *>(wrow + (uint64_t)r * opitch);
             const uint4 *sv = reinterpret_cast<const uint4 *>(wstage);
@@ -359,16 +364,13 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
             if (xmax == 7 && ((reinterpret_cast<uintptr_t>(o) & 7u) == 0)) {
                 uint2 *o2 = reinterpret_cast<uint2 *>(o);
 #pragma unroll
-                for (int k = 0; k < 3; k++)
-                    o2[k] = make_uint2(px[8 * k] | (px[8 * k + 1] << 8) | (px[8 * k + 2] << 16) | (px[8 * k + 3] << 24),
-                                       px[8 * k + 4] | (px[8 * k + 5] << 8) | (px[8 * k + 6] << 16) | (px[8 * k + 7] << 24));
+                for (int k = 0; k < 3; k++) o2[k] = make_uint2(wd[2 * k], wd[2 * k + 1]);
             } else {
 #pragma unroll
                 for (int x = 0; x < 8; x++) {
                     if (x <= xmax) {
-                        o[3 * x] = (uint8_t)px[3 * x];
-                        o[3 * x + 1] = (uint8_t)px[3 * x + 1];
-                        o[3 * x + 2] = (uint8_t)px[3 * x + 2];
+#pragma unroll
+                        for (int i = 3 * x; i < 3 * x + 3; i++) o[i] = (uint8_t)(wd[i >> 2] >> (8 * (i & 3)));
                     }
                 }
             }
@@ -414,37 +416,16 @@ int launch_recon(const ReconLaunch &l, void *stream, int *launches) {
         n++;
     }
     dim3 grid((l.max_bw0 + 31) / 32, (l.max_bh0 + kThreadsB / 32 - 1) / (kThreadsB / 32), l.n_frames);
-    // Optional occupancy cap for stage b (B200JPG_RECON_CTAS_PER_SM = 1..3): b2 fills the register file with 4 CTAs per
-    // SM; capping it leaves room for the entropy CTAs of the next batch to run next to it (pipelined callers, bench.py).
-    // Implemented by padding the CTA's shared memory so that only that many fit in 227 KB.
-    static int pad_bytes = -1;
-    if (pad_bytes < 0) {
-        pad_bytes = 0;
-        const char *env = getenv("B200JPG_RECON_CTAS_PER_SM");
-        int want = env ? atoi(env) : 0;
-        if (want >= 1 && want <= 3) {
-            const int per_cta = (227 * 1024) / want - 1024;          // 1 KB per CTA is reserved by the system
-            const int stat = 64 * kThreadsB * 4 + (kThreadsB / 32) * 32 * 6 * 4;
-            pad_bytes = per_cta - stat - 2048;                        // just below the limit for `want`, above for want + 1
-            if (pad_bytes < 0) pad_bytes = 0;
-            cudaFuncSetAttribute(reconstruct_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_bytes);
-            cudaFuncSetAttribute(reconstruct_kernel<3, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_bytes);
-            cudaFuncSetAttribute(reconstruct_kernel<3, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_bytes);
-            cudaFuncSetAttribute(reconstruct_kernel<3, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_bytes);
-            cudaFuncSetAttribute(reconstruct_kernel<3, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_bytes);
-        }
-    }
-    const size_t dyn = (size_t)pad_bytes;
     if (l.ncomp == 1) {
-        reconstruct_kernel<1, 1, 1><<<grid, kThreadsB, dyn, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+        reconstruct_kernel<1, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else if (l.subx == 2 && l.suby == 2) {
-        reconstruct_kernel<3, 2, 2><<<grid, kThreadsB, dyn, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+        reconstruct_kernel<3, 2, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else if (l.subx == 2 && l.suby == 1) {
-        reconstruct_kernel<3, 2, 1><<<grid, kThreadsB, dyn, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+        reconstruct_kernel<3, 2, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else if (l.subx == 1 && l.suby == 2) {
-        reconstruct_kernel<3, 1, 2><<<grid, kThreadsB, dyn, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+        reconstruct_kernel<3, 1, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     } else {
-        reconstruct_kernel<3, 1, 1><<<grid, kThreadsB, dyn, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
+        reconstruct_kernel<3, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
     }
     n++;
     if (launches) *launches = n;
