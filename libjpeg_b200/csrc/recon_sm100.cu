@@ -298,87 +298,92 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
 
     auto lines = [&](auto mode_tag) {
         constexpr int MODE = decltype(mode_tag)::value;
-#pragma unroll 1
-        for (int r = 0; r < 8; r++) {
-            if (r > ymax) break;  // uniform over the warp (same block row)
-        uint32_t wd[6];
-        if (valid) {
-            int px[24];
-            int v1[NW], v2[NW];
-            if (SY == 2) {  // VerticalFilterCore<2>, upsampler.cpp:136-168: even lines lean on top, odd lines on bot
-                const bool odd = (r & 1) != 0;
-                const int ra = odd ? 1 : 2, rb = odd ? 2 : 1;  // rounding of even / odd window columns
+        // one output line; for SY == 2 the line parity is a compile-time constant (the loop below is unrolled by two),
+        // so the choice of the neighbour line and of the rounding needs no selects
+        auto one_line = [&](int r, auto odd_tag) {
+            constexpr bool odd = decltype(odd_tag)::value;
+            uint32_t wd[6];
+            if (valid) {
+                int px[24];
+                int v1[NW], v2[NW];
+                if (SY == 2) {  // VerticalFilterCore<2>, upsampler.cpp:136-168: even lines lean on top, odd lines on bot
+                    constexpr int ra = odd ? 1 : 2, rb = odd ? 2 : 1;  // rounding of even / odd window columns
 #pragma unroll
-                for (int j = 0; j < NW; j++) {
-                    const int n1 = odd ? bot1[j] : top1[j], n2 = odd ? bot2[j] : top2[j];
-                    v1[j] = WADD(WADD(n1, WMUL(3, cur1[j])), (j & 1) ? rb : ra) >> 2;
-                    v2[j] = WADD(WADD(n2, WMUL(3, cur2[j])), (j & 1) ? rb : ra) >> 2;
+                    for (int j = 0; j < NW; j++) {
+                        const int n1 = odd ? bot1[j] : top1[j], n2 = odd ? bot2[j] : top2[j];
+                        v1[j] = WADD(WADD(n1, WMUL(3, cur1[j])), (j & 1) ? rb : ra) >> 2;
+                        v2[j] = WADD(WADD(n2, WMUL(3, cur2[j])), (j & 1) ? rb : ra) >> 2;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NW; j++) {
+                        v1[j] = cur1[j];
+                        v2[j] = cur2[j];
+                    }
                 }
-            } else {
+                int c1[8], c2[8];
+                if (SX == 2) {
+                    int w1[6], w2[6];
 #pragma unroll
-                for (int j = 0; j < NW; j++) {
-                    v1[j] = cur1[j];
-                    v2[j] = cur2[j];
+                    for (int j = 0; j < 6; j++) {
+                        w1[j] = v1[j];
+                        w2[j] = v2[j];
+                    }
+                    hfilter2(w1, c1);
+                    hfilter2(w2, c2);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        c1[j] = v1[j];
+                        c2[j] = v2[j];
+                    }
                 }
-            }
-            int c1[8], c2[8];
-            if (SX == 2) {
-                int w1[6], w2[6];
-#pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    w1[j] = v1[j];
-                    w2[j] = v2[j];
-                }
-                hfilter2(w1, c1);
-                hfilter2(w2, c2);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    c1[j] = v1[j];
-                    c2[j] = v2[j];
-                }
-            }
-#pragma unroll
-            for (int x = 0; x < 8; x++) {
-                const int yv = my[(8 * r + x) * kThreadsB];
-                int R, G, B;
-                to_rgb<MODE>(yv, c1[x], c2[x], R, G, B);
-                px[3 * x] = R;
-                px[3 * x + 1] = G;
-                px[3 * x + 2] = B;
-            }
-#pragma unroll
-            for (int k = 0; k < 6; k++) wd[k] = pack_sat4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
-        }
-        if (vec_line) {
-#pragma unroll
-            for (int k = 0; k < 6; k++) wstage[lane * 6 + k] = wd[k];
-            __syncwarp();
-            uint4 *dst = reinterpret_cast<uint4 *>(wrow + (uint64_t)r * opitch);
-            const uint4 *sv = reinterpret_cast<const uint4 *>(wstage);
-            dst[lane] = sv[lane];
-            if (lane < 16) dst[32 + lane] = sv[32 + lane];
-            __syncwarp();
-        } else if (valid) {
-            uint8_t *o = obase + (uint64_t)r * opitch;
-            if (xmax == 7 && ((reinterpret_cast<uintptr_t>(o) & 7u) == 0)) {
-                uint2 *o2 = reinterpret_cast<uint2 *>(o);
-#pragma unroll
-                for (int k = 0; k < 3; k++) o2[k] = make_uint2(wd[2 * k], wd[2 * k + 1]);
-            } else {
 #pragma unroll
                 for (int x = 0; x < 8; x++) {
-                    if (x <= xmax) {
+                    const int yv = my[(8 * r + x) * kThreadsB];
+                    int R, G, B;
+                    to_rgb<MODE>(yv, c1[x], c2[x], R, G, B);
+                    px[3 * x] = R;
+                    px[3 * x + 1] = G;
+                    px[3 * x + 2] = B;
+                }
 #pragma unroll
-                        for (int i = 3 * x; i < 3 * x + 3; i++) o[i] = (uint8_t)(wd[i >> 2] >> (8 * (i & 3)));
+                for (int k = 0; k < 6; k++) wd[k] = pack_sat4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+            }
+            if (vec_line) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) wstage[lane * 6 + k] = wd[k];
+                __syncwarp();
+                uint4 *dst = reinterpret_cast<uint4 *>(wrow + (uint64_t)r * opitch);
+                const uint4 *sv = reinterpret_cast<const uint4 *>(wstage);
+                dst[lane] = sv[lane];
+                if (lane < 16) dst[32 + lane] = sv[32 + lane];
+                __syncwarp();
+            } else if (valid) {
+                uint8_t *o = obase + (uint64_t)r * opitch;
+                if (xmax == 7 && ((reinterpret_cast<uintptr_t>(o) & 7u) == 0)) {
+                    uint2 *o2 = reinterpret_cast<uint2 *>(o);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) o2[k] = make_uint2(wd[2 * k], wd[2 * k + 1]);
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 8; x++) {
+                        if (x <= xmax) {
+#pragma unroll
+                            for (int i = 3 * x; i < 3 * x + 3; i++) o[i] = (uint8_t)(wd[i >> 2] >> (8 * (i & 3)));
+                        }
                     }
                 }
             }
-        }
-        // advance the line window after every odd output line (upsampler.cpp:160-165) / every line for SY == 1
-        if (valid) {
-            if (SY == 2) {
-                if (r & 1) {
+        };
+        if (SY == 2) {
+#pragma unroll 1
+            for (int r = 0; r < 8; r += 2) {
+                if (r > ymax) break;  // uniform over the warp (same block row)
+                one_line(r, std::false_type());
+                if (r + 1 <= ymax) one_line(r + 1, std::true_type());
+                // advance the line window after every odd output line (upsampler.cpp:160-165)
+                if (valid) {
 #pragma unroll
                     for (int j = 0; j < NW; j++) {
                         top1[j] = cur1[j];
@@ -386,17 +391,23 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
                         top2[j] = cur2[j];
                         cur2[j] = bot2[j];
                     }
-                    if (r < 7) {
+                    if (r < 6) {
                         load_row<NW>(p1, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, interior, bot1);
                         load_row<NW>(p2, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, interior, bot2);
                     }
                 }
-            } else if (r < 7) {
-                load_row<NW>(p1, cpitch, cy0 + r + 1, cx0, cw, ch, interior, cur1);
-                load_row<NW>(p2, cpitch, cy0 + r + 1, cx0, cw, ch, interior, cur2);
+            }
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < 8; r++) {
+                if (r > ymax) break;
+                one_line(r, std::false_type());
+                if (valid && r < 7) {
+                    load_row<NW>(p1, cpitch, cy0 + r + 1, cx0, cw, ch, interior, cur1);
+                    load_row<NW>(p2, cpitch, cy0 + r + 1, cx0, cw, ch, interior, cur2);
+                }
             }
         }
-    }
     };
     // one instantiation per colour mode keeps every per-pixel branch out of the line loop
     if (!ycbcr) lines(std::integral_constant<int, 2>());
