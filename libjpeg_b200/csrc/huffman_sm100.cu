@@ -210,7 +210,7 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
 // =====================================================================================================
 // a1: Huffman decode, one restart interval per lane
 // =====================================================================================================
-constexpr int kQzBytes = 4 * 128 * 8;  // four quantisation tables x 128 (q, offset) pairs
+constexpr int kQzBytes = 4 * kQzEntries * 8;  // four quantisation tables of (q, offset) pairs
 
 template <bool kLutShared>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -265,17 +265,18 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         uint32_t frame = 0;
         {
             const ClassScan &cs = scans[lane_valid ? j : 0];
-    #pragma unroll
+#pragma unroll
             for (int c = 0; c < 4; c++) plane[c] = cs.coef_base[c];
             frame = cs.frame;
         }
 
         // an interval the stream does not contain keeps its blocks zero (sequentialscan.cpp:415-419)
         const bool decoding = lane_valid && len_bytes != 0u;
-        // bit window: MSB-aligned 64 bits in (hi, lo), n valid bits; wpos = 32-bit words taken from the stream;
-        // req = 16-byte chunks requested from HBM so far, safe = chunks known to have landed in the ring
-        uint32_t hi = 0, lo = 0, wpos = 0, req = 0, safe = 0;
-        int n = 0;
+        // Bit reader. bp = bits consumed so far; x0, x1, x2 = the stream words bp/32, +1 and +2 (x2 is a prefetch, so the
+        // shared-memory latency of the ring never sits on the decode chain). The 32 bits at bp are one funnel shift of
+        // (x0, x1); consuming bits is an addition, and when bp enters the next word the three registers move up by one.
+        // req = 16-byte chunks requested from HBM so far, safe = chunks known to have landed in the ring.
+        uint32_t bp = 0, xw = 0, x0 = 0, x1 = 0, x2 = 0, req = 0, safe = 0;
         // chunk `c` of the interval into its ring slot; past the end of the interval the reader sees zeros, exactly what
         // the reference's bit reader hands out once it stands in front of a marker (io/bitstream.cpp:96-101)
         auto request = [&](uint32_t c) {
@@ -283,103 +284,89 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
             else sts_v4_zero(s_ring + ((c & 3u) << 4));
         };
         if (decoding) {
-    #pragma unroll
+#pragma unroll
             for (uint32_t i = 0; i < 4; i++) request(i);
             req = 4;
         }
         cp_async_commit();
         cp_async_wait<0>();
         safe = req;
+        if (decoding) {
+            x0 = lds_u32_v(s_ring);
+            x1 = lds_u32_v(s_ring + 4);
+            x2 = lds_u32_v(s_ring + 8);
+        }
 
         uint32_t errbits = 0;  // bit 31: an entry that must not be decoded was decoded
         uint32_t ovf = 0;      // | (v + 32768): bits 16.. set when a dequantised coefficient left the int16 range
         int pred[4] = {0, 0, 0, 0};
         uint32_t dc_off[4], ac_off[4], q_addr[4];
-    #pragma unroll
+#pragma unroll
         for (int c = 0; c < 4; c++) {
             dc_off[c] = (c < p.ns) ? s_lut + 4u * lut_off[p.dc_slot[c]] : 0;
             ac_off[c] = (c < p.ns) ? s_lut + 4u * lut_off[4 + p.ac_slot[c]] : 0;
-            q_addr[c] = s_qz + ((c < p.ns) ? 1024u * p.q_slot[c] : 0u);
+            q_addr[c] = s_qz + ((c < p.ns) ? (uint32_t)(kQzEntries * 8) * p.q_slot[c] : 0u);
         }
 
-        // `nxt` always holds the stream word at wpos, loaded one refill ahead so that the shared-memory latency of the
-        // ring never sits on the decode chain
-        uint32_t nxt = 0;
-        // `go` selects the lanes that really load: the load is predicated and writes the loop-carried register directly, so
-        // no move waits for it and lanes that do not refill keep their word
-        auto preload = [&](bool go) {
-            const uint32_t ch = wpos >> 2;
-            if (go && ch >= safe) {  // rare: ran past what the block-boundary top-up guarantees
-                while (req <= ch) request(req++);
+        // A symbol has fewer than 32 bits, so bp crosses at most one word boundary. The moves and the load of the new x2
+        // are predicated: lanes that stay inside their word keep their registers, and no move waits for the load.
+        auto advance = [&](uint32_t e) {
+            bp += e >> 26;  // total bits of the symbol (error entries: + 32, the lane stops anyway)
+            const uint32_t w = bp >> 5, nw = w + 2u;
+            if ((nw >> 2) >= safe) {  // rare: about to run past what the block-boundary top-up guarantees
+                while (req <= (nw >> 2)) request(req++);
                 cp_async_commit();
                 cp_async_wait<0>();
                 safe = req;
             }
-            asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.u32 %0, [%1]; }"
-                         : "+r"(nxt)
-                         : "r"(s_ring + ((wpos & 15u) << 2)), "r"((uint32_t)go)
-                         : "memory");
+            asm volatile(
+                "{ .reg .pred c;\n\t"
+                "setp.ne.u32 c, %3, %4;\n\t"
+                "@c mov.u32 %0, %1;\n\t"
+                "@c mov.u32 %1, %2;\n\t"
+                "@c ld.shared.u32 %2, [%5]; }"
+                : "+r"(x0), "+r"(x1), "+r"(x2)
+                : "r"(w), "r"(xw), "r"(s_ring + ((nw & 15u) << 2))
+                : "memory");
+            xw = w;
         };
-        preload(decoding);
-        // Branch-free refill: when fewer than 33 bits are left, the preloaded word enters the window and the next one is
-        // fetched; otherwise nothing changes (x = 0 ORs nothing in). Every lane executes this each iteration: cheaper than a
-        // divergent branch that some lane of the warp takes nine iterations out of ten.
-        auto refill = [&]() {
-            const bool take = n <= 32;
-            const uint32_t x = take ? nxt : 0u;
-            hi |= __funnelshift_rc(x, 0u, (uint32_t)n);  // x >> n          (0 for n == 32); n > 32 only when x == 0
-            lo |= __funnelshift_rc(0u, x, (uint32_t)n);  // x << (32 - n)   (0 for n == 0)
-            n += take ? 32 : 0;
-            wpos += take ? 1u : 0u;
-            preload(take);
-        };
-        // two-level lookup; `tab` is the shared-space address of the table (kLutShared) or its word offset (global)
-        auto lookup = [&](uint32_t tab) -> uint32_t {
+        // two-level lookup in the window `hi`; `tab` is the shared-space address of the table (kLutShared) or stands for
+        // its word offset (global). Codes longer than kLutL1Bits are rare.
+        auto lookup = [&](uint32_t tab, uint32_t hi) -> uint32_t {
+            constexpr uint32_t kSubMask = (1u << (16 - kLutL1Bits)) - 1u;
             uint32_t e;
             if (kLutShared) {
-                e = lds_u32(tab + ((hi >> (32 - kLutL1Bits)) << 2));
-                // codes longer than kLutL1Bits are rare: a real branch (not a predicated load) keeps the second lookup and
-                // its latency out of the iterations in which no lane of the warp needs it
-                while (__builtin_expect((e & (31u << 5)) == 0, 0)) {
-                    e = lds_u32_v(tab + (((1u << kLutL1Bits) + ((e >> 22) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u))) << 2));
-                    break;
-                }
+                e = lds_u32(tab + ((hi >> (30 - kLutL1Bits)) & (((1u << kLutL1Bits) - 1u) << 2)));
+                if ((e & (31u << 5)) == 0) e = lds_u32(tab + (((1u << kLutL1Bits) + ((e >> 10) << (16 - kLutL1Bits)) + ((hi >> 16) & kSubMask)) << 2));
             } else {
                 const uint32_t *t = g_lut + ((tab - s_lut) >> 2);
                 e = __ldg(t + (hi >> (32 - kLutL1Bits)));
-                if ((e & (31u << 5)) == 0)
-                    e = __ldg(t + (1u << kLutL1Bits) + ((e >> 22) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u)));
+                if ((e & (31u << 5)) == 0) e = __ldg(t + (1u << kLutL1Bits) + ((e >> 10) << (16 - kLutL1Bits)) + ((hi >> 16) & kSubMask));
             }
             return e;
         };
-        // value bits of entry e, sign-extended as sequentialscan.cpp:692-696 / 757-762. All shifts are funnel shifts in
+        // value bits of entry e, sign-extended as sequentialscan.cpp:692-696 / 757-762: first value bit set = the bits
+        // are the value, otherwise their complement is the magnitude of a negative value. All shifts are funnel shifts in
         // wrap mode, which use only the low five bits of the count: the fields of e need no masking.
-        auto value_of = [&](uint32_t e) -> int {
-            const uint32_t t = __funnelshift_l(0u, hi, e >> 5);     // hi << len
-            const uint32_t u = __funnelshift_l(t, 0u, e);           // t >> (32 - s), 0 for s == 0
-            const uint32_t m = (uint32_t)((int)t >> 31);            // all ones: first value bit set = non-negative
-            const uint32_t ext = (1u - __funnelshift_l(0u, 1u, e)) & ~m;  // (-1 << s) + 1 for negative values
-            return (int)(u + ext);
-        };
-        auto consume = [&](uint32_t e) {
-            const uint32_t t = e >> 16;  // total bits (< 32); error entries carry garbage here and stop the lane anyway
-            hi = __funnelshift_l(lo, hi, t);
-            lo = __funnelshift_l(0u, lo, t);
-            n -= (int)(t & 63u);
+        auto value_of = [&](uint32_t e, uint32_t hi) -> int {
+            const uint32_t t = __funnelshift_l(0u, hi, e >> 5);   // hi << len: value bits at the top
+            const int pos = (int)t >> 31;                         // -1: non-negative value, 0: negative
+            const uint32_t mag = __funnelshift_l(t ^ ~(uint32_t)pos, 0u, e);  // >> (32 - s); 0 for s == 0
+            return (int)mag * (-2 * pos - 1);
         };
 
         for (uint32_t mi = 0; mi < p.dri; mi++) {
             const bool has_mcu = mi < nmcu;
-    #pragma unroll
+#pragma unroll
             for (int c = 0; c < 4; c++) {
                 if (c >= p.ns) break;
                 for (int y = 0; y < p.mh[c]; y++) {
                     for (int x = 0; x < p.mw[c]; x++) {
                         // ---- convergent ring top-up: keep the reader two to four 16-byte chunks ahead
                         {
-                            const uint32_t ch = wpos >> 2;
+                            const uint32_t ch = bp >> 7;
                             const uint32_t landed = req;  // requested before this point: lands at the wait below
-    #pragma unroll
+#pragma unroll
                             for (int t = 0; t < 2; t++) {
                                 if (decoding && req < ch + 4u) request(req++);
                                 cp_async_commit();
@@ -387,9 +374,9 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                             cp_async_wait<2>();
                             safe = landed;
                         }
-                        // a lane that met an error keeps its blocks zero from there on
-                        bool busy = has_mcu && decoding && (int)errbits >= 0;
-                        int k = 1;
+                        // a lane that met an error keeps its blocks zero from there on. k = zig-zag index of the next
+                        // coefficient; k > 63: the lane has nothing (more) to decode in this block
+                        int k = 64;
                         // The dequantise + store of a coefficient is deferred by one symbol: its table pair (pq) is loaded
                         // when the symbol is decoded and consumed after the NEXT symbol's table lookup has been issued, so
                         // neither shared-memory latency is exposed. {0, 128} parks a "nothing pending" store in the pad slot.
@@ -397,50 +384,41 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                         int pd = 0;
                         auto drain = [&]() {
                             const int v = pd * (int)pq.x;
-                            errbits |= pq.x;                 // bit 31: coefficient index >= 64 (:764-766)
                             ovf |= (uint32_t)(v + 32768);
                             sts_u16(s_stage + pq.y, v);
                         };
                         // ---- DC: sequentialscan.cpp:682-701
-                        if (busy) {
-                            refill();
-                            const uint32_t e = lookup(dc_off[c]);
+                        if (has_mcu && decoding && (int)errbits >= 0) {
+                            const uint32_t hi = __funnelshift_l(x1, x0, bp);
+                            const uint32_t e = lookup(dc_off[c], hi);
                             errbits |= e;
                             if ((int)e >= 0) {
-                                pred[c] += value_of(e);
-                                consume(e);
+                                pred[c] += value_of(e, hi);
+                                advance(e);
                                 pd = pred[c];
                                 asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c]));
-                            } else {
-                                busy = false;
+                                k = 1;
                             }
                         }
-                        // ---- AC: sequentialscan.cpp:704-771, one symbol per warp-convergent iteration
-                        while (__any_sync(kFull, busy)) {
-                            if (busy) {
-                                refill();
-                                const uint32_t e = lookup(ac_off[c]);
+                        // ---- AC: sequentialscan.cpp:704-771, one symbol per warp-convergent iteration. The table entry
+                        // carries the step of the zig-zag index: run + 1 for a coefficient, 16 for ZRL (the reference
+                        // re-tests k <= 63 and silently ends the block, :717-719), kQzBlockEnds for EOB and for entries
+                        // that must not be decoded (bit 31). The table pair is fetched at k - 1 in every case: symbols
+                        // without value bits store a zero (ZRL: in a position that is zero anyway; block end: pad slot),
+                        // a run that leaves the block hits a flagged pair (bit 31 of q, :764-766).
+                        while (__any_sync(kFull, k <= 63)) {
+                            if (k <= 63) {
+                                const uint32_t hi = __funnelshift_l(x1, x0, bp);
+                                const uint32_t e = lookup(ac_off[c], hi);
                                 drain();
-                                errbits |= e;
-                                const int diff = value_of(e);
-                                consume(e);
-                                if ((e & 31u) == 0u) {
-                                    // EOB, ZRL (the reference re-tests k <= 63 and silently ends the block, :717-719),
-                                    // or an error entry (bit 31, zero fields): the block ends
-                                    k += 16;
-                                    busy = (((e >> 10) & 15u) == 15u) && (k <= 63);
-                                    pq = make_uint2(0u, 128u);
-                                    pd = 0;
-                                } else {
-                                    k += (int)((e >> 10) & 15u);
-                                    // {delta (bit 31: k >= 64), byte offset of the raster position}
-                                    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c] + ((uint32_t)k << 3)));
-                                    pd = diff;
-                                    k++;
-                                    busy = (k <= 63);
-                                }
+                                errbits |= e | pq.x;
+                                pd = value_of(e, hi);  // 0 when the symbol carries no value bits
+                                advance(e);
+                                k += (int)((e >> 19) & 127u);
+                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c] + ((uint32_t)k << 3) - 8u));
                             }
                         }
+                        errbits |= pq.x;
                         drain();
                         // ---- flush (zeros included) and clear the staging blocks, the whole warp together: every lane
                         // publishes where its block goes (0 = nowhere) in the pad of its staging block, then each store
@@ -451,7 +429,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                             const int16_t *d = coef + plane[c] + ((uint64_t)by * p.bw[c] + bx) * 64u;
                             sts_u64(s_stage + 136, has_mcu ? (uint64_t)d : 0ull);
                             __syncwarp();
-    #pragma unroll
+#pragma unroll
                             for (int i = 0; i < 8; i++) {
                                 const uint32_t a = s_flush + i * (4 * kStageStride);
                                 const uint64_t dst = lds_u64(a + 136 - s_flush_sub);
@@ -474,7 +452,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
             err = kErrMalformed;  // invalid code / out-of-sync coefficient index / coefficient beyond the int16 store
         } else if (decoding) {
             // a valid stream never consumes bits beyond the marker that ends its interval
-            const uint64_t consumed = (uint64_t)wpos * 32u - (uint64_t)n;
+            const uint64_t consumed = bp;
             if (consumed > (uint64_t)len_bytes * 8u) err = kErrUnexpectedEof;
         }
         if (err) atomicMax(frame_status + frame, err);

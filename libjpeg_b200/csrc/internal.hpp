@@ -62,16 +62,20 @@ extern const uint8_t kZigZagToRaster[64];  // dct/dct.cpp:57-73
 // Serialised, device independent (this blob is what rank 0 broadcasts over NCCL):
 //   uint32 magic, uint32 total_bytes, uint32 lut_words, uint32 flags
 //   uint16 lut_off[8]        word offset of the first-level LUT of DC0..3, AC0..3 (0xFFFF = undefined)
-//   uint32 qz[4][128][2]     per quantisation table, index = zig-zag position k: {delta << lowbit, byte offset of the
-//                            raster position inside a block}; k >= 64 entries carry bit 31 (out-of-sync error) and
-//                            point at the staging block's pad slot
+//   uint32 qz[4][160][2]     per quantisation table, index = zig-zag position k: {delta << lowbit, byte offset of the
+//                            raster position inside a block}; entries 64..95 carry bit 31 (a run that leaves the block:
+//                            out-of-sync error), entries 96..159 are where "the block ends" symbols land (no error);
+//                            both kinds point at the staging block's pad slot
 //   uint32 lut[lut_words]    per table: 2^kLutL1Bits first-level entries, then 2^(16-kLutL1Bits) per second-level table
 // LUT entry: [4:0] s = value bits that follow the code, [9:5] code length (0: pointer to second-level table
-// [29:22]; 31: unused code, coding/huffmandecoder.hpp:87), [13:10] zero run, [21:16] total = length + s,
-// [31] decoding this entry is an error (unused code, DC category > 15, AC symbol that baseline does not define).
+// [17:10], all other fields 0; 31: unused code, coding/huffmandecoder.hpp:87), [25:19] step of the zig-zag index
+// (AC: run + 1, ZRL 16, EOB and error entries kQzBlockEnds), [30:26] total = length + s, [31] decoding this entry is
+// an error (unused code, DC category > 15, AC symbol that baseline does not define).
 constexpr uint32_t kTableMagic = 0x4a54424du;  // "MBTJ"
 constexpr int kLutL1Bits = 11;  // 2 KB entries per table; at q75 fewer than 0.4 % of the AC codes are longer
-constexpr int kTableHeaderBytes = 16 + 16 + 4 * 128 * 2 * 4;
+constexpr int kQzEntries = 160;    // per quantisation table, see above
+constexpr int kQzBlockEnds = 96;   // zig-zag step of symbols that end the block: lands in the entries 96..159
+constexpr int kTableHeaderBytes = 16 + 16 + 4 * kQzEntries * 2 * 4;
 
 struct TableSet {
     std::vector<uint8_t> blob;

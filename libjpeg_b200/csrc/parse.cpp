@@ -276,12 +276,10 @@ uint32_t TableSet::lut_words() const {
 }
 
 int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
-    // LUT entry (see internal.hpp): [4:0] value bits s, [9:5] code length (0 = pointer to a second-level table,
-    // 31 = unused code), [13:10] zero run r, [21:16] total bits = length + s, [29:22] second-level table index,
-    // [31] "decoding this entry is an error".  First level: top kLutL1Bits bits of the 16-bit window.
+    // LUT entry layout: internal.hpp.  First level: top kLutL1Bits bits of the 16-bit window.
     std::vector<uint32_t> lut;
     uint16_t lut_off[8];
-    const uint32_t kUnused = 0x80000000u | (31u << 5);
+    const uint32_t kUnused = 0x80000000u | ((uint32_t)kQzBlockEnds << 19) | (31u << 5);
     const int L1 = kLutL1Bits, L2 = 16 - kLutL1Bits;
     for (int t = 0; t < 8; t++) {
         const HuffSpec &h = (t < 4) ? scan.dc[t] : scan.ac[t - 4];
@@ -320,7 +318,9 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
                         s = 0;
                     }
                 }
-                const uint32_t entry = (bad << 31) | ((len + s) << 16) | (r << 10) | (len << 5) | s;
+                uint32_t step = 0;
+                if (is_ac) step = bad ? (uint32_t)kQzBlockEnds : (s != 0 ? r + 1u : (r == 15 ? 16u : (uint32_t)kQzBlockEnds));
+                const uint32_t entry = (bad << 31) | ((len + s) << 26) | (step << 19) | (len << 5) | s;
                 if ((int)len <= L1) {
                     for (uint32_t q = code >> L2, qlast = last >> L2; q < qlast; q++) lut[base + q] = entry;
                 } else {
@@ -330,7 +330,7 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
                             sub_of[q] = ++nsub;
                             if (nsub > 255) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "Huffman tables too large for the B200 decoder tables");
                             lut.resize(base + ((size_t)1 << L1) + ((size_t)nsub << L2), kUnused);
-                            lut[base + q] = (uint32_t)(sub_of[q] - 1) << 22;  // len field 0 -> second level
+                            lut[base + q] = (uint32_t)(sub_of[q] - 1) << 10;  // len field 0 -> second level
                         }
                         lut[base + ((size_t)1 << L1) + ((size_t)(sub_of[q] - 1) << L2) + (c16 & ((1u << L2) - 1))] = entry;
                     }
@@ -340,8 +340,9 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
         }
     }
     if (lut.size() > 0xffffu) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "Huffman tables too large for the B200 decoder tables");
-    // quantisation + de-zigzag: per table 128 (q, byte offset) pairs indexed by the zig-zag position k; k >= 64 is
-    // the "AC coefficient decoding out of sync" case of sequentialscan.cpp:764-766: flagged, parked in the pad slot
+    // quantisation + de-zigzag: per table kQzEntries (q, byte offset) pairs indexed by the zig-zag position k. 64..95 is
+    // the "AC coefficient decoding out of sync" case of sequentialscan.cpp:764-766 (flagged); 96.. is where symbols that
+    // end the block point (EOB, error entries): a zero parked in the pad slot, like the flagged ones
     size_t total = kTableHeaderBytes + lut.size() * 4;
     total = (total + 15) & ~(size_t)15;
     out.blob.assign(total, 0);
@@ -350,7 +351,7 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
     memcpy(out.blob.data() + 16, lut_off, 16);
     uint32_t *qz = (uint32_t *)(out.blob.data() + 32);
     for (int t = 0; t < 4; t++)
-        for (int k = 0; k < 128; k++) {
+        for (int k = 0; k < kQzEntries; k++) {
             uint32_t q, off;
             if (k < 64) {
                 uint32_t delta = scan.quant_defined[t] ? scan.quant[t][k] : 0;
@@ -359,11 +360,11 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
                 q = delta << scan.lowbit;
                 off = 2u * kZigZagToRaster[k];
             } else {
-                q = 0x80000000u;
+                q = (k < kQzBlockEnds) ? 0x80000000u : 0u;
                 off = 128;  // first pad halfword of the lane's staging block
             }
-            qz[(t * 128 + k) * 2] = q;
-            qz[(t * 128 + k) * 2 + 1] = off;
+            qz[(t * kQzEntries + k) * 2] = q;
+            qz[(t * kQzEntries + k) * 2 + 1] = off;
         }
     memcpy(out.blob.data() + kTableHeaderBytes, lut.data(), lut.size() * 4);
     return B200JPG_OK;
