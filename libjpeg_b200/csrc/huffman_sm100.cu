@@ -73,6 +73,23 @@ __device__ __forceinline__ uint64_t lds_u64(uint32_t a) {
 __device__ __forceinline__ void sts_v4_zero(uint32_t a) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
 }
+// Integer work that the multiply-add pipe can do is routed there explicitly: the decode loop is bound by the ALU pipe
+// (shifts, logic, compares), which takes a warp instruction every other cycle, while the IMAD pipe idles.
+__device__ __forceinline__ uint32_t mulhi_u32(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t xnor_u32(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, 0, 0xC3;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const uint8_t *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
@@ -275,8 +292,8 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         // Bit reader. bp = bits consumed so far; x0, x1, x2 = the stream words bp/32, +1 and +2 (x2 is a prefetch, so the
         // shared-memory latency of the ring never sits on the decode chain). The 32 bits at bp are one funnel shift of
         // (x0, x1); consuming bits is an addition, and when bp enters the next word the three registers move up by one.
-        // req = 16-byte chunks requested from HBM so far, safe = chunks known to have landed in the ring.
-        uint32_t bp = 0, xw = 0, x0 = 0, x1 = 0, x2 = 0, req = 0, safe = 0;
+        // req = 16-byte chunks requested from HBM so far, safe_w = stream words known to have landed in the ring.
+        uint32_t bp = 0, xw = 0, x0 = 0, x1 = 0, x2 = 0, req = 0, safe_w = 0;
         // chunk `c` of the interval into its ring slot; past the end of the interval the reader sees zeros, exactly what
         // the reference's bit reader hands out once it stands in front of a marker (io/bitstream.cpp:96-101)
         auto request = [&](uint32_t c) {
@@ -290,7 +307,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         }
         cp_async_commit();
         cp_async_wait<0>();
-        safe = req;
+        safe_w = req << 2;
         if (decoding) {
             x0 = lds_u32_v(s_ring);
             x1 = lds_u32_v(s_ring + 4);
@@ -313,21 +330,19 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         auto advance = [&](uint32_t e) {
             bp += e >> 26;  // total bits of the symbol (error entries: + 32, the lane stops anyway)
             const uint32_t w = bp >> 5, nw = w + 2u;
-            if ((nw >> 2) >= safe) {  // rare: about to run past what the block-boundary top-up guarantees
+            if (nw >= safe_w) {  // rare: about to run past what the block-boundary top-up guarantees
                 while (req <= (nw >> 2)) request(req++);
                 cp_async_commit();
                 cp_async_wait<0>();
-                safe = req;
+                safe_w = req << 2;
             }
-            asm volatile(
-                "{ .reg .pred c;\n\t"
-                "setp.ne.u32 c, %3, %4;\n\t"
-                "@c mov.u32 %0, %1;\n\t"
-                "@c mov.u32 %1, %2;\n\t"
-                "@c ld.shared.u32 %2, [%5]; }"
-                : "+r"(x0), "+r"(x1), "+r"(x2)
-                : "r"(w), "r"(xw), "r"(s_ring + ((nw & 15u) << 2))
-                : "memory");
+            const uint32_t c = w - xw;  // 0 or 1
+            x0 = mad_u32(c, x1 - x0, x0);
+            x1 = mad_u32(c, x2 - x1, x1);
+            asm volatile("{ .reg .pred c; setp.ne.u32 c, %1, 0; @c ld.shared.u32 %0, [%2]; }"
+                         : "+r"(x2)
+                         : "r"(c), "r"(s_ring + (mad_u32(nw, 4u, 0u) & 0x3cu))
+                         : "memory");
             xw = w;
         };
         // two-level lookup in the window `hi`; `tab` is the shared-space address of the table (kLutShared) or stands for
@@ -336,7 +351,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
             constexpr uint32_t kSubMask = (1u << (16 - kLutL1Bits)) - 1u;
             uint32_t e;
             if (kLutShared) {
-                e = lds_u32(tab + ((hi >> (30 - kLutL1Bits)) & (((1u << kLutL1Bits) - 1u) << 2)));
+                e = lds_u32(mad_u32(mulhi_u32(hi, 1u << kLutL1Bits), 4u, tab));
                 if ((e & (31u << 5)) == 0) e = lds_u32(tab + (((1u << kLutL1Bits) + ((e >> 10) << (16 - kLutL1Bits)) + ((hi >> 16) & kSubMask)) << 2));
             } else {
                 const uint32_t *t = g_lut + ((tab - s_lut) >> 2);
@@ -351,7 +366,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         auto value_of = [&](uint32_t e, uint32_t hi) -> int {
             const uint32_t t = __funnelshift_l(0u, hi, e >> 5);   // hi << len: value bits at the top
             const int pos = (int)t >> 31;                         // -1: non-negative value, 0: negative
-            const uint32_t mag = __funnelshift_l(t ^ ~(uint32_t)pos, 0u, e);  // >> (32 - s); 0 for s == 0
+            const uint32_t mag = __funnelshift_l(xnor_u32(t, (uint32_t)pos), 0u, e);  // >> (32 - s); 0 for s == 0
             return (int)mag * (-2 * pos - 1);
         };
 
@@ -372,7 +387,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                                 cp_async_commit();
                             }
                             cp_async_wait<2>();
-                            safe = landed;
+                            safe_w = landed << 2;
                         }
                         // a lane that met an error keeps its blocks zero from there on. k = zig-zag index of the next
                         // coefficient; k > 63: the lane has nothing (more) to decode in this block
@@ -384,7 +399,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                         int pd = 0;
                         auto drain = [&]() {
                             const int v = pd * (int)pq.x;
-                            ovf |= (uint32_t)(v + 32768);
+                            ovf |= mad_u32((uint32_t)pd, pq.x, 32768u);
                             sts_u16(s_stage + pq.y, v);
                         };
                         // ---- DC: sequentialscan.cpp:682-701
@@ -414,8 +429,8 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                                 errbits |= e | pq.x;
                                 pd = value_of(e, hi);  // 0 when the symbol carries no value bits
                                 advance(e);
-                                k += (int)((e >> 19) & 127u);
-                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c] + ((uint32_t)k << 3) - 8u));
+                                k += (int)mulhi_u32(mad_u32(e, 64u, 0u), 128u);  // bits 25:19
+                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(mad_u32((uint32_t)k, 8u, q_addr[c] - 8u)));
                             }
                         }
                         errbits |= pq.x;
