@@ -5,17 +5,22 @@
     python bench.py --impl reference --gpus N --steps K --warmup W
 
 Workload (config.workload): BASELINE.json configs[2] -- 3840x2160 4:2:0 q75 baseline frames, one restart
-interval per MCU row (DRI = 240), Annex-K tables; 512 frames per GPU (4096 at 8 GPUs, weak scaling), built from
-`--distinct` distinct synthetic frames S(3840,2160,seed) tiled over the batch.  One "step" = one
-pass of the hot path (entropy kernel + reconstruction kernels) over the GPU's whole batch.
+interval per MCU row (DRI = 240), Annex-K tables, built from `--distinct` distinct synthetic frames
+S(3840,2160,seed) tiled over the batch.  One "step" = one pass of the hot path (unstuff + entropy +
+reconstruction kernels) over 840 frames per GPU: 840 x 135 restart intervals = one full wave of the persistent
+entropy kernel (148 SMs x 24 warps x 32 lanes); cfg3's 4096-frame batch is 4.9 such steps on one GPU, weak scaling
+(840 frames per GPU per step) over N GPUs.
 
 value  : frames/s with the compressed bytes already resident in HBM (device-timed, CUDA events, max over ranks).
 e2e    : frames/s through the C ABI with HOST buffers: every step uploads the packed codestreams from pinned
          host memory, decodes, and downloads every decoded pixel into pinned host memory (chunked, three
          streams).  Host-side marker indexing / packing (b200jpg_batch_create) happens once, outside the timing.
-roofline: entropy kernel (the dominant one), algorithmic bytes = ECS bytes + 128 B x stored blocks,
-         over its CUDA-event duration; peak = MEASURED_PEAKS.json hbm_gbs.  roofline_recon: the reconstruction
-         kernels against the measured int32 issue rate (b200jpg_microbench_int32).
+roofline: the dominant stage by time, reconstruction (idct_planes_kernel + reconstruct_kernel): algorithmic bytes
+         = 128 B x stored blocks + 3 W H over its CUDA-event duration against MEASURED_PEAKS.json
+         hbm_gbs, plus `int32`: the same launches against the measured int32 issue rate (b200jpg_microbench_int32),
+         the roofline north_star names for this stage.  roofline_entropy: stage a (unstuff + entropy kernels),
+         algorithmic bytes = ECS bytes + 128 B x stored blocks, against hbm_gbs.  `traffic` = DRAM bytes per launch
+         measured by ncu (profiles/), scaled from the per-frame figure of the captured run.
 cpu_baseline / --impl reference: the unmodified reference (oracle/_ref/refharness: public API, memory hook,
          8-row stripes), one process per hardware thread, on a bounded sample of the same frames.
 """
@@ -34,7 +39,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 W, H, QUALITY, SUB, DRI = 3840, 2160, 75, (2, 2), 240
-FRAMES_PER_GPU = 512
+FRAMES_PER_GPU = 840
+# DRAM bytes per cfg3 frame measured with ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum), profiles/r01_*:
+#   unstuff 2.51 MB, entropy_decode 26.83 MB, idct_planes 24.82 MB, reconstruct 58.02 MB  (r01_840frames_metrics.csv / 840)
+NCU_DRAM_BYTES_PER_FRAME = {"entropy": 2.51e6 + 26.83e6, "recon": 24.82e6 + 58.02e6}
 INT_OPS_PER_4K_FRAME = 520e6  # IDCT 205 M + upsample 133 M + colour 182 M
 
 
@@ -172,7 +180,7 @@ def main():
     ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--distinct", type=int, default=64)
     ap.add_argument("--e2e-chunk", type=int, default=32)
-    ap.add_argument("--streams", type=int, default=2, help="batches in flight per GPU (each on its own CUDA stream)")
+    ap.add_argument("--streams", type=int, default=1, help="batches in flight per GPU (each on its own CUDA stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -184,7 +192,8 @@ def main():
     config = {"workload": "cfg3: 3840x2160 4:2:0 q75 baseline, DRI=240 (one restart interval per MCU row), Annex-K tables",
               "frames_per_gpu": args.frames_per_gpu, "global_batch": args.frames_per_gpu * max(world, 1), "steps_in_flight": args.streams,
               "distinct_frames": args.distinct, "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
-              "l2": "inputs larger than L2 (no flush needed): >= 0.6 GB codestreams + 12.7 GB coefficients per step vs 126 MB L2"}
+              "l2": "inputs larger than L2 (no flush needed): %.1f GB codestreams + %.1f GB coefficients per step vs 126 MB L2"
+                    % (args.frames_per_gpu * 1.27e-3, args.frames_per_gpu * 24.9e-3)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -342,21 +351,30 @@ def main():
     uns = statistics.mean(uns_ms)
 
     peaks, peak_kind = measured_peaks()
-    algo_bytes = dec.ecs_bytes + 128 * dec.stored_blocks
-    roof = {"bound": "hbm", "kernel": "stage a = unstuff_kernel + entropy_decode_kernel", "ms_unstuff": uns, "ms_decode": ent - uns, "achieved": algo_bytes / (ent * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-            "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s", "traffic": None,
-            "algorithmic_bytes_per_launch": algo_bytes, "ms_per_launch": ent, "share_of_step": ent / (ent + rec)}
-    roof["frac"] = roof["achieved"] / roof["peak"]
+    is_cfg3 = True  # the ncu traffic figures below were captured on this workload
+    algo_a = dec.ecs_bytes + 128 * dec.stored_blocks
+    roof_a = {"bound": "hbm", "kernel": "stage a = unstuff_kernel + entropy_decode_kernel", "ms_unstuff": uns, "ms_decode": ent - uns,
+              "achieved": algo_a / (ent * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+              "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
+              "traffic": NCU_DRAM_BYTES_PER_FRAME["entropy"] * nf if is_cfg3 else None,
+              "algorithmic_bytes_per_launch": algo_a, "ms_per_launch": ent, "share_of_step": ent / (ent + rec)}
+    roof_a["frac"] = roof_a["achieved"] / roof_a["peak"]
     import ctypes
     fi, fa, fm = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
     native.lib.b200jpg_microbench_int32(local_rank, ctypes.byref(fi), ctypes.byref(fa), ctypes.byref(fm))
     int_peak = max(fi.value, fa.value, fm.value)
-    roof_recon = {"bound": "int32", "kernel": "idct_planes_kernel + reconstruct_kernel", "unit": "Gop/s",
-                  "achieved": INT_OPS_PER_4K_FRAME * nf / (rec * 1e-3) / 1e9, "peak": int_peak,
-                  "peak_source": "measured here: b200jpg_microbench_int32 (imad %.0f, alu %.0f, mix %.0f Gop/s; multiply-add = 2 ops)" % (fi.value, fa.value, fm.value),
-                  "algorithmic_ops_per_frame": INT_OPS_PER_4K_FRAME, "ms_per_launch_pair": rec,
-                  "hbm_gbs": (128 * dec.stored_blocks + 3 * W * H * nf) / (rec * 1e-3) / 1e9}
-    roof_recon["frac"] = roof_recon["achieved"] / int_peak if int_peak > 0 else None
+    algo_b = 128 * dec.stored_blocks + 3 * W * H * nf
+    roof = {"bound": "hbm", "kernel": "stage b = idct_planes_kernel + reconstruct_kernel (dominant by time)",
+            "achieved": algo_b / (rec * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+            "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
+            "traffic": NCU_DRAM_BYTES_PER_FRAME["recon"] * nf if is_cfg3 else None,
+            "algorithmic_bytes_per_launch": algo_b, "ms_per_launch": rec, "share_of_step": rec / (ent + rec),
+            "int32": {"unit": "Gop/s", "achieved": INT_OPS_PER_4K_FRAME * nf / (rec * 1e-3) / 1e9, "peak": int_peak,
+                      "peak_source": "measured here: b200jpg_microbench_int32 (imad %.0f, alu %.0f, mix %.0f Gop/s; multiply-add = 2 ops)"
+                                     % (fi.value, fa.value, fm.value),
+                      "algorithmic_ops_per_frame": INT_OPS_PER_4K_FRAME}}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["int32"]["frac"] = roof["int32"]["achieved"] / int_peak if int_peak > 0 else None
 
     # ---- e2e: the calls a user makes, per chunk of frames, all inside the timed region:
     #   b200jpg_batch_create (host: parse markers, index restart intervals, pack into pinned memory; a producer thread
@@ -441,7 +459,7 @@ def main():
         line = {"metric": "4K 4:2:0 q75 frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic", "config": dict(config, mean_codestream_bytes=mean_bytes),
-                "clocks": clocks, "gpu_launches": launches, "roofline": roof, "roofline_recon": roof_recon,
+                "clocks": clocks, "gpu_launches": launches, "roofline": roof, "roofline_entropy": roof_a,
                 "stage_ms": {"entropy": ent, "entropy_unstuff_share": uns, "reconstruction": rec}, "pipeline": overlap}
         if e2e:
             line["e2e"] = e2e

@@ -11,12 +11,12 @@ echo "== smoke"; python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail 
 echo "== bench"; python bench.py --steps 10 --warmup 3 2>&1 | tail -2 | tee $OUT/bench.json
 if [ "$2" != "quick" ]; then
 echo "== bench reference arm"; python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 | tee $OUT/bench_reference.json
-echo "== ncu launch list"
-ncu --metrics gpu__time_duration.sum --clock-control none -s 6 -c 12 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 2 --warmup 1 --frames-per-gpu 128 --distinct 4 --no-e2e --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
-tail -15 $OUT/launches.csv
-echo "== ncu full"
-ncu --set full --clock-control none --import-source on -k regex:"entropy_decode|reconstruct_kernel|idct_planes" -s 9 -c 3 -o $OUT/prof -f \
-    python bench.py --steps 2 --warmup 1 --frames-per-gpu 128 --distinct 4 --no-e2e --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1
+echo "== ncu launch list (same workload as the bench line: 840 frames per step)"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 2 --warmup 3 --distinct 4 --no-e2e --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
+tail -12 $OUT/launches.csv
+echo "== ncu full (one launch of each of the four kernels)"
+ncu --set full --clock-control none --import-source on -k regex:"unstuff|entropy_decode|reconstruct_kernel|idct_planes" -s 8 -c 4 -o $OUT/prof -f \
+    python bench.py --steps 2 --warmup 3 --distinct 4 --no-e2e --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1
 ls -la $OUT
 fi
