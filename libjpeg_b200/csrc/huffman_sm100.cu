@@ -14,17 +14,19 @@
 //     32-bit loads), finds stuffed zeros (FF 00 -> FF) and the terminating marker with byte tests, resolves every
 //     kept byte's destination with warp ballots + population-count prefix sums, stages the compacted bytes in shared
 //     memory and writes them out as big-endian 32-bit words (coalesced).  What the reference's Fill() does byte by
-//     byte (io/bitstream.cpp:56-118) is done here once, in parallel, so the decoder's refill is branch-free.
+//     byte (io/bitstream.cpp:56-118) is done here once, in parallel, so the decoder reads plain words.
 //
-// a1  entropy_decode_kernel -- a warp decodes 32 restart intervals, one per lane, in lock step block by block.
-//     Every lane owns a 64-bit bit window (two registers) fed from a 64-byte shared-memory ring that cp.async
-//     (LDGSTS, 16-byte chunks, topped up at block boundaries, two to four chunks ahead of the reader) keeps filled,
-//     so HBM latency never sits on the decode chain.  The scan's Huffman tables live in shared memory as combined
-//     (total bits | code length | symbol) entries; each coefficient is de-zigzagged and dequantised with one more
-//     shared-memory lookup and scattered into the lane's private 128-byte shared-memory block, which is flushed to
-//     HBM as eight 16-byte vector stores -- explicit zeros included, so the coefficient store needs no memset and
-//     every 128-byte block line is written exactly once.  Warp votes keep the per-symbol loop convergent.
-//     All intervals of all frames that share scan geometry and tables form one launch.
+// a1  entropy_decode_kernel -- a warp decodes 32 restart intervals, one per lane, in lock step block by block;
+//     persistent CTAs (one per SM, 24 warps) walk the groups of 32 intervals.  Every lane keeps its bit position and
+//     the three stream words around it in registers, fed from a 64-byte shared-memory ring that cp.async (LDGSTS,
+//     16-byte chunks, topped up at block boundaries, two to four chunks ahead of the reader) keeps filled, so HBM
+//     latency never sits on the decode chain.  The scan's Huffman tables live in shared memory as combined
+//     (total bits | zig-zag step | code length | value bits) entries; each coefficient is de-zigzagged and
+//     dequantised with one more shared-memory lookup and scattered into the lane's 128-byte shared-memory block.
+//     At the block boundary the warp stores its 32 blocks together, four complete 128-byte lines per instruction --
+//     explicit zeros included, so the coefficient store needs no memset and every line is written exactly once.
+//     Warp votes keep the per-symbol loop convergent.  All intervals of all frames that share scan geometry and
+//     tables form one launch.
 #include <cuda_runtime.h>
 
 #include <cstdint>
