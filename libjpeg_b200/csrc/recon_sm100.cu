@@ -145,6 +145,22 @@ __device__ __forceinline__ void load_row(const int32_t *__restrict__ plane, uint
     }
 }
 
+// The same window for a warp whose 32 blocks all lie inside the plane horizontally: a lane fetches its own 8/SX samples
+// with 16-byte loads (4 instead of 24 L1 wavefronts per warp instruction) and, for SX == 2, the two neighbouring columns
+// xl, xr (already clamped = the edge replication above) with one load each; the line is clamped here.
+template <int NW, int SX>
+__device__ __forceinline__ void load_row_own(const int32_t *__restrict__ plane, uint32_t pitch, int y, int ch, uint32_t bx, int xl, int xr,
+                                             int (&v)[NW]) {
+    const int32_t *row = plane + (uint64_t)clampi(y, 0, ch - 1) * pitch;
+    if (SX == 2) {
+        const int4 a = __ldg(reinterpret_cast<const int4 *>(row) + bx);
+        v[0] = __ldg(row + xl), v[1] = a.x, v[2] = a.y, v[3] = a.z, v[4] = a.w, v[NW - 1] = __ldg(row + xr);
+    } else {
+        const int4 a = __ldg(reinterpret_cast<const int4 *>(row) + 2 * bx), b = __ldg(reinterpret_cast<const int4 *>(row) + 2 * bx + 1);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[NW - 4] = b.x, v[NW - 3] = b.y, v[NW - 2] = b.z, v[NW - 1] = b.w;
+    }
+}
+
 // HorizontalFilterCore<2> on a window w[0..5] (w[j] = sample at subsampled x0 - 1 + j): upsampler.cpp:283-307.
 __device__ __forceinline__ void hfilter2(const int (&w)[6], int (&o)[8]) {
     o[7] = WADD(WADD(w[5], WMUL(3, w[4])), 1) >> 2;
@@ -198,7 +214,6 @@ __global__ void __launch_bounds__(kThreadsB, 4)
 reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, const int32_t *__restrict__ samples,
                    const uint32_t *__restrict__ wide_flags, uint8_t *__restrict__ out) {
     __shared__ int ys[64 * kThreadsB];                                   // [coefficient][thread]
-    __shared__ __align__(16) uint32_t stage[kThreadsB / 32][32 * 6];     // one RGB line of 32 blocks per warp
 
     const FrameRecon &f = frames[blockIdx.z];
     const uint32_t W = f.width, H = f.height;
@@ -278,23 +293,27 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
     const bool wide = (wide_flags[f.status_idx] != 0u) || mx > kWide || mn < -kWide;
     // the whole window lies inside the plane: no clamping needed
     const bool interior = valid && cx0 >= 0 && cx0 + NW <= cw && cy0 - 1 >= 0 && cy0 + ((SY == 2) ? 5 : 8) <= ch;
-    // a full line of the warp leaves as 48 aligned 16-byte stores
-    const bool vec_line = (bx0 + 32 <= vbw) && ((W & 7u) == 0) && (((f.out_base | opitch) & 15u) == 0);
-    uint32_t *wstage = stage[warp];
-    uint8_t *wrow = out + f.out_base + (uint64_t)Y * opitch + (uint64_t)bx0 * 8u * NC;  // first byte of the warp's line 0
+    // warp-uniform: every block of the warp is visible and every lane's own samples lie inside the plane
+    constexpr int OWN = 8 / SX;
+    const bool fast = (bx0 + 32 <= vbw) && ((int)((bx0 + 32) * OWN) <= cw);
+    const int xl = (cx0 > 0) ? cx0 : 0, xr = (cx0 + NW - 1 < cw) ? cx0 + NW - 1 : cw - 1;
+    auto fetch = [&](int y, int (&d1)[NW], int (&d2)[NW]) {
+        if (fast) {
+            load_row_own<NW, SX>(p1, cpitch, y, ch, bx, xl, xr, d1);
+            load_row_own<NW, SX>(p2, cpitch, y, ch, bx, xl, xr, d2);
+        } else if (valid) {
+            load_row<NW>(p1, cpitch, y, cx0, cw, ch, interior, d1);
+            load_row<NW>(p2, cpitch, y, cx0, cw, ch, interior, d2);
+        }
+    };
 
     // rolling lines: SY == 2 keeps top/cur/bot (upsampler.cpp:92-106), SY == 1 only cur
     int top1[NW], cur1[NW], bot1[NW], top2[NW], cur2[NW], bot2[NW];
-    if (valid) {
-        if (SY == 2) {
-            load_row<NW>(p1, cpitch, cy0 - 1, cx0, cw, ch, interior, top1);
-            load_row<NW>(p2, cpitch, cy0 - 1, cx0, cw, ch, interior, top2);
-            load_row<NW>(p1, cpitch, cy0 + 1, cx0, cw, ch, interior, bot1);
-            load_row<NW>(p2, cpitch, cy0 + 1, cx0, cw, ch, interior, bot2);
-        }
-        load_row<NW>(p1, cpitch, cy0, cx0, cw, ch, interior, cur1);
-        load_row<NW>(p2, cpitch, cy0, cx0, cw, ch, interior, cur2);
+    if (SY == 2) {
+        fetch(cy0 - 1, top1, top2);
+        fetch(cy0 + 1, bot1, bot2);
     }
+    fetch(cy0, cur1, cur2);
 
     auto lines = [&](auto mode_tag) {
         constexpr int MODE = decltype(mode_tag)::value;
@@ -350,16 +369,7 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
 #pragma unroll
                 for (int k = 0; k < 6; k++) wd[k] = pack_sat4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
             }
-            if (vec_line) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) wstage[lane * 6 + k] = wd[k];
-                __syncwarp();
-                uint4 *dst = reinterpret_cast<uint4 *>(wrow + (uint64_t)r * opitch);
-                const uint4 *sv = reinterpret_cast<const uint4 *>(wstage);
-                dst[lane] = sv[lane];
-                if (lane < 16) dst[32 + lane] = sv[32 + lane];
-                __syncwarp();
-            } else if (valid) {
+            if (valid) {
                 uint8_t *o = obase + (uint64_t)r * opitch;
                 if (xmax == 7 && ((reinterpret_cast<uintptr_t>(o) & 7u) == 0)) {
                     uint2 *o2 = reinterpret_cast<uint2 *>(o);
@@ -391,21 +401,15 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
                         top2[j] = cur2[j];
                         cur2[j] = bot2[j];
                     }
-                    if (r < 6) {
-                        load_row<NW>(p1, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, interior, bot1);
-                        load_row<NW>(p2, cpitch, cy0 + (r >> 1) + 2, cx0, cw, ch, interior, bot2);
-                    }
                 }
+                if (r < 6) fetch(cy0 + (r >> 1) + 2, bot1, bot2);
             }
         } else {
 #pragma unroll 1
             for (int r = 0; r < 8; r++) {
                 if (r > ymax) break;
                 one_line(r, std::false_type());
-                if (valid && r < 7) {
-                    load_row<NW>(p1, cpitch, cy0 + r + 1, cx0, cw, ch, interior, cur1);
-                    load_row<NW>(p2, cpitch, cy0 + r + 1, cx0, cw, ch, interior, cur2);
-                }
+                if (r < 7) fetch(cy0 + r + 1, cur1, cur2);
             }
         }
     };
