@@ -14,13 +14,14 @@
 //  b1 idct_planes_kernel: blocks of the non-luma components -> int32 sample planes (the whole-frame equivalent of
 //     the reference's upsampler line buffers); both 1-D passes in registers.
 //  b2 reconstruct_kernel: a warp owns 32 horizontally adjacent luma blocks (256 x 8 pixels), a CTA four such rows.
-//     The row pass and the column pass of the luma IDCT run as two compact loops over a shared-memory tile laid out
-//     [coefficient][thread] (bank-conflict free, thread-private columns, so no barrier is needed); a third loop walks
-//     the eight output lines: chroma window from the planes (clamped addressing = the reference's edge replication at
-//     the true subsampled size), vertical + horizontal filter cores, colour transform, and the line's 768 bytes of
-//     interleaved RGB are staged per warp in shared memory and leave as 16-byte vector stores.  Small loop bodies keep
-//     the kernel inside the instruction cache and at ~100 registers (the fully unrolled register-resident version
-//     stalled on instruction fetch).
+//     The warp's 4 KB of coefficients come in with coalesced 16-byte loads and are handed to their lanes through
+//     shared memory; the row pass and the column pass of the luma IDCT run as two compact loops over a shared-memory
+//     tile laid out [coefficient][thread] (bank-conflict free, thread-private columns); a third loop walks the eight
+//     output lines: chroma window from the planes (clamped addressing = the reference's edge replication at the true
+//     subsampled size), vertical + horizontal filter cores, colour transform, and each lane stores its 24 bytes of
+//     interleaved RGB per line.  The kernel is co-limited by instruction issue and by the L1 data pipe, so global
+//     accesses are shaped for few L1 wavefronts; small loop bodies keep it inside the instruction cache (the fully
+//     unrolled register-resident version stalled on instruction fetch).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -225,17 +226,46 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
     const int X = 8 * (int)bx, Y = 8 * (int)by;
     int *my = ys + threadIdx.x;
 
-    // ---- luma IDCT, row pass (dct/idct.cpp:237-287): one 16-byte load per block row, next row in flight
+    // ---- luma coefficients: the warp's 32 blocks are 4 KB of contiguous HBM. Eight coalesced 16-byte loads per lane
+    // (four full lines per warp instruction instead of 32 partial ones) park them in the upper half of the warp's tile
+    // columns, 16-byte piece (block, row) at row segment 32 + 4*row + block/8, slot (block%8) ^ row: conflict-free for
+    // these writes and for the per-lane reads below. The row pass overwrites a segment only after its piece was consumed.
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(coef + f.coef_base[0] + ((uint64_t)by * f.bw[0] + (valid ? bx : 0)) * 64u);
-        uint4 q = __ldg(src);
+        const uint32_t wseg = (uint32_t)__cvta_generic_to_shared(ys) + 128u * warp;  // bytes; row segment j at + 512*j
+        const uint4 *src = reinterpret_cast<const uint4 *>(coef + f.coef_base[0] + ((uint64_t)by * f.bw[0] + bx0) * 64u);
+        const uint32_t prow = lane & 7u, sub = lane >> 3;
+        uint4 pc[8];
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++) {
+            const bool have = bx0 + 4u * i + sub < f.bw[0];  // past the end of the block row: nothing (those lanes store nothing)
+            pc[i] = have ? __ldg(src + i * 32u + lane) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++) {
+            const uint32_t blk = 4u * i + sub;
+            const uint32_t dst = wseg + 512u * (32u + 4u * prow + (blk >> 3)) + 16u * ((blk & 7u) ^ prow);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pc[i].x), "r"(pc[i].y), "r"(pc[i].z), "r"(pc[i].w) : "memory");
+        }
+        __syncwarp();
+        // ---- row pass (dct/idct.cpp:237-287): the next row's piece is read before this row's results are written
+        const uint32_t mine = wseg + 512u * (32u + (lane >> 3));
+        auto piece = [&](int r) {
+            uint4 q;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                         : "r"(mine + 2048u * (uint32_t)r + 16u * ((lane & 7u) ^ (uint32_t)r))
+                         : "memory");
+            return q;
+        };
+        uint4 q = piece(0);
 #pragma unroll 1
         for (int r = 0; r < 8; r++) {
-            const uint4 qn = __ldg(src + ((r < 7) ? r + 1 : r));
+            const uint4 qn = piece((r < 7) ? r + 1 : r);
             int v[8];
             unpack_row(q, v);
             if (r == 0) v[0] = WADD(v[0], 128 << 7);  // dcoffset << (preshift + 3), idct.cpp:233,244
             idct8<256, 9>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+            __syncwarp();
 #pragma unroll
             for (int k = 0; k < 8; k++) my[(8 * r + k) * kThreadsB] = v[k];
             q = qn;
