@@ -96,3 +96,20 @@ def reference_decode(jpg_path, tmp_raw):
         return None
     w, h, d = map(int, r.stdout.split())
     return np.fromfile(tmp_raw, dtype=np.uint8).reshape(h, w, d)
+
+
+def with_dc_quantiser(data, value):
+    """The same codestream with the DC entry of every 8-bit quantisation table replaced: the coefficients stay within
+    int16, but the IDCT samples leave the ranges the GPU fast paths are built for (int16 planes, 32-bit colour)."""
+    b = bytearray(data.tobytes() if hasattr(data, "tobytes") else data)
+    i = 2
+    while i + 4 <= len(b) and b[i] == 0xFF and b[i + 1] != 0xDA:
+        seglen = (b[i + 2] << 8) | b[i + 3]
+        if b[i + 1] == 0xDB:
+            j = i + 4
+            while j < i + 2 + seglen:
+                assert b[j] >> 4 == 0, "8-bit tables expected"
+                b[j + 1] = value
+                j += 65
+        i += 2 + seglen
+    return bytes(b)

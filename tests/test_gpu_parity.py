@@ -101,6 +101,29 @@ def test_batch_of_identical_geometry_is_frame_independent(built, oracle):
         assert torch.equal(dec.frame_view(out, i), dec.frame_view(out2, i))
 
 
+@pytest.mark.parametrize("w,h,sub,z,dcq,copies", [(96, 80, (2, 2), 3, 255, 1), (200, 120, (2, 1), 0, 160, 1), (64, 64, (1, 1), 4, 255, 1),
+                                                   (130, 70, (1, 2), 2, 200, 1), (320, 176, (2, 2), 20, 255, 5), (640, 360, (2, 2), 40, 160, 3)])
+def test_samples_beyond_the_fast_ranges_match_oracle(built, oracle, w, h, sub, z, dcq, copies):
+    """DC quantiser 255 on a full-range image: chroma samples beyond int16 (narrow planes) and luma / chroma beyond
+    +-65535 (32-bit colour arithmetic) -- the exact paths (int32 planes, 64-bit colour) must give the reference's
+    pixels; ordinary frames in the same batch must be unaffected."""
+    from libjpeg_b200 import synth
+    normal = synth.encode(synth.source_image(w, h, 5), 75, sub, z)
+    from tests import oracle_binding
+    hot = oracle_binding.with_dc_quantiser(normal, dcq)
+    frames = []
+    for _ in range(copies):
+        frames += [normal, hot]
+    dec, out = gpu_decode(built, frames)
+    rc_n, ref_n = oracle.decode(normal.tobytes())
+    rc_h, ref_h = oracle.decode(hot)
+    assert rc_n == 0 and rc_h == 0
+    assert not np.array_equal(ref_n, ref_h)
+    for i, fr in enumerate(frames):
+        assert dec.status(i) == 0
+        assert np.array_equal(dec.frame_view(out, i).cpu().numpy(), ref_h if i & 1 else ref_n), i
+
+
 def test_corrupt_stream_is_reported_not_crashing(built):
     from libjpeg_b200 import synth
     good = synth.encode(synth.source_image(128, 64, 5), 75, (2, 2), 8)

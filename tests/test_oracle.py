@@ -47,6 +47,21 @@ def test_oracle_matches_reference_on_synthetic_streams(oracle, built, tmp_path, 
     assert rc == 0 and np.array_equal(px, ref)
 
 
+@pytest.mark.skipif(not oracle_binding.have_reference(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("w,h,sub,z,dcq", [(96, 80, (2, 2), 3, 255), (200, 120, (2, 1), 0, 160), (64, 64, (1, 1), 4, 255), (130, 70, (1, 2), 2, 200)])
+def test_oracle_matches_reference_beyond_the_usual_sample_range(oracle, built, tmp_path, w, h, sub, z, dcq):
+    """DC quantiser patched to a large value: IDCT samples leave int16 and the 32-bit colour range (the reference
+    computes the colour matrix in 64 bits); the oracle must follow the reference there too."""
+    from libjpeg_b200 import synth
+    data = oracle_binding.with_dc_quantiser(synth.encode(synth.source_image(w, h, 5), 75, sub, z), dcq)
+    jpg = tmp_path / "hot.jpg"
+    jpg.write_bytes(data)
+    ref = oracle_binding.reference_decode(str(jpg), str(tmp_path / "hot.raw"))
+    assert ref is not None
+    rc, px = oracle.decode(data)
+    assert rc == 0 and np.array_equal(px, ref)
+
+
 def test_oracle_idct_dc_only(oracle):
     """DC-only block: every sample = ((dc*q*16 + 128*128) * 512 + 256 >> 9) * 512 + 2048 >> 12 (idct.cpp:233-334)."""
     blk = np.zeros(64, dtype=np.int32)
