@@ -139,7 +139,8 @@ struct b200jpg_batch {
     uint8_t *d_input = nullptr;
     int16_t *d_coef = nullptr;
     uint64_t coef_elems = 0;
-    int32_t *d_samples = nullptr;
+    int32_t *d_samples = nullptr;     // int32 planes: exact pass of frames flagged `narrow`
+    int16_t *d_samples16 = nullptr;   // int16 planes: every frame
     uint64_t sample_elems = 0;
     uint8_t *d_clean = nullptr;
     uint64_t clean_bytes = 0;
@@ -245,6 +246,7 @@ void b200jpg_batch_destroy(b200jpg_batch *b) {
     b->ctx->put(1, b->d_input, b->input_bytes);
     b->ctx->put(1, b->d_coef, b->coef_elems * sizeof(int16_t));
     b->ctx->put(1, b->d_samples, b->sample_elems * sizeof(int32_t));
+    b->ctx->put(1, b->d_samples16, b->sample_elems * sizeof(int16_t));
     b->ctx->put(1, b->d_clean, b->clean_bytes);
     b->ctx->put(1, b->d_interval_len, b->sz_ilen);
     b->ctx->put(1, b->d_status, b->sz_status);
@@ -550,10 +552,11 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
     for (auto &g : b->groups) memcpy(b->h_input + g.dev_frames, g.frames.data(), g.frames.size() * sizeof(FrameRecon));
 
     b->sz_ilen = sizeof(uint32_t) * (size_t)std::max<uint64_t>(b->n_intervals, 1);
-    b->sz_status = sizeof(uint32_t) * 2 * (size_t)n;  // status words + wide flags
+    b->sz_status = sizeof(uint32_t) * (4 * (size_t)n + 1);  // status words, wide flags, narrow flags, narrow list
     b->d_input = (uint8_t *)ctx->get(1, b->input_bytes, &ce);
     if (ce == cudaSuccess && b->coef_elems) b->d_coef = (int16_t *)ctx->get(1, b->coef_elems * sizeof(int16_t), &ce);
     if (ce == cudaSuccess && b->sample_elems) b->d_samples = (int32_t *)ctx->get(1, b->sample_elems * sizeof(int32_t), &ce);
+    if (ce == cudaSuccess && b->sample_elems) b->d_samples16 = (int16_t *)ctx->get(1, b->sample_elems * sizeof(int16_t), &ce);
     if (ce == cudaSuccess) b->d_clean = (uint8_t *)ctx->get(1, b->clean_bytes, &ce);
     if (ce == cudaSuccess) b->d_interval_len = (uint32_t *)ctx->get(1, b->sz_ilen, &ce);
     if (ce == cudaSuccess) b->d_status = (uint32_t *)ctx->get(1, b->sz_status, &ce);
@@ -640,7 +643,7 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
 }
 
 static int run_recon(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
-    cudaError_t me = cudaMemsetAsync(b->d_status + b->n, 0, sizeof(uint32_t) * (size_t)b->n, (cudaStream_t)stream);
+    cudaError_t me = cudaMemsetAsync(b->d_status + b->n, 0, sizeof(uint32_t) * 2 * (size_t)b->n, (cudaStream_t)stream);
     if (me != cudaSuccess) return b->ctx->fail_cuda(me, "flag reset");
     for (auto &g : b->groups) {
         ReconLaunch l{};
@@ -654,8 +657,11 @@ static int run_recon(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
         l.subx = g.subx;
         l.suby = g.suby;
         l.coef = b->d_coef;
-        l.samples = b->d_samples;
+        l.samples16 = b->d_samples16;
+        l.samples32 = b->d_samples;
         l.wide_flags = b->d_status + b->n;
+        l.narrow_flags = b->d_status + 2 * (size_t)b->n;
+        l.narrow_list = b->d_status + 3 * (size_t)b->n;
         l.out = out_dev;
         int launches = 0;
         // grid.y carries the frame index: at most 65535 frames per launch

@@ -104,7 +104,7 @@ struct ScanClassParams {  // uniform over a launch of the entropy kernel
 
 struct FrameRecon {       // per frame, for the reconstruction kernels
     uint64_t coef_base[4];    // int16 element offsets
-    uint64_t sample_base[4];  // int32 element offsets (subsampled components only)
+    uint64_t sample_base[4];  // element offsets into the sample planes (subsampled components only)
     uint64_t out_base;        // byte offset into the output buffer
     uint32_t width, height;
     uint32_t bw[4], bh[4];
@@ -137,8 +137,11 @@ struct ReconLaunch {
     uint32_t max_bwc, max_bhc;     // largest chroma block grid in the group
     uint32_t ncomp, subx, suby;    // uniform over the group
     const int16_t *coef;
-    int32_t *samples;
-    uint32_t *wide_flags;          // [n_frames in batch], zeroed per decode: set when a sample leaves the 32-bit colour range
+    int16_t *samples16;            // chroma sample planes every frame goes through
+    int32_t *samples32;            // the same planes for the exact pass over frames flagged `narrow`
+    uint32_t *narrow_flags;        // [frames in batch], zeroed per decode: a chroma sample does not fit int16
+    uint32_t *wide_flags;          // [frames in batch], zeroed per decode: a chroma sample leaves the 32-bit colour range
+    uint32_t *narrow_list;         // [1 + frames in group] scratch: {count, group-local indices of the flagged frames}
     uint8_t *out;
 };
 int launch_recon(const ReconLaunch &l, void *stream, int *launches);

@@ -88,14 +88,16 @@ __device__ __forceinline__ void unpack_row(const uint4 q, int (&v)[8]) {
 }
 
 // ---- b1: non-luma components -> sample planes ---------------------------------------------------------
-__global__ void __launch_bounds__(kThreadsB)
-idct_planes_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, int32_t *__restrict__ samples,
-                   uint32_t *__restrict__ wide_flags) {
-    const FrameRecon &f = frames[blockIdx.y];
-    const int c = 1 + blockIdx.z;
-    if (c >= (int)f.ncomp) return;
+// Samples of real images fit 16 bits with room to spare, so the planes that every frame goes through are int16
+// (half the HBM traffic of this memory-bound kernel). A frame in which any sample does not fit is flagged `narrow`
+// and redone by the same kernels instantiated for int32 planes (kListed: they walk the list of flagged frames
+// instead of the whole group, so the exact pass costs three tiny launches when nothing is flagged).
+constexpr int kWideSlots = 4;  // grid extent of the exact pass in the frame dimension; each slot strides over the list
+
+template <typename T>
+__device__ __forceinline__ void idct_planes_block(const FrameRecon &f, int c, uint32_t t, const int16_t *__restrict__ coef,
+                                                  T *__restrict__ samples, uint32_t *__restrict__ flags) {
     const uint32_t bw = f.bw[c], bh = f.bh[c];
-    const uint32_t t = blockIdx.x * kThreadsB + threadIdx.x;
     if (t >= bw * bh) return;
     const uint32_t bx = t % bw, by = t / bw;
     int s[8][8];
@@ -115,15 +117,56 @@ idct_planes_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
             mn = __vimin3_s32(mn, s[r][k], s[r + 1][k]);
         }
     }
-    if (mx > kWide || mn < -kWide) atomicOr(wide_flags + f.status_idx, 1u);  // damaged stream: colour needs 64 bits
     const uint32_t pitch = 8u * bw;
-    int32_t *dst = samples + f.sample_base[c] + (uint64_t)(8u * by) * pitch + 8u * bx;
+    T *dst = samples + f.sample_base[c] + (uint64_t)(8u * by) * pitch + 8u * bx;
+    if (sizeof(T) == 2) {
+        if (mx > 32767 || mn < -32768) atomicOr(flags + f.status_idx, 1u);  // `narrow`: the frame needs the int32 planes
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        int4 *d = reinterpret_cast<int4 *>(dst + (uint64_t)r * pitch);
-        d[0] = make_int4(s[r][0], s[r][1], s[r][2], s[r][3]);
-        d[1] = make_int4(s[r][4], s[r][5], s[r][6], s[r][7]);
+        for (int r = 0; r < 8; r++) {
+            uint4 w;
+            w.x = ((uint32_t)s[r][0] & 0xffffu) | ((uint32_t)s[r][1] << 16);
+            w.y = ((uint32_t)s[r][2] & 0xffffu) | ((uint32_t)s[r][3] << 16);
+            w.z = ((uint32_t)s[r][4] & 0xffffu) | ((uint32_t)s[r][5] << 16);
+            w.w = ((uint32_t)s[r][6] & 0xffffu) | ((uint32_t)s[r][7] << 16);
+            *reinterpret_cast<uint4 *>(dst + (uint64_t)r * pitch) = w;
+        }
+    } else {
+        if (mx > kWide || mn < -kWide) atomicOr(flags + f.status_idx, 1u);  // `wide`: colour needs 64 bits
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            int4 *d = reinterpret_cast<int4 *>(dst + (uint64_t)r * pitch);
+            d[0] = make_int4(s[r][0], s[r][1], s[r][2], s[r][3]);
+            d[1] = make_int4(s[r][4], s[r][5], s[r][6], s[r][7]);
+        }
     }
+}
+
+// grid (blocks / 128, frames or kWideSlots, components - 1); list = {count, frame indices...} for kListed
+template <typename T, bool kListed>
+__global__ void __launch_bounds__(kThreadsB)
+idct_planes_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, T *__restrict__ samples, uint32_t *__restrict__ flags,
+                   const uint32_t *__restrict__ list) {
+    const int c = 1 + blockIdx.z;
+    const uint32_t t = blockIdx.x * kThreadsB + threadIdx.x;
+    if (!kListed) {
+        const FrameRecon &f = frames[blockIdx.y];
+        if (c < (int)f.ncomp) idct_planes_block<T>(f, c, t, coef, samples, flags);
+    } else {
+        const uint32_t n = list[0];
+        for (uint32_t k = blockIdx.y; k < n; k += gridDim.y) {
+            const FrameRecon &f = frames[list[1 + k]];
+            if (c < (int)f.ncomp) idct_planes_block<T>(f, c, t, coef, samples, flags);
+        }
+    }
+}
+
+// the frames of a group whose `narrow` flag is set -> list = {count, group-local indices}
+__global__ void __launch_bounds__(256)
+narrow_list_kernel(const FrameRecon *__restrict__ frames, uint32_t n_frames, const uint32_t *__restrict__ narrow_flags, uint32_t *__restrict__ list) {
+    if (threadIdx.x == 0) list[0] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_frames; i += blockDim.x)
+        if (narrow_flags[frames[i].status_idx]) list[1 + atomicAdd(list, 1u)] = i;
 }
 
 // ---- b2 ------------------------------------------------------------------------------------------------
@@ -132,15 +175,14 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // NW samples of line y of a sample plane starting at column x0. Away from the frame edge this is a plain run;
 // at the edge the clamped addressing reproduces dest[-1] = dest[0], dest[width] = dest[width-1]
 // (upsamplerbase.cpp:322-323) and the duplicated first / last line (upsampler.cpp:100-106).
-template <int NW>
-__device__ __forceinline__ void load_row(const int32_t *__restrict__ plane, uint32_t pitch, int y, int x0, int cw, int ch, bool interior,
-                                         int (&v)[NW]) {
+template <int NW, typename T>
+__device__ __forceinline__ void load_row(const T *__restrict__ plane, uint32_t pitch, int y, int x0, int cw, int ch, bool interior, int (&v)[NW]) {
     if (interior) {
-        const int32_t *row = plane + (uint64_t)y * pitch + x0;
+        const T *row = plane + (uint64_t)y * pitch + x0;
 #pragma unroll
         for (int j = 0; j < NW; j++) v[j] = __ldg(row + j);
     } else {
-        const int32_t *row = plane + (uint64_t)clampi(y, 0, ch - 1) * pitch;
+        const T *row = plane + (uint64_t)clampi(y, 0, ch - 1) * pitch;
 #pragma unroll
         for (int j = 0; j < NW; j++) v[j] = __ldg(row + clampi(x0 + j, 0, cw - 1));
     }
@@ -149,11 +191,20 @@ __device__ __forceinline__ void load_row(const int32_t *__restrict__ plane, uint
 // The same window for a warp whose 32 blocks all lie inside the plane horizontally: a lane fetches its own 8/SX samples
 // with 16-byte loads (4 instead of 24 L1 wavefronts per warp instruction) and, for SX == 2, the two neighbouring columns
 // xl, xr (already clamped = the edge replication above) with one load each; the line is clamped here.
-template <int NW, int SX>
-__device__ __forceinline__ void load_row_own(const int32_t *__restrict__ plane, uint32_t pitch, int y, int ch, uint32_t bx, int xl, int xr,
-                                             int (&v)[NW]) {
-    const int32_t *row = plane + (uint64_t)clampi(y, 0, ch - 1) * pitch;
-    if (SX == 2) {
+template <int NW, int SX, typename T>
+__device__ __forceinline__ void load_row_own(const T *__restrict__ plane, uint32_t pitch, int y, int ch, uint32_t bx, int xl, int xr, int (&v)[NW]) {
+    const T *row = plane + (uint64_t)clampi(y, 0, ch - 1) * pitch;
+    if (sizeof(T) == 2) {
+        if (SX == 2) {
+            const uint2 a = __ldg(reinterpret_cast<const uint2 *>(row) + bx);
+            v[0] = __ldg(row + xl), v[NW - 1] = __ldg(row + xr);
+            v[1] = (int)(short)(a.x & 0xffffu), v[2] = (int)a.x >> 16, v[3] = (int)(short)(a.y & 0xffffu), v[4] = (int)a.y >> 16;
+        } else {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(row) + bx);
+            v[0] = (int)(short)(a.x & 0xffffu), v[1] = (int)a.x >> 16, v[2] = (int)(short)(a.y & 0xffffu), v[3] = (int)a.y >> 16;
+            v[NW - 4] = (int)(short)(a.z & 0xffffu), v[NW - 3] = (int)a.z >> 16, v[NW - 2] = (int)(short)(a.w & 0xffffu), v[NW - 1] = (int)a.w >> 16;
+        }
+    } else if (SX == 2) {
         const int4 a = __ldg(reinterpret_cast<const int4 *>(row) + bx);
         v[0] = __ldg(row + xl), v[1] = a.x, v[2] = a.y, v[3] = a.z, v[4] = a.w, v[NW - 1] = __ldg(row + xr);
     } else {
@@ -210,13 +261,9 @@ __device__ __forceinline__ void to_rgb(int y, int cbv, int crv, int &r, int &g, 
     }
 }
 
-template <int NC, int SX, int SY>
-__global__ void __launch_bounds__(kThreadsB, 4)
-reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, const int32_t *__restrict__ samples,
-                   const uint32_t *__restrict__ wide_flags, uint8_t *__restrict__ out) {
-    __shared__ int ys[64 * kThreadsB];                                   // [coefficient][thread]
-
-    const FrameRecon &f = frames[blockIdx.z];
+template <int NC, int SX, int SY, typename T>
+__device__ __forceinline__ void reconstruct_tile(const FrameRecon &f, int *ys, const int16_t *__restrict__ coef, const T *__restrict__ samples,
+                                                 const uint32_t *__restrict__ wide_flags, uint8_t *__restrict__ out) {
     const uint32_t W = f.width, H = f.height;
     const uint32_t vbw = (W + 7) >> 3, vbh = (H + 7) >> 3;  // blocks that carry visible pixels
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -315,12 +362,13 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
     constexpr int NW = (SX == 2) ? 6 : 8;
     const int cw = (int)f.cw, ch = (int)f.ch;
     const uint32_t cpitch = 8u * f.bw[1];
-    const int32_t *p1 = samples + f.sample_base[1];
-    const int32_t *p2 = samples + f.sample_base[2];
+    const T *p1 = samples + f.sample_base[1];
+    const T *p2 = samples + f.sample_base[2];
     const int cx0 = X / SX - ((SX == 2) ? 1 : 0);  // window column 0 (upsampler.cpp:87,108-109)
     const int cy0 = Y / SY;
     const bool ycbcr = f.ycbcr != 0;
-    const bool wide = (wide_flags[f.status_idx] != 0u) || mx > kWide || mn < -kWide;
+    // int16 planes: chroma is inside the guarded range by construction, only this block's luma can leave it
+    const bool wide = (sizeof(T) == 4 && wide_flags[f.status_idx] != 0u) || mx > kWide || mn < -kWide;
     // the whole window lies inside the plane: no clamping needed
     const bool interior = valid && cx0 >= 0 && cx0 + NW <= cw && cy0 - 1 >= 0 && cy0 + ((SY == 2) ? 5 : 8) <= ch;
     // warp-uniform: every block of the warp is visible and every lane's own samples lie inside the plane
@@ -329,11 +377,11 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
     const int xl = (cx0 > 0) ? cx0 : 0, xr = (cx0 + NW - 1 < cw) ? cx0 + NW - 1 : cw - 1;
     auto fetch = [&](int y, int (&d1)[NW], int (&d2)[NW]) {
         if (fast) {
-            load_row_own<NW, SX>(p1, cpitch, y, ch, bx, xl, xr, d1);
-            load_row_own<NW, SX>(p2, cpitch, y, ch, bx, xl, xr, d2);
+            load_row_own<NW, SX, T>(p1, cpitch, y, ch, bx, xl, xr, d1);
+            load_row_own<NW, SX, T>(p2, cpitch, y, ch, bx, xl, xr, d2);
         } else if (valid) {
-            load_row<NW>(p1, cpitch, y, cx0, cw, ch, interior, d1);
-            load_row<NW>(p2, cpitch, y, cx0, cw, ch, interior, d2);
+            load_row<NW, T>(p1, cpitch, y, cx0, cw, ch, interior, d1);
+            load_row<NW, T>(p2, cpitch, y, cx0, cw, ch, interior, d2);
         }
     };
 
@@ -449,30 +497,59 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
     else lines(std::integral_constant<int, 0>());
 }
 
+// grid (luma block columns / 32, luma block rows / 4, frames or kWideSlots)
+template <int NC, int SX, int SY, typename T, bool kListed>
+__global__ void __launch_bounds__(kThreadsB, 4)
+reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, const T *__restrict__ samples,
+                   const uint32_t *__restrict__ wide_flags, const uint32_t *__restrict__ list, uint8_t *__restrict__ out) {
+    __shared__ int ys[64 * kThreadsB];  // [coefficient][thread]; warps only ever touch their own 32 columns
+    if (!kListed) {
+        reconstruct_tile<NC, SX, SY, T>(frames[blockIdx.z], ys, coef, samples, wide_flags, out);
+    } else {
+        const uint32_t n = list[0];
+        for (uint32_t k = blockIdx.z; k < n; k += gridDim.z) {
+            reconstruct_tile<NC, SX, SY, T>(frames[list[1 + k]], ys, coef, samples, wide_flags, out);
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace
+
+template <typename T, bool kListed>
+static void launch_b2(const ReconLaunch &l, dim3 grid, const T *samples, cudaStream_t s) {
+    if (l.ncomp == 1) {
+        reconstruct_kernel<1, 1, 1, T, kListed><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, samples, l.wide_flags, l.narrow_list, l.out);
+    } else if (l.subx == 2 && l.suby == 2) {
+        reconstruct_kernel<3, 2, 2, T, kListed><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, samples, l.wide_flags, l.narrow_list, l.out);
+    } else if (l.subx == 2 && l.suby == 1) {
+        reconstruct_kernel<3, 2, 1, T, kListed><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, samples, l.wide_flags, l.narrow_list, l.out);
+    } else if (l.subx == 1 && l.suby == 2) {
+        reconstruct_kernel<3, 1, 2, T, kListed><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, samples, l.wide_flags, l.narrow_list, l.out);
+    } else {
+        reconstruct_kernel<3, 1, 1, T, kListed><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, samples, l.wide_flags, l.narrow_list, l.out);
+    }
+}
 
 int launch_recon(const ReconLaunch &l, void *stream, int *launches) {
     cudaStream_t s = (cudaStream_t)stream;
     int n = 0;
+    const uint32_t cblocks = (l.max_bwc * l.max_bhc + kThreadsB - 1) / kThreadsB;
+    const uint32_t gx = (l.max_bw0 + 31) / 32, gy = (l.max_bh0 + kThreadsB / 32 - 1) / (kThreadsB / 32);
+    // every frame through the int16 planes
     if (l.ncomp > 1) {
-        uint32_t blocks = l.max_bwc * l.max_bhc;
-        dim3 grid((blocks + kThreadsB - 1) / kThreadsB, l.n_frames, l.ncomp - 1);
-        idct_planes_kernel<<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags);
+        idct_planes_kernel<int16_t, false><<<dim3(cblocks, l.n_frames, l.ncomp - 1), kThreadsB, 0, s>>>(l.frames, l.coef, l.samples16, l.narrow_flags, nullptr);
         n++;
     }
-    dim3 grid((l.max_bw0 + 31) / 32, (l.max_bh0 + kThreadsB / 32 - 1) / (kThreadsB / 32), l.n_frames);
-    if (l.ncomp == 1) {
-        reconstruct_kernel<1, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
-    } else if (l.subx == 2 && l.suby == 2) {
-        reconstruct_kernel<3, 2, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
-    } else if (l.subx == 2 && l.suby == 1) {
-        reconstruct_kernel<3, 2, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
-    } else if (l.subx == 1 && l.suby == 2) {
-        reconstruct_kernel<3, 1, 2><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
-    } else {
-        reconstruct_kernel<3, 1, 1><<<grid, kThreadsB, 0, s>>>(l.frames, l.coef, l.samples, l.wide_flags, l.out);
-    }
+    launch_b2<int16_t, false>(l, dim3(gx, gy, l.n_frames), l.samples16, s);
     n++;
+    // the exact pass over the frames that were flagged `narrow` (none for real images: three near-empty launches)
+    if (l.ncomp > 1) {
+        narrow_list_kernel<<<1, 256, 0, s>>>(l.frames, l.n_frames, l.narrow_flags, l.narrow_list);
+        idct_planes_kernel<int32_t, true><<<dim3(cblocks, kWideSlots, l.ncomp - 1), kThreadsB, 0, s>>>(l.frames, l.coef, l.samples32, l.wide_flags, l.narrow_list);
+        launch_b2<int32_t, true>(l, dim3(gx, gy, kWideSlots), l.samples32, s);
+        n += 3;
+    }
     if (launches) *launches = n;
     return (int)cudaGetLastError();
 }
