@@ -498,8 +498,13 @@ __device__ __forceinline__ void reconstruct_tile(const FrameRecon &f, int *ys, c
 }
 
 // grid (luma block columns / 32, luma block rows / 4, frames or kWideSlots)
+// five CTAs per SM: ptxas fits the kernel into 86 registers without spilling, and 20 resident warps hide the load latency
+// better than 16 (six CTAs = 80 registers is slower again)
+#ifndef B200JPG_B2_MINCTAS
+#define B200JPG_B2_MINCTAS 5
+#endif
 template <int NC, int SX, int SY, typename T, bool kListed>
-__global__ void __launch_bounds__(kThreadsB, 4)
+__global__ void __launch_bounds__(kThreadsB, B200JPG_B2_MINCTAS)
 reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, const T *__restrict__ samples,
                    const uint32_t *__restrict__ wide_flags, const uint32_t *__restrict__ list, uint8_t *__restrict__ out) {
     __shared__ int ys[64 * kThreadsB];  // [coefficient][thread]; warps only ever touch their own 32 columns
