@@ -41,8 +41,8 @@ if ROOT not in sys.path:
 W, H, QUALITY, SUB, DRI = 3840, 2160, 75, (2, 2), 240
 FRAMES_PER_GPU = 840
 # DRAM bytes per cfg3 frame measured with ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum), profiles/r01_*:
-#   unstuff 2.51 MB, entropy_decode 26.83 MB, idct_planes 24.82 MB, reconstruct 58.02 MB  (r01_840frames_metrics.csv / 840)
-NCU_DRAM_BYTES_PER_FRAME = {"entropy": 2.51e6 + 26.83e6, "recon": 24.82e6 + 58.02e6}
+#   unstuff 2.51 MB, entropy_decode 26.83 MB, idct_planes 16.53 MB, reconstruct 49.72 MB  (r01_840frames_metrics.csv / 840)
+NCU_DRAM_BYTES_PER_FRAME = {"entropy": 2.51e6 + 26.83e6, "recon": 16.53e6 + 49.72e6}
 INT_OPS_PER_4K_FRAME = 520e6  # IDCT 205 M + upsample 133 M + colour 182 M
 
 

@@ -15,8 +15,8 @@ echo "== ncu launch list (same workload as the bench line: 840 frames per step)"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --distinct 4 --no-e2e --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
 tail -12 $OUT/launches.csv
-echo "== ncu full (one launch of each of the four kernels)"
-ncu --set full --clock-control none --import-source on -k regex:"unstuff|entropy_decode|reconstruct_kernel|idct_planes" -s 8 -c 4 -o $OUT/prof -f \
+echo "== ncu full (one step: every kernel once)"
+ncu --set full --clock-control none --import-source on -k regex:"unstuff|entropy_decode|reconstruct_kernel|idct_planes|narrow_list" -s 14 -c 7 -o $OUT/prof -f \
     python bench.py --steps 2 --warmup 3 --distinct 4 --no-e2e --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1
 ls -la $OUT
 fi

@@ -1,5 +1,6 @@
 #!/bin/bash
-# compute-sanitizer over a small heterogeneous batch (all golden vectors + a 1080p frame + a corrupt + a truncated stream)
+# compute-sanitizer over a small heterogeneous batch (all golden vectors + a 641x479 frame + a corrupt + a truncated stream
+# + a stream whose samples leave int16)
 OUT=gpurun_out/sanitize
 mkdir -p $OUT
 cat > /tmp/san.py <<'PY'
@@ -16,6 +17,9 @@ for k in range(i + 40, i + 400):
     if bad[k] != 0xFF and bad[k - 1] != 0xFF: bad[k] = 0xF7
 frames.append(bytes(bad))
 frames.append(good[:good.rfind(b"\xff\xd3")] + b"\xff\xd9")
+sys.path.insert(0, "tests")
+import oracle_binding
+frames.append(oracle_binding.with_dc_quantiser(good, 255))  # samples beyond int16: exercises the exact int32 pass
 dec = libjpeg_b200.BatchDecoder(frames)
 out = dec.new_output(); dec.upload(); dec.decode(out); torch.cuda.synchronize()
 print("statuses", [dec.status(i) for i in range(len(frames))])
