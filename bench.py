@@ -170,6 +170,27 @@ def _oracle_worker(args):
         assert rc == 0
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank (and the threads it starts: host packing, pinned-buffer first touch) to the CPUs next to its GPU, so
+    the pinned host buffers of the e2e path are NUMA-local to the PCIe root the GPU hangs on. Best effort."""
+    if os.environ.get("B200JPG_NO_AFFINITY"):
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus (%d..%d)" % (len(cpus), cpus[0], cpus[-1])
+    except Exception as e:  # no NVML, no permission: run unpinned
+        return "unavailable: %s" % type(e).__name__
+    return "none"
+
+
 # ---------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -225,6 +246,7 @@ def main():
     from libjpeg_b200 import native
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    config["cpu_affinity"] = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
