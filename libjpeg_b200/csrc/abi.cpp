@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <array>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -100,6 +101,8 @@ struct ScanClass {
     std::vector<uint64_t> interval_off;  // absolute offsets into the packed byte buffer
     std::vector<uint64_t> interval_end;
     std::vector<uint64_t> clean_off;     // offsets into the unstuffed buffer
+    std::vector<uint8_t> scan_on_device; // per scan: its restart index is built by restart_index_kernel
+    std::vector<uint64_t> scan_ecs_off, scan_ecs_end;  // per scan, absolute
     uint64_t interval_base = 0;          // index of this class's first interval in d_interval_len
     // offsets (bytes) of the device copies inside the input buffer
     uint64_t dev_scans = 0, dev_intervals = 0, dev_interval_end = 0, dev_clean_off = 0;
@@ -130,6 +133,8 @@ struct b200jpg_batch {
     std::vector<uint64_t> dev_tables;  // offset of each table blob inside the input buffer
     std::vector<ScanClass> classes;
     std::vector<ReconGroup> groups;
+    std::vector<IndexScan> index_scans;  // scans whose restart index is built on the device, at upload
+    uint64_t dev_index_scans = 0;
     uint64_t ecs_bytes = 0, stored_blocks = 0;
 
     // staging / device memory
@@ -271,7 +276,9 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
     b->parse_status.assign(n, 0);
     std::vector<std::string> errs(n);
 
-    // ---- parse (host threads: the marker scan is a memchr over every entropy coded byte)
+    // ---- parse (host threads). Interleaved scans with restart markers get their restart index on the device (8f1);
+    // B200JPG_HOST_INDEX=1 keeps the memchr pass over every entropy coded byte on the host for all of them.
+    const bool device_index = getenv("B200JPG_HOST_INDEX") == nullptr;
     {
         unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
         nt = std::min<unsigned>(nt, (unsigned)n);
@@ -279,7 +286,7 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
         for (unsigned t = 0; t < nt; t++)
             pool.emplace_back([&, t]() {
                 for (int i = (int)t; i < n; i += (int)nt)
-                    b->parse_status[i] = parse_codestream(frames[i], lens[i], b->frames[i], errs[i]);
+                    b->parse_status[i] = parse_codestream(frames[i], lens[i], b->frames[i], errs[i], device_index);
             });
         for (auto &th : pool) th.join();
     }
@@ -421,6 +428,9 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
             for (int k = 0; k < sc.ns; k++) cs.coef_base[k] = coef_base[i][sc.comp[k]];
             cs.frame = (uint32_t)i;
             cl.scans.push_back(cs);
+            cl.scan_on_device.push_back(sc.device_index ? 1 : 0);
+            cl.scan_ecs_off.push_back(byte_off[i] + (uint64_t)sc.ecs_off);
+            cl.scan_ecs_end.push_back(byte_off[i] + (uint64_t)sc.ecs_end);
             for (size_t k = 0; k < sc.interval_off.size(); k++) {
                 size_t off = sc.interval_off[k], end = sc.interval_end[k];
                 cl.interval_off.push_back(off == SIZE_MAX ? ~0ull : byte_off[i] + (uint64_t)off);
@@ -428,17 +438,37 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
             }
         }
     }
-    // unstuffed-buffer layout: every interval gets its source length rounded up to 16 bytes + 48 bytes of zero tail
+    // unstuffed-buffer layout. Host-indexed scans: every interval gets its source length rounded up to 16 bytes + 48 bytes
+    // of zero tail. Device-indexed scans: one region of ECS length + kCleanSlackPerInterval per interval, inside which the
+    // index kernel places interval k at (its source offset) + kCleanSlackPerInterval * k -- no lengths are known here.
     {
         uint64_t ccur = 0, ibase = 0;
-        for (auto &cl : b->classes) {
+        for (size_t ci = 0; ci < b->classes.size(); ci++) {
+            auto &cl = b->classes[ci];
             cl.p.n_scans = (uint32_t)cl.scans.size();
             cl.interval_base = ibase;
             cl.clean_off.resize(cl.interval_off.size());
-            for (size_t k = 0; k < cl.interval_off.size(); k++) {
-                cl.clean_off[k] = ccur;
-                uint64_t len = cl.interval_off[k] == ~0ull ? 0 : cl.interval_end[k] - cl.interval_off[k];
-                ccur += align_up(len, 16) + 48;
+            const size_t nint = cl.p.intervals_per_scan;
+            for (size_t j = 0; j < cl.scans.size(); j++) {
+                if (cl.scan_on_device[j]) {
+                    IndexScan is{};
+                    is.ecs_off = cl.scan_ecs_off[j];
+                    is.ecs_end = cl.scan_ecs_end[j];
+                    is.off_arr = (uint64_t)ci;  // class index for now: becomes the array offset once the layout is known
+                    is.end_arr = (uint64_t)(j * nint);
+                    is.clean_base = ccur;
+                    is.n_intervals = (uint32_t)nint;
+                    is.frame = cl.scans[j].frame;
+                    b->index_scans.push_back(is);
+                    for (size_t k = 0; k < nint; k++) cl.clean_off[j * nint + k] = ccur;
+                    ccur += align_up((is.ecs_end - is.ecs_off) + (uint64_t)kCleanSlackPerInterval * nint + 64, 16);
+                } else {
+                    for (size_t k = j * nint; k < (j + 1) * nint; k++) {
+                        cl.clean_off[k] = ccur;
+                        uint64_t len = cl.interval_off[k] == ~0ull ? 0 : cl.interval_end[k] - cl.interval_off[k];
+                        ccur += align_up(len, 16) + 48;
+                    }
+                }
             }
             ibase += cl.interval_off.size();
         }
@@ -508,6 +538,15 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
         g.dev_frames = cur;
         cur = align_up(cur + g.frames.size() * sizeof(FrameRecon), 256);
     }
+    b->dev_index_scans = cur;
+    cur = align_up(cur + b->index_scans.size() * sizeof(IndexScan), 256);
+    for (auto &is : b->index_scans) {  // class index + first interval -> offsets of the scan's slices
+        const ScanClass &cl = b->classes[(size_t)is.off_arr];
+        const uint64_t first = is.end_arr * sizeof(uint64_t);
+        is.off_arr = cl.dev_intervals + first;
+        is.end_arr = cl.dev_interval_end + first;
+        is.clean_arr = cl.dev_clean_off + first;
+    }
     b->input_bytes = cur;
 
     // ---- pinned staging + device memory
@@ -550,9 +589,10 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
         memcpy(b->h_input + cl.dev_clean_off, cl.clean_off.data(), cl.clean_off.size() * sizeof(uint64_t));
     }
     for (auto &g : b->groups) memcpy(b->h_input + g.dev_frames, g.frames.data(), g.frames.size() * sizeof(FrameRecon));
+    if (!b->index_scans.empty()) memcpy(b->h_input + b->dev_index_scans, b->index_scans.data(), b->index_scans.size() * sizeof(IndexScan));
 
     b->sz_ilen = sizeof(uint32_t) * (size_t)std::max<uint64_t>(b->n_intervals, 1);
-    b->sz_status = sizeof(uint32_t) * (4 * (size_t)n + 1);  // status words, wide flags, narrow flags, narrow list
+    b->sz_status = sizeof(uint32_t) * (5 * (size_t)n + 1);  // status words, wide flags, narrow flags, narrow list, index status
     b->d_input = (uint8_t *)ctx->get(1, b->input_bytes, &ce);
     if (ce == cudaSuccess && b->coef_elems) b->d_coef = (int16_t *)ctx->get(1, b->coef_elems * sizeof(int16_t), &ce);
     if (ce == cudaSuccess && b->sample_elems) b->d_samples = (int32_t *)ctx->get(1, b->sample_elems * sizeof(int32_t), &ce);
@@ -610,13 +650,24 @@ int b200jpg_batch_upload(b200jpg_batch *b, void *stream) {
     cudaSetDevice(b->ctx->device);
     cudaError_t e = cudaMemcpyAsync(b->d_input, b->h_input, b->input_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
     if (e != cudaSuccess) return b->ctx->fail_cuda(e, "upload");
+    // the restart index of device-indexed scans: built once per upload, right behind the copy
+    uint32_t *index_status = b->d_status + 4 * (size_t)b->n + 1;
+    e = cudaMemsetAsync(index_status, 0, sizeof(uint32_t) * (size_t)b->n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return b->ctx->fail_cuda(e, "index status reset");
+    if (!b->index_scans.empty()) {
+        int rc = launch_restart_index(reinterpret_cast<const IndexScan *>(b->d_input + b->dev_index_scans), (uint32_t)b->index_scans.size(),
+                                      b->d_input, index_status, stream);
+        if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "restart index kernel launch");
+    }
     cudaEventRecord(b->ev_last, (cudaStream_t)stream);
     b->uploaded = true;
     return B200JPG_OK;
 }
 
 static int run_entropy(b200jpg_batch *b, void *stream) {
-    cudaError_t e = cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * (size_t)b->n, (cudaStream_t)stream);
+    // the status words start from what the restart index found at upload (out-of-sequence restart markers)
+    cudaError_t e = cudaMemcpyAsync(b->d_status, b->d_status + 4 * (size_t)b->n + 1, sizeof(uint32_t) * (size_t)b->n, cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)stream);
     if (e != cudaSuccess) return b->ctx->fail_cuda(e, "status reset");
     for (int pass = 0; pass < 2; pass++) {  // a0 for every class, then a1 for every class
         if (pass == 1 && b->timing && b->ev[3]) cudaEventRecord(b->ev[3], (cudaStream_t)stream);

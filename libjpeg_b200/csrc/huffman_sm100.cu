@@ -476,7 +476,134 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
     }
 }
 
+
+// =====================================================================================================
+// restart index: one CTA per scan
+// =====================================================================================================
+// What the host parser's walk over the entropy coded segment does with memchr (parse.cpp index_ecs: FF 00 is a
+// stuffed byte, FF FF a fill byte in front of a marker, entropyparser.cpp:121-125; RSTn ends an interval; anything
+// else ends the segment), byte-parallel: 256 threads test 16 bytes each per step, a block-wide prefix sum numbers the
+// restart markers in stream order, and the scan's slices of the interval arrays are written in place:
+//   interval k = [off[k], end[k]);  off[0] = ecs_off, off[k+1] = RST_k + 2, end[k] = RST_k (last one: the marker that ends
+//   the segment, or a surplus RST);  intervals the stream does not contain: off = ~0 (zero-filled by the decoder);
+//   RST_k must be RST(k mod 8) (entropyparser.cpp:137-199 would resynchronise; here: MALFORMED_STREAM, like the host path);
+//   clean_off[k] = base + (off[k] - ecs_off) + 80 k rounded up to 16: unstuffing never grows the data, so the pieces
+//   cannot overlap and no lengths have to be known on the host.
+constexpr int kIndexThreads = 256;
+
+__global__ void __launch_bounds__(kIndexThreads)
+restart_index_kernel(const IndexScan *__restrict__ scans, uint8_t *__restrict__ input, uint32_t *__restrict__ index_status) {
+    const IndexScan s = scans[blockIdx.x];
+    uint64_t *off = reinterpret_cast<uint64_t *>(input + s.off_arr);
+    uint64_t *end = reinterpret_cast<uint64_t *>(input + s.end_arr);
+    uint64_t *cln = reinterpret_cast<uint64_t *>(input + s.clean_arr);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nint = s.n_intervals;
+    __shared__ uint32_t warp_cnt[kIndexThreads / 32];
+    __shared__ unsigned long long first_other;  // lowest offset of a marker that is not RSTn, ~0 = none so far
+    if (tid == 0) first_other = ~0ull;
+    __syncthreads();
+
+    uint32_t running = 0;  // restart markers found so far (uniform)
+    bool bad = false;
+    for (uint64_t chunk = s.ecs_off & ~15ull; chunk < s.ecs_end; chunk += 16ull * kIndexThreads) {
+        const uint64_t p0 = chunk + 16ull * tid;
+        uint32_t rst = 0, ids = 0;  // bit j: byte p0 + j starts an RSTn marker; ids: 3-bit n per such byte, packed
+        uint64_t other = ~0ull;
+        if (p0 < s.ecs_end) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(input + p0);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            if ((__vcmpeq4(v.x, 0xffffffffu) | __vcmpeq4(v.y, 0xffffffffu) | __vcmpeq4(v.z, 0xffffffffu) | __vcmpeq4(v.w, 0xffffffffu)) != 0u) {
+                const uint32_t nxt = input[p0 + 16];  // the byte behind these 16 (inside the buffer: EOI follows ecs_end)
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    const uint32_t nb = (j < 15) ? ((w[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xffu) : nxt;
+                    const uint64_t q = p0 + (uint64_t)j;
+                    if (c == 0xffu && nb != 0u && nb != 0xffu && q >= s.ecs_off && q < s.ecs_end) {
+                        if ((nb & 0xf8u) == 0xd0u) {
+                            ids |= (nb & 7u) << (3 * __popc(rst));  // at most 8 markers fit 16 bytes
+                            rst |= 1u << j;
+                        } else if (other == ~0ull) {
+                            other = q;
+                        }
+                    }
+                }
+            }
+        }
+        // the first marker that is not a restart marker ends the segment: restart markers behind it do not count
+        if (other != ~0ull) atomicMin(&first_other, (unsigned long long)other);
+        __syncthreads();
+        const uint64_t fo = first_other;
+        if (fo != ~0ull) {
+            uint32_t keep = 0, kids = 0, m = rst, i = 0;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                if (p0 + (uint64_t)j < fo) {
+                    kids |= ((ids >> (3 * i)) & 7u) << (3 * __popc(keep));
+                    keep |= 1u << j;
+                }
+                i++;
+            }
+            rst = keep;
+            ids = kids;
+        }
+        // exclusive prefix sum of the per-thread counts
+        const uint32_t cnt = __popc(rst);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        if (lane == 31) warp_cnt[warp] = inc;
+        __syncthreads();
+        uint32_t before = running + inc - cnt, total = 0;
+#pragma unroll
+        for (int wi = 0; wi < kIndexThreads / 32; wi++) {
+            const uint32_t c = warp_cnt[wi];
+            if (wi < (int)warp) before += c;
+            total += c;
+        }
+        uint32_t m = rst, i = 0;
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t k = before + i;  // this is restart marker number k of the scan
+            const uint64_t pos = p0 + (uint64_t)j;
+            if (k < nint) end[k] = pos;
+            if (k + 1 < nint) {
+                off[k + 1] = pos + 2;
+                if (((ids >> (3 * i)) & 7u) != (k & 7u)) bad = true;
+            }
+            i++;
+        }
+        running += total;
+        __syncthreads();  // warp_cnt is reused by the next step
+        if (fo != ~0ull) break;
+    }
+    const uint64_t seg_end = (first_other != ~0ull) ? (uint64_t)first_other : s.ecs_end;
+    if (tid == 0) off[0] = s.ecs_off;
+    for (uint32_t k = tid; k < nint; k += kIndexThreads) {
+        if (k >= running) end[k] = seg_end;
+        if (k > running) off[k] = ~0ull;
+    }
+    __syncthreads();
+    for (uint32_t k = tid; k < nint; k += kIndexThreads) {
+        const uint64_t o = off[k];
+        cln[k] = (o == ~0ull) ? s.clean_base : ((s.clean_base + (o - s.ecs_off) + (uint64_t)kCleanSlackPerInterval * k + 15ull) & ~15ull);
+    }
+    if (bad) atomicMax(index_status + s.frame, kErrMalformed);
+}
+
 }  // namespace
+
+int launch_restart_index(const IndexScan *scans_dev, uint32_t n_scans, uint8_t *input_dev, uint32_t *index_status, void *stream) {
+    if (n_scans == 0) return 0;
+    restart_index_kernel<<<n_scans, kIndexThreads, 0, (cudaStream_t)stream>>>(scans_dev, input_dev, index_status);
+    return (int)cudaGetLastError();
+}
 
 int launch_unstuff(const EntropyLaunch &l, void *stream) {
     const uint64_t total = (uint64_t)l.p.n_scans * l.p.intervals_per_scan;

@@ -43,6 +43,9 @@ struct ScanInfo {  // one SOS + its entropy coded segment
     // codestream/sequentialscan.cpp:415-419)
     std::vector<size_t> interval_off;
     std::vector<size_t> interval_end;  // offset of the marker (or end of data) that terminates the interval
+    // true: the host did not walk the entropy coded segment; ecs_end is the offset of the closing EOI and the restart
+    // index above is a placeholder that restart_index_kernel fills in on the device
+    bool device_index = false;
     HuffSpec dc[4], ac[4];       // tables in effect at this SOS
     uint16_t quant[4][64];       // zig-zag order as transmitted, in effect at this SOS
     bool quant_defined[4] = {false, false, false, false};
@@ -53,8 +56,9 @@ struct ParsedFrame {
     std::vector<ScanInfo> scans;
 };
 
-// Returns 0 or a negative reference error code; `err` receives a message.
-int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::string &err);
+// Returns 0 or a negative reference error code; `err` receives a message. With `device_index` a scan that carries all
+// components of the frame and uses restart markers is not walked on the host (ScanInfo::device_index).
+int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::string &err, bool device_index = false);
 
 extern const uint8_t kZigZagToRaster[64];  // dct/dct.cpp:57-73
 
@@ -91,6 +95,17 @@ struct ClassScan {        // one scan of one frame inside a scan class
     uint32_t frame;         // index into the batch
     uint32_t pad;
 };
+
+// One scan whose restart index is built on the device. Offsets are bytes inside the batch's input buffer; the three
+// arrays are this scan's slices of its class's interval arrays.
+struct IndexScan {
+    uint64_t ecs_off, ecs_end;                 // first entropy coded byte, offset of the closing EOI
+    uint64_t off_arr, end_arr, clean_arr;      // uint64[n_intervals] each
+    uint64_t clean_base;                       // start of the scan's region in the unstuffed buffer (16-byte aligned)
+    uint32_t n_intervals, frame;
+};
+constexpr uint32_t kCleanSlackPerInterval = 80;  // device-indexed scans: clean_off[k] = base + (off[k] - ecs_off) + 80 k, 16-aligned
+int launch_restart_index(const IndexScan *scans_dev, uint32_t n_scans, uint8_t *input_dev, uint32_t *index_status, void *stream);
 
 struct ScanClassParams {  // uniform over a launch of the entropy kernel
     int ns;

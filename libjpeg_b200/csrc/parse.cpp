@@ -65,7 +65,7 @@ size_t index_ecs(const Cursor &c, size_t pos, std::vector<size_t> &rst_at, std::
 
 }  // namespace
 
-int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::string &err) {
+int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::string &err, bool device_index) {
     Cursor c{data, len};
     b200jpg_frame_info &fi = out.info;
     memset(&fi, 0, sizeof(fi));
@@ -230,13 +230,36 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
                 if (!quant_defined[fi.tq[sc.comp[i]]])
                     FAIL(B200JPG_ERR_MALFORMED_STREAM, "quantization table for a component of the scan is not defined");
             }
+            uint64_t total = (uint64_t)sc.mcu_cols * sc.mcu_rows;
+            uint64_t per = sc.dri ? sc.dri : total;
+            uint64_t nint = (total + per - 1) / per;
+            // A scan with restart markers that carries every component is the only scan of the frame: its entropy coded
+            // segment runs up to the closing EOI, which is looked for from the end (bytes behind EOI are legal), and the
+            // restart index is left to the device (restart_index_kernel) instead of a memchr pass over every byte here.
+            if (device_index && sc.dri != 0 && sc.ns == (int)fi.ncomp) {
+                size_t lo = (len > 4096) ? len - 4096 : 0, eoi = SIZE_MAX;
+                if (lo < sc.ecs_off) lo = sc.ecs_off;
+                for (size_t q = len; q >= lo + 2; q--)
+                    if (data[q - 2] == 0xff && data[q - 1] == 0xd9) {
+                        eoi = q - 2;
+                        break;
+                    }
+                if (eoi != SIZE_MAX) {
+                    sc.device_index = true;
+                    sc.ecs_end = eoi;
+                    sc.interval_off.assign((size_t)nint, sc.ecs_off);
+                    sc.interval_end.assign((size_t)nint, eoi);
+                    fi.n_intervals += (uint32_t)nint;
+                    fi.ecs_bytes += sc.ecs_end - sc.ecs_off;
+                    if (out.scans.empty()) fi.restart_interval = dri;
+                    out.scans.push_back(std::move(sc));
+                    goto parsed;  // nothing behind this scan is looked at
+                }
+            }
             // restart-interval index
             std::vector<size_t> rst_at;
             std::vector<uint8_t> rst_id;
             sc.ecs_end = index_ecs(c, sc.ecs_off, rst_at, rst_id);
-            uint64_t total = (uint64_t)sc.mcu_cols * sc.mcu_rows;
-            uint64_t per = sc.dri ? sc.dri : total;
-            uint64_t nint = (total + per - 1) / per;
             sc.interval_off.assign((size_t)nint, SIZE_MAX);
             sc.interval_end.assign((size_t)nint, sc.ecs_end);
             sc.interval_off[0] = sc.ecs_off;
@@ -262,6 +285,7 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
         }
         pos += (size_t)seglen;
     }
+parsed:
     if (!have_sof) FAIL(B200JPG_ERR_MALFORMED_STREAM, "codestream contains no frame header");
     if (out.scans.empty()) FAIL(B200JPG_ERR_MALFORMED_STREAM, "codestream contains no scan");
     fi.nscans = (uint32_t)out.scans.size();

@@ -113,3 +113,38 @@ def with_dc_quantiser(data, value):
                 j += 65
         i += 2 + seglen
     return bytes(b)
+
+
+def with_fill_bytes(data, every=2, count=1):
+    """The same codestream with `count` fill bytes (0xFF) in front of every `every`-th restart marker / EOI of the
+    entropy coded segment (legal: entropyparser.cpp:121-125, tables.cpp:1371-1373)."""
+    b = bytes(data.tobytes() if hasattr(data, "tobytes") else data)
+    sos = b.find(b"\xff\xda")
+    start = sos + 2 + ((b[sos + 2] << 8) | b[sos + 3])
+    out, n, i = bytearray(b[:start]), 0, start
+    while i < len(b):
+        if b[i] == 0xFF and i + 1 < len(b) and (0xD0 <= b[i + 1] <= 0xD7 or b[i + 1] == 0xD9):
+            if n % every == 0:
+                out += b"\xff" * count
+            n += 1
+            out += b[i:i + 2]
+            i += 2
+        else:
+            out.append(b[i])
+            i += 1
+    return bytes(out)
+
+
+def with_swapped_restart_ids(data, first=1):
+    """The same codestream with the ids of restart markers number `first` and `first + 1` exchanged (out of sequence)."""
+    b = bytearray(data.tobytes() if hasattr(data, "tobytes") else data)
+    sos = bytes(b).find(b"\xff\xda")
+    i, at = sos + 2 + ((b[sos + 2] << 8) | b[sos + 3]), []
+    while i + 1 < len(b):
+        if b[i] == 0xFF and 0xD0 <= b[i + 1] <= 0xD7:
+            at.append(i + 1)
+            i += 2
+        else:
+            i += 1
+    b[at[first]], b[at[first + 1]] = b[at[first + 1]], b[at[first]]
+    return bytes(b)

@@ -124,6 +124,56 @@ def test_samples_beyond_the_fast_ranges_match_oracle(built, oracle, w, h, sub, z
         assert np.array_equal(dec.frame_view(out, i).cpu().numpy(), ref_h if i & 1 else ref_n), i
 
 
+def _damaged_fixtures():
+    d = os.path.join(GOLDEN, "damaged")
+    px = np.load(os.path.join(d, "damaged_pixels.npz"))
+    return [(n, open(os.path.join(d, n + ".jpg"), "rb").read(), px[n]) for n in sorted(px.files)]
+
+
+def test_truncated_streams_match_reference_fixtures(built):
+    """Streams that end where a restart marker should stand: the reference marks the remaining intervals invalid and
+    clears their MCUs (entropyparser.cpp:137-199, sequentialscan.cpp:415-419); the fixtures hold ITS pixels (the oracle
+    only restates the in-sequence case)."""
+    fx = _damaged_fixtures()
+    dec, out = gpu_decode(built, [f[1] for f in fx])
+    for i, (name, _, want) in enumerate(fx):
+        assert dec.status(i) == 0, name
+        got = dec.frame_view(out, i).cpu().numpy()
+        assert np.array_equal(got.reshape(want.shape), want), name
+
+
+def test_device_restart_index_equals_host_index(built, oracle, monkeypatch):
+    """the restart index built by restart_index_kernel (default for interleaved scans with restart markers)
+    against the host memchr walk (B200JPG_HOST_INDEX=1), the oracle and the reference's fixtures -- plain streams, fill
+    bytes in front of markers, truncated streams, trailing bytes behind EOI, restart ids out of sequence."""
+    import torch
+    from libjpeg_b200 import synth
+    from tests import oracle_binding
+    a = synth.encode(synth.source_image(200, 136, 3), 75, (2, 2), 2)          # 59 intervals, ids wrap around
+    b_ = synth.encode(synth.source_image(96, 80, 5), 80, (2, 1), 3).tobytes()
+    c = synth.encode(synth.source_image(640, 360, 9), 75, (2, 2), 40).tobytes()   # intervals of several KB
+    valid = [a.tobytes(), oracle_binding.with_fill_bytes(a, 2, 1), oracle_binding.with_fill_bytes(a, 3, 7), b_, c,
+             a.tobytes() + b"\x00\x11\x22" * 5]
+    fx = _damaged_fixtures()
+    frames = valid + [f[1] for f in fx] + [oracle_binding.with_swapped_restart_ids(a, 4)]
+    dec, out = gpu_decode(built, frames, tolerate_bad=True)
+    monkeypatch.setenv("B200JPG_HOST_INDEX", "1")
+    dec_h, out_h = gpu_decode(built, frames, tolerate_bad=True)
+    monkeypatch.delenv("B200JPG_HOST_INDEX")
+    torch.cuda.synchronize()
+    for i, fr in enumerate(frames[:-1]):
+        if i < len(valid):
+            rc, want = oracle.decode(fr)
+            assert rc == 0
+        else:
+            want = fx[i - len(valid)][2]
+        assert dec.status(i) == 0 and dec_h.status(i) == 0, i
+        assert np.array_equal(dec.frame_view(out, i).cpu().numpy().reshape(want.shape), want), i
+        assert torch.equal(dec.frame_view(out, i), dec_h.frame_view(out_h, i)), i
+    # MALFORMED_STREAM, restart markers out of sequence: found by the kernel / by the host walk at parse time
+    assert dec.status(len(frames) - 1) == -1038 and dec_h.status(len(frames) - 1) == -1038
+
+
 def test_corrupt_stream_is_reported_not_crashing(built):
     from libjpeg_b200 import synth
     good = synth.encode(synth.source_image(128, 64, 5), 75, (2, 2), 8)
