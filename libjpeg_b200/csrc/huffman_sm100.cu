@@ -160,20 +160,33 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
         }
         // byte in front of this lane's word: the previous lane's last byte (lane 0: carried from the last step)
         uint32_t prev_word = __shfl_up_sync(kFull, cur, 1);
-        uint32_t pb = (lane == 0) ? (carry_ff ? 0xffu : 0u) : ((wo - 1 >= src0) ? (prev_word >> 24) : 0u);
         uint32_t keep[4];
         uint32_t mk = 4;  // index of the first marker byte in this word, 4 = none
+        // steps that lie inside the interval with room to spare need none of the per-byte range tests
+        if (base >= src0 + 4 && base + 132 <= src1) {
+            uint32_t pb = (lane == 0) ? (carry_ff ? 0xffu : 0u) : (prev_word >> 24);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint64_t q = wo + k;
-            const uint32_t v = (cur >> (8 * k)) & 0xffu;
-            const uint32_t nb = (k < 3) ? ((cur >> (8 * k + 8)) & 0xffu) : (nxt & 0xffu);
-            const bool in = (q >= src0) && (q < src1);
-            const bool stuffed = (v == 0u) && (pb == 0xffu);      // the 00 of FF 00 (io/bitstream.cpp:87-95)
-            const bool marker = in && (v == 0xffu) && (nb != 0u);  // FF followed by non-zero (:96-101)
-            if (marker && mk == 4) mk = k;
-            keep[k] = (in && !stuffed) ? 1u : 0u;
-            pb = in ? v : 0u;
+            for (int k = 0; k < 4; k++) {
+                const uint32_t v = (cur >> (8 * k)) & 0xffu;
+                const uint32_t nb = (k < 3) ? ((cur >> (8 * k + 8)) & 0xffu) : (nxt & 0xffu);
+                if (v == 0xffu && nb != 0u && mk == 4) mk = k;        // FF followed by non-zero (:96-101)
+                keep[k] = (v == 0u && pb == 0xffu) ? 0u : 1u;         // the 00 of FF 00 (io/bitstream.cpp:87-95)
+                pb = v;
+            }
+        } else {
+            uint32_t pb = (lane == 0) ? (carry_ff ? 0xffu : 0u) : ((wo - 1 >= src0) ? (prev_word >> 24) : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint64_t q = wo + k;
+                const uint32_t v = (cur >> (8 * k)) & 0xffu;
+                const uint32_t nb = (k < 3) ? ((cur >> (8 * k + 8)) & 0xffu) : (nxt & 0xffu);
+                const bool in = (q >= src0) && (q < src1);
+                const bool stuffed = (v == 0u) && (pb == 0xffu);      // the 00 of FF 00 (io/bitstream.cpp:87-95)
+                const bool marker = in && (v == 0xffu) && (nb != 0u);  // FF followed by non-zero (:96-101)
+                if (marker && mk == 4) mk = k;
+                keep[k] = (in && !stuffed) ? 1u : 0u;
+                pb = in ? v : 0u;
+            }
         }
         // the first lane that holds a marker byte ends the interval: nothing at or after it is data
         const uint32_t mmask = __ballot_sync(kFull, mk < 4);
