@@ -191,9 +191,11 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
         // the first lane that holds a marker byte ends the interval: nothing at or after it is data
         const uint32_t mmask = __ballot_sync(kFull, mk < 4);
         const uint32_t first = mmask ? (uint32_t)(__ffs(mmask) - 1) : 32u;
+        if (mmask) {
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (lane > first || (lane == first && k >= (int)mk)) keep[k] = 0;
+            for (int k = 0; k < 4; k++)
+                if (lane > first || (lane == first && k >= (int)mk)) keep[k] = 0;
+        }
         // destination of every kept byte: one ballot per byte column + population-count prefix sums
         const uint32_t b0 = __ballot_sync(kFull, keep[0]), b1 = __ballot_sync(kFull, keep[1]);
         const uint32_t b2 = __ballot_sync(kFull, keep[2]), b3 = __ballot_sync(kFull, keep[3]);
