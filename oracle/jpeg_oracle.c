@@ -223,6 +223,118 @@ static void decode_block(int32_t *block, const hufftab *dc, const hufftab *ac, i
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Progressive scans.  First passes: codestream/sequentialscan.cpp:678-773 with m_bProgressive (EOB runs
+ * :722-726, point transform `<< lowbit`); refinement passes: codestream/refinementscan.cpp:584-690.
+ * `skip` is the number of blocks an EOB run still covers (reset by Restart()).                        */
+static void decode_block_first(int32_t *block, const hufftab *dc, const hufftab *ac, int32_t *prevdc, const jpgo_scan *sc,
+                               unsigned *skip, bitreader *br) {
+    if (sc->ss == 0) { /* DC, first pass: like the sequential case, :682-701 */
+        int32_t diff = 0;
+        int value = huff_get(dc, br);
+        if (br->error) return;
+        if (value > 0) {
+            if (value > 15) {
+                br->error = JPGO_ERR_MALFORMED_STREAM;
+                return;
+            }
+            diff = (int32_t)br_get(br, value);
+            if (br->error) return;
+            if (diff < ((int32_t)1 << (value - 1))) diff += (int32_t)(-(1 << value)) + 1;
+        }
+        *prevdc += diff;
+        block[0] = (int32_t)((uint32_t)*prevdc << sc->al);
+    }
+    if (sc->se) { /* AC, first pass */
+        int k = sc->ss;
+        if (*skip > 0) { /* inside an EOB run: the block stays as it is */
+            (*skip)--;
+            return;
+        }
+        do {
+            int rs = huff_get(ac, br);
+            int r = rs >> 4, s = rs & 15;
+            int32_t d;
+            if (br->error) return;
+            if (s == 0) {
+                if (r == 15) { /* ZRL; `continue` re-tests k <= Se */
+                    k += 16;
+                    continue;
+                }
+                *skip = 1u << r; /* EOBn: this block and 2^r + extra - 1 more */
+                if (r) *skip |= br_get(br, r);
+                (*skip)--;
+                return;
+            }
+            k += r;
+            d = (int32_t)br_get(br, s);
+            if (br->error) return;
+            if (d < ((int32_t)1 << (s - 1))) d += (int32_t)(-(1 << s)) + 1;
+            if (k >= 64) { /* the reference tests against 64, not against Se */
+                br->error = JPGO_ERR_MALFORMED_STREAM;
+                return;
+            }
+            block[jpgo_scan_order[k]] = (int32_t)((uint32_t)d << sc->al);
+            k++;
+        } while (k <= sc->se);
+    }
+}
+
+static void correct(int32_t *c, int al, bitreader *br) { /* one correction bit, away from zero (:616-626) */
+    if (br_get(br, 1)) *c += (*c > 0) ? ((int32_t)1 << al) : -((int32_t)1 << al);
+}
+
+static void decode_block_refine(int32_t *block, const hufftab *ac, const jpgo_scan *sc, unsigned *skip, bitreader *br) {
+    if (sc->ss == 0) { /* DC refinement: one raw bit, :588-592 */
+        block[0] |= (int32_t)br_get(br, 1) << sc->al;
+        return;
+    }
+    {
+        int k = sc->ss;
+        if (*skip == 0) {
+            while (k <= sc->se) {
+                int rs = huff_get(ac, br);
+                int r = rs >> 4, s = rs & 15;
+                int32_t val = 0;
+                if (br->error) return;
+                if (s == 0) {
+                    if (r != 15) { /* EOBn: the rest of this block (and of the run) only takes correction bits */
+                        *skip = 1u << r;
+                        if (r) *skip |= br_get(br, r);
+                        break;
+                    }
+                    /* ZRL: sixteen zero-valued positions */
+                } else if (s != 1) { /* the reference warns and keeps going with a zero amplitude, :659-668 */
+                    r = 0;
+                } else {
+                    val = br_get(br, 1) ? ((int32_t)1 << sc->al) : -((int32_t)1 << sc->al);
+                }
+                /* pass r zero-valued coefficients; the significant ones on the way take their correction bit */
+                while (k <= sc->se) {
+                    int32_t *c = &block[jpgo_scan_order[k]];
+                    if (*c) {
+                        correct(c, sc->al, br);
+                    } else {
+                        if (r == 0) break;
+                        r--;
+                    }
+                    k++;
+                }
+                if (br->error) return;
+                if (k <= sc->se) block[jpgo_scan_order[k]] = val; /* the zero-valued position that ends the run */
+                k++;
+            }
+        }
+        if (*skip > 0) {
+            for (; k <= sc->se; k++) {
+                int32_t *c = &block[jpgo_scan_order[k]];
+                if (*c) correct(c, sc->al, br);
+            }
+            (*skip)--;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* marker parser                                                                                       */
 typedef struct {
     hufftab dc[4], ac[4];
@@ -329,11 +441,12 @@ static int walk(const uint8_t *d, size_t n, jpgo_info *info, decoder_tables *tab
             if (len >= 14 && memcmp(d + pos + 2, "Adobe", 5) == 0) adobe_none = (d[pos + 13] == 0);
             break;
         case 0xc0:
-        case 0xc1: { /* SOF0 / SOF1, marker/frame.cpp:111-214, marker/component.cpp:86-111 */
+        case 0xc1:
+        case 0xc2: { /* SOF0 / SOF1, marker/frame.cpp:111-214, marker/component.cpp:86-111 */
             size_t p = pos + 2;
             if (have_sof) return JPGO_ERR_MALFORMED_STREAM;
             if (len < 8) return JPGO_ERR_MALFORMED_STREAM;
-            info->frame_type = (m == 0xc1);
+            info->frame_type = m - 0xc0;
             info->precision = d[p];
             if (info->precision != 8) return (m == 0xc0) ? JPGO_ERR_MALFORMED_STREAM : JPGO_ERR_NOT_IMPLEMENTED;
             info->height = rd16(d, n, p + 1);
@@ -395,9 +508,20 @@ static int walk(const uint8_t *d, size_t n, jpgo_info *info, decoder_tables *tab
                 sc->ta[i] = sel & 15;
                 if (sc->td[i] > 3 || sc->ta[i] > 3) return JPGO_ERR_MALFORMED_STREAM;
             }
-            if (d[p + 1 + 2 * ns] != 0 || d[p + 2 + 2 * ns] != 63) return JPGO_ERR_MALFORMED_STREAM; /* :273-276 */
-            if ((d[p + 3 + 2 * ns] >> 4) != 0) return JPGO_ERR_MALFORMED_STREAM;                      /* :280-282 */
-            if (tabs) tabs->lowbit[info->nscans] = d[p + 3 + 2 * ns] & 15;
+            sc->ss = d[p + 1 + 2 * ns];
+            sc->se = d[p + 2 + 2 * ns];
+            sc->ah = d[p + 3 + 2 * ns] >> 4;
+            sc->al = d[p + 3 + 2 * ns] & 15;
+            if (info->frame_type == 2) { /* marker/scan.cpp:257-302 */
+                if (sc->ss > sc->se || sc->se > 63) return JPGO_ERR_MALFORMED_STREAM;
+                if (sc->ss == 0 && sc->se != 0) return JPGO_ERR_MALFORMED_STREAM; /* DC and AC must be coded separately */
+                if (sc->ss != 0 && ns != 1) return JPGO_ERR_MALFORMED_STREAM;       /* AC scans carry one component */
+                if (sc->ah != 0 && sc->ah != sc->al + 1) return JPGO_ERR_MALFORMED_STREAM; /* one bit per refinement */
+            } else {
+                if (sc->ss != 0 || sc->se != 63) return JPGO_ERR_MALFORMED_STREAM; /* :273-276 */
+                if (sc->ah != 0) return JPGO_ERR_MALFORMED_STREAM;                  /* :280-282 */
+            }
+            if (tabs) tabs->lowbit[info->nscans] = sc->al;
             sc->restart_interval = dri;
             sc->ecs_offset = pos + (size_t)len;
             sc->ecs_end = find_ecs_end(d, n, sc->ecs_offset);
@@ -417,8 +541,8 @@ static int walk(const uint8_t *d, size_t n, jpgo_info *info, decoder_tables *tab
             continue;
         }
         default:
-            if (m == 0xc2 || m == 0xc3 || (m >= 0xc5 && m <= 0xcf && m != 0xc8 && m != 0xcc))
-                return JPGO_ERR_NOT_IMPLEMENTED; /* progressive / lossless / arithmetic / hierarchical */
+            if (m == 0xc3 || (m >= 0xc5 && m <= 0xcf && m != 0xc8 && m != 0xcc))
+                return JPGO_ERR_NOT_IMPLEMENTED; /* lossless / arithmetic / hierarchical */
             break; /* APPn, COM, everything else: skipped by length (tables.cpp:1057-1072,1385-1399) */
         }
         pos += (size_t)len;
@@ -438,13 +562,16 @@ static int decode_scan(const uint8_t *d, const jpgo_info *info, const jpgo_scan 
                        int lowbit, int32_t *const planes[]) {
     bitreader br;
     int32_t pred[JPGO_MAX_COMP] = {0, 0, 0, 0};
+    unsigned skip[JPGO_MAX_COMP] = {0, 0, 0, 0};
     int32_t dummy[64];
     const uint8_t *end = d + sc->ecs_end;
+    const int progressive = (info->frame_type == 2);
     int total = sc->mcu_cols * sc->mcu_rows;
     int togo = sc->restart_interval, next_rst = 0xd0;
     int m, c;
-    for (c = 0; c < sc->ns; c++) {
-        if (!tabs->dc[sc->td[c]].defined || !tabs->ac[sc->ta[c]].defined) return JPGO_ERR_MALFORMED_STREAM;
+    for (c = 0; c < sc->ns; c++) { /* a progressive scan only needs the tables it decodes with */
+        const int need_dc = !progressive || (sc->ss == 0 && sc->ah == 0), need_ac = !progressive || sc->se != 0;
+        if ((need_dc && !tabs->dc[sc->td[c]].defined) || (need_ac && !tabs->ac[sc->ta[c]].defined)) return JPGO_ERR_MALFORMED_STREAM;
     }
     br_open(&br, d + sc->ecs_offset, end);
     for (m = 0; m < total; m++) {
@@ -456,6 +583,7 @@ static int decode_scan(const uint8_t *d, const jpgo_info *info, const jpgo_scan 
                 if (!(p + 1 < end && p[0] == 0xff && p[1] == next_rst)) return JPGO_ERR_MALFORMED_STREAM;
                 br_open(&br, p + 2, end); /* SequentialScan::Restart, sequentialscan.cpp:266-274 */
                 memset(pred, 0, sizeof(pred));
+                memset(skip, 0, sizeof(skip));
                 next_rst = 0xd0 + ((next_rst + 1) & 7);
                 togo = sc->restart_interval;
             }
@@ -472,7 +600,10 @@ static int decode_scan(const uint8_t *d, const jpgo_info *info, const jpgo_scan 
                     /* blocks outside the reference's stored grid are decoded and dropped (:407-412);
                      * this oracle keeps the MCU-padded grid, the extra blocks are simply never read back */
                     if (bx < info->bw[ci] && by < info->bh[ci]) blk = planes[ci] + 64 * ((size_t)by * info->bw[ci] + bx);
-                    decode_block(blk, &tabs->dc[sc->td[c]], &tabs->ac[sc->ta[c]], &pred[c], lowbit, &br);
+                    else if (progressive) memset(dummy, 0, sizeof(dummy));
+                    if (!progressive) decode_block(blk, &tabs->dc[sc->td[c]], &tabs->ac[sc->ta[c]], &pred[c], lowbit, &br);
+                    else if (sc->ah == 0) decode_block_first(blk, &tabs->dc[sc->td[c]], &tabs->ac[sc->ta[c]], &pred[c], sc, &skip[c], &br);
+                    else decode_block_refine(blk, &tabs->ac[sc->ta[c]], sc, &skip[c], &br);
                     if (br.error) return br.error;
                 }
             }

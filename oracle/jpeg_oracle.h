@@ -1,7 +1,9 @@
 /*
  * oracle/jpeg_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * Plain-C CPU restatement of the reference's (thorfdbg/libjpeg) sequential-Huffman decode path:
+ * Plain-C CPU restatement of the reference's (thorfdbg/libjpeg) Huffman decode path -- sequential
+ * (SOF0/SOF1) and, as groundwork for SURVEY 8f2, progressive (SOF2: first passes in
+ * codestream/sequentialscan.cpp, refinement passes in codestream/refinementscan.cpp):
  * marker parse -> Huffman decode -> dequant + integer IDCT -> centred-bilinear chroma upsampling ->
  * YCbCr->RGB -> 8-bit store.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
  * use it, and only as the checker.  The product (libjpeg_b200/) never links or calls it.
@@ -28,7 +30,7 @@ extern "C" {
 #define JPGO_ERR_OUT_OF_MEMORY (-2048)
 
 #define JPGO_MAX_COMP 4
-#define JPGO_MAX_SCANS 8
+#define JPGO_MAX_SCANS 16
 
 typedef struct {
     int ns;                      /* components in scan */
@@ -38,11 +40,12 @@ typedef struct {
     size_t ecs_offset;           /* first byte after the SOS header */
     size_t ecs_end;              /* offset of the first non-RST marker after the ECS */
     int mcu_cols, mcu_rows;      /* MCU grid of THIS scan (block grid for ns==1) */
+    int ss, se, ah, al;          /* spectral selection and successive approximation (0, 63, 0, point transform for sequential) */
 } jpgo_scan;
 
 typedef struct {
     int width, height, ncomp, precision;
-    int frame_type;              /* 0 = SOF0 baseline, 1 = SOF1 extended sequential */
+    int frame_type;              /* 0 = SOF0 baseline, 1 = SOF1 extended sequential, 2 = SOF2 progressive */
     int cid[JPGO_MAX_COMP], hs[JPGO_MAX_COMP], vs[JPGO_MAX_COMP], tq[JPGO_MAX_COMP];
     int hmax, vmax;
     int subx[JPGO_MAX_COMP], suby[JPGO_MAX_COMP];

@@ -15,7 +15,8 @@ REF_CLI = os.path.join(ORACLE_DIR, "_ref", "jpeg")
 class ScanStruct(ctypes.Structure):
     _fields_ = [("ns", ctypes.c_int), ("comp", ctypes.c_int * 4), ("td", ctypes.c_int * 4), ("ta", ctypes.c_int * 4),
                 ("restart_interval", ctypes.c_int), ("ecs_offset", ctypes.c_size_t), ("ecs_end", ctypes.c_size_t),
-                ("mcu_cols", ctypes.c_int), ("mcu_rows", ctypes.c_int)]
+                ("mcu_cols", ctypes.c_int), ("mcu_rows", ctypes.c_int), ("ss", ctypes.c_int), ("se", ctypes.c_int),
+                ("ah", ctypes.c_int), ("al", ctypes.c_int)]
 
 
 class InfoStruct(ctypes.Structure):
@@ -24,7 +25,7 @@ class InfoStruct(ctypes.Structure):
                 ("tq", ctypes.c_int * 4), ("hmax", ctypes.c_int), ("vmax", ctypes.c_int), ("subx", ctypes.c_int * 4),
                 ("suby", ctypes.c_int * 4), ("mcu_cols", ctypes.c_int), ("mcu_rows", ctypes.c_int), ("bw", ctypes.c_int * 4),
                 ("bh", ctypes.c_int * 4), ("sbw", ctypes.c_int * 4), ("sbh", ctypes.c_int * 4), ("ycbcr", ctypes.c_int),
-                ("nscans", ctypes.c_int), ("scan", ScanStruct * 8), ("quant", (ctypes.c_uint16 * 64) * 4),
+                ("nscans", ctypes.c_int), ("scan", ScanStruct * 16), ("quant", (ctypes.c_uint16 * 64) * 4),
                 ("quant_defined", ctypes.c_int * 4)]
 
 

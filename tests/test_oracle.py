@@ -73,14 +73,34 @@ def test_oracle_idct_dc_only(oracle):
     assert np.all(out == ((p1 * 512 + 2048) >> 12))
 
 
-def test_oracle_rejects_progressive_and_garbage(oracle):
+def test_oracle_rejects_lossless_and_garbage(oracle):
     data = bytearray(open(os.path.join(GOLDEN, NAMES[0] + ".jpg"), "rb").read())
     i = data.find(b"\xff\xc0")
-    data[i + 1] = 0xC2
+    data[i + 1] = 0xC3
     rc, _ = oracle.decode(bytes(data))
     assert rc == -1034  # NOT_IMPLEMENTED
     rc, _ = oracle.decode(b"\x00\x01\x02\x03")
     assert rc == -1038  # MALFORMED_STREAM
+
+
+PROGRESSIVE = os.path.join(GOLDEN, "progressive")
+PNAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(PROGRESSIVE, "*.jpg")))
+
+
+@pytest.mark.parametrize("name", PNAMES)
+def test_oracle_matches_progressive_golden(oracle, name):
+    """SURVEY 8f2 groundwork: SOF2 streams of the reference encoder (DC first, AC bands, DC and AC refinement scans, with
+    and without restart markers) decode to the reference's pixels (codestream/sequentialscan.cpp first passes,
+    codestream/refinementscan.cpp)."""
+    want = np.load(os.path.join(PROGRESSIVE, "progressive_pixels.npz"))[name]
+    rc, px = oracle.decode(open(os.path.join(PROGRESSIVE, name + ".jpg"), "rb").read())
+    assert rc == 0
+    assert np.array_equal(px.reshape(want.shape), want)
+
+
+def test_progressive_golden_is_complete():
+    assert len(PNAMES) >= 7
+    assert set(np.load(os.path.join(PROGRESSIVE, "progressive_pixels.npz")).files) == set(PNAMES)
 
 
 @pytest.mark.skipif(not oracle_binding.have_reference(), reason="reference build (oracle/_ref) not present")
