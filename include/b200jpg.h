@@ -48,12 +48,12 @@ extern "C" {
 #define B200JPG_ERR_CUDA (-8194)
 
 #define B200JPG_MAX_COMPONENTS 4
-#define B200JPG_MAX_SCANS 8
+#define B200JPG_MAX_SCANS 16
 
 /* Geometry of one parsed codestream (host only, no GPU needed). */
 typedef struct b200jpg_frame_info {
     uint32_t width, height;
-    uint8_t ncomp, precision, frame_type /* 0 = SOF0, 1 = SOF1 */, ycbcr /* 1: YCbCr->RGB applies */;
+    uint8_t ncomp, precision, frame_type /* 0 = SOF0, 1 = SOF1, 2 = SOF2 (progressive) */, ycbcr /* 1: YCbCr->RGB applies */;
     uint8_t comp_id[B200JPG_MAX_COMPONENTS];
     uint8_t hs[B200JPG_MAX_COMPONENTS], vs[B200JPG_MAX_COMPONENTS];     /* sampling factors of the SOF */
     uint8_t subx[B200JPG_MAX_COMPONENTS], suby[B200JPG_MAX_COMPONENTS]; /* hmax/hs, vmax/vs (reference's SubX/SubY) */

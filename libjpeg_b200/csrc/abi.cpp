@@ -135,6 +135,9 @@ struct b200jpg_batch {
     std::vector<ReconGroup> groups;
     std::vector<IndexScan> index_scans;  // scans whose restart index is built on the device, at upload
     uint64_t dev_index_scans = 0;
+    std::vector<ProgFrame> prog_frames;  // progressive frames: dequantised after their last scan
+    uint64_t dev_prog_frames = 0;
+    uint32_t prog_max_blocks = 0;
     uint64_t ecs_bytes = 0, stored_blocks = 0;
 
     // staging / device memory
@@ -310,7 +313,7 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
                 for (auto &sc : pf.scans)
                     for (int k = 0; k < sc.ns; k++) seen[sc.comp[k]]++;
                 for (int c = 0; c < fi.ncomp; c++)
-                    if (seen[c] != 1) {
+                    if (fi.frame_type != 2 && seen[c] != 1) {
                         st = B200JPG_ERR_MALFORMED_STREAM;
                         errs[i] = "sequential frame does not code every component exactly once";
                     }
@@ -361,7 +364,8 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
         if (b->parse_status[i] != 0) continue;
         ParsedFrame &pf = b->frames[i];
         const b200jpg_frame_info &fi = pf.info;
-        for (auto &sc : pf.scans) {
+        for (size_t si = 0; si < pf.scans.size(); si++) {
+            auto &sc = pf.scans[si];
             TableSet ts;
             std::string err;
             int rc = build_table_set(sc, ts, err);
@@ -395,6 +399,12 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
             p.dri = sc.dri ? sc.dri : p.total_mcus;
             p.intervals_per_scan = (uint32_t)sc.interval_off.size();
             p.lut_words = b->table_sets[ti].lut_words();
+            p.progressive = sc.progressive ? 1 : 0;
+            p.ss = sc.ss;
+            p.se = sc.se;
+            p.ah = sc.ah;
+            p.al = sc.lowbit;
+            p.ordinal = sc.progressive ? (int)si : 0;
             ClassKey key{};
             int kk = 0;
             key.v[kk++] = p.ns;
@@ -411,6 +421,12 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
             key.v[kk++] = (int)p.dri;
             key.v[kk++] = (int)p.intervals_per_scan;
             key.v[kk++] = ti;
+            key.v[kk++] = p.progressive;
+            key.v[kk++] = p.ss;
+            key.v[kk++] = p.se;
+            key.v[kk++] = p.ah;
+            key.v[kk++] = p.al;
+            key.v[kk++] = p.ordinal;
             int cidx;
             auto cit = class_index.find(key);
             if (cit == class_index.end()) {
@@ -438,6 +454,23 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
             }
         }
     }
+    // the scans of a progressive frame build on each other: launch order = scan order (sequential classes: ordinal 0)
+    std::stable_sort(b->classes.begin(), b->classes.end(), [](const ScanClass &x, const ScanClass &y) { return x.p.ordinal < y.p.ordinal; });
+    for (int i = 0; i < n; i++) {
+        if (b->parse_status[i] != 0 || b->frames[i].info.frame_type != 2) continue;
+        const ParsedFrame &pf = b->frames[i];
+        ProgFrame f{};
+        f.frame = (uint32_t)i;
+        for (int c = 0; c < pf.info.ncomp; c++) {
+            f.coef_base[c] = coef_base[i][c];
+            f.n_blocks[c] = pf.info.blocks_w[c] * pf.info.blocks_h[c];
+            b->prog_max_blocks = std::max(b->prog_max_blocks, f.n_blocks[c]);
+            const ScanInfo &last = pf.scans.back();  // quantisers in effect at the end of the frame
+            for (int k = 0; k < 64; k++) f.q_raster[c][kZigZagToRaster[k]] = last.quant_defined[pf.info.tq[c]] ? last.quant[pf.info.tq[c]][k] : 0;
+        }
+        b->prog_frames.push_back(f);
+    }
+
     // unstuffed-buffer layout. Host-indexed scans: every interval gets its source length rounded up to 16 bytes + 48 bytes
     // of zero tail. Device-indexed scans: one region of ECS length + kCleanSlackPerInterval per interval, inside which the
     // index kernel places interval k at (its source offset) + kCleanSlackPerInterval * k -- no lengths are known here.
@@ -538,6 +571,8 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
         g.dev_frames = cur;
         cur = align_up(cur + g.frames.size() * sizeof(FrameRecon), 256);
     }
+    b->dev_prog_frames = cur;
+    cur = align_up(cur + b->prog_frames.size() * sizeof(ProgFrame), 256);
     b->dev_index_scans = cur;
     cur = align_up(cur + b->index_scans.size() * sizeof(IndexScan), 256);
     for (auto &is : b->index_scans) {  // class index + first interval -> offsets of the scan's slices
@@ -590,6 +625,7 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
     }
     for (auto &g : b->groups) memcpy(b->h_input + g.dev_frames, g.frames.data(), g.frames.size() * sizeof(FrameRecon));
     if (!b->index_scans.empty()) memcpy(b->h_input + b->dev_index_scans, b->index_scans.data(), b->index_scans.size() * sizeof(IndexScan));
+    if (!b->prog_frames.empty()) memcpy(b->h_input + b->dev_prog_frames, b->prog_frames.data(), b->prog_frames.size() * sizeof(ProgFrame));
 
     b->sz_ilen = sizeof(uint32_t) * (size_t)std::max<uint64_t>(b->n_intervals, 1);
     b->sz_status = sizeof(uint32_t) * (5 * (size_t)n + 1);  // status words, wide flags, narrow flags, narrow list, index status
@@ -669,6 +705,10 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
     cudaError_t e = cudaMemcpyAsync(b->d_status, b->d_status + 4 * (size_t)b->n + 1, sizeof(uint32_t) * (size_t)b->n, cudaMemcpyDeviceToDevice,
                                     (cudaStream_t)stream);
     if (e != cudaSuccess) return b->ctx->fail_cuda(e, "status reset");
+    if (!b->prog_frames.empty()) {  // progressive scans accumulate into the coefficient store: it starts from zero
+        e = cudaMemsetAsync(b->d_coef, 0, b->coef_elems * sizeof(int16_t), (cudaStream_t)stream);
+        if (e != cudaSuccess) return b->ctx->fail_cuda(e, "coefficient store reset");
+    }
     for (int pass = 0; pass < 2; pass++) {  // a0 for every class, then a1 for every class
         if (pass == 1 && b->timing && b->ev[3]) cudaEventRecord(b->ev[3], (cudaStream_t)stream);
         for (auto &cl : b->classes) {
@@ -684,10 +724,16 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
             l.tables = b->d_input + b->dev_tables[cl.table_set];
             l.coef = b->d_coef;
             l.frame_status = b->d_status;
-            int rc = pass == 0 ? launch_unstuff(l, stream) : launch_entropy(l, stream);
+            int rc = pass == 0 ? launch_unstuff(l, stream) : (cl.p.progressive ? launch_progressive_scan(l, stream) : launch_entropy(l, stream));
             if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, pass == 0 ? "unstuff kernel launch" : "entropy kernel launch");
             b->last_launches++;
         }
+    }
+    if (!b->prog_frames.empty()) {  // quantised levels -> the dequantised coefficients stage b expects
+        int rc = launch_progressive_dequant(reinterpret_cast<const ProgFrame *>(b->d_input + b->dev_prog_frames), (uint32_t)b->prog_frames.size(),
+                                            b->prog_max_blocks, b->d_coef, b->d_status, stream);
+        if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "progressive dequantisation kernel launch");
+        b->last_launches++;
     }
     cudaEventRecord(b->ev_last, (cudaStream_t)stream);
     return B200JPG_OK;

@@ -34,7 +34,11 @@ struct ScanInfo {  // one SOS + its entropy coded segment
     int ns = 0;
     int comp[4] = {0, 0, 0, 0};  // frame component index, SOS order
     int td[4] = {0, 0, 0, 0}, ta[4] = {0, 0, 0, 0};
-    int lowbit = 0;
+    int lowbit = 0;              // point transform Al
+    // progressive frames (SOF2): spectral selection Ss..Se and the bit position Ah of the previous pass of this band
+    // (0: first pass); sequential scans have 0, 63, 0
+    bool progressive = false;
+    int ss = 0, se = 63, ah = 0;
     uint32_t dri = 0;            // MCUs per restart interval, 0 = none
     size_t ecs_off = 0, ecs_end = 0;
     uint32_t mcu_cols = 0, mcu_rows = 0;
@@ -115,6 +119,18 @@ struct ScanClassParams {  // uniform over a launch of the entropy kernel
     uint32_t mcu_cols, total_mcus, dri /* MCUs per interval, >= 1 */, intervals_per_scan;
     uint32_t n_scans;       // scans in this class
     uint32_t lut_words;
+    // progressive scans (SOF2): handled by progressive_scan_kernel instead of entropy_decode_kernel
+    int progressive, ss, se, ah, al;
+    int ordinal;            // position of the scan inside its frame: progressive classes are launched in this order
+};
+
+// One progressive frame for the dequantisation pass that follows its last scan: the progressive kernels keep
+// quantised levels in the coefficient store, stage b expects dequantised coefficients.
+struct ProgFrame {
+    uint64_t coef_base[4];   // int16 element offsets of the component planes
+    uint32_t n_blocks[4];    // blocks per plane (MCU-padded grid), 0 = component absent
+    uint16_t q_raster[4][64];  // quantiser of the component in raster order
+    uint32_t frame, pad;
 };
 
 struct FrameRecon {       // per frame, for the reconstruction kernels
@@ -144,6 +160,10 @@ struct EntropyLaunch {
 };
 int launch_unstuff(const EntropyLaunch &l, void *stream);
 int launch_entropy(const EntropyLaunch &l, void *stream);
+// progressive_sm100.cu: one scan class of progressive frames; quantised levels -> dequantised coefficients afterwards
+int launch_progressive_scan(const EntropyLaunch &l, void *stream);
+int launch_progressive_dequant(const ProgFrame *frames_dev, uint32_t n_frames, uint32_t max_blocks, int16_t *coef, uint32_t *frame_status,
+                               void *stream);
 
 struct ReconLaunch {
     const FrameRecon *frames;  // device

@@ -137,14 +137,15 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
             if (rem >= 12 && memcmp(s, "Adobe", 5) == 0) adobe_none = (s[11] == 0);
             break;
         case 0xc0:
-        case 0xc1: {
+        case 0xc1:
+        case 0xc2: {
             if (have_sof) FAIL(B200JPG_ERR_MALFORMED_STREAM, "found a second frame header, hierarchical JPEG is not supported");
             if (seglen < 8) FAIL(B200JPG_ERR_MALFORMED_STREAM, "start of frame marker size invalid");
-            fi.frame_type = (m == 0xc1);
+            fi.frame_type = (uint8_t)(m - 0xc0);
             fi.precision = s[0];
             if (m == 0xc0 && fi.precision != 8) FAIL(B200JPG_ERR_MALFORMED_STREAM, "frame precision in baseline mode must be 8");
             if (fi.precision != 8 && fi.precision != 12) FAIL(B200JPG_ERR_MALFORMED_STREAM, "frame precision in lossy mode must be 8 or 12");
-            if (fi.precision != 8) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "12 bit extended sequential frames are not supported by the B200 path");
+            if (fi.precision != 8) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "12 bit frames are not supported by the B200 path");
             fi.height = (uint32_t)((s[1] << 8) | s[2]);
             fi.width = (uint32_t)((s[3] << 8) | s[4]);
             if (fi.width == 0) FAIL(B200JPG_ERR_MALFORMED_STREAM, "image width must not be zero");
@@ -202,11 +203,25 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
                 if (sc.ta[i] > 3) FAIL(B200JPG_ERR_MALFORMED_STREAM, "AC table index in SOS marker is out of range, must be at most 4");
             }
             const uint8_t *t = s + 1 + 2 * sc.ns;
-            if (t[0] != 0 || t[1] != 63)
-                FAIL(B200JPG_ERR_MALFORMED_STREAM, "scan start must be zero and scan stop must be 63 for the sequential operating modes");
-            if ((t[2] >> 4) != 0)
-                FAIL(B200JPG_ERR_MALFORMED_STREAM, "successive approximation parameters must be zero for the sequential operating modes");
+            sc.progressive = fi.frame_type == 2;
+            sc.ss = t[0];
+            sc.se = t[1];
+            sc.ah = t[2] >> 4;
             sc.lowbit = t[2] & 15;
+            if (sc.progressive) {  // marker/scan.cpp:257-302
+                if (sc.ss > sc.se || sc.se > 63) FAIL(B200JPG_ERR_MALFORMED_STREAM, "spectral selection of the scan is invalid");
+                if (sc.ss == 0 && sc.se != 0)
+                    FAIL(B200JPG_ERR_MALFORMED_STREAM, "DC and AC coefficients must be coded in separate scans in the progressive mode");
+                if (sc.ss != 0 && sc.ns != 1)
+                    FAIL(B200JPG_ERR_MALFORMED_STREAM, "AC scans of the progressive mode must contain a single component");
+                if (sc.ah != 0 && sc.ah != sc.lowbit + 1)
+                    FAIL(B200JPG_ERR_MALFORMED_STREAM, "successive approximation must refine by one bit per scan");
+            } else {
+                if (sc.ss != 0 || sc.se != 63)
+                    FAIL(B200JPG_ERR_MALFORMED_STREAM, "scan start must be zero and scan stop must be 63 for the sequential operating modes");
+                if (sc.ah != 0)
+                    FAIL(B200JPG_ERR_MALFORMED_STREAM, "successive approximation parameters must be zero for the sequential operating modes");
+            }
             sc.dri = dri;
             sc.ecs_off = pos + (size_t)seglen;
             if (sc.ns > 1) {
@@ -225,7 +240,8 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
                 sc.quant_defined[i] = quant_defined[i];
             }
             for (int i = 0; i < sc.ns; i++) {
-                if (!dc[sc.td[i]].defined || !ac[sc.ta[i]].defined)
+                const bool need_dc = !sc.progressive || (sc.ss == 0 && sc.ah == 0), need_ac = !sc.progressive || sc.se != 0;
+                if ((need_dc && !dc[sc.td[i]].defined) || (need_ac && !ac[sc.ta[i]].defined))
                     FAIL(B200JPG_ERR_MALFORMED_STREAM, "Huffman decoder not specified for all components included in scan");  // sequentialscan.cpp:117-129
                 if (!quant_defined[fi.tq[sc.comp[i]]])
                     FAIL(B200JPG_ERR_MALFORMED_STREAM, "quantization table for a component of the scan is not defined");
@@ -236,7 +252,7 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
             // A scan with restart markers that carries every component is the only scan of the frame: its entropy coded
             // segment runs up to the closing EOI, which is looked for from the end (bytes behind EOI are legal), and the
             // restart index is left to the device (restart_index_kernel) instead of a memchr pass over every byte here.
-            if (device_index && sc.dri != 0 && sc.ns == (int)fi.ncomp) {
+            if (device_index && !sc.progressive && sc.dri != 0 && sc.ns == (int)fi.ncomp) {
                 size_t lo = (len > 4096) ? len - 4096 : 0, eoi = SIZE_MAX;
                 if (lo < sc.ecs_off) lo = sc.ecs_off;
                 for (size_t q = len; q >= lo + 2; q--)
@@ -279,8 +295,8 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
             continue;
         }
         default:
-            if (m == 0xc2 || m == 0xc3 || (m >= 0xc5 && m <= 0xcf && m != 0xc8 && m != 0xcc))
-                FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "only baseline / extended sequential Huffman frames are supported by the B200 path");
+            if (m == 0xc3 || (m >= 0xc5 && m <= 0xcf && m != 0xc8 && m != 0xcc))
+                FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "only baseline, extended sequential and progressive Huffman frames are supported by the B200 path");
             break;  // APPn, COM, JPG extensions: skipped by length (tables.cpp:1057-1072,1385-1399)
         }
         pos += (size_t)seglen;
@@ -305,11 +321,14 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
     uint16_t lut_off[8];
     const uint32_t kUnused = 0x80000000u | ((uint32_t)kQzBlockEnds << 19) | (31u << 5);
     const int L1 = kLutL1Bits, L2 = 16 - kLutL1Bits;
+    // Progressive scans decode with the raw (run, size) of a symbol -- EOBn is a legal AC symbol there -- kept in [13:10]
+    // and [4:0]; only the tables the scan kind reads are built.
+    const bool need_dc = !scan.progressive || (scan.ss == 0 && scan.ah == 0), need_ac = !scan.progressive || scan.se != 0;
     for (int t = 0; t < 8; t++) {
         const HuffSpec &h = (t < 4) ? scan.dc[t] : scan.ac[t - 4];
         const bool is_ac = t >= 4;
         lut_off[t] = 0xffff;
-        if (!h.defined) continue;
+        if (!h.defined || !(is_ac ? need_ac : need_dc)) continue;
         bool used = false;
         for (int i = 0; i < scan.ns; i++) used |= is_ac ? (scan.ta[i] == t - 4) : (scan.td[i] == t);
         if (!used) continue;
@@ -333,7 +352,7 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
                 if (is_ac) {
                     s = sym & 15u;
                     r = sym >> 4;
-                    if (s == 0 && r != 0 && r != 15) bad = 1;  // sequentialscan.cpp:750-752: not a baseline symbol
+                    if (s == 0 && r != 0 && r != 15 && !scan.progressive) bad = 1;  // sequentialscan.cpp:750-752: not a baseline symbol
                 } else {
                     s = sym;
                     r = 0;
@@ -344,7 +363,8 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
                 }
                 uint32_t step = 0;
                 if (is_ac) step = bad ? (uint32_t)kQzBlockEnds : (s != 0 ? r + 1u : (r == 15 ? 16u : (uint32_t)kQzBlockEnds));
-                const uint32_t entry = (bad << 31) | ((len + s) << 26) | (step << 19) | (len << 5) | s;
+                uint32_t entry = (bad << 31) | ((len + s) << 26) | (step << 19) | (len << 5) | s;
+                if (scan.progressive) entry = (bad << 31) | ((len + s) << 26) | (r << 10) | (len << 5) | s;
                 if ((int)len <= L1) {
                     for (uint32_t q = code >> L2, qlast = last >> L2; q < qlast; q++) lut[base + q] = entry;
                 } else {
@@ -370,7 +390,7 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
     size_t total = kTableHeaderBytes + lut.size() * 4;
     total = (total + 15) & ~(size_t)15;
     out.blob.assign(total, 0);
-    uint32_t hdr[4] = {kTableMagic, (uint32_t)total, (uint32_t)lut.size(), 0};
+    uint32_t hdr[4] = {kTableMagic, (uint32_t)total, (uint32_t)lut.size(), scan.progressive ? 1u : 0u};
     memcpy(out.blob.data(), hdr, 16);
     memcpy(out.blob.data() + 16, lut_off, 16);
     uint32_t *qz = (uint32_t *)(out.blob.data() + 32);

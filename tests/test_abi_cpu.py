@@ -45,11 +45,16 @@ def test_parser_error_codes(built):
     with pytest.raises(NativeError) as e:
         built.parse(b"\x00\x01\x02\x03\x04")
     assert e.value.code == -1038
-    prog = bytearray(data)
+    lossless = bytearray(data)
+    lossless[lossless.find(b"\xff\xc0") + 1] = 0xC3
+    with pytest.raises(NativeError) as e:
+        built.parse(bytes(lossless))
+    assert e.value.code == -1034  # NOT_IMPLEMENTED
+    prog = bytearray(data)  # a sequential scan (Ss..Se = 0..63) inside a progressive frame is malformed
     prog[prog.find(b"\xff\xc0") + 1] = 0xC2
     with pytest.raises(NativeError) as e:
         built.parse(bytes(prog))
-    assert e.value.code == -1034
+    assert e.value.code == -1038
     with pytest.raises(NativeError) as e:
         built.parse(bytes(data[:200]))
     assert e.value.code in (-1025, -1038)

@@ -174,6 +174,39 @@ def test_device_restart_index_equals_host_index(built, oracle, monkeypatch):
     assert dec.status(len(frames) - 1) == -1038 and dec_h.status(len(frames) - 1) == -1038
 
 
+PROGRESSIVE = os.path.join(GOLDEN, "progressive")
+PNAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(PROGRESSIVE, "*.jpg")))
+
+
+@pytest.mark.parametrize("name", PNAMES)
+def test_progressive_golden_vector_bit_exact(built, name):
+    """SOF2 streams of the reference encoder (DC first, AC bands, DC / AC refinement) through the progressive
+    scan kernels + dequantisation + the same stage b: the reference's pixels."""
+    want = np.load(os.path.join(PROGRESSIVE, "progressive_pixels.npz"))[name]
+    dec, out = gpu_decode(built, [open(os.path.join(PROGRESSIVE, name + ".jpg"), "rb").read()])
+    assert dec.status(0) == 0
+    assert np.array_equal(dec.frame_view(out, 0).cpu().numpy().reshape(want.shape), want)
+
+
+def test_progressive_coefficients_and_mixed_batch(built, oracle, golden_pixels):
+    """Quantised levels after all scans x quantiser == the oracle's planes; progressive and sequential frames share a batch."""
+    prog = [open(os.path.join(PROGRESSIVE, n + ".jpg"), "rb").read() for n in PNAMES]
+    base = [open(os.path.join(GOLDEN, n + ".jpg"), "rb").read() for n in NAMES[:5]]
+    frames = [prog[0], base[0], prog[3], base[1], prog[1], base[2], prog[5], base[3], prog[6], base[4], prog[2], prog[4]]
+    dec, out = gpu_decode(built, frames)
+    px = np.load(os.path.join(PROGRESSIVE, "progressive_pixels.npz"))
+    order = [("p", 0), ("b", 0), ("p", 3), ("b", 1), ("p", 1), ("b", 2), ("p", 5), ("b", 3), ("p", 6), ("b", 4), ("p", 2), ("p", 4)]
+    for i, (kind, j) in enumerate(order):
+        want = px[PNAMES[j]] if kind == "p" else golden_pixels[NAMES[j]]
+        assert dec.status(i) == 0, i
+        assert np.array_equal(dec.frame_view(out, i).cpu().numpy().reshape(want.shape), want), (i, kind, j)
+    rc, s, planes = oracle.coefficients(prog[0])
+    assert rc == 0
+    for c in range(s.ncomp):
+        q = np.array(s.quant[s.tq[c]], dtype=np.int32).reshape(8, 8)
+        assert np.array_equal(dec.coefficients(0, c).astype(np.int32), planes[c] * q), "component %d" % c
+
+
 def test_corrupt_stream_is_reported_not_crashing(built):
     from libjpeg_b200 import synth
     good = synth.encode(synth.source_image(128, 64, 5), 75, (2, 2), 8)
