@@ -39,6 +39,25 @@ def test_parser_agrees_with_oracle(built, oracle, name):
     assert bool(fi.ycbcr) == bool(s.ycbcr)
 
 
+def test_parser_agrees_with_oracle_on_progressive_streams(built, oracle):
+    """SOF2: ten scans (DC first, AC bands, refinements), every one indexed per restart interval on the host."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "progressive", "*.jpg"))):
+        data = open(path, "rb").read()
+        fi = built.parse(data)
+        rc, s = oracle.info(data)
+        assert rc == 0 and s.frame_type == 2
+        assert (fi.width, fi.height, fi.ncomp, fi.nscans) == (s.width, s.height, s.ncomp, s.nscans)
+        assert fi.ecs_bytes == sum(s.scan[k].ecs_end - s.scan[k].ecs_offset for k in range(s.nscans))
+        want = 0
+        for k in range(s.nscans):
+            sc = s.scan[k]
+            total = sc.mcu_cols * sc.mcu_rows
+            per = sc.restart_interval or total
+            want += (total + per - 1) // per
+        assert fi.n_intervals == want
+
+
 def test_parser_error_codes(built):
     from libjpeg_b200 import NativeError
     data = bytearray(open(os.path.join(GOLDEN, NAMES[0] + ".jpg"), "rb").read())
