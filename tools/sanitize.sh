@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer over a small heterogeneous batch (all golden vectors + a 641x479 frame + a corrupt + a truncated stream
-# + a stream whose samples leave int16)
+# + a stream whose samples leave int16 + three progressive streams)
 OUT=gpurun_out/sanitize
 mkdir -p $OUT
 cat > /tmp/san.py <<'PY'
@@ -20,6 +20,7 @@ frames.append(good[:good.rfind(b"\xff\xd3")] + b"\xff\xd9")
 sys.path.insert(0, "tests")
 import oracle_binding
 frames.append(oracle_binding.with_dc_quantiser(good, 255))  # samples beyond int16: exercises the exact int32 pass
+frames += [open(p, "rb").read() for p in sorted(glob.glob("tests/golden/progressive/*.jpg"))[:3]]  # progressive scans
 dec = libjpeg_b200.BatchDecoder(frames)
 out = dec.new_output(); dec.upload(); dec.decode(out); torch.cuda.synchronize()
 print("statuses", [dec.status(i) for i in range(len(frames))])
