@@ -151,10 +151,10 @@ def run_reference(frames, procs, iters):
 def best_reference_config(frames, ncpu):
     """The reference is single threaded and allocation heavy: beyond a few dozen processes this box's memory system, not
     its cores, limits it. Scan the process count (short samples) and keep the fastest: that is the CPU arm's best case."""
-    cands = sorted(set(max(1, c) for c in (ncpu, ncpu // 2, ncpu // 4, ncpu // 8, 3 * ncpu // 8)))
+    cands = sorted(set(max(1, c) for c in (1, ncpu, ncpu // 2, ncpu // 4, ncpu // 8, 3 * ncpu // 8)))  # 1: the per-core rate
     best, scan = None, {}
     for procs in cands:
-        d = run_reference(frames, procs, max(2, 128 // procs))
+        d = run_reference(frames, procs, 8 if procs == 1 else max(2, 128 // procs))
         scan[procs] = round(d["fps"], 1)
         if best is None or d["fps"] > best[1]:
             best = (procs, d["fps"])
