@@ -474,7 +474,7 @@ static int walk(const uint8_t *d, size_t n, jpgo_info *info, decoder_tables *tab
                     return JPGO_ERR_NOT_IMPLEMENTED; /* marker/component.hpp:99-106 */
                 info->subx[i] = info->hmax / info->hs[i];
                 info->suby[i] = info->vmax / info->vs[i];
-                if (info->subx[i] > 2 || info->suby[i] > 2) return JPGO_ERR_NOT_IMPLEMENTED; /* oracle scope */
+                if (info->subx[i] > 4 || info->suby[i] > 4) return JPGO_ERR_NOT_IMPLEMENTED; /* upsamplerbase.cpp:335-404 */
                 info->bw[i] = info->mcu_cols * info->hs[i];
                 info->bh[i] = info->mcu_rows * info->vs[i];
                 cw = (info->width + info->subx[i] - 1) / info->subx[i];
@@ -744,42 +744,114 @@ static int32_t sp_at(const splane *p, int x, int y) { /* x in [-1, w] after edge
 }
 
 /* Upsampler<sx,sy>::UpsampleRegion for one 8x8 output block whose top-left output pixel is (X,Y):
- * upsampling/upsampler.cpp:83-112, VerticalFilterCore<1|2> :114-168, HorizontalFilterCore<1|2> :270-307.
- * out[8*row + col].                                                                                   */
+ * upsampling/upsampler.cpp:83-112, VerticalFilterCore<1..4> :114-268, HorizontalFilterCore<1..4> :270-386.
+ * The weights are (1,3)/4 for factors 2 and 3 (3: every third line / column is the sample itself) and
+ * (3,5)/8, (1,7)/8 for factor 4; the rounding constant alternates between neighbouring columns / lines.
+ * The horizontal cores work IN PLACE on the row (input shifted by one pixel), so a few outputs read
+ * positions that were already overwritten -- that is part of the contract and is reproduced by doing
+ * the same stores in the same order.  out[8*row + col].                                              */
+static int32_t mix(int32_t a, int wa, int32_t b, int wb, int rnd, int sh) { return ADD(ADD(MUL(wa, a), MUL(wb, b)), rnd) >> sh; }
+
 static void upsample_block(const splane *p, int sx, int sy, int X, int Y, int32_t *out) {
     int y = Y / sy;
     int x0 = X / sx - ((sx > 1) ? 1 : 0); /* window col 0; one extra pixel on the left when expanding */
     int row, j;
     int top = (y > 0) ? y - 1 : y, cur = y, bot = (y + 1 < p->h) ? y + 1 : y;
-    int ymod = 0;
+    int ymod = Y % sy, xmod = X % sx;
     for (row = 0; row < 8; row++) {
         int32_t *o = out + 8 * row;
+        int advance = 0;
+        /* ---- vertical: line `cur` leaning on `top` in the upper part of its sy output lines, on `bot` in the lower */
         if (sy == 1) {
             for (j = 0; j < 8; j++) o[j] = sp_at(p, x0 + j, cur);
             if (cur + 1 < p->h) cur++;
-        } else if (ymod == 0) {
-            for (j = 0; j < 8; j++)
-                o[j] = ADD(ADD(sp_at(p, x0 + j, top), MUL(3, sp_at(p, x0 + j, cur))), (j & 1) ? 1 : 2) >> 2;
-            ymod = 1;
-        } else {
-            for (j = 0; j < 8; j++)
-                o[j] = ADD(ADD(sp_at(p, x0 + j, bot), MUL(3, sp_at(p, x0 + j, cur))), (j & 1) ? 2 : 1) >> 2;
-            ymod = 0;
-            top = cur;
-            cur = bot;
-            if (bot + 1 < p->h) bot++;
+        } else if (sy == 2) {
+            const int nb = (ymod == 0) ? top : bot;
+            for (j = 0; j < 8; j++) o[j] = mix(sp_at(p, x0 + j, nb), 1, sp_at(p, x0 + j, cur), 3, ((j & 1) == ymod) ? 2 : 1, 2);
+            advance = (ymod == 1);
+        } else if (sy == 3) {
+            if (ymod == 1) {
+                for (j = 0; j < 8; j++) o[j] = sp_at(p, x0 + j, cur);
+            } else {
+                const int nb = (ymod == 0) ? top : bot;
+                for (j = 0; j < 8; j++) o[j] = mix(sp_at(p, x0 + j, nb), 1, sp_at(p, x0 + j, cur), 3, (((j & 1) == 0) == (ymod == 0)) ? 2 : 1, 2);
+            }
+            advance = (ymod == 2);
+        } else { /* sy == 4 */
+            const int nb = (ymod < 2) ? top : bot, far = (ymod == 0 || ymod == 3); /* far from the sample line: 3:5, else 1:7 */
+            for (j = 0; j < 8; j++) {
+                int rnd;
+                if (ymod == 0 || ymod == 2 || ymod == 3) rnd = (j & 1) ? 3 : 4;
+                else rnd = (j & 1) ? 4 : 3;
+                o[j] = mix(sp_at(p, x0 + j, nb), far ? 3 : 1, sp_at(p, x0 + j, cur), far ? 5 : 7, rnd, 3);
+            }
+            advance = (ymod == 3);
         }
-        if (sx == 2) { /* in place, in the reference's store order: note out[1] reads the NEW out[2] */
+        if (sy > 1) {
+            if (advance) {
+                ymod = 0;
+                top = cur;
+                cur = bot;
+                if (bot + 1 < p->h) bot++;
+            } else {
+                ymod++;
+            }
+        }
+        /* ---- horizontal, in place, in the reference's store order */
+        if (sx == 2) {
             int32_t *src = o + 1, t;
-            o[7] = ADD(ADD(src[4], MUL(3, src[3])), 1) >> 2;
-            o[6] = ADD(ADD(src[2], MUL(3, src[3])), 2) >> 2;
-            o[5] = ADD(ADD(src[3], MUL(3, src[2])), 1) >> 2;
-            o[4] = ADD(ADD(src[1], MUL(3, src[2])), 2) >> 2;
-            o[3] = ADD(ADD(src[2], MUL(3, src[1])), 1) >> 2;
-            o[2] = ADD(ADD(src[0], MUL(3, src[1])), 2) >> 2;
+            o[7] = mix(src[4], 1, src[3], 3, 1, 2);
+            o[6] = mix(src[2], 1, src[3], 3, 2, 2);
+            o[5] = mix(src[3], 1, src[2], 3, 1, 2);
+            o[4] = mix(src[1], 1, src[2], 3, 2, 2);
+            o[3] = mix(src[2], 1, src[1], 3, 1, 2);
+            o[2] = mix(src[0], 1, src[1], 3, 2, 2);
             t = src[0];
-            o[1] = ADD(ADD(src[1], MUL(3, t)), 1) >> 2;
-            o[0] = ADD(ADD(src[-1], MUL(3, t)), 2) >> 2;
+            o[1] = mix(src[1], 1, t, 3, 1, 2); /* src[1] is the NEW o[2] */
+            o[0] = mix(src[-1], 1, t, 3, 2, 2);
+        } else if (sx == 3) {
+            int32_t *src = o + 1, t;
+            if (xmod == 0) {
+                o[7] = src[2];
+                o[6] = mix(src[1], 1, src[2], 3, 2, 2);
+                o[5] = mix(src[2], 1, src[1], 3, 1, 2);
+                o[4] = src[1];
+                o[3] = mix(src[0], 1, src[1], 3, 2, 2);
+                o[2] = mix(src[1], 1, src[0], 3, 1, 2);
+                o[0] = mix(src[-1], 1, src[0], 3, 2, 2);
+                o[1] = src[0];
+            } else if (xmod == 1) {
+                o[7] = mix(src[3], 1, src[2], 3, 1, 2);
+                o[6] = src[2];
+                o[5] = mix(src[1], 1, src[2], 3, 2, 2);
+                o[4] = mix(src[2], 1, src[1], 3, 1, 2);
+                o[3] = src[1];
+                t = src[0];
+                o[2] = mix(t, 1, src[1], 3, 2, 2);
+                o[1] = mix(src[1], 1, t, 3, 1, 2);
+                o[0] = t;
+            } else {
+                o[7] = mix(src[2], 1, src[3], 3, 2, 2);
+                o[6] = mix(src[3], 1, src[2], 3, 1, 2);
+                o[5] = src[2];
+                o[4] = mix(src[1], 1, src[2], 3, 2, 2);
+                o[3] = mix(src[2], 1, src[1], 3, 1, 2);
+                o[2] = src[1];
+                t = src[0];
+                o[1] = mix(t, 1, src[1], 3, 2, 2);
+                o[0] = mix(src[1], 1, t, 3, 1, 2);
+            }
+        } else if (sx == 4) {
+            int32_t *src = o + 1, t;
+            o[7] = mix(src[2], 3, src[1], 5, 1, 3);
+            o[6] = mix(src[2], 1, src[1], 7, 2, 3);
+            o[5] = mix(src[0], 1, src[1], 7, 1, 3);
+            o[4] = mix(src[0], 3, src[1], 5, 2, 3);
+            t = src[0];
+            o[3] = mix(src[1], 3, t, 5, 1, 3);
+            o[2] = mix(src[1], 1, t, 7, 2, 3);
+            o[1] = mix(src[-1], 1, t, 7, 1, 3);
+            o[0] = mix(src[-1], 3, t, 5, 2, 3);
         }
     }
 }

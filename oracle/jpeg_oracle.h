@@ -4,7 +4,7 @@
  * Plain-C CPU restatement of the reference's (thorfdbg/libjpeg) Huffman decode path -- sequential
  * (SOF0/SOF1) and, as groundwork for SURVEY 8f2, progressive (SOF2: first passes in
  * codestream/sequentialscan.cpp, refinement passes in codestream/refinementscan.cpp):
- * marker parse -> Huffman decode -> dequant + integer IDCT -> centred-bilinear chroma upsampling ->
+ * marker parse -> Huffman decode -> dequant + integer IDCT -> centred chroma upsampling (factors 1..4) ->
  * YCbCr->RGB -> 8-bit store.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
  * use it, and only as the checker.  The product (libjpeg_b200/) never links or calls it.
  *

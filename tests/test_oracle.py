@@ -98,6 +98,38 @@ def test_oracle_matches_progressive_golden(oracle, name):
     assert np.array_equal(px.reshape(want.shape), want)
 
 
+SUBSAMPLING = os.path.join(GOLDEN, "subsampling")
+SNAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(SUBSAMPLING, "*.jpg")))
+
+
+@pytest.mark.parametrize("name", SNAMES)
+def test_oracle_matches_3x_4x_subsampling_golden(oracle, name):
+    """SURVEY 8f4 groundwork: chroma subsampled by 3 and 4 (4:1:1, 4:1:0, 3x3 ...) -- the reference's filter cores for those
+    factors (upsampling/upsampler.cpp:171-268, 310-386), including their in-place store order."""
+    want = np.load(os.path.join(SUBSAMPLING, "subsampling_pixels.npz"))[name]
+    rc, px = oracle.decode(open(os.path.join(SUBSAMPLING, name + ".jpg"), "rb").read())
+    assert rc == 0
+    assert np.array_equal(px.reshape(want.shape), want)
+
+
+@pytest.mark.skipif(not oracle_binding.have_reference(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("sub", ["1x1,4x1,4x1", "1x1,3x2,3x2", "1x1,2x3,2x3", "1x1,1x4,1x4", "1x1,3x4,3x4", "1x1,4x3,4x3", "1x1,2x1,4x2"])
+def test_oracle_matches_reference_on_other_subsampling(oracle, tmp_path, sub):
+    """Fresh streams from the reference's encoder (its CLI takes the sampling factors), decoded by reference and oracle."""
+    import subprocess
+    from libjpeg_b200 import synth
+    w, h = 75, 61
+    ppm = tmp_path / "in.ppm"
+    ppm.write_bytes(b"P6\n%d %d\n255\n" % (w, h) + synth.source_image(w, h, 17).tobytes())
+    jpg = tmp_path / "s.jpg"
+    r = subprocess.run([oracle_binding.REF_CLI, "-q", "80", "-bl", "-s", sub, "-z", "3", str(ppm), str(jpg)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = oracle_binding.reference_decode(str(jpg), str(tmp_path / "s.raw"))
+    rc, px = oracle.decode(jpg.read_bytes())
+    assert rc == 0 and np.array_equal(px.reshape(ref.shape), ref)
+
+
 def test_progressive_golden_is_complete():
     assert len(PNAMES) >= 7
     assert set(np.load(os.path.join(PROGRESSIVE, "progressive_pixels.npz")).files) == set(PNAMES)
