@@ -6,6 +6,8 @@ sys.path.insert(0, '.')
 import numpy as np, torch
 import libjpeg_b200
 base = [open(p, 'rb').read() for p in sorted(glob.glob('libjpeg_b200/build/prog4k/*.jpg'))]
+if not base:
+    sys.exit('no frames under libjpeg_b200/build/prog4k/: make them in the build container first (see the docstring)')
 print('frames', [len(b) for b in base])
 for nf in [int(a) for a in sys.argv[1:]] or [64, 256]:
     frames = [base[i % len(base)] for i in range(nf)]
