@@ -556,16 +556,17 @@ int jpgo_read_info(const uint8_t *data, size_t len, jpgo_info *info) { return wa
 
 /* ------------------------------------------------------------------------------------------------ */
 /* Entropy decode of one scan.  MCU order follows codestream/sequentialscan.cpp:381-428; restart
- * handling follows codestream/entropyparser.hpp:147-160 and entropyparser.cpp:117-136 (the in-sequence
- * case only: a missing / out-of-order RSTn is reported as MALFORMED instead of being resynchronised). */
-static int decode_scan(const uint8_t *d, const jpgo_info *info, const jpgo_scan *sc, decoder_tables *tabs,
+ * handling follows codestream/entropyparser.hpp:147-160 and entropyparser.cpp:117-199, including the
+ * resynchronisation after a missing / out-of-order RSTn.                                              */
+static int decode_scan(const uint8_t *d, size_t len, const jpgo_info *info, const jpgo_scan *sc, decoder_tables *tabs,
                        int lowbit, int32_t *const planes[]) {
     bitreader br;
     int32_t pred[JPGO_MAX_COMP] = {0, 0, 0, 0};
     unsigned skip[JPGO_MAX_COMP] = {0, 0, 0, 0};
     int32_t dummy[64];
-    const uint8_t *end = d + sc->ecs_end;
+    const uint8_t *end = d + sc->ecs_end, *file_end = d + len;
     const int progressive = (info->frame_type == 2);
+    int valid = 1;
     int total = sc->mcu_cols * sc->mcu_rows;
     int togo = sc->restart_interval, next_rst = 0xd0;
     int m, c;
@@ -577,11 +578,34 @@ static int decode_scan(const uint8_t *d, const jpgo_info *info, const jpgo_scan 
     for (m = 0; m < total; m++) {
         int mx = m % sc->mcu_cols, my = m / sc->mcu_cols;
         if (sc->restart_interval) {
-            if (togo == 0) { /* BeginReadMCU -> ParseRestartMarker */
+            if (togo == 0) { /* BeginReadMCU -> ParseRestartMarker, entropyparser.cpp:117-199 */
                 const uint8_t *p = br.p;
                 while (p + 1 < end && p[0] == 0xff && p[1] == 0xff) p++; /* fill bytes, :121-125 */
-                if (!(p + 1 < end && p[0] == 0xff && p[1] == next_rst)) return JPGO_ERR_MALFORMED_STREAM;
-                br_open(&br, p + 2, end); /* SequentialScan::Restart, sequentialscan.cpp:266-274 */
+                if (p + 1 < end && p[0] == 0xff && p[1] == next_rst) {
+                    p += 2;
+                    valid = 1;
+                } else { /* out of sync: advance to the next marker and decide from its id, :137-199 */
+                    valid = -1;
+                    while (valid < 0) {
+                        while (p < file_end && p[0] != 0xff) p++;
+                        if (p + 1 >= file_end) return JPGO_ERR_UNEXPECTED_EOF; /* ran out of data while resynchronising */
+                        if (p[1] >= 0xd0 && p[1] <= 0xd7) {
+                            if (p[1] == next_rst) { /* the decoder was behind: back in step */
+                                p += 2;
+                                valid = 1;
+                            } else if (((p[1] - next_rst) & 7) >= 4) {
+                                p += 2; /* a marker the decoder is already past: drop it, keep looking */
+                            } else {
+                                valid = 0; /* the marker is ahead: this interval is lost, the marker stays */
+                            }
+                        } else if (p[1] >= 0xc0 && p[1] < 0xf0) {
+                            valid = 0; /* some other marker: the segment is over, everything that follows is lost */
+                        } else {
+                            p++; /* FF 00 or garbage: eat the FF and go on */
+                        }
+                    }
+                }
+                br_open(&br, p, end); /* SequentialScan::Restart, sequentialscan.cpp:266-274 (only read when valid) */
                 memset(pred, 0, sizeof(pred));
                 memset(skip, 0, sizeof(skip));
                 next_rst = 0xd0 + ((next_rst + 1) & 7);
@@ -589,6 +613,7 @@ static int decode_scan(const uint8_t *d, const jpgo_info *info, const jpgo_scan 
             }
             togo--;
         }
+        if (!valid) continue; /* the MCUs of an invalid segment are cleared (sequentialscan.cpp:415-419): they stay zero */
         for (c = 0; c < sc->ns; c++) {
             int ci = sc->comp[c];
             int mw = (sc->ns > 1) ? info->hs[ci] : 1, mh = (sc->ns > 1) ? info->vs[ci] : 1;
@@ -652,7 +677,7 @@ int jpgo_decode_coefficients(const uint8_t *data, size_t len, const jpgo_info *i
         if (rc) break;
         rc = build_tables(tabs);
         if (rc) break;
-        rc = decode_scan(data, info, &info->scan[s], tabs, tabs->lowbit[s], planes);
+        rc = decode_scan(data, len, info, &info->scan[s], tabs, tabs->lowbit[s], planes);
     }
     free_tables(tabs);
     free(tabs);

@@ -1,6 +1,7 @@
 """Regenerates tests/golden/damaged/: golden codestreams damaged on purpose, with the pixels the UNMODIFIED reference
-(oracle/_ref/refharness) produces for them. The plain-C oracle only restates the in-sequence restart handling
-(it reports these streams as malformed), so for them the reference's own output is the fixture.
+(oracle/_ref/refharness) produces for them (its resynchronisation, entropyparser.cpp:137-199, clears the intervals the
+stream no longer contains). They pin the oracle's restatement of that logic and the CUDA path's handling of streams
+that end early.
 
 Run in the build container only (needs `make -C oracle ref`):  python tests/golden/make_damaged.py
 """

@@ -130,6 +130,63 @@ def test_oracle_matches_reference_on_other_subsampling(oracle, tmp_path, sub):
     assert rc == 0 and np.array_equal(px.reshape(ref.shape), ref)
 
 
+DAMAGED = os.path.join(GOLDEN, "damaged")
+DNAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(DAMAGED, "*.jpg")))
+
+
+@pytest.mark.parametrize("name", DNAMES)
+def test_oracle_matches_damaged_golden(oracle, name):
+    """Streams that end where a restart marker should stand: the reference's resynchronisation (entropyparser.cpp:137-199)
+    marks the remaining intervals invalid and their MCUs stay cleared; the fixtures hold the reference's pixels."""
+    want = np.load(os.path.join(DAMAGED, "damaged_pixels.npz"))[name]
+    rc, px = oracle.decode(open(os.path.join(DAMAGED, name + ".jpg"), "rb").read())
+    assert rc == 0
+    assert np.array_equal(px.reshape(want.shape), want)
+
+
+@pytest.mark.skipif(not oracle_binding.have_reference(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("damage", ["swap", "drop_marker", "drop_interval", "duplicate", "id_plus_4", "id_plus_2", "id_minus_1",
+                                    "garbage", "cut_mid_interval", "no_eoi"])
+def test_oracle_resynchronises_like_the_reference(oracle, tmp_path, damage):
+    """Restart markers out of sequence, missing, duplicated, buried in garbage: same verdict and same pixels as the reference."""
+    from libjpeg_b200 import synth
+    a = synth.encode(synth.source_image(200, 136, 3), 75, (2, 2), 2).tobytes()
+    sos = a.find(b"\xff\xda")
+    i, at = sos + 2 + ((a[sos + 2] << 8) | a[sos + 3]), []
+    while i + 1 < len(a):
+        if a[i] == 0xFF and 0xD0 <= a[i + 1] <= 0xD7:
+            at.append(i)
+            i += 2
+        else:
+            i += 1
+    b = bytearray(a)
+    if damage == "swap":
+        b[at[2] + 1], b[at[3] + 1] = b[at[3] + 1], b[at[2] + 1]
+    elif damage == "drop_marker":
+        del b[at[3]:at[3] + 2]
+    elif damage == "drop_interval":
+        del b[at[3]:at[4]]
+    elif damage == "duplicate":
+        b[at[2]:at[2]] = a[at[2]:at[2] + 2]
+    elif damage.startswith("id_"):
+        delta = {"id_plus_4": 4, "id_plus_2": 2, "id_minus_1": 7}[damage]
+        b[at[1] + 1] = 0xD0 + ((b[at[1] + 1] - 0xD0 + delta) & 7)
+    elif damage == "garbage":
+        b[at[2]:at[2]] = b"\x12\x34\xff\x00\x56"
+    elif damage == "cut_mid_interval":
+        b = bytearray(a[:at[3] + 20] + b"\xff\xd9")
+    else:
+        b = bytearray(a[:at[3] + 20])
+    jpg = tmp_path / "d.jpg"
+    jpg.write_bytes(bytes(b))
+    ref = oracle_binding.reference_decode(str(jpg), str(tmp_path / "d.raw"))
+    rc, px = oracle.decode(bytes(b))
+    if ref is None:
+        assert rc != 0
+    else:
+        assert rc == 0 and np.array_equal(px.reshape(ref.shape), ref)
+
+
 def test_progressive_golden_is_complete():
     assert len(PNAMES) >= 7
     assert set(np.load(os.path.join(PROGRESSIVE, "progressive_pixels.npz")).files) == set(PNAMES)
