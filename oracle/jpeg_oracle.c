@@ -448,7 +448,8 @@ static int walk(const uint8_t *d, size_t n, jpgo_info *info, decoder_tables *tab
             if (len < 8) return JPGO_ERR_MALFORMED_STREAM;
             info->frame_type = m - 0xc0;
             info->precision = d[p];
-            if (info->precision != 8) return (m == 0xc0) ? JPGO_ERR_MALFORMED_STREAM : JPGO_ERR_NOT_IMPLEMENTED;
+            if (m == 0xc0 && info->precision != 8) return JPGO_ERR_MALFORMED_STREAM; /* frame.cpp: baseline is 8 bit */
+            if (info->precision != 8 && info->precision != 12) return JPGO_ERR_NOT_IMPLEMENTED; /* lossy modes: 8 or 12 */
             info->height = rd16(d, n, p + 1);
             info->width = rd16(d, n, p + 3);
             info->ncomp = d[p + 5];
@@ -881,9 +882,15 @@ static void upsample_block(const splane *p, int sx, int sy, int X, int Y, int32_
     }
 }
 
-static uint8_t clamp255(int64_t v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); } /* ycbcrtrafo.cpp:61 */
+static int64_t clampmax(int64_t v, int64_t max) { return v < 0 ? 0 : (v > max ? max : v); } /* CLAMP(max, v), ycbcrtrafo.cpp:61 */
 
-int jpgo_reconstruct(const jpgo_info *info, int32_t *const planes[], uint8_t *out) {
+/* out8 for 8-bit frames (one byte per sample) or out16 (native-endian 16-bit samples, any precision): what the
+ * reference writes for CTYP_UBYTE / CTYP_UWORD client bitmaps. Level shift, chroma offset and clamp scale with the
+ * precision (1 << (precision - 1), (1 << precision) - 1); the arithmetic is the same (tables.cpp:1877-1891: the LONG
+ * IDCT up to 12 bits).                                                                                  */
+static int reconstruct(const jpgo_info *info, int32_t *const planes[], uint8_t *out8, uint16_t *out16) {
+    const int32_t dcshift = (int32_t)1 << (info->precision - 1);
+    const int64_t maxval = ((int64_t)1 << info->precision) - 1;
     splane sp[JPGO_MAX_COMP];
     int c, rc = JPGO_OK, bx, by, i;
     int W = info->width, H = info->height, nc = info->ncomp;
@@ -910,7 +917,7 @@ int jpgo_reconstruct(const jpgo_info *info, int32_t *const planes[], uint8_t *ou
                 int r;
                 /* blocks outside the reference's stored grid do not exist there; they only ever feed
                  * samples at x >= w or y >= h, which the edge replication below overwrites / nobody reads */
-                jpgo_idct_block(blk, planes[c] + 64 * ((size_t)by * info->bw[c] + bx), info->quant[info->tq[c]], 128);
+                jpgo_idct_block(blk, planes[c] + 64 * ((size_t)by * info->bw[c] + bx), info->quant[info->tq[c]], dcshift);
                 for (r = 0; r < 8; r++) memcpy(p->s + (size_t)(8 * by + r) * p->pw + 1 + 8 * bx, blk + 8 * r, 32);
             }
         }
@@ -936,16 +943,21 @@ int jpgo_reconstruct(const jpgo_info *info, int32_t *const planes[], uint8_t *ou
             /* YCbCrTrafo<UBYTE,count,ClampFlag,trafo,Zero>::YCbCr2RGB, colortrafo/ycbcrtrafo.cpp:679-1008 */
             for (y = 0; y <= ymax; y++) {
                 for (x = 0; x <= xmax; x++) {
-                    uint8_t *px = out + ((size_t)(8 * by + y) * W + (8 * bx + x)) * nc;
+                    const size_t at = ((size_t)(8 * by + y) * W + (8 * bx + x)) * nc;
+                    int64_t v[JPGO_MAX_COMP];
                     if (nc == 3 && info->ycbcr) { /* :842-850, matrix colortransformerfactory.cpp:136-138 */
                         int64_t yv = buf[0][8 * y + x];
-                        int64_t cb = (int64_t)buf[1][8 * y + x] - (128 << 4);
-                        int64_t cr = (int64_t)buf[2][8 * y + x] - (128 << 4);
-                        px[0] = clamp255((yv * 8192 + cb * 0 + cr * 11485 + 65536) >> 17);
-                        px[1] = clamp255((yv * 8192 + cb * -2819 + cr * -5850 + 65536) >> 17);
-                        px[2] = clamp255((yv * 8192 + cb * 14516 + cr * 0 + 65536) >> 17);
+                        int64_t cb = (int64_t)buf[1][8 * y + x] - ((int64_t)dcshift << 4);
+                        int64_t cr = (int64_t)buf[2][8 * y + x] - ((int64_t)dcshift << 4);
+                        v[0] = clampmax((yv * 8192 + cb * 0 + cr * 11485 + 65536) >> 17, maxval);
+                        v[1] = clampmax((yv * 8192 + cb * -2819 + cr * -5850 + 65536) >> 17, maxval);
+                        v[2] = clampmax((yv * 8192 + cb * 14516 + cr * 0 + 65536) >> 17, maxval);
                     } else { /* identity: COLOR_TO_INT, tools/numerics.hpp:69 */
-                        for (c = 0; c < nc; c++) px[c] = clamp255(((int64_t)buf[c][8 * y + x] + 8) >> 4);
+                        for (c = 0; c < nc; c++) v[c] = clampmax(((int64_t)buf[c][8 * y + x] + 8) >> 4, maxval);
+                    }
+                    for (c = 0; c < nc; c++) {
+                        if (out16) out16[at + c] = (uint16_t)v[c];
+                        else out8[at + c] = (uint8_t)v[c];
                     }
                 }
             }
@@ -956,7 +968,24 @@ done:
     return rc;
 }
 
+int jpgo_reconstruct(const jpgo_info *info, int32_t *const planes[], uint8_t *out) {
+    if (info->precision != 8) return JPGO_ERR_INVALID_PARAMETER; /* one byte per sample only holds 8-bit frames */
+    return reconstruct(info, planes, out, NULL);
+}
+
+int jpgo_reconstruct16(const jpgo_info *info, int32_t *const planes[], uint16_t *out) { return reconstruct(info, planes, NULL, out); }
+
+static int decode_any(const uint8_t *data, size_t len, uint8_t *out8, uint16_t *out16, size_t cap, jpgo_info *info_out);
+
 int jpgo_decode(const uint8_t *data, size_t len, uint8_t *out, size_t cap, jpgo_info *info_out) {
+    return decode_any(data, len, out, NULL, cap, info_out);
+}
+
+int jpgo_decode16(const uint8_t *data, size_t len, uint16_t *out, size_t cap_samples, jpgo_info *info_out) {
+    return decode_any(data, len, NULL, out, cap_samples, info_out);
+}
+
+static int decode_any(const uint8_t *data, size_t len, uint8_t *out8, uint16_t *out16, size_t cap, jpgo_info *info_out) {
     jpgo_info info;
     int32_t *planes[JPGO_MAX_COMP] = {0, 0, 0, 0};
     int rc, c;
@@ -969,7 +998,7 @@ int jpgo_decode(const uint8_t *data, size_t len, uint8_t *out, size_t cap, jpgo_
         if (!planes[c]) rc = JPGO_ERR_OUT_OF_MEMORY;
     }
     if (!rc) rc = jpgo_decode_coefficients(data, len, &info, planes);
-    if (!rc) rc = jpgo_reconstruct(&info, planes, out);
+    if (!rc) rc = out16 ? jpgo_reconstruct16(&info, planes, out16) : jpgo_reconstruct(&info, planes, out8);
     for (c = 0; c < info.ncomp; c++) free(planes[c]);
     return rc;
 }

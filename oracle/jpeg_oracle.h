@@ -8,7 +8,7 @@
  * YCbCr->RGB -> 8-bit store.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
  * use it, and only as the checker.  The product (libjpeg_b200/) never links or calls it.
  *
- * Parity is PINNED: tests/test_oracle_vs_reference.py compares this restatement byte for byte with the
+ * Parity is PINNED: tests/test_oracle.py compares this restatement byte for byte with the
  * unmodified reference built by oracle/Makefile (oracle/_ref/refharness) and with the committed golden
  * fixtures under tests/golden/ that were produced by that reference build.
  */
@@ -70,8 +70,11 @@ int jpgo_decode_coefficients(const uint8_t *data, size_t len, const jpgo_info *i
  * row pitch width*ncomp (what the reference writes through BitMapHook with BytesPerPixel = depth). */
 int jpgo_reconstruct(const jpgo_info *info, int32_t *const planes[], uint8_t *out);
 
-/* Whole path. out must hold width*height*ncomp bytes. */
+/* Whole path. out must hold width*height*ncomp bytes; 8-bit frames only. */
 int jpgo_decode(const uint8_t *data, size_t len, uint8_t *out, size_t out_capacity, jpgo_info *info_out);
+/* The same into native-endian 16-bit samples (what a CTYP_UWORD client bitmap receives): 8- and 12-bit frames. */
+int jpgo_decode16(const uint8_t *data, size_t len, uint16_t *out, size_t capacity_in_samples, jpgo_info *info_out);
+int jpgo_reconstruct16(const jpgo_info *info, int32_t *const planes[], uint16_t *out);
 
 /* building blocks, exported so the tests can hit them directly */
 void jpgo_idct_block(int32_t *target, const int32_t *source, const uint16_t *delta_raster, int32_t dcoffset);

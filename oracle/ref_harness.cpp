@@ -50,6 +50,7 @@ static JPG_LONG MemIOHook(struct JPG_Hook *hook, struct JPG_TagItem *tags) {
 struct Canvas {
     unsigned char *mem;
     unsigned width, height, depth;
+    unsigned bytes; /* per sample: 1 for precision <= 8 (CTYP_UBYTE), 2 above (CTYP_UWORD) */
 };
 
 static JPG_LONG BitmapHookFn(struct JPG_Hook *hook, struct JPG_TagItem *tags) {
@@ -59,12 +60,12 @@ static JPG_LONG BitmapHookFn(struct JPG_Hook *hook, struct JPG_TagItem *tags) {
         unsigned maxy = (unsigned)tags->GetTagData(JPGTAG_BIO_MAXY);
         /* whole-frame canvas; height rounded up so that the partial last block row is written (the
          * reference reconstructs BIO_HEIGHT >> 3 block rows, control/blockbitmaprequester.cpp:1240) */
-        tags->SetTagPtr(JPGTAG_BIO_MEMORY, cv->mem + comp);
+        tags->SetTagPtr(JPGTAG_BIO_MEMORY, cv->mem + comp * cv->bytes);
         tags->SetTagData(JPGTAG_BIO_WIDTH, cv->width);
         tags->SetTagData(JPGTAG_BIO_HEIGHT, ((maxy + 8) & ~7u));
-        tags->SetTagData(JPGTAG_BIO_BYTESPERROW, cv->width * cv->depth);
-        tags->SetTagData(JPGTAG_BIO_BYTESPERPIXEL, cv->depth);
-        tags->SetTagData(JPGTAG_BIO_PIXELTYPE, CTYP_UBYTE);
+        tags->SetTagData(JPGTAG_BIO_BYTESPERROW, cv->width * cv->depth * cv->bytes);
+        tags->SetTagData(JPGTAG_BIO_BYTESPERPIXEL, cv->depth * cv->bytes);
+        tags->SetTagData(JPGTAG_BIO_PIXELTYPE, cv->bytes == 2 ? CTYP_UWORD : CTYP_UBYTE);
     }
     return 0;
 }
@@ -112,12 +113,14 @@ static int decode_once(const unsigned char *data, size_t size, unsigned stripe, 
         if (jpeg->GetInformation(itags)) {
             unsigned w = itags->GetTagData(JPGTAG_IMAGE_WIDTH), h = itags->GetTagData(JPGTAG_IMAGE_HEIGHT);
             unsigned d = itags->GetTagData(JPGTAG_IMAGE_DEPTH);
-            if (!cv->mem || cv->width != w || cv->height != h || cv->depth != d) {
+            unsigned bytes = (itags->GetTagData(JPGTAG_IMAGE_PRECISION) > 8) ? 2 : 1;
+            if (!cv->mem || cv->width != w || cv->height != h || cv->depth != d || cv->bytes != bytes) {
                 free(cv->mem);
-                cv->mem = (unsigned char *)calloc((size_t)w * ((h + 7) & ~7u) * d, 1);
+                cv->mem = (unsigned char *)calloc((size_t)w * ((h + 7) & ~7u) * d * bytes, 1);
                 cv->width = w;
                 cv->height = h;
                 cv->depth = d;
+                cv->bytes = bytes;
             }
             struct JPG_Hook bmhook(BitmapHookFn, cv);
             struct JPG_TagItem dtags[] = {JPG_PointerTag(JPGTAG_BIH_HOOK, &bmhook), JPG_ValueTag(JPGTAG_DECODER_MINY, 0),
@@ -153,7 +156,7 @@ int main(int argc, char **argv) {
         size_t size;
         unsigned char *data = slurp(argv[2], &size);
         unsigned stripe = (argc > 4) ? (unsigned)atoi(argv[4]) : 8;
-        Canvas cv = {NULL, 0, 0, 0};
+        Canvas cv = {NULL, 0, 0, 0, 1};
         int err = 0;
         if (!data) return 2;
         if (decode_once(data, size, stripe, &cv, NULL, NULL, &err)) {
@@ -161,9 +164,10 @@ int main(int argc, char **argv) {
             return 1;
         }
         FILE *o = fopen(argv[3], "wb");
-        fwrite(cv.mem, 1, (size_t)cv.width * cv.height * cv.depth, o);
+        fwrite(cv.mem, 1, (size_t)cv.width * cv.height * cv.depth * cv.bytes, o);
         fclose(o);
-        printf("%u %u %u\n", cv.width, cv.height, cv.depth);
+        if (cv.bytes == 2) printf("%u %u %u 16\n", cv.width, cv.height, cv.depth); /* native-endian 16-bit samples */
+        else printf("%u %u %u\n", cv.width, cv.height, cv.depth);
         return 0;
     }
     if (argc >= 5 && !strcmp(argv[1], "bench")) {
@@ -186,7 +190,7 @@ int main(int argc, char **argv) {
         double t0 = now();
         for (int p = 0; p < procs; p++) {
             if (fork() == 0) {
-                Canvas cv = {NULL, 0, 0, 0};
+                Canvas cv = {NULL, 0, 0, 0, 1};
                 double tr = 0, td = 0;
                 int fail = 0;
                 for (int i = 0; i < iters; i++) fail |= decode_once(datas[(p + i) % nfiles], sizes[(p + i) % nfiles], 8, &cv, &tr, &td, NULL);

@@ -36,6 +36,8 @@ class Oracle:
         lib.jpgo_read_info.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(InfoStruct)]
         lib.jpgo_decode.restype = ctypes.c_int
         lib.jpgo_decode.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(InfoStruct)]
+        lib.jpgo_decode16.restype = ctypes.c_int
+        lib.jpgo_decode16.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(InfoStruct)]
         lib.jpgo_decode_coefficients.restype = ctypes.c_int
         lib.jpgo_decode_coefficients.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(InfoStruct), ctypes.POINTER(ctypes.c_void_p)]
         lib.jpgo_idct_block.restype = None
@@ -55,6 +57,16 @@ class Oracle:
             return rc, None
         out = np.zeros((s.height, s.width, s.ncomp), dtype=np.uint8)
         rc = self.lib.jpgo_decode(data.ctypes.data, data.size, out.ctypes.data, out.size, ctypes.byref(s))
+        return rc, (out if rc == 0 else None)
+
+    def decode16(self, data):
+        """-> (rc, pixels [H,W,C] uint16 or None): 8- and 12-bit frames, what a CTYP_UWORD client bitmap receives"""
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        rc, s = self.info(data)
+        if rc != 0:
+            return rc, None
+        out = np.zeros((s.height, s.width, s.ncomp), dtype=np.uint16)
+        rc = self.lib.jpgo_decode16(data.ctypes.data, data.size, out.ctypes.data, out.size, ctypes.byref(s))
         return rc, (out if rc == 0 else None)
 
     def coefficients(self, data):
@@ -95,8 +107,10 @@ def reference_decode(jpg_path, tmp_raw):
     r = subprocess.run([REF_HARNESS, "decode", jpg_path, tmp_raw], capture_output=True, text=True)
     if r.returncode != 0:
         return None
-    w, h, d = map(int, r.stdout.split())
-    return np.fromfile(tmp_raw, dtype=np.uint8).reshape(h, w, d)
+    fields = r.stdout.split()
+    w, h, d = map(int, fields[:3])
+    wide = len(fields) > 3  # "16": native-endian 16-bit samples (precision above 8)
+    return np.fromfile(tmp_raw, dtype=np.uint16 if wide else np.uint8).reshape(h, w, d)
 
 
 def with_dc_quantiser(data, value):

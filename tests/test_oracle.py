@@ -187,6 +187,28 @@ def test_oracle_resynchronises_like_the_reference(oracle, tmp_path, damage):
         assert rc == 0 and np.array_equal(px.reshape(ref.shape), ref)
 
 
+DEEP12 = os.path.join(GOLDEN, "deep12")
+D12NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(DEEP12, "*.jpg")))
+
+
+@pytest.mark.parametrize("name", D12NAMES)
+def test_oracle_matches_12bit_golden(oracle, name):
+    """SURVEY 8f4 groundwork: 12-bit frames (SOF1 and SOF2) into 16-bit samples, level shift 2048, clamp 4095."""
+    want = np.load(os.path.join(DEEP12, "deep12_pixels.npz"))[name]
+    data = open(os.path.join(DEEP12, name + ".jpg"), "rb").read()
+    rc, px = oracle.decode16(data)
+    assert rc == 0 and px.dtype == np.uint16
+    assert np.array_equal(px, want)
+    rc8, _ = oracle.decode(data)   # one byte per sample cannot hold a 12-bit frame
+    assert rc8 == -1024
+
+
+def test_oracle_16bit_output_of_8bit_frames(oracle, golden_pixels):
+    for name in NAMES[:4]:
+        rc, px = oracle.decode16(open(os.path.join(GOLDEN, name + ".jpg"), "rb").read())
+        assert rc == 0 and np.array_equal(px.reshape(golden_pixels[name].shape), golden_pixels[name].astype(np.uint16))
+
+
 def test_progressive_golden_is_complete():
     assert len(PNAMES) >= 7
     assert set(np.load(os.path.join(PROGRESSIVE, "progressive_pixels.npz")).files) == set(PNAMES)
