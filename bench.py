@@ -3,26 +3,36 @@
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
     python bench.py --impl reference --gpus N --steps K --warmup W
+    python bench.py --workload cfg2|cfg3|cfg4|cfg3n ...       (default cfg3 = the configuration the metric is quoted on)
+    python bench.py --global-batch 4096 ...                   (strong scaling: BASELINE config 3's batch split over N GPUs)
 
-Workload (config.workload): BASELINE.json configs[2] -- 3840x2160 4:2:0 q75 baseline frames, one restart
-interval per MCU row (DRI = 240), Annex-K tables, built from `--distinct` distinct synthetic frames
-S(3840,2160,seed) tiled over the batch.  One "step" = one pass of the hot path (unstuff + entropy +
-reconstruction kernels) over 840 frames per GPU: 840 x 135 restart intervals = one full wave of the persistent
-entropy kernel (148 SMs x 24 warps x 32 lanes); cfg3's 4096-frame batch is 4.9 such steps on one GPU, weak scaling
-(840 frames per GPU per step) over N GPUs.
+Workloads (config.workload; tools/bench_inputs.py): the synthetic source images S(w,h,seed) of SURVEY.md 8d encoded by the
+REFERENCE ENCODER (oracle/_ref/jpeg, named in config.encoder; the repo's own generator only where that binary is absent),
+`--distinct` distinct frames tiled over the batch.
+  cfg3 (default): 3840x2160 4:2:0 q75 baseline, DRI = 240.  One step = one pass of the hot path over 840 frames per GPU
+        (840 x 135 restart intervals = one full wave of the persistent entropy kernel); cfg3's 4096-frame batch is 4.9 steps
+        of one GPU.  Weak scaling (840 frames per GPU per step) unless --global-batch is given.
+  cfg2: 1920x1080 4:2:0 q75, DRI = 120, 4096 frames per step on one GPU (BASELINE configs[1]).
+  cfg4: 3840x2160 4:2:0 q75 progressive (ten scans), 1024 frames per step on one GPU (BASELINE configs[3]).
+  cfg3n: cfg3 without restart markers (DRI-less streams).
 
-value  : frames/s with the compressed bytes already resident in HBM (device-timed, CUDA events, max over ranks).
-e2e    : frames/s through the C ABI with HOST buffers: every step uploads the packed codestreams from pinned
-         host memory, decodes, and downloads every decoded pixel into pinned host memory (chunked, three
-         streams).  Host-side marker indexing / packing (b200jpg_batch_create) happens once, outside the timing.
-roofline: the dominant stage by time, reconstruction (idct_planes_kernel + reconstruct_kernel): algorithmic bytes
-         = 128 B x stored blocks + 3 W H over its CUDA-event duration against MEASURED_PEAKS.json
-         hbm_gbs, plus `int32`: the same launches against the measured int32 issue rate (b200jpg_microbench_int32),
-         the roofline north_star names for this stage.  roofline_entropy: stage a (unstuff + entropy kernels),
-         algorithmic bytes = ECS bytes + 128 B x stored blocks, against hbm_gbs.  `traffic` = DRAM bytes per launch
-         measured by ncu (profiles/), scaled from the per-frame figure of the captured run.
-cpu_baseline / --impl reference: the unmodified reference (oracle/_ref/refharness: public API, memory hook,
-         8-row stripes), one process per hardware thread, on a bounded sample of the same frames.
+value  : frames/s with the compressed bytes AND the restart index already resident in HBM (device-timed, CUDA events on the
+         launching stream, max over ranks): K x (unstuff + entropy + reconstruction kernels) on one stream.
+         `restart_index_ms` is the once-per-upload restart_index_kernel stated beside it; `value_with_restart_index` folds it in.
+pinned_to_device_rgb : SURVEY 8d's primary accounting -- compressed bytes resident in PINNED HOST memory -> RGB resident in
+         DEVICE memory: per chunk H2D + restart_index_kernel + all decode kernels, chunks pipelined over three streams, no D2H;
+         host marker parsing / packing (b200jpg_batch_create) happened before the timed region.
+e2e    : frames/s through the C ABI with HOST buffers, everything inside the timed region: per chunk b200jpg_batch_create
+         (host marker parse + packing into pinned memory, one chunk ahead in a second thread) -> H2D -> kernels -> D2H of
+         every decoded pixel into pinned host memory -> batch_destroy.
+roofline: the dominant stage by time. Reconstruction: algorithmic bytes = 128 B x stored blocks + output bytes
+         over its CUDA-event duration against MEASURED_PEAKS.json hbm_gbs, plus `int32`: the same launches against the
+         measured int32 issue rate (b200jpg_microbench_int32), the roofline north_star names for this stage.
+         roofline_entropy: stage a (unstuff + entropy kernels), algorithmic bytes = ECS bytes + 128 B x stored blocks.
+         `traffic` = DRAM bytes per launch measured by ncu (profiles/), scaled from the per-frame figure of the captured run.
+cpu_baseline / --impl reference: the unmodified reference (oracle/_ref/refharness: public API, memory hook, 8-row stripes)
+         as forked worker processes on a bounded sample of the same frames; reports the processes used, the physical cores,
+         CPU model, affinity and cgroup quota of the box, and the parallelism the box actually delivered.
 """
 import argparse
 import json
@@ -38,26 +48,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-W, H, QUALITY, SUB, DRI = 3840, 2160, 75, (2, 2), 240
-FRAMES_PER_GPU = 840
-# DRAM bytes per cfg3 frame measured with ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum), profiles/r01_*:
-#   unstuff 2.51 MB, entropy_decode 26.83 MB, idct_planes 16.53 MB, reconstruct 49.72 MB  (r01_840frames_metrics.csv / 840)
-NCU_DRAM_BYTES_PER_FRAME = {"entropy": 2.51e6 + 26.83e6, "recon": 16.53e6 + 49.72e6}
-INT_OPS_PER_4K_FRAME = 520e6  # IDCT 205 M + upsample 133 M + colour 182 M
+from tools import bench_inputs  # noqa: E402
 
-
-def _gen_one(seed):
-    from libjpeg_b200 import synth
-    return synth.frame(W, H, seed, QUALITY, SUB, DRI).tobytes()
-
-
-def make_frames(distinct, workers):
-    from concurrent.futures import ProcessPoolExecutor
-    seeds = list(range(1, distinct + 1))
-    if workers <= 1:
-        return [_gen_one(s) for s in seeds]
-    with ProcessPoolExecutor(max_workers=workers) as ex:
-        return list(ex.map(_gen_one, seeds))
+DEFAULT_FRAMES = {"cfg3": 840, "cfg2": 4096, "cfg4": 1024, "cfg3n": 840, "cfg2n": 4096, "cfg1": 8192}
+# DRAM bytes per cfg3 frame measured with ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum); see profiles/
+NCU_DRAM_BYTES_PER_FRAME = {"cfg3": {"entropy": None, "recon": None}}
+try:
+    NCU_DRAM_BYTES_PER_FRAME.update(json.load(open(os.path.join(ROOT, "profiles", "dram_bytes_per_frame.json"))))
+except Exception:
+    pass
+INT_OPS_PER_PIXEL_420 = 520e6 / (3840 * 2160)  # IDCT 205 M + upsample 133 M + colour 182 M per 4K 4:2:0 frame
 
 
 class ClockSampler:
@@ -119,7 +119,45 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline
+# host CPU facts for the CPU arm
+def cpu_facts():
+    """Physical cores, model, what this process may use (affinity, cgroup quota): the denominators of the CPU arm."""
+    model, cores, logical = None, set(), 0
+    try:
+        phys = core = None
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name") and model is None:
+                model = ln.split(":", 1)[1].strip()
+            elif ln.startswith("processor"):
+                logical += 1
+            elif ln.startswith("physical id"):
+                phys = ln.split(":", 1)[1].strip()
+            elif ln.startswith("core id"):
+                core = ln.split(":", 1)[1].strip()
+                cores.add((phys, core))
+    except Exception:
+        pass
+    try:
+        affinity = len(os.sched_getaffinity(0))
+    except Exception:
+        affinity = None
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                quota = "unlimited" if txt[0] == "max" else round(int(txt[0]) / int(txt[1]), 2)
+            else:
+                q = int(txt[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                quota = "unlimited" if q < 0 else round(q / period, 2)
+            break
+        except Exception:
+            continue
+    return {"cpu_model": model, "physical_cores": len(cores) or None, "logical_cpus": logical or os.cpu_count(),
+            "affinity_cpus": affinity, "cgroup_cpu_quota": quota}
+
+
 def run_reference(frames, procs, iters):
     """Unmodified reference through its public API (oracle/_ref/refharness), `procs` forked workers each decoding
     `iters` frames (cycling over the distinct frames). Falls back to the plain-C oracle port when the reference
@@ -148,19 +186,6 @@ def run_reference(frames, procs, iters):
     return {"frames": procs * iters, "procs": procs, "wall_s": wall, "fps": procs * iters / wall, "kind": "port"}
 
 
-def best_reference_config(frames, ncpu):
-    """The reference is single threaded and allocation heavy: beyond a few dozen processes this box's memory system, not
-    its cores, limits it. Scan the process count (short samples) and keep the fastest: that is the CPU arm's best case."""
-    cands = sorted(set(max(1, c) for c in (1, ncpu, ncpu // 2, ncpu // 4, ncpu // 8, 3 * ncpu // 8)))  # 1: the per-core rate
-    best, scan = None, {}
-    for procs in cands:
-        d = run_reference(frames, procs, 8 if procs == 1 else max(2, 128 // procs))
-        scan[procs] = round(d["fps"], 1)
-        if best is None or d["fps"] > best[1]:
-            best = (procs, d["fps"])
-    return best[0], scan
-
-
 def _oracle_worker(args):
     frames, iters, p = args
     from tests import oracle_binding
@@ -168,6 +193,41 @@ def _oracle_worker(args):
     for i in range(iters):
         rc, _ = o.decode(frames[(p + i) % len(frames)])
         assert rc == 0
+
+
+def best_reference_config(frames, ncpu, per_frame_s):
+    """The reference is single threaded and allocation heavy: beyond a few dozen processes the box's memory system (or a
+    CPU quota), not its core count, limits it. Scan the process count (short samples) and keep the fastest: that is the
+    CPU arm's best case. Returns (procs, {procs: fps})."""
+    cands = sorted(set(max(1, c) for c in (1, ncpu, ncpu // 2, ncpu // 4, ncpu // 8, 3 * ncpu // 8)))  # 1: the per-core rate
+    best, scan = None, {}
+    for procs in cands:
+        iters = max(2, int(round(1.5 / max(per_frame_s, 1e-3)))) if procs == 1 else max(2, int(round(4.0 / max(per_frame_s, 1e-3) / 8)))
+        d = run_reference(frames, procs, min(iters, 64))
+        scan[procs] = round(d["fps"], 1)
+        if best is None or d["fps"] > best[1]:
+            best = (procs, d["fps"])
+    return best[0], scan
+
+
+def cpu_arm(frames, ncpu, workload, budget_s=20.0):
+    """-> the cpu_baseline object + the fps. A bounded sample: about `budget_s` seconds of wall time on the best process count."""
+    w, h = bench_inputs.WORKLOADS[workload][:2]
+    per_frame_s = 0.11 * (w * h) / (3840 * 2160)  # about 9 frames/s per process at 4K on this class of host
+    procs, scan = best_reference_config(frames, ncpu, per_frame_s)
+    iters = max(4, int(budget_s * max(scan[procs], 1.0) / procs))
+    cb = run_reference(frames, procs, iters)
+    facts = cpu_facts()
+    one = scan.get(1) or None
+    out = {"value": cb["fps"], "unit": "frames/s", "cores": cb["procs"], "kind": cb["kind"],
+           "sample": "%d frames (%d distinct %s frames cycled) in %d worker processes = the fastest of the process counts scanned "
+                     "(%s fps); Read + 8-row-striped DisplayRectangle through the reference's public API"
+                     % (cb["frames"], min(len(frames), 8), workload, cb["procs"], scan),
+           "processes": cb["procs"], "fps_one_process": one,
+           "effective_parallelism": round(cb["fps"] / one, 1) if one else None,
+           "read_ms_per_frame": cb.get("read_ms_per_frame"), "display_ms_per_frame": cb.get("display_ms_per_frame")}
+    out.update(facts)
+    return out
 
 
 def bind_to_gpu_numa_node(index):
@@ -198,10 +258,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
+    ap.add_argument("--workload", default="cfg3", choices=sorted(DEFAULT_FRAMES))
+    ap.add_argument("--frames-per-gpu", type=int, default=0, help="frames per GPU per step (default: per workload)")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: total frames per step, split over the GPUs")
     ap.add_argument("--distinct", type=int, default=64)
     ap.add_argument("--e2e-chunk", type=int, default=32)
-    ap.add_argument("--streams", type=int, default=1, help="batches in flight per GPU (each on its own CUDA stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -210,33 +271,43 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ncpu = os.cpu_count() or 8
-    config = {"workload": "cfg3: 3840x2160 4:2:0 q75 baseline, DRI=240 (one restart interval per MCU row), Annex-K tables",
-              "frames_per_gpu": args.frames_per_gpu, "global_batch": args.frames_per_gpu * max(world, 1), "steps_in_flight": args.streams,
+    W, H, QUALITY, SUB, DRI, PROG, desc = bench_inputs.WORKLOADS[args.workload]
+    strong = args.global_batch > 0
+    if strong:
+        nf = (args.global_batch + world - 1) // world
+        global_batch = args.global_batch
+    else:
+        nf = args.frames_per_gpu or DEFAULT_FRAMES[args.workload]
+        global_batch = nf * max(world, 1)
+    mb_codestream = {"cfg2": 0.37, "cfg2n": 0.37, "cfg1": 0.25}.get(args.workload, 1.45)
+    config = {"workload": desc, "encoder": bench_inputs.encoder_name(args.workload), "frames_per_gpu": nf, "global_batch": global_batch,
               "distinct_frames": args.distinct, "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
-              "l2": "inputs larger than L2 (no flush needed): %.1f GB codestreams + %.1f GB coefficients per step vs 126 MB L2"
-                    % (args.frames_per_gpu * 1.27e-3, args.frames_per_gpu * 24.9e-3)}
+              "l2": "inputs larger than L2 (no flush needed): about %.1f GB codestreams + %.1f GB coefficients per step vs 126 MB L2"
+                    % (nf * mb_codestream * 1e-3, nf * W * H * 3e-9)}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        frames = make_frames(8, min(8, ncpu))
-        procs, scan = best_reference_config(frames, ncpu)  # doubles as the warm-up
-        iters = max(8, 512 // procs)
+        frames = bench_inputs.make_frames(args.workload, 8, min(8, ncpu))
         vals, last = [], None
+        # warm-up = the scan over process counts inside cpu_arm; each timed step is a bounded sample of the same workload
+        first = cpu_arm(frames, ncpu, args.workload, budget_s=8.0)
+        procs = first["processes"]
+        iters = max(4, int(12.0 * max(first["value"], 1.0) / procs))
         t0 = time.time()
         for _ in range(args.steps):
             last = run_reference(frames, procs, iters)
             vals.append(last["fps"])
         dt = time.time() - t0
         v = statistics.mean(vals)
+        cb = dict(first)
+        cb.update({"value": v, "read_ms_per_frame": last.get("read_ms_per_frame"), "display_ms_per_frame": last.get("display_ms_per_frame"),
+                   "sample": "%d frames per step (8 distinct %s frames cycled) in %d worker processes; " % (procs * iters, args.workload, procs)
+                             + first["sample"]})
         line = {"impl": "reference", "metric": "4K 4:2:0 q75 frames/sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": v, "unit": "frames/s", "cores": procs, "kind": last["kind"],
-                                 "sample": "%d frames per step (8 distinct cfg3 frames cycled), %d worker processes = the fastest of the "
-                                           "process counts scanned on this %d-thread host (%s fps), "
-                                           "Read + 8-row-striped DisplayRectangle through the reference's public API" % (procs * iters, procs, ncpu, scan),
-                                 "read_ms_per_frame": last.get("read_ms_per_frame"), "display_ms_per_frame": last.get("display_ms_per_frame")},
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+                "cpu_baseline": cb,
                 "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return 0
@@ -252,42 +323,26 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # ---- inputs (untimed): distinct synthetic frames, tiled over this rank's shard of the global batch
+    # ---- inputs (untimed): distinct frames of the workload, tiled over this rank's shard of the global batch
     workers = max(1, min(16, ncpu // max(world, 1)))
-    base = make_frames(args.distinct, workers)
+    base = bench_inputs.make_frames(args.workload, args.distinct, workers)
     from libjpeg_b200 import sharding
-    nf = args.frames_per_gpu
-    first, last = sharding.shard_range(nf * world, rank, world)  # weak scaling: the global batch grows with N
+    first, last = sharding.shard_range(global_batch, rank, world)
     frames = [base[i % len(base)] for i in range(first, last)]
+    nf = len(frames)
     mean_bytes = sum(len(b) for b in base) / len(base)
 
-    # `--streams` batches in flight per GPU: step k runs on stream k % streams with its own coefficient / sample /
-    # output buffers, so the latency-bound entropy kernel of one step overlaps the issue-bound reconstruction of another
-    nstreams = max(1, args.streams)
-    decs = [libjpeg_b200.BatchDecoder(frames, device=local_rank) for _ in range(nstreams)]
-    dec = decs[0]
+    dec = libjpeg_b200.BatchDecoder(frames, device=local_rank)
     # ---- the ONE collective of the path: rank 0 broadcasts the shared Huffman/quantisation table blob (NCCL)
-    blob = torch.from_numpy(dec.export_tables()).cuda()
     if dist is not None:
+        blob = torch.from_numpy(dec.export_tables()).cuda()
         mine = blob.clone()
         dist.broadcast(blob, src=0)
         assert torch.equal(mine, blob), "frames of this rank use tables different from rank 0's"
-        for d in decs:
-            d.import_tables(blob.cpu().numpy())
-    outs = [d.new_output() for d in decs]
-    out = outs[0]
-    # Stage a (few, long-running, latency-bound CTAs) runs on a HIGH-priority stream, stage b (half a million short,
-    # issue-bound CTAs) on a low-priority one: the block scheduler then slots the entropy CTAs of step k+1 in between the
-    # reconstruction CTAs of step k instead of queueing them behind the whole grid.
-    try:
-        lo_pri, hi_pri = torch.cuda.Stream.priority_range()  # (lowest, highest) = e.g. (0, -5)
-    except Exception:
-        lo_pri, hi_pri = 0, -1
-    s_a = torch.cuda.Stream(priority=hi_pri)
-    s_b = torch.cuda.Stream(priority=lo_pri)
-    stream = s_a
-    for d in decs:
-        d.upload(s_a)
+        dec.import_tables(blob.cpu().numpy())
+    out = dec.new_output()
+    stream = torch.cuda.Stream()
+    dec.upload(stream)
     torch.cuda.synchronize()
 
     def barrier():
@@ -295,71 +350,52 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    ev_a = [torch.cuda.Event() for _ in range(nstreams)]
-    ev_b = [torch.cuda.Event() for _ in range(nstreams)]
-    launch_count = [0]
-    trace = []  # (event at start of a, end of a, start of b, end of b) of every timed step, for the overlap diagnosis
-
-    def run_steps(k0, count):
-        """steps k0 .. k0+count-1: entropy of step k on s_a, reconstruction on s_b; batch k % nstreams is reused only
-        after its previous reconstruction has finished"""
-        for k in range(k0, k0 + count):
-            i = k % nstreams
-            d = decs[i]
-            if k >= nstreams:
-                s_a.wait_event(ev_b[i])
-            t = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            t[0].record(s_a)
-            d.decode_entropy(s_a)
-            launch_count[0] += d.launches
-            t[1].record(s_a)
-            ev_a[i].record(s_a)
-            s_b.wait_event(ev_a[i])
-            t[2].record(s_b)
-            d.reconstruct(outs[i], s_b)
-            launch_count[0] += d.launches
-            t[3].record(s_b)
-            ev_b[i].record(s_b)
-            trace.append(t)
-
-    run_steps(0, max(args.warmup, 3))
+    for _ in range(max(args.warmup, 3)):
+        dec.decode(out, stream)
     torch.cuda.synchronize()
-    for d in decs:
-        bad = [i for i in range(nf) if d.status(i) != 0]
-        assert not bad, "decode reported errors for frames %s" % bad[:8]
-    for o in outs[1:]:
-        assert torch.equal(o, outs[0])
+    bad = [i for i in range(nf) if dec.status(i) != 0]
+    assert not bad, "decode reported errors for frames %s" % bad[:8]
 
-    # ---- value: K steps, device-timed
+    # ---- value: K steps on one stream, device-timed
     sampler = ClockSampler(local_rank)
-    ent_ms, rec_ms, uns_ms = [], [], []
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(s_a)
-    s_b.wait_event(e0)
-    launch_count[0] = 0
-    run_steps(nstreams, args.steps)  # k0 >= nstreams: the reuse guards are active from the first timed step
-    s_a.wait_stream(s_b)
-    e1.record(s_a)
+    launches = 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        dec.decode(out, stream)
+        launches += dec.launches
+    e1.record(stream)
     barrier()
-    launches = launch_count[0]
     clocks = sampler.stop()
     total_ms = e0.elapsed_time(e1)
-    timed = trace[-args.steps:]
-    overlap = {"entropy_ms_in_pipeline": statistics.mean(t[0].elapsed_time(t[1]) for t in timed),
-               "reconstruction_ms_in_pipeline": statistics.mean(t[2].elapsed_time(t[3]) for t in timed),
-               "a_start_offsets_ms": [round(e0.elapsed_time(t[0]), 2) for t in timed[:6]],
-               "b_start_offsets_ms": [round(e0.elapsed_time(t[2]), 2) for t in timed[:6]]}
     t = torch.tensor([total_ms], device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = nf * world * args.steps / (total_ms * 1e-3)
+    nframes_all = global_batch
+    value = nframes_all * args.steps / (total_ms * 1e-3)
 
-    # per-stage durations for the rooflines: single stream, one step at a time, CUDA events recorded by the library
-    # on the launching stream around each stage
+    # the once-per-upload restart index, timed alone (idempotent re-run)
+    idx_ms = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        dec.reindex(stream)
+        b.record(stream)
+        torch.cuda.synchronize()
+        idx_ms.append(a.elapsed_time(b))
+    index_ms = statistics.mean(idx_ms)
+    ti = torch.tensor([index_ms], device="cuda")
+    if dist is not None:
+        dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+    index_ms = float(ti.item())
+
+    # per-stage durations for the rooflines: one step at a time, CUDA events recorded by the library on the launching
+    # stream around each stage
+    ent_ms, rec_ms, uns_ms = [], [], []
     dec.enable_timing(True)
     for _ in range(3):
         dec.decode(out, stream)
@@ -368,39 +404,92 @@ def main():
         ent_ms.append(a)
         rec_ms.append(b)
         uns_ms.append(dec.last_unstuff_ms())
+    dec.enable_timing(False)
     ent = statistics.mean(ent_ms)
     rec = statistics.mean(rec_ms)
     uns = statistics.mean(uns_ms)
 
     peaks, peak_kind = measured_peaks()
-    is_cfg3 = True  # the ncu traffic figures below were captured on this workload
+    ncu = NCU_DRAM_BYTES_PER_FRAME.get(args.workload, {})
     algo_a = dec.ecs_bytes + 128 * dec.stored_blocks
-    roof_a = {"bound": "hbm", "kernel": "stage a = unstuff_kernel + entropy_decode_kernel", "ms_unstuff": uns, "ms_decode": ent - uns,
+    roof_a = {"bound": "hbm", "kernel": "stage a = unstuff_kernel + %s" % ("progressive_scan_kernel x scans + dequant" if PROG else "entropy_decode_kernel"),
+              "ms_unstuff": uns, "ms_decode": ent - uns,
               "achieved": algo_a / (ent * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
               "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
-              "traffic": NCU_DRAM_BYTES_PER_FRAME["entropy"] * nf if is_cfg3 else None,
+              "traffic": ncu["entropy"] * nf if ncu.get("entropy") else None,
               "algorithmic_bytes_per_launch": algo_a, "ms_per_launch": ent, "share_of_step": ent / (ent + rec)}
     roof_a["frac"] = roof_a["achieved"] / roof_a["peak"]
     import ctypes
     fi, fa, fm = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
     native.lib.b200jpg_microbench_int32(local_rank, ctypes.byref(fi), ctypes.byref(fa), ctypes.byref(fm))
     int_peak = max(fi.value, fa.value, fm.value)
-    algo_b = 128 * dec.stored_blocks + 3 * W * H * nf
-    roof = {"bound": "hbm", "kernel": "stage b = idct_planes_kernel + reconstruct_kernel (dominant by time)",
-            "achieved": algo_b / (rec * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-            "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
-            "traffic": NCU_DRAM_BYTES_PER_FRAME["recon"] * nf if is_cfg3 else None,
-            "algorithmic_bytes_per_launch": algo_b, "ms_per_launch": rec, "share_of_step": rec / (ent + rec),
-            "int32": {"unit": "Gop/s", "achieved": INT_OPS_PER_4K_FRAME * nf / (rec * 1e-3) / 1e9, "peak": int_peak,
-                      "peak_source": "measured here: b200jpg_microbench_int32 (imad %.0f, alu %.0f, mix %.0f Gop/s; multiply-add = 2 ops)"
-                                     % (fi.value, fa.value, fm.value),
-                      "algorithmic_ops_per_frame": INT_OPS_PER_4K_FRAME}}
-    roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["int32"]["frac"] = roof["int32"]["achieved"] / int_peak if int_peak > 0 else None
+    int_ops = INT_OPS_PER_PIXEL_420 * W * H * nf
+    algo_b = 128 * dec.stored_blocks + dec.out_bytes
+    roof_b = {"bound": "hbm", "kernel": "stage b = reconstruction kernel(s): IDCT + upsampling + colour + store",
+              "achieved": algo_b / (rec * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+              "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
+              "traffic": ncu["recon"] * nf if ncu.get("recon") else None,
+              "algorithmic_bytes_per_launch": algo_b, "ms_per_launch": rec, "share_of_step": rec / (ent + rec),
+              "int32": {"unit": "Gop/s", "achieved": int_ops / (rec * 1e-3) / 1e9, "peak": int_peak,
+                        "peak_source": "measured here: b200jpg_microbench_int32 (imad %.0f, alu %.0f, mix %.0f Gop/s; multiply-add = 2 ops)"
+                                       % (fi.value, fa.value, fm.value),
+                        "algorithmic_ops_per_frame": INT_OPS_PER_PIXEL_420 * W * H}}
+    roof_b["frac"] = roof_b["achieved"] / roof_b["peak"]
+    roof_b["int32"]["frac"] = roof_b["int32"]["achieved"] / int_peak if int_peak > 0 else None
+    roof, roof_other, other_key = (roof_b, roof_a, "roofline_entropy") if rec >= ent else (roof_a, roof_b, "roofline_reconstruction")
+
+    ctx = dec.ctx
+    # ---- SURVEY 8d primary accounting: compressed bytes in PINNED host memory -> RGB in DEVICE memory.
+    # The batch is cut into chunks that were parsed and packed into pinned memory before the timed region; timed per chunk:
+    # H2D + restart_index_kernel + unstuff + entropy + reconstruction, chunks rotating over three streams; no D2H.
+    p2d = None
+    chunk_frames = max(1, min(nf, max(args.e2e_chunk, (nf + 7) // 8)))
+    if not args.no_e2e:
+        dec.close()
+        dec = None
+        ctx.trim()  # the whole-batch buffers go back to the driver: the chunk batches allocate their own
+        chunks = [frames[c:c + chunk_frames] for c in range(0, nf, chunk_frames)]
+        bds = [libjpeg_b200.BatchDecoder(ch, ctx=ctx) for ch in chunks]
+        offs, cur = [], 0
+        for bd in bds:
+            offs.append(cur)
+            cur += (bd.out_bytes + 255) // 256 * 256
+        big = out if out.numel() >= cur else torch.empty(cur, dtype=torch.uint8, device="cuda")
+        streams = [torch.cuda.Stream() for _ in range(min(3, len(bds)))]
+
+        def p2d_step():
+            for i, bd in enumerate(bds):
+                s = streams[i % len(streams)]
+                bd.upload(s)
+                bd.decode(big[offs[i]:offs[i] + bd.out_bytes], s)
+
+        for _ in range(2):
+            p2d_step()
+        barrier()
+        psteps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(psteps):
+            p2d_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        assert all(bd.status(i) == 0 for bd in bds for i in (0, bd.n - 1))
+        p2d = {"value": nframes_all * psteps / dt, "unit": "frames/s", "steps": psteps, "chunk_frames": chunk_frames, "streams": len(streams),
+               "h2d_bytes_per_step": int(sum(bd.h2d_bytes for bd in bds)), "d2h_bytes_per_step": 0,
+               "timed_region": "per chunk: H2D of the packed codestreams from pinned host memory + restart_index_kernel + unstuff + "
+                               "entropy + reconstruction kernels, chunks rotating over the streams; RGB stays in device memory; host "
+                               "marker parsing / packing (b200jpg_batch_create) before the timed region; wall clock between barriers"}
+        for bd in bds:
+            bd.close()
+        del bds, big
+        ctx.trim()
 
     # ---- e2e: the calls a user makes, per chunk of frames, all inside the timed region:
-    #   b200jpg_batch_create (host: parse markers, index restart intervals, pack into pinned memory; a producer thread
-    #   runs one chunk ahead) -> upload (H2D) -> decode -> D2H of every pixel into pinned host memory -> destroy.
+    #   b200jpg_batch_create (host: parse markers, pack into pinned memory; a producer thread runs one chunk ahead) -> upload
+    #   (H2D + restart index) -> decode -> D2H of every pixel into pinned host memory -> destroy.
     # Chunks rotate over three CUDA streams; device / pinned buffers are recycled by the context's pool.
     e2e = None
     if not args.no_e2e:
@@ -408,11 +497,8 @@ def main():
         chunk = max(1, min(args.e2e_chunk, nf))
         nchunks = (nf + chunk - 1) // chunk
         nslots = min(3, nchunks)
-        ctx = dec.ctx
         probe_b = libjpeg_b200.BatchDecoder(frames[:chunk], ctx=ctx)
         ob = probe_b.out_bytes
-        h2d_chunk = probe_b.h2d_bytes
-        last_off, last_fi = None, None
         probe_b.close()
         slots = [{"stream": torch.cuda.Stream(), "out": torch.empty(ob, dtype=torch.uint8, device="cuda"),
                   "host": torch.empty(ob, dtype=torch.uint8).pin_memory()} for _ in range(nslots)]
@@ -428,7 +514,7 @@ def main():
 
             th = threading.Thread(target=producer, daemon=True)
             th.start()
-            inflight, c, last = [], 0, None
+            inflight, c = [], 0
             while True:
                 bd = q.get()
                 if bd is None:
@@ -465,34 +551,36 @@ def main():
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        e2e = {"value": nf * world * esteps / dt, "unit": "frames/s", "h2d_bytes_per_step": int(counters["h2d"] // esteps),
+        e2e = {"value": nframes_all * esteps / dt, "unit": "frames/s", "h2d_bytes_per_step": int(counters["h2d"] // esteps),
                "d2h_bytes_per_step": int(counters["d2h"] // esteps), "steps": esteps, "chunk_frames": chunk, "streams": nslots,
-               "timed_region": "per chunk: b200jpg_batch_create on the host codestreams (marker parse, restart index, packing into pinned "
-                               "memory) -> H2D -> unstuff + entropy + reconstruction kernels -> D2H of every pixel into pinned host memory "
-                               "-> batch_destroy; host preparation runs one chunk ahead in a second thread"}
-        # sanity: what came back is what the device-resident path produced
-        ref_view = dec.frame_view(out, nf - 1)
+               "timed_region": "per chunk: b200jpg_batch_create on the host codestreams (marker parse, packing into pinned memory) -> H2D "
+                               "+ restart index -> unstuff + entropy + reconstruction kernels -> D2H of every pixel into pinned host "
+                               "memory -> batch_destroy; host preparation runs one chunk ahead in a second thread"}
+        # sanity: what came back is what the device-resident path produced (frame nf-1 is in `out` from the value run)
+        fi_last = last_bd.info(last_bd.n - 1)
+        nbytes = fi_last.width * fi_last.height * fi_last.ncomp
         got = last_bd.frame_view(slots[(nchunks - 1) % nslots]["host"], last_bd.n - 1)
-        assert torch.equal(ref_view.cpu(), got), "e2e output differs from the device-resident decode"
+        # the value run's buffer holds frame nf-1 at the whole-batch offset: recompute it from the frame sizes (uniform frames)
+        stride = (nbytes + 255) // 256 * 256
+        want = out[(nf - 1) * stride:(nf - 1) * stride + nbytes].view(fi_last.height, fi_last.width, fi_last.ncomp)
+        assert torch.equal(want.cpu(), got), "e2e output differs from the device-resident decode"
         last_bd.close()
         del slots
 
     if rank == 0:
-        line = {"metric": "4K 4:2:0 q75 frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int32", "data": "synthetic", "config": dict(config, mean_codestream_bytes=mean_bytes),
-                "clocks": clocks, "gpu_launches": launches, "roofline": roof, "roofline_entropy": roof_a,
-                "stage_ms": {"entropy": ent, "entropy_unstuff_share": uns, "reconstruction": rec}, "pipeline": overlap}
+        line = {"metric": "4K 4:2:0 q75 frames/sec" if args.workload.startswith("cfg3") else "%s frames/sec" % args.workload,
+                "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": dict(config, mean_codestream_bytes=mean_bytes),
+                "clocks": clocks, "gpu_launches": launches, "roofline": roof, other_key: roof_other,
+                "restart_index_ms": index_ms, "value_with_restart_index": nframes_all / ((ms_per_step + index_ms) * 1e-3),
+                "stage_ms": {"entropy": ent, "entropy_unstuff_share": uns, "reconstruction": rec, "restart_index_once_per_upload": index_ms}}
+        if p2d:
+            line["pinned_to_device_rgb"] = p2d
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
-            procs, scan = best_reference_config(base, ncpu)
-            cb = run_reference(base, procs, max(16, 1024 // procs))
-            line["cpu_baseline"] = {"value": cb["fps"], "unit": "frames/s", "cores": cb["procs"], "kind": cb["kind"],
-                                    "sample": "%d frames (8 distinct cfg3 frames cycled), %d worker processes = the fastest of the process "
-                                              "counts scanned on this %d-thread host (%s fps), Read + 8-row-striped DisplayRectangle via the "
-                                              "reference's public API" % (cb["frames"], cb["procs"], ncpu, scan),
-                                    "read_ms_per_frame": cb.get("read_ms_per_frame"), "display_ms_per_frame": cb.get("display_ms_per_frame")}
+            line["cpu_baseline"] = cpu_arm(base, ncpu, args.workload)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -82,6 +82,8 @@ typedef struct b200jpg_ctx b200jpg_ctx;
 /* Creates a decode context on CUDA device `device` (current device if < 0). */
 B200JPG_API int b200jpg_create(int device, b200jpg_ctx **ctx);
 B200JPG_API void b200jpg_destroy(b200jpg_ctx *ctx);
+/* Frees the device / pinned buffers the context keeps for reuse by later batches (buffers of live batches are untouched). */
+B200JPG_API void b200jpg_trim(b200jpg_ctx *ctx);
 /* Message and code of the last failure on this context (code 0 / "" when none). ctx may be NULL for
  * failures of b200jpg_create / b200jpg_parse on the calling thread. */
 B200JPG_API int b200jpg_last_error(b200jpg_ctx *ctx, const char **message);
@@ -117,6 +119,10 @@ B200JPG_API int b200jpg_batch_import_tables(b200jpg_batch *batch, const uint8_t 
 
 /* H2D of the packed codestream bytes + descriptors on `stream` (a cudaStream_t, 0 = default). */
 B200JPG_API int b200jpg_batch_upload(b200jpg_batch *batch, void *stream);
+
+/* Re-runs only the device-side restart index that b200jpg_batch_upload builds behind its copy (EntropyParser::
+ * ParseRestartMarker bookkeeping, codestream/entropyparser.cpp:117-136) -- idempotent; lets a caller time it. */
+B200JPG_API int b200jpg_batch_reindex(b200jpg_batch *batch, void *stream);
 
 /* The hot path: entropy decode kernel(s) then reconstruction kernel(s), asynchronous on `stream`.
  * `out_dev` is a DEVICE pointer to b200jpg_batch_out_bytes(batch,-1) bytes. */

@@ -139,6 +139,7 @@ struct b200jpg_batch {
     uint64_t dev_prog_frames = 0;
     uint32_t prog_max_blocks = 0;
     uint64_t ecs_bytes = 0, stored_blocks = 0;
+    bool clear_coef = false;  // some component of some frame is coded by no scan: its plane must read as zeros
 
     // staging / device memory
     uint8_t *h_input = nullptr;  // pinned
@@ -171,7 +172,13 @@ extern "C" {
 int b200jpg_parse(const uint8_t *data, size_t len, b200jpg_frame_info *info) {
     ParsedFrame pf;
     std::string err;
-    int rc = parse_codestream(data, len, pf, err);
+    int rc;
+    try {
+        rc = parse_codestream(data, len, pf, err);
+    } catch (const std::bad_alloc &) {
+        rc = B200JPG_ERR_OUT_OF_MEMORY;
+        err = "out of memory while parsing the codestream";
+    }
     g_tls_code = rc;
     g_tls_error = err;
     if (info) *info = pf.info;
@@ -181,13 +188,19 @@ int b200jpg_parse(const uint8_t *data, size_t len, b200jpg_frame_info *info) {
 uint64_t b200jpg_build_tables(const uint8_t *data, size_t len, int scan, uint8_t *dst, uint64_t capacity) {
     ParsedFrame pf;
     std::string err;
-    int rc = parse_codestream(data, len, pf, err);
-    if (rc == 0 && (scan < 0 || scan >= (int)pf.scans.size())) {
-        rc = B200JPG_ERR_INVALID_PARAMETER;
-        err = "scan index out of range";
-    }
     TableSet ts;
-    if (rc == 0) rc = build_table_set(pf.scans[scan], ts, err);
+    int rc;
+    try {
+        rc = parse_codestream(data, len, pf, err);
+        if (rc == 0 && (scan < 0 || scan >= (int)pf.scans.size())) {
+            rc = B200JPG_ERR_INVALID_PARAMETER;
+            err = "scan index out of range";
+        }
+        if (rc == 0) rc = build_table_set(pf.scans[scan], ts, err);
+    } catch (const std::bad_alloc &) {
+        rc = B200JPG_ERR_OUT_OF_MEMORY;
+        err = "out of memory while building the decoder tables";
+    }
     g_tls_code = rc;
     g_tls_error = err;
     if (rc) return 0;
@@ -234,6 +247,12 @@ void b200jpg_destroy(b200jpg_ctx *ctx) {
     delete ctx;
 }
 
+void b200jpg_trim(b200jpg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->trim();
+}
+
 int b200jpg_last_error(b200jpg_ctx *ctx, const char **message) {
     if (ctx) {
         if (message) *message = ctx->error.c_str();
@@ -263,9 +282,23 @@ void b200jpg_batch_destroy(b200jpg_batch *b) {
     delete b;
 }
 
+static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad, b200jpg_batch **out);
+
 int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad,
                          b200jpg_batch **out) {
     if (!ctx) return B200JPG_ERR_INVALID_PARAMETER;
+    try {  // no exception crosses the C ABI
+        return batch_create_impl(ctx, frames, lens, n, tolerate_bad, out);
+    } catch (const std::bad_alloc &) {
+        if (out) *out = nullptr;
+        return ctx->fail(B200JPG_ERR_OUT_OF_MEMORY, "out of host memory while preparing the batch");
+    } catch (...) {
+        if (out) *out = nullptr;
+        return ctx->fail(B200JPG_ERR_INVALID_PARAMETER, "unexpected failure while preparing the batch");
+    }
+}
+
+static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad, b200jpg_batch **out) {
     if (!out || !frames || !lens || n <= 0) return ctx->fail(B200JPG_ERR_INVALID_PARAMETER, "invalid batch arguments");
     *out = nullptr;
     cudaError_t ce = cudaSetDevice(ctx->device);
@@ -288,11 +321,21 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < nt; t++)
             pool.emplace_back([&, t]() {
-                for (int i = (int)t; i < n; i += (int)nt)
-                    b->parse_status[i] = parse_codestream(frames[i], lens[i], b->frames[i], errs[i], device_index);
+                for (int i = (int)t; i < n; i += (int)nt) {
+                    try {  // an exception must not leave the thread (std::terminate): it fails this frame only
+                        b->parse_status[i] = parse_codestream(frames[i], lens[i], b->frames[i], errs[i], device_index);
+                    } catch (const std::bad_alloc &) {
+                        b->parse_status[i] = B200JPG_ERR_OUT_OF_MEMORY;
+                        errs[i] = "out of memory while parsing the codestream";
+                    } catch (...) {
+                        b->parse_status[i] = B200JPG_ERR_MALFORMED_STREAM;
+                        errs[i] = "codestream could not be parsed";
+                    }
+                }
             });
         for (auto &th : pool) th.join();
     }
+    std::vector<std::vector<TableSet>> frame_tables(n);
     for (int i = 0; i < n; i++) {
         ParsedFrame &pf = b->frames[i];
         int &st = b->parse_status[i];
@@ -308,15 +351,32 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
                 st = B200JPG_ERR_NOT_IMPLEMENTED;
                 errs[i] = "only 1x1, 2x1, 1x2 and 2x2 chroma subsampling (equal for both chroma components) is supported";
             } else {
-                // every component must be covered by exactly one scan
+                // A sequential frame codes a component at most once. A component no scan codes (the stream ends early: the
+                // reference just stops at the EOI / the end of the data, Frame::ParseTrailer marker/frame.cpp:1062-1092)
+                // keeps zero coefficients: the coefficient store is cleared for such batches.
                 int seen[4] = {0, 0, 0, 0};
                 for (auto &sc : pf.scans)
                     for (int k = 0; k < sc.ns; k++) seen[sc.comp[k]]++;
-                for (int c = 0; c < fi.ncomp; c++)
-                    if (fi.frame_type != 2 && seen[c] != 1) {
-                        st = B200JPG_ERR_MALFORMED_STREAM;
-                        errs[i] = "sequential frame does not code every component exactly once";
+                for (int c = 0; c < fi.ncomp; c++) {
+                    if (fi.frame_type != 2 && seen[c] > 1) {
+                        st = B200JPG_ERR_NOT_IMPLEMENTED;
+                        errs[i] = "sequential frame codes a component more than once, not supported by the B200 path";
                     }
+                    if (seen[c] == 0) b->clear_coef = true;
+                }
+            }
+        }
+        // all table sets of the frame before any of its scans joins a launch class: a frame that fails here must not leave
+        // scans behind that decode bytes nobody uploads
+        if (st == 0) {
+            frame_tables[i].resize(pf.scans.size());
+            for (size_t si = 0; si < pf.scans.size() && st == 0; si++) {
+                try {
+                    st = build_table_set(pf.scans[si], frame_tables[i][si], errs[i]);
+                } catch (const std::bad_alloc &) {
+                    st = B200JPG_ERR_OUT_OF_MEMORY;
+                    errs[i] = "out of memory while building the decoder tables";
+                }
             }
         }
         if (st != 0 && !tolerate_bad) return ctx->fail(st, "frame " + std::to_string(i) + ": " + errs[i]);
@@ -366,14 +426,7 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
         const b200jpg_frame_info &fi = pf.info;
         for (size_t si = 0; si < pf.scans.size(); si++) {
             auto &sc = pf.scans[si];
-            TableSet ts;
-            std::string err;
-            int rc = build_table_set(sc, ts, err);
-            if (rc != 0) {
-                b->parse_status[i] = rc;
-                if (!tolerate_bad) return ctx->fail(rc, "frame " + std::to_string(i) + ": " + err);
-                break;
-            }
+            TableSet &ts = frame_tables[i][si];
             int ti;
             auto it = table_index.find(ts.blob);
             if (it == table_index.end()) {
@@ -450,7 +503,10 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
             for (size_t k = 0; k < sc.interval_off.size(); k++) {
                 size_t off = sc.interval_off[k], end = sc.interval_end[k];
                 cl.interval_off.push_back(off == SIZE_MAX ? ~0ull : byte_off[i] + (uint64_t)off);
-                cl.interval_end.push_back(off == SIZE_MAX ? 0ull : byte_off[i] + (uint64_t)end);
+                uint64_t e = off == SIZE_MAX ? 0ull : byte_off[i] + (uint64_t)end;
+                // the data ends inside the scan's last interval: flagged for the decoder (kIntervalEofFlag)
+                if (sc.eof_tail && off != SIZE_MAX && k + 1 == sc.interval_off.size()) e |= kIntervalEofFlag;
+                cl.interval_end.push_back(e);
             }
         }
     }
@@ -498,7 +554,7 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
                 } else {
                     for (size_t k = j * nint; k < (j + 1) * nint; k++) {
                         cl.clean_off[k] = ccur;
-                        uint64_t len = cl.interval_off[k] == ~0ull ? 0 : cl.interval_end[k] - cl.interval_off[k];
+                        uint64_t len = cl.interval_off[k] == ~0ull ? 0 : (cl.interval_end[k] & ~kIntervalEofFlag) - cl.interval_off[k];
                         ccur += align_up(len, 16) + 48;
                     }
                 }
@@ -681,14 +737,10 @@ int b200jpg_batch_import_tables(b200jpg_batch *b, const uint8_t *src, uint64_t s
     return B200JPG_OK;
 }
 
-int b200jpg_batch_upload(b200jpg_batch *b, void *stream) {
-    if (!b) return B200JPG_ERR_INVALID_PARAMETER;
-    cudaSetDevice(b->ctx->device);
-    cudaError_t e = cudaMemcpyAsync(b->d_input, b->h_input, b->input_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
-    if (e != cudaSuccess) return b->ctx->fail_cuda(e, "upload");
-    // the restart index of device-indexed scans: built once per upload, right behind the copy
+// the restart index of device-indexed scans (restart_index_kernel): depends only on the uploaded bytes
+static int run_restart_index(b200jpg_batch *b, void *stream) {
     uint32_t *index_status = b->d_status + 4 * (size_t)b->n + 1;
-    e = cudaMemsetAsync(index_status, 0, sizeof(uint32_t) * (size_t)b->n, (cudaStream_t)stream);
+    cudaError_t e = cudaMemsetAsync(index_status, 0, sizeof(uint32_t) * (size_t)b->n, (cudaStream_t)stream);
     if (e != cudaSuccess) return b->ctx->fail_cuda(e, "index status reset");
     if (!b->index_scans.empty()) {
         int rc = launch_restart_index(reinterpret_cast<const IndexScan *>(b->d_input + b->dev_index_scans), (uint32_t)b->index_scans.size(),
@@ -696,8 +748,25 @@ int b200jpg_batch_upload(b200jpg_batch *b, void *stream) {
         if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "restart index kernel launch");
     }
     cudaEventRecord(b->ev_last, (cudaStream_t)stream);
+    return B200JPG_OK;
+}
+
+int b200jpg_batch_upload(b200jpg_batch *b, void *stream) {
+    if (!b) return B200JPG_ERR_INVALID_PARAMETER;
+    cudaSetDevice(b->ctx->device);
+    cudaError_t e = cudaMemcpyAsync(b->d_input, b->h_input, b->input_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) return b->ctx->fail_cuda(e, "upload");
+    int rc = run_restart_index(b, stream);  // built once per upload, right behind the copy
+    if (rc) return rc;
     b->uploaded = true;
     return B200JPG_OK;
+}
+
+int b200jpg_batch_reindex(b200jpg_batch *b, void *stream) {
+    if (!b) return B200JPG_ERR_INVALID_PARAMETER;
+    if (!b->uploaded) return b->ctx->fail(B200JPG_ERR_OBJECT_DOESNT_EXIST, "batch has not been uploaded");
+    cudaSetDevice(b->ctx->device);
+    return run_restart_index(b, stream);
 }
 
 static int run_entropy(b200jpg_batch *b, void *stream) {
@@ -705,7 +774,7 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
     cudaError_t e = cudaMemcpyAsync(b->d_status, b->d_status + 4 * (size_t)b->n + 1, sizeof(uint32_t) * (size_t)b->n, cudaMemcpyDeviceToDevice,
                                     (cudaStream_t)stream);
     if (e != cudaSuccess) return b->ctx->fail_cuda(e, "status reset");
-    if (!b->prog_frames.empty()) {  // progressive scans accumulate into the coefficient store: it starts from zero
+    if (!b->prog_frames.empty() || b->clear_coef) {  // progressive scans accumulate into the coefficient store: it starts from zero
         e = cudaMemsetAsync(b->d_coef, 0, b->coef_elems * sizeof(int16_t), (cudaStream_t)stream);
         if (e != cudaSuccess) return b->ctx->fail_cuda(e, "coefficient store reset");
     }

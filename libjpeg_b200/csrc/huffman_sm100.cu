@@ -119,7 +119,9 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
         if (lane == 0) interval_len[g] = 0;
         return;
     }
-    const uint64_t src1 = interval_end[g];  // offset of the marker that ends the interval
+    const uint64_t src1_raw = interval_end[g];
+    const uint64_t src1 = src1_raw & ~kIntervalEofFlag;  // offset of the marker (or the end of the data) that ends the interval
+    const uint32_t eof_flag = (src1_raw & kIntervalEofFlag) ? kIntervalLenEofFlag : 0u;
     uint32_t *dst = reinterpret_cast<uint32_t *>(clean + clean_off[g]);
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(&sbuf[wib][0]);
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -238,7 +240,7 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
         if (lane < padded) dst[written + lane] = w;
         if (lane + 32 < padded) dst[written + 32 + lane] = 0;
     }
-    if (lane == 0) interval_len[g] = total;
+    if (lane == 0) interval_len[g] = total | eof_flag;
 }
 
 // =====================================================================================================
@@ -287,7 +289,8 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
             j = (uint32_t)(g / p.intervals_per_scan);
             iv = (uint32_t)(g % p.intervals_per_scan);
         }
-        const uint32_t len_bytes = lane_valid ? interval_len[g] : 0u;
+        const uint32_t len_raw = lane_valid ? interval_len[g] : 0u;
+        const uint32_t len_bytes = len_raw & ~kIntervalLenEofFlag;
         const uint8_t *src = clean + (lane_valid ? clean_off[g] : 0ull);
         const uint32_t max_chunks = (len_bytes + 15u) / 16u + 2u;  // data + the 32 zero bytes a0 appended
         const uint32_t mcu0 = iv * p.dri;
@@ -437,7 +440,8 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                         // re-tests k <= 63 and silently ends the block, :717-719), kQzBlockEnds for EOB and for entries
                         // that must not be decoded (bit 31). The table pair is fetched at k - 1 in every case: symbols
                         // without value bits store a zero (ZRL: in a position that is zero anyway; block end: pad slot),
-                        // a run that leaves the block hits a flagged pair (bit 31 of q, :764-766).
+                        // a coefficient whose run leaves the block hits a pair that multiplies it out of the int16 range
+                        // (:764-766: out of sync), a ZRL that leaves it multiplies its zero and just ends the block.
                         while (__any_sync(kFull, k <= 63)) {
                             if (k <= 63) {
                                 const uint32_t hi = __funnelshift_l(x1, x0, bp);
@@ -485,7 +489,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         } else if (decoding) {
             // a valid stream never consumes bits beyond the marker that ends its interval
             const uint64_t consumed = bp;
-            if (consumed > (uint64_t)len_bytes * 8u) err = kErrUnexpectedEof;
+            if (consumed > (uint64_t)len_bytes * 8u && !(len_raw & kIntervalLenEofFlag)) err = kErrUnexpectedEof;
         }
         if (err) atomicMax(frame_status + frame, err);
     }
@@ -501,7 +505,8 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
 // restart markers in stream order, and the scan's slices of the interval arrays are written in place:
 //   interval k = [off[k], end[k]);  off[0] = ecs_off, off[k+1] = RST_k + 2, end[k] = RST_k (last one: the marker that ends
 //   the segment, or a surplus RST);  intervals the stream does not contain: off = ~0 (zero-filled by the decoder);
-//   RST_k must be RST(k mod 8) (entropyparser.cpp:137-199 would resynchronise; here: MALFORMED_STREAM, like the host path);
+//   RST_k is expected to be RST(k mod 8); otherwise the reference's resynchronisation (entropyparser.cpp:137-199) is replayed
+//   over the marker list by one thread (lost intervals: off = ~0);
 //   clean_off[k] = base + (off[k] - ecs_off) + 80 k rounded up to 16: unstuffing never grows the data, so the pieces
 //   cannot overlap and no lengths have to be known on the host.
 constexpr int kIndexThreads = 256;
@@ -539,8 +544,8 @@ restart_index_kernel(const IndexScan *__restrict__ scans, uint8_t *__restrict__ 
                         if ((nb & 0xf8u) == 0xd0u) {
                             ids |= (nb & 7u) << (3 * __popc(rst));  // at most 8 markers fit 16 bytes
                             rst |= 1u << j;
-                        } else if (other == ~0ull) {
-                            other = q;
+                        } else if (nb >= 0xc0u && nb < 0xf0u && other == ~0ull) {
+                            other = q;  // 0xff 01..bf / f0..fe is no marker to ParseRestartMarker (entropyparser.cpp:191-196)
                         }
                     }
                 }
@@ -599,17 +604,63 @@ restart_index_kernel(const IndexScan *__restrict__ scans, uint8_t *__restrict__ 
         if (fo != ~0ull) break;
     }
     const uint64_t seg_end = (first_other != ~0ull) ? (uint64_t)first_other : s.ecs_end;
-    if (tid == 0) off[0] = s.ecs_off;
-    for (uint32_t k = tid; k < nint; k += kIndexThreads) {
-        if (k >= running) end[k] = seg_end;
-        if (k > running) off[k] = ~0ull;
+    if (!__syncthreads_or(bad ? 1 : 0)) {
+        if (tid == 0) off[0] = s.ecs_off;
+        for (uint32_t k = tid; k < nint; k += kIndexThreads) {
+            if (k >= running) end[k] = seg_end;
+            if (k > running) off[k] = ~0ull;
+        }
+    } else {
+        // Restart markers out of sequence (damaged stream): the reference resynchronises (entropyparser.cpp:137-199), and what
+        // it does is a function of the marker sequence alone -- the bit reader never passes a marker, so after interval k-1
+        // the parser stands at, or scans forward to, the first marker behind that interval's data: the expected RSTn is
+        // consumed; one that is 4..7 ids behind is dropped with the data after it; one that is 1..3 ids ahead costs
+        // interval k (cleared) and stays; the marker that ends the segment costs every interval that is left. Rare and
+        // inherently sequential: one thread walks the marker list the parallel pass left in end[] (copied to cln[]).
+        const uint32_t nm = running < nint ? running : nint;
+        for (uint32_t k = tid; k < nm; k += kIndexThreads) cln[k] = end[k];
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t p = 0, next = 0;
+            bool overflow = false;
+            off[0] = s.ecs_off;
+            end[0] = nm ? cln[0] : seg_end;
+            for (uint32_t k = 1; k < nint; k++) {
+                bool valid = false;
+                for (;;) {
+                    if (p >= nm) {  // the end of the segment -- or of the list, if the stream holds more markers than intervals
+                        overflow = overflow || running > nint;
+                        break;
+                    }
+                    const uint32_t id = input[cln[p] + 1] & 7u;
+                    if (id == next) {
+                        off[k] = cln[p] + 2;
+                        p++;
+                        valid = true;
+                        break;
+                    }
+                    if (((id - next) & 7u) >= 4u) {
+                        p++;
+                        continue;
+                    }
+                    break;
+                }
+                next = (next + 1u) & 7u;
+                if (valid) {
+                    end[k] = p < nm ? cln[p] : seg_end;
+                } else {
+                    off[k] = ~0ull;
+                    end[k] = seg_end;
+                }
+            }
+            if (overflow) atomicMax(index_status + s.frame, kErrMalformed);  // not resolvable with the list kept here
+        }
     }
     __syncthreads();
     for (uint32_t k = tid; k < nint; k += kIndexThreads) {
         const uint64_t o = off[k];
         cln[k] = (o == ~0ull) ? s.clean_base : ((s.clean_base + (o - s.ecs_off) + (uint64_t)kCleanSlackPerInterval * k + 15ull) & ~15ull);
     }
-    if (bad) atomicMax(index_status + s.frame, kErrMalformed);
 }
 
 }  // namespace

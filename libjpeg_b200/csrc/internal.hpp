@@ -50,6 +50,9 @@ struct ScanInfo {  // one SOS + its entropy coded segment
     // true: the host did not walk the entropy coded segment; ecs_end is the offset of the closing EOI and the restart
     // index above is a placeholder that restart_index_kernel fills in on the device
     bool device_index = false;
+    // the data ends inside this scan's last restart interval (no marker behind it): the decoder reads zero bits there and
+    // must not report the overrun (the reference does not, io/bitstream.cpp:103-105)
+    bool eof_tail = false;
     HuffSpec dc[4], ac[4];       // tables in effect at this SOS
     uint16_t quant[4][64];       // zig-zag order as transmitted, in effect at this SOS
     bool quant_defined[4] = {false, false, false, false};
@@ -64,6 +67,11 @@ struct ParsedFrame {
 // components of the frame and uses restart markers is not walked on the host (ScanInfo::device_index).
 int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::string &err, bool device_index = false);
 
+// Restart bookkeeping with the reference's resynchronisation (codestream/entropyparser.cpp:117-199) over the marker
+// sequence of one entropy coded segment; off / end are sized to the number of restart intervals (parse.cpp).
+int resolve_restart_sequence(const std::vector<size_t> &rst_at, const std::vector<uint8_t> &rst_id, size_t ecs_off, size_t ecs_end,
+                             bool ended_by_eof, std::vector<size_t> &off, std::vector<size_t> &end);
+
 extern const uint8_t kZigZagToRaster[64];  // dct/dct.cpp:57-73
 
 // ---- table sets: what the entropy kernel needs besides the bytes ------------------------------------
@@ -71,9 +79,10 @@ extern const uint8_t kZigZagToRaster[64];  // dct/dct.cpp:57-73
 //   uint32 magic, uint32 total_bytes, uint32 lut_words, uint32 flags
 //   uint16 lut_off[8]        word offset of the first-level LUT of DC0..3, AC0..3 (0xFFFF = undefined)
 //   uint32 qz[4][160][2]     per quantisation table, index = zig-zag position k: {delta << lowbit, byte offset of the
-//                            raster position inside a block}; entries 64..95 carry bit 31 (a run that leaves the block:
-//                            out-of-sync error), entries 96..159 are where "the block ends" symbols land (no error);
-//                            both kinds point at the staging block's pad slot
+//                            raster position inside a block}; entries 64..95 multiply by 2^16 (a coefficient whose run
+//                            leaves the block overflows the int16 store: out-of-sync error; a ZRL that leaves it carries
+//                            amplitude 0 and just ends the block), entries 96..159 are where "the block ends" symbols
+//                            land (no error); both kinds point at the staging block's pad slot
 //   uint32 lut[lut_words]    per table: 2^kLutL1Bits first-level entries, then 2^(16-kLutL1Bits) per second-level table
 // LUT entry: [4:0] s = value bits that follow the code, [9:5] code length (0: pointer to second-level table
 // [17:10], all other fields 0; 31: unused code, coding/huffmandecoder.hpp:87), [25:19] step of the zig-zag index
@@ -110,6 +119,11 @@ struct IndexScan {
 };
 constexpr uint32_t kCleanSlackPerInterval = 80;  // device-indexed scans: clean_off[k] = base + (off[k] - ecs_off) + 80 k, 16-aligned
 int launch_restart_index(const IndexScan *scans_dev, uint32_t n_scans, uint8_t *input_dev, uint32_t *index_status, void *stream);
+
+// bit 63 of an interval_end entry / bit 31 of an interval_len entry: the data (not a marker) ends this interval -- the
+// decoder reads zero bits behind it like the reference's bit reader at EOF and does not report the overrun
+constexpr uint64_t kIntervalEofFlag = 1ull << 63;
+constexpr uint32_t kIntervalLenEofFlag = 1u << 31;
 
 struct ScanClassParams {  // uniform over a launch of the entropy kernel
     int ns;

@@ -37,8 +37,11 @@ struct Cursor {
         return code;    \
     } while (0)
 
-// Walks one entropy coded segment, recording where every restart interval begins.
-// Returns the offset of the first marker that is neither RSTn nor a fill byte (or n).
+// Walks one entropy coded segment, recording every restart marker (position of its 0xff, id byte).
+// Returns the offset of the marker that ends the segment -- the first 0xff followed by a byte in c0..ef that is no restart
+// marker -- or n. 0xff followed by 01..bf / f0..fe is no marker to EntropyParser::ParseRestartMarker (it eats such bytes while
+// it resynchronises, codestream/entropyparser.cpp:191-196); the bit reader of the interval in which they stand stops there
+// all the same (io/bitstream.cpp:96-101), which the unstuff kernel reproduces.
 size_t index_ecs(const Cursor &c, size_t pos, std::vector<size_t> &rst_at, std::vector<uint8_t> &rst_id) {
     const uint8_t *d = c.d;
     size_t n = c.n;
@@ -56,12 +59,61 @@ size_t index_ecs(const Cursor &c, size_t pos, std::vector<size_t> &rst_at, std::
             rst_at.push_back(pos);
             rst_id.push_back(m);
             pos += 2;
-        } else {
+        } else if (m >= 0xc0 && m < 0xf0) {
             return pos;
+        } else {
+            pos += 1;  // garbage
         }
     }
     return n;
 }
+
+}  // namespace
+
+// The reference's restart-marker bookkeeping including its resynchronisation (EntropyParser::ParseRestartMarker,
+// codestream/entropyparser.cpp:117-199), as a function of the marker sequence alone: the bit reader never passes a marker, so
+// when interval k-1 is done the parser stands at, or scans forward to, the first marker behind that interval's data --
+//   the expected RSTn                  : consumed, interval k starts behind it;
+//   an RSTn that is 4..7 ids "behind"  : dropped together with the data that follows it, the scan goes on;
+//   an RSTn that is 1..3 ids "ahead"   : interval k is lost (its MCUs stay cleared), the marker stays for the next interval;
+//   any other marker (the segment end) : interval k and everything after it is lost;
+//   the end of the data                : UNEXPECTED_EOF.
+// off[k] = SIZE_MAX marks a lost interval. Returns 0 or B200JPG_ERR_UNEXPECTED_EOF.
+int resolve_restart_sequence(const std::vector<size_t> &rst_at, const std::vector<uint8_t> &rst_id, size_t ecs_off, size_t ecs_end,
+                             bool ended_by_eof, std::vector<size_t> &off, std::vector<size_t> &end) {
+    const size_t nint = off.size();
+    size_t p = 0;  // index of the marker the parser stands at / looks for next
+    unsigned next = 0;
+    off[0] = ecs_off;
+    end[0] = rst_at.empty() ? ecs_end : rst_at[0];
+    for (size_t k = 1; k < nint; k++) {
+        bool valid = false;
+        for (;;) {
+            if (p >= rst_at.size()) {  // the marker that ends the segment, or the end of the data
+                if (ended_by_eof) return B200JPG_ERR_UNEXPECTED_EOF;
+                break;
+            }
+            const unsigned id = rst_id[p] & 7u;
+            if (id == next) {
+                off[k] = rst_at[p] + 2;
+                p++;
+                valid = true;
+                break;
+            }
+            if (((id - next) & 7u) >= 4u) {
+                p++;  // behind: drop it and keep looking
+                continue;
+            }
+            break;  // ahead: this interval is lost, the marker stays
+        }
+        next = (next + 1u) & 7u;
+        if (valid) end[k] = p < rst_at.size() ? rst_at[p] : ecs_end;
+        else off[k] = SIZE_MAX, end[k] = ecs_end;
+    }
+    return 0;
+}
+
+namespace {
 
 }  // namespace
 
@@ -82,10 +134,24 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
     size_t pos = 2;
 
     for (;;) {
-        if (pos + 1 >= len) FAIL(B200JPG_ERR_UNEXPECTED_EOF, "run out of data while looking for the next marker");
-        if (data[pos] != 0xff) FAIL(B200JPG_ERR_MALFORMED_STREAM, "expected a marker segment");
+        // Behind the first scan the reference only warns about a missing EOI or bytes that are no marker and still delivers
+        // the image (Frame::ParseTrailer marker/frame.cpp:1089-1110, Image::ParseTrailer codestream/image.cpp:1466-1486):
+        // the end of the data is the end of the image, garbage is skipped up to the next 0xff.
+        if (pos + 1 >= len) {
+            if (!out.scans.empty()) break;
+            FAIL(B200JPG_ERR_UNEXPECTED_EOF, "run out of data while looking for the next marker");
+        }
+        if (data[pos] != 0xff) {
+            if (out.scans.empty()) FAIL(B200JPG_ERR_MALFORMED_STREAM, "expected a marker segment");
+            const void *q = memchr(data + pos, 0xff, len - pos);
+            pos = q ? (size_t)((const uint8_t *)q - data) : len;
+            continue;
+        }
         while (pos + 1 < len && data[pos + 1] == 0xff) pos++;  // filler, tables.cpp:1371-1373
-        if (pos + 1 >= len) FAIL(B200JPG_ERR_UNEXPECTED_EOF, "run out of data while looking for the next marker");
+        if (pos + 1 >= len) {
+            if (!out.scans.empty()) break;
+            FAIL(B200JPG_ERR_UNEXPECTED_EOF, "run out of data while looking for the next marker");
+        }
         int m = data[pos + 1];
         pos += 2;
         if (m == 0xd9) break;  // EOI
@@ -249,6 +315,16 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
             uint64_t total = (uint64_t)sc.mcu_cols * sc.mcu_rows;
             uint64_t per = sc.dri ? sc.dri : total;
             uint64_t nint = (total + per - 1) / per;
+            // Untrusted header fields must not size allocations: every restart interval but the last is followed by a two
+            // byte marker, so a stream of this length cannot hold more of them than that -- the rest would have to be
+            // absent, which the reference turns into a failed resynchronisation or cleared MCUs. The index keeps at most
+            // that many entries + 1; a frame that claims more is refused before anything is allocated.
+            {
+                const uint64_t room = (len - (pos + (size_t)seglen)) / 2 + 2;
+                if (nint > room && nint > (1u << 16))
+                    FAIL(B200JPG_ERR_MALFORMED_STREAM, "frame header promises more restart intervals than the stream can hold");
+                if (total > (1ull << 31)) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "frame too large for the B200 path");
+            }
             // A scan with restart markers that carries every component is the only scan of the frame: its entropy coded
             // segment runs up to the closing EOI, which is looked for from the end (bytes behind EOI are legal), and the
             // restart index is left to the device (restart_index_kernel) instead of a memchr pass over every byte here.
@@ -276,17 +352,17 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
             std::vector<size_t> rst_at;
             std::vector<uint8_t> rst_id;
             sc.ecs_end = index_ecs(c, sc.ecs_off, rst_at, rst_id);
+            // The data ends inside the entropy coded segment (no marker follows). The reference's bit reader then hands out
+            // zero bits without complaint (io/bitstream.cpp:103-105), so a cut inside the LAST interval still decodes; a cut
+            // in front of a restart marker the scan needs makes ParseRestartMarker run out of data while resynchronising
+            // (codestream/entropyparser.cpp:141-147): UNEXPECTED_EOF.
+            sc.eof_tail = sc.ecs_end >= len;
             sc.interval_off.assign((size_t)nint, SIZE_MAX);
             sc.interval_end.assign((size_t)nint, sc.ecs_end);
-            sc.interval_off[0] = sc.ecs_off;
-            for (size_t k = 0; k + 1 < nint; k++) {
-                if (k >= rst_at.size()) break;  // stream ends early: remaining intervals stay absent (zero-filled)
-                if (rst_id[k] != 0xd0 + (k & 7))
-                    FAIL(B200JPG_ERR_MALFORMED_STREAM, "restart markers are out of sequence, resynchronisation is not supported by the B200 path");
-                sc.interval_end[k] = rst_at[k];
-                sc.interval_off[k + 1] = rst_at[k] + 2;
-            }
-            if (nint - 1 < rst_at.size()) sc.interval_end[nint - 1] = rst_at[nint - 1];  // surplus RSTn: stop there
+            if (resolve_restart_sequence(rst_at, rst_id, sc.ecs_off, sc.ecs_end, sc.eof_tail, sc.interval_off, sc.interval_end) != 0)
+                FAIL(B200JPG_ERR_UNEXPECTED_EOF, "run into end of file while trying to resync the entropy parser");
+            // the data ends inside the scan's LAST interval: only then does the decoder read zero bits behind it
+            sc.eof_tail = sc.eof_tail && sc.interval_off[nint - 1] != SIZE_MAX && sc.interval_end[nint - 1] >= len;
             fi.n_intervals += (uint32_t)nint;
             fi.ecs_bytes += sc.ecs_end - sc.ecs_off;
             if (out.scans.empty()) fi.restart_interval = dri;
@@ -404,7 +480,11 @@ int build_table_set(const ScanInfo &scan, TableSet &out, std::string &err) {
                 q = delta << scan.lowbit;
                 off = 2u * kZigZagToRaster[k];
             } else {
-                q = (k < kQzBlockEnds) ? 0x80000000u : 0u;
+                // 64..95: a coefficient whose run left the block (sequentialscan.cpp:764-766). The multiplier 2^16 turns any
+                // non-zero amplitude into a product beyond the int16 store -- reported as MALFORMED_STREAM like a genuine
+                // overflow --, while a ZRL that steps over position 63 lands here with amplitude 0 and ends the block
+                // silently, as in the reference (:717-719)
+                q = (k < kQzBlockEnds) ? 0x00010000u : 0u;
                 off = 128;  // first pad halfword of the lane's staging block
             }
             qz[(t * kQzEntries + k) * 2] = q;

@@ -86,7 +86,8 @@ progressive_scan_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, co
     const uint64_t g = (uint64_t)blockIdx.x * kThreadsP + threadIdx.x;
     if (g >= total_intervals) return;
     const uint32_t j = (uint32_t)(g / p.intervals_per_scan), iv = (uint32_t)(g % p.intervals_per_scan);
-    const uint32_t len_bytes = interval_len[g];
+    const uint32_t len_raw = interval_len[g];
+    const uint32_t len_bytes = len_raw & ~kIntervalLenEofFlag;
     if (len_bytes == 0) return;  // an interval the stream does not contain leaves its blocks as they are
     const ClassScan &cs = scans[j];
     const uint32_t mcu0 = iv * p.dri;
@@ -211,7 +212,7 @@ progressive_scan_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, co
     }
     uint32_t err = 0;
     if (bad) err = kErrMalformed;
-    else if ((uint64_t)b.bp > (uint64_t)len_bytes * 8u) err = kErrUnexpectedEof;  // consumed bits beyond the interval's marker
+    else if ((uint64_t)b.bp > (uint64_t)len_bytes * 8u && !(len_raw & kIntervalLenEofFlag)) err = kErrUnexpectedEof;  // consumed bits beyond the interval's marker
     if (err) atomicMax(frame_status + cs.frame, err);
 }
 
@@ -257,8 +258,11 @@ int launch_progressive_scan(const EntropyLaunch &l, void *stream) {
 int launch_progressive_dequant(const ProgFrame *frames_dev, uint32_t n_frames, uint32_t max_blocks, int16_t *coef, uint32_t *frame_status,
                                void *stream) {
     if (n_frames == 0 || max_blocks == 0) return 0;
-    dim3 grid((max_blocks * 8u + 255u) / 256u, n_frames, 4);
-    progressive_dequant_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames_dev, coef, frame_status);
+    for (uint32_t first = 0; first < n_frames; first += 65535u) {  // grid.y carries the frame index
+        const uint32_t part = n_frames - first < 65535u ? n_frames - first : 65535u;
+        dim3 grid((max_blocks * 8u + 255u) / 256u, part, 4);
+        progressive_dequant_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames_dev + first, coef, frame_status);
+    }
     return (int)cudaGetLastError();
 }
 

@@ -70,6 +70,11 @@ class Context:
         rc = lib.b200jpg_create(device, ctypes.byref(self.handle))
         native.check(rc)
 
+    def trim(self):
+        """Returns the pooled (idle) device / pinned buffers to the driver."""
+        if self.handle:
+            lib.b200jpg_trim(self.handle)
+
     def close(self):
         if self.handle:
             lib.b200jpg_destroy(self.handle)
@@ -128,7 +133,7 @@ class BatchDecoder:
     def export_tables(self):
         size = lib.b200jpg_batch_export_tables(self.handle, None, 0)
         if size == 0:
-            raise NativeError(-1024, "batch does not have exactly one table set")
+            raise native.NativeError(-1024, "batch does not have exactly one table set")
         buf = np.zeros(size, dtype=np.uint8)
         lib.b200jpg_batch_export_tables(self.handle, buf.ctypes.data, size)
         return buf
@@ -149,6 +154,10 @@ class BatchDecoder:
 
     def upload(self, stream=None):
         native.check(lib.b200jpg_batch_upload(self.handle, self._stream_ptr(stream)), self.ctx.handle)
+
+    def reindex(self, stream=None):
+        """Re-runs the device-side restart index alone (upload() already built it); for timing."""
+        native.check(lib.b200jpg_batch_reindex(self.handle, self._stream_ptr(stream)), self.ctx.handle)
 
     def new_output(self, device=None):
         import torch

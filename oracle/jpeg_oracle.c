@@ -379,10 +379,23 @@ static int walk(const uint8_t *d, size_t n, jpgo_info *info, decoder_tables *tab
     memset(info, 0, sizeof(*info));
     for (;;) {
         int m, len;
-        if (pos + 1 >= n) return JPGO_ERR_UNEXPECTED_EOF;
-        if (d[pos] != 0xff) return JPGO_ERR_MALFORMED_STREAM;
+        /* Behind the first scan the reference only WARNS about a missing EOI or out-of-sync bytes and delivers the
+         * image (Frame::ParseTrailer marker/frame.cpp:1089-1110, Image::ParseTrailer codestream/image.cpp:1466-1486):
+         * end of data = end of image, garbage is skipped up to the next 0xff. */
+        if (pos + 1 >= n) {
+            if (info->nscans > 0) break;
+            return JPGO_ERR_UNEXPECTED_EOF;
+        }
+        if (d[pos] != 0xff) {
+            if (info->nscans == 0) return JPGO_ERR_MALFORMED_STREAM;
+            while (pos < n && d[pos] != 0xff) pos++;
+            continue;
+        }
         while (pos + 1 < n && d[pos + 1] == 0xff) pos++; /* filler bytes, tables.cpp:1371-1373 */
-        if (pos + 1 >= n) return JPGO_ERR_UNEXPECTED_EOF;
+        if (pos + 1 >= n) {
+            if (info->nscans > 0) break;
+            return JPGO_ERR_UNEXPECTED_EOF;
+        }
         m = d[pos + 1];
         pos += 2;
         if (m == 0xd9) break; /* EOI */

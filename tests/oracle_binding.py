@@ -163,3 +163,71 @@ def with_swapped_restart_ids(data, first=1):
             i += 1
     b[at[first]], b[at[first + 1]] = b[at[first + 1]], b[at[first]]
     return bytes(b)
+
+
+def handmade_grey_stream(blocks_bits, width=8, height=8, dri=0):
+    """A tiny grey SOF0 codestream with hand-picked Huffman tables, for cases an encoder never writes:
+    DC table: category 0 = '0', category 1 = '10'; AC table: ZRL (0xF0) = '0', EOB (0x00) = '10', 0/1 (0x01) = '110',
+    2/1 (0x21) = '1110'.
+    `blocks_bits` is the bit string of the whole entropy coded segment ('0'/'1'), padded with ones to a byte boundary."""
+    bits = blocks_bits + "1" * (-len(blocks_bits) % 8)
+    ecs = bytearray()
+    for i in range(0, len(bits), 8):
+        v = int(bits[i:i + 8], 2)
+        ecs.append(v)
+        if v == 0xFF:
+            ecs.append(0)
+    seg = lambda marker, payload: bytes([0xFF, marker]) + (len(payload) + 2).to_bytes(2, "big") + bytes(payload)
+    dqt = seg(0xDB, [0] + [16] * 64)
+    sof = seg(0xC0, [8] + list(height.to_bytes(2, "big")) + list(width.to_bytes(2, "big")) + [1, 1, 0x11, 0])
+    dht_dc = [0x00] + [1, 1] + [0] * 14 + [0, 1]
+    dht_ac = [0x10] + [1, 1, 1, 1] + [0] * 12 + [0xF0, 0x00, 0x01, 0x21]
+    dht = seg(0xC4, dht_dc + dht_ac)
+    drim = seg(0xDD, list(dri.to_bytes(2, "big"))) if dri else b""
+    sos = seg(0xDA, [1, 1, 0x00, 0, 63, 0])
+    return b"\xff\xd8" + dqt + sof + dht + drim + sos + bytes(ecs) + b"\xff\xd9"
+
+
+def zrl_overrun_stream():
+    """One 8x8 block: DC category 1 (value +1), one AC coefficient at k = 1, then four ZRLs -- the fourth steps from k = 50
+    over position 63. The reference re-tests k <= 63 after a ZRL and silently ends the block (sequentialscan.cpp:717-719)."""
+    return handmade_grey_stream("10" + "1" + "110" + "1" + "0000")
+
+
+RESTART_DAMAGES = ["swap", "drop_marker", "drop_interval", "duplicate", "id_plus_4", "id_plus_2", "id_minus_1", "garbage",
+                   "cut_mid_interval", "no_eoi"]
+
+
+def with_restart_damage(data, damage):
+    """The codestream with its restart markers damaged: ids exchanged / shifted, a marker or a whole interval dropped, a
+    marker duplicated, garbage in front of a marker, the stream cut inside an interval (with and without a closing EOI)."""
+    a = bytes(data.tobytes() if hasattr(data, "tobytes") else data)
+    sos = a.find(b"\xff\xda")
+    i, at = sos + 2 + ((a[sos + 2] << 8) | a[sos + 3]), []
+    while i + 1 < len(a):
+        if a[i] == 0xFF and 0xD0 <= a[i + 1] <= 0xD7:
+            at.append(i)
+            i += 2
+        else:
+            i += 1
+    b = bytearray(a)
+    if damage == "swap":
+        b[at[2] + 1], b[at[3] + 1] = b[at[3] + 1], b[at[2] + 1]
+    elif damage == "drop_marker":
+        del b[at[3]:at[3] + 2]
+    elif damage == "drop_interval":
+        del b[at[3]:at[4]]
+    elif damage == "duplicate":
+        b[at[2]:at[2]] = a[at[2]:at[2] + 2]
+    elif damage.startswith("id_"):
+        delta = {"id_plus_4": 4, "id_plus_2": 2, "id_minus_1": 7}[damage]
+        b[at[1] + 1] = 0xD0 + ((b[at[1] + 1] - 0xD0 + delta) & 7)
+    elif damage == "garbage":
+        b[at[2]:at[2]] = b"\x12\x34\xff\x00\x56"
+    elif damage == "cut_mid_interval":
+        b = bytearray(a[:at[3] + 20] + b"\xff\xd9")
+    elif damage == "no_eoi":
+        b = bytearray(a[:at[3] + 20])
+    else:
+        raise ValueError(damage)
+    return bytes(b)

@@ -135,3 +135,37 @@ def test_synthetic_generator_roundtrip_through_oracle(built, oracle):
     rc, px = oracle.decode(data.tobytes())
     assert rc == 0 and px.shape == img.shape
     assert np.abs(px.astype(int) - img.astype(int)).mean() < 12  # a lossy codec, not garbage
+
+
+def test_parser_on_streams_without_eoi(built, oracle):
+    """The host parser gives the reference's verdict for streams whose tail is cut off (tests/golden/noeoi, make_noeoi.py)."""
+    import json
+    from libjpeg_b200 import NativeError
+    d = os.path.join(GOLDEN, "noeoi")
+    for name, status in json.load(open(os.path.join(d, "noeoi_status.json"))).items():
+        data = open(os.path.join(d, name + ".jpg"), "rb").read()
+        if status == 0:
+            fi = built.parse(data)
+            rc, s = oracle.info(data)
+            assert rc == 0 and (fi.width, fi.height, fi.nscans) == (s.width, s.height, s.nscans), name
+        else:
+            with pytest.raises(NativeError) as e:
+                built.parse(data)
+            assert e.value.code == status, name
+
+
+def test_hostile_header_cannot_size_allocations(built):
+    """a 689-byte stream that claims 65535 x 65535 pixels with DRI = 1 (67 M restart intervals) must be refused
+    by the parser instead of allocating gigabytes for its restart index."""
+    import resource
+    from libjpeg_b200 import NativeError
+    from libjpeg_b200 import synth
+    b = bytearray(synth.encode(synth.source_image(16, 16, 1), 75, (1, 1), 1).tobytes())
+    sof = bytes(b).find(b"\xff\xc0")
+    b[sof + 5:sof + 9] = b"\xff\xff\xff\xff"  # height, width
+    assert len(b) < 2000
+    before = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    with pytest.raises(NativeError) as e:
+        built.parse(bytes(b))
+    assert e.value.code in (-1038, -1034)
+    assert resource.getrusage(resource.RUSAGE_SELF).ru_maxrss - before < 64 * 1024  # KiB: nothing of that order was touched

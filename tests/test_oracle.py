@@ -145,38 +145,11 @@ def test_oracle_matches_damaged_golden(oracle, name):
 
 
 @pytest.mark.skipif(not oracle_binding.have_reference(), reason="reference build (oracle/_ref) not present")
-@pytest.mark.parametrize("damage", ["swap", "drop_marker", "drop_interval", "duplicate", "id_plus_4", "id_plus_2", "id_minus_1",
-                                    "garbage", "cut_mid_interval", "no_eoi"])
+@pytest.mark.parametrize("damage", oracle_binding.RESTART_DAMAGES)
 def test_oracle_resynchronises_like_the_reference(oracle, tmp_path, damage):
     """Restart markers out of sequence, missing, duplicated, buried in garbage: same verdict and same pixels as the reference."""
     from libjpeg_b200 import synth
-    a = synth.encode(synth.source_image(200, 136, 3), 75, (2, 2), 2).tobytes()
-    sos = a.find(b"\xff\xda")
-    i, at = sos + 2 + ((a[sos + 2] << 8) | a[sos + 3]), []
-    while i + 1 < len(a):
-        if a[i] == 0xFF and 0xD0 <= a[i + 1] <= 0xD7:
-            at.append(i)
-            i += 2
-        else:
-            i += 1
-    b = bytearray(a)
-    if damage == "swap":
-        b[at[2] + 1], b[at[3] + 1] = b[at[3] + 1], b[at[2] + 1]
-    elif damage == "drop_marker":
-        del b[at[3]:at[3] + 2]
-    elif damage == "drop_interval":
-        del b[at[3]:at[4]]
-    elif damage == "duplicate":
-        b[at[2]:at[2]] = a[at[2]:at[2] + 2]
-    elif damage.startswith("id_"):
-        delta = {"id_plus_4": 4, "id_plus_2": 2, "id_minus_1": 7}[damage]
-        b[at[1] + 1] = 0xD0 + ((b[at[1] + 1] - 0xD0 + delta) & 7)
-    elif damage == "garbage":
-        b[at[2]:at[2]] = b"\x12\x34\xff\x00\x56"
-    elif damage == "cut_mid_interval":
-        b = bytearray(a[:at[3] + 20] + b"\xff\xd9")
-    else:
-        b = bytearray(a[:at[3] + 20])
+    b = oracle_binding.with_restart_damage(synth.encode(synth.source_image(200, 136, 3), 75, (2, 2), 2), damage)
     jpg = tmp_path / "d.jpg"
     jpg.write_bytes(bytes(b))
     ref = oracle_binding.reference_decode(str(jpg), str(tmp_path / "d.raw"))
@@ -227,3 +200,40 @@ def test_oracle_matches_reference_on_stream_variants(oracle, built, tmp_path, fl
     assert ref is not None
     rc, px = oracle.decode(data.tobytes())
     assert rc == 0 and np.array_equal(px, ref)
+
+
+NOEOI = os.path.join(GOLDEN, "noeoi")
+NENAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(NOEOI, "*.jpg")))
+
+
+@pytest.mark.parametrize("name", NENAMES)
+def test_oracle_matches_reference_on_streams_without_eoi(oracle, name):
+    """Streams cut off at the end (no EOI, possibly inside the entropy coded data): the reference only warns when nothing but
+    the tail of the LAST restart interval is missing (Frame::ParseTrailer marker/frame.cpp:1089, zero bits behind the end of
+    the data io/bitstream.cpp:103-105) and fails with UNEXPECTED_EOF when a restart marker it needs is gone
+    (entropyparser.cpp:141-147). The fixtures hold the reference's verdict and pixels (make_noeoi.py)."""
+    import json
+    status = json.load(open(os.path.join(NOEOI, "noeoi_status.json")))[name]
+    rc, px = oracle.decode(open(os.path.join(NOEOI, name + ".jpg"), "rb").read())
+    assert rc == status
+    if status == 0:
+        want = np.load(os.path.join(NOEOI, "noeoi_pixels.npz"))[name]
+        assert np.array_equal(px.reshape(want.shape), want)
+
+
+def test_noeoi_fixtures_cover_both_verdicts():
+    import json
+    status = json.load(open(os.path.join(NOEOI, "noeoi_status.json")))
+    assert sorted(status) == NENAMES and 0 in status.values() and -1025 in status.values()
+
+
+@pytest.mark.skipif(not oracle_binding.have_reference(), reason="reference build (oracle/_ref) not present")
+def test_zrl_that_steps_over_position_63_ends_the_block_silently(oracle, tmp_path):
+    """sequentialscan.cpp:717-719: after a ZRL the reference re-tests k <= 63 and leaves the block without an error."""
+    data = oracle_binding.zrl_overrun_stream()
+    jpg = tmp_path / "z.jpg"
+    jpg.write_bytes(data)
+    ref = oracle_binding.reference_decode(str(jpg), str(tmp_path / "z.raw"))
+    assert ref is not None
+    rc, px = oracle.decode(data)
+    assert rc == 0 and np.array_equal(px.reshape(ref.shape), ref)
