@@ -154,6 +154,8 @@ struct b200jpg_batch {
     uint8_t *d_clean = nullptr;
     uint64_t clean_bytes = 0;
     uint32_t *d_interval_len = nullptr;
+    uint32_t *d_overrun = nullptr;    // per class {count, interval indices}: class ci starts at interval_base + ci
+    size_t sz_overrun = 0;
     uint64_t n_intervals = 0;
     uint32_t *d_status = nullptr;
     std::vector<uint32_t> h_status;
@@ -276,6 +278,7 @@ void b200jpg_batch_destroy(b200jpg_batch *b) {
     b->ctx->put(1, b->d_samples16, b->sample_elems * sizeof(int16_t));
     b->ctx->put(1, b->d_clean, b->clean_bytes);
     b->ctx->put(1, b->d_interval_len, b->sz_ilen);
+    b->ctx->put(1, b->d_overrun, b->sz_overrun);
     b->ctx->put(1, b->d_status, b->sz_status);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
@@ -687,10 +690,19 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     b->sz_status = sizeof(uint32_t) * (5 * (size_t)n + 1);  // status words, wide flags, narrow flags, narrow list, index status
     b->d_input = (uint8_t *)ctx->get(1, b->input_bytes, &ce);
     if (ce == cudaSuccess && b->coef_elems) b->d_coef = (int16_t *)ctx->get(1, b->coef_elems * sizeof(int16_t), &ce);
+    // sample planes only for the reconstruction groups that still go through them: 4:2:0 frames are reconstructed by the fused
+    // kernel (coefficients -> pixels, chroma samples live in shared memory)
+    {
+        bool need_planes = getenv("B200JPG_NO_FUSED") != nullptr;
+        for (auto &g : b->groups) need_planes = need_planes || (g.ncomp > 1 && !(g.ncomp == 3 && g.subx == 2 && g.suby == 2));
+        if (!need_planes) b->sample_elems = 0;
+    }
     if (ce == cudaSuccess && b->sample_elems) b->d_samples = (int32_t *)ctx->get(1, b->sample_elems * sizeof(int32_t), &ce);
     if (ce == cudaSuccess && b->sample_elems) b->d_samples16 = (int16_t *)ctx->get(1, b->sample_elems * sizeof(int16_t), &ce);
     if (ce == cudaSuccess) b->d_clean = (uint8_t *)ctx->get(1, b->clean_bytes, &ce);
     if (ce == cudaSuccess) b->d_interval_len = (uint32_t *)ctx->get(1, b->sz_ilen, &ce);
+    b->sz_overrun = sizeof(uint32_t) * (size_t)(b->n_intervals + b->classes.size() + 1);
+    if (ce == cudaSuccess) b->d_overrun = (uint32_t *)ctx->get(1, b->sz_overrun, &ce);
     if (ce == cudaSuccess) b->d_status = (uint32_t *)ctx->get(1, b->sz_status, &ce);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->ev_last, cudaEventDisableTiming);
     if (ce != cudaSuccess) return ctx->fail(B200JPG_ERR_OUT_OF_MEMORY, std::string("device allocation failed: ") + cudaGetErrorString(ce));
@@ -778,10 +790,16 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
         e = cudaMemsetAsync(b->d_coef, 0, b->coef_elems * sizeof(int16_t), (cudaStream_t)stream);
         if (e != cudaSuccess) return b->ctx->fail_cuda(e, "coefficient store reset");
     }
+    for (size_t ci = 0; ci < b->classes.size(); ci++) {  // the overrun lists start empty
+        e = cudaMemsetAsync(b->d_overrun + b->classes[ci].interval_base + ci, 0, sizeof(uint32_t), (cudaStream_t)stream);
+        if (e != cudaSuccess) return b->ctx->fail_cuda(e, "overrun list reset");
+    }
     for (int pass = 0; pass < 2; pass++) {  // a0 for every class, then a1 for every class
         if (pass == 1 && b->timing && b->ev[3]) cudaEventRecord(b->ev[3], (cudaStream_t)stream);
-        for (auto &cl : b->classes) {
+        for (size_t ci = 0; ci < b->classes.size(); ci++) {
+            auto &cl = b->classes[ci];
             EntropyLaunch l{};
+            l.overrun_list = b->d_overrun + cl.interval_base + ci;
             l.p = cl.p;
             l.bytes = b->d_input;
             l.interval_off = reinterpret_cast<const uint64_t *>(b->d_input + cl.dev_intervals);
@@ -796,6 +814,11 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
             int rc = pass == 0 ? launch_unstuff(l, stream) : (cl.p.progressive ? launch_progressive_scan(l, stream) : launch_entropy(l, stream));
             if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, pass == 0 ? "unstuff kernel launch" : "entropy kernel launch");
             b->last_launches++;
+            if (pass == 1 && !cl.p.progressive) {
+                rc = launch_overrun_verdict(l, stream);
+                if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "overrun verdict kernel launch");
+                b->last_launches++;
+            }
         }
     }
     if (!b->prog_frames.empty()) {  // quantised levels -> the dequantised coefficients stage b expects

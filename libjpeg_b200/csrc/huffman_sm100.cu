@@ -116,7 +116,7 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
     if (g >= n_intervals) return;  // whole warp
     const uint64_t src0 = interval_off[g];
     if (src0 == ~0ull) {  // interval not present in the stream
-        if (lane == 0) interval_len[g] = 0;
+        if (lane == 0) interval_len[g] = kIntervalLenAbsent;
         return;
     }
     const uint64_t src1_raw = interval_end[g];
@@ -252,7 +252,8 @@ template <bool kLutShared>
 __global__ void __launch_bounds__(kThreads, 1)
 entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uint64_t *__restrict__ clean_off,
                       const uint32_t *__restrict__ interval_len, const ClassScan *__restrict__ scans,
-                      const uint8_t *__restrict__ tables, int16_t *__restrict__ coef, uint32_t *__restrict__ frame_status) {
+                      const uint8_t *__restrict__ tables, int16_t *__restrict__ coef, uint32_t *__restrict__ frame_status,
+                      uint32_t *__restrict__ overrun_list) {
     extern __shared__ __align__(16) uint8_t smem[];
     // layout (bytes): [stage: kThreads*144][ring: kThreads*64][qz: 4*128*8][lut: lut_words*4 (if shared)]
     uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
@@ -290,7 +291,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
             iv = (uint32_t)(g % p.intervals_per_scan);
         }
         const uint32_t len_raw = lane_valid ? interval_len[g] : 0u;
-        const uint32_t len_bytes = len_raw & ~kIntervalLenEofFlag;
+        const uint32_t len_bytes = len_raw & kIntervalLenMask;
         const uint8_t *src = clean + (lane_valid ? clean_off[g] : 0ull);
         const uint32_t max_chunks = (len_bytes + 15u) / 16u + 2u;  // data + the 32 zero bytes a0 appended
         const uint32_t mcu0 = iv * p.dri;
@@ -308,7 +309,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         }
 
         // an interval the stream does not contain keeps its blocks zero (sequentialscan.cpp:415-419)
-        const bool decoding = lane_valid && len_bytes != 0u;
+        const bool decoding = lane_valid && !(len_raw & kIntervalLenAbsent);
         // Bit reader. bp = bits consumed so far; x0, x1, x2 = the stream words bp/32, +1 and +2 (x2 is a prefetch, so the
         // shared-memory latency of the ring never sits on the decode chain). The 32 bits at bp are one funnel shift of
         // (x0, x1); consuming bits is an addition, and when bp enters the next word the three registers move up by one.
@@ -487,14 +488,106 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         if ((int)errbits < 0 || (ovf >> 16) != 0u) {
             err = kErrMalformed;  // invalid code / out-of-sync coefficient index / coefficient beyond the int16 store
         } else if (decoding) {
-            // a valid stream never consumes bits beyond the marker that ends its interval
+            // A valid stream never consumes bits beyond the marker that ends its interval. One that does is not necessarily an
+            // error to the reference (its bit reader hands out a byte of zero bits per refill in front of a marker and only
+            // throws when one request cannot be met, io/bitstream.hpp:168-208): overrun_verdict_kernel decides.
             const uint64_t consumed = bp;
-            if (consumed > (uint64_t)len_bytes * 8u && !(len_raw & kIntervalLenEofFlag)) err = kErrUnexpectedEof;
+            if (consumed > (uint64_t)len_bytes * 8u && !(len_raw & kIntervalLenEofFlag)) overrun_list[1u + atomicAdd(overrun_list, 1u)] = (uint32_t)g;
         }
         if (err) atomicMax(frame_status + frame, err);
     }
 }
 
+
+// =====================================================================================================
+// overrun verdict: the intervals whose decoder read past their terminating marker, replayed with the reference's bit reader
+// =====================================================================================================
+// BitStream<false> (io/bitstream.hpp:168-208, io/bitstream.cpp:56-118) keeps m_ucBits buffered bits. Fill() -- called by
+// PeekWord() when fewer than 16 bits are buffered and by Get(n) when fewer than n are -- pulls bytes while at most 24 bits are
+// buffered; standing in front of a marker it adds ONE byte of zero bits per call and returns. SkipBits(n) (the code length
+// after a PeekWord) and Get(n) (the value bits) throw UNEXPECTED_EOF when, after that, fewer than n bits are buffered. So a
+// damaged interval may run on through zero bits for as long as every single request is small -- with the usual tables it
+// always does -- and the frame decodes (with whatever those zero bits mean); only this replay knows. One thread per listed
+// interval, symbol lengths only; rare by construction (damaged streams), so nothing here is tuned.
+__global__ void __launch_bounds__(128)
+overrun_verdict_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uint64_t *__restrict__ clean_off,
+                       const uint32_t *__restrict__ interval_len, const ClassScan *__restrict__ scans, const uint8_t *__restrict__ tables,
+                       const uint32_t *__restrict__ list, uint32_t *__restrict__ frame_status) {
+    const uint32_t n = list[0];
+    const uint32_t *g_lut = reinterpret_cast<const uint32_t *>(tables + kTableHeaderBytes);
+    const uint16_t *lut_off = reinterpret_cast<const uint16_t *>(tables + 16);
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const uint32_t g = list[1 + idx];
+        const uint32_t j = g / p.intervals_per_scan, iv = g % p.intervals_per_scan;
+        const uint32_t len_bytes = interval_len[g] & kIntervalLenMask;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(clean + clean_off[g]);
+        const uint32_t nwords = (len_bytes + 3u) / 4u;
+        const uint32_t real = len_bytes * 8u;  // bits in front of the marker
+        const uint32_t mcu0 = iv * p.dri;
+        const uint32_t nmcu = (p.total_mcus - mcu0 < p.dri) ? (p.total_mcus - mcu0) : p.dri;
+        uint32_t bp = 0, loaded = 0;  // bits consumed; bits pulled into the reader's buffer (zero bytes in front of the marker included)
+        bool thrown = false, stop = false;
+        auto fill = [&]() {
+            do {
+                const bool at_marker = loaded >= real;
+                loaded += 8u;
+                if (at_marker) break;
+            } while (loaded - bp <= 24u);
+        };
+        auto window = [&]() -> uint32_t {  // the 32 bits at bp; zero bits behind the data
+            const uint32_t i = bp >> 5;
+            const uint32_t w0 = i < nwords ? __ldg(w + i) : 0u, w1 = i + 1u < nwords ? __ldg(w + i + 1u) : 0u;
+            return __funnelshift_l(w1, w0, bp);
+        };
+        auto symbol = [&](uint32_t slot) -> uint32_t {  // HuffmanDecoder::Get: PeekWord + SkipBits
+            if (loaded - bp < 16u) fill();
+            const uint32_t hi = window();
+            const uint32_t *t = g_lut + lut_off[slot];
+            uint32_t e = __ldg(t + (hi >> (32 - kLutL1Bits)));
+            if ((e & (31u << 5)) == 0) e = __ldg(t + (1u << kLutL1Bits) + ((e >> 10) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u)));
+            if ((int)e < 0) {  // a code the tables do not define: the sequential kernel has reported it already
+                stop = true;
+                return e;
+            }
+            const uint32_t len = (e >> 5) & 31u;
+            if (len > loaded - bp) thrown = true;
+            bp += len;
+            return e;
+        };
+        auto get = [&](uint32_t s) {  // BitStream::Get(s), s >= 1
+            if (s > loaded - bp) {
+                fill();
+                if (s > loaded - bp) thrown = true;
+            }
+            bp += s;
+        };
+        for (uint32_t mi = 0; mi < nmcu && !thrown && !stop; mi++)
+            for (int c = 0; c < p.ns && !thrown && !stop; c++)
+                for (int b = 0; b < p.mw[c] * p.mh[c] && !thrown && !stop; b++) {
+                    uint32_t e = symbol((uint32_t)p.dc_slot[c]);
+                    if (thrown || stop) break;
+                    if (e & 31u) get(e & 31u);
+                    int k = 1;
+                    while (k <= 63 && !thrown && !stop) {
+                        e = symbol(4u + (uint32_t)p.ac_slot[c]);
+                        if (thrown || stop) break;
+                        const uint32_t s = e & 31u, step = (e >> 19) & 127u;
+                        if (s == 0u) {
+                            if (step == 16u) {
+                                k += 16;  // ZRL
+                                continue;
+                            }
+                            break;  // EOB
+                        }
+                        k += (int)step - 1;
+                        get(s);
+                        if (k >= 64) stop = true;  // out of sync: reported by the sequential kernel
+                        k++;
+                    }
+                }
+        if (thrown) atomicMax(frame_status + scans[j].frame, kErrUnexpectedEof);
+    }
+}
 
 // =====================================================================================================
 // restart index: one CTA per scan
@@ -698,13 +791,22 @@ int launch_entropy(const EntropyLaunch &l, void *stream) {
             e = cudaFuncSetAttribute(entropy_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
         }
-        entropy_decode_kernel<true><<<grid, kThreads, smem, s>>>(l.p, l.clean, l.clean_off, l.interval_len, l.scans, l.tables, l.coef, l.frame_status);
+        entropy_decode_kernel<true><<<grid, kThreads, smem, s>>>(l.p, l.clean, l.clean_off, l.interval_len, l.scans, l.tables, l.coef, l.frame_status,
+                                                                  l.overrun_list);
     } else {
         entropy_decode_kernel<false><<<grid, kThreads, base_smem, s>>>(l.p, l.clean, l.clean_off, l.interval_len, l.scans, l.tables, l.coef,
-                                                                       l.frame_status);
+                                                                       l.frame_status, l.overrun_list);
     }
     e = cudaGetLastError();
     return (int)e;
+}
+
+int launch_overrun_verdict(const EntropyLaunch &l, void *stream) {
+    const uint64_t total = (uint64_t)l.p.n_scans * l.p.intervals_per_scan;
+    if (total == 0) return 0;
+    overrun_verdict_kernel<<<8, 128, 0, (cudaStream_t)stream>>>(l.p, l.clean, l.clean_off, l.interval_len, l.scans, l.tables, l.overrun_list,
+                                                               l.frame_status);
+    return (int)cudaGetLastError();
 }
 
 }  // namespace b200jpg

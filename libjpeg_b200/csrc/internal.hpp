@@ -124,6 +124,10 @@ int launch_restart_index(const IndexScan *scans_dev, uint32_t n_scans, uint8_t *
 // decoder reads zero bits behind it like the reference's bit reader at EOF and does not report the overrun
 constexpr uint64_t kIntervalEofFlag = 1ull << 63;
 constexpr uint32_t kIntervalLenEofFlag = 1u << 31;
+// bit 30 of an interval_len entry: the stream does not contain this interval (its MCUs stay cleared). An interval that is
+// present but EMPTY (two restart markers back to back) is decoded -- from zero bits, like the reference does
+constexpr uint32_t kIntervalLenAbsent = 1u << 30;
+constexpr uint32_t kIntervalLenMask = (1u << 30) - 1u;
 
 struct ScanClassParams {  // uniform over a launch of the entropy kernel
     int ns;
@@ -171,9 +175,14 @@ struct EntropyLaunch {
     const uint8_t *tables;          // device copy of the table-set blob
     int16_t *coef;
     uint32_t *frame_status;         // [n_frames]
+    // sequential scans: {count, interval indices ...} of the intervals whose decoder read past the marker that ends them;
+    // overrun_verdict_kernel replays exactly those with the reference's bit-reader bookkeeping to decide whether the
+    // reference would have thrown (io/bitstream.hpp:168-208, bitstream.cpp:56-118)
+    uint32_t *overrun_list;
 };
 int launch_unstuff(const EntropyLaunch &l, void *stream);
 int launch_entropy(const EntropyLaunch &l, void *stream);
+int launch_overrun_verdict(const EntropyLaunch &l, void *stream);
 // progressive_sm100.cu: one scan class of progressive frames; quantised levels -> dequantised coefficients afterwards
 int launch_progressive_scan(const EntropyLaunch &l, void *stream);
 int launch_progressive_dequant(const ProgFrame *frames_dev, uint32_t n_frames, uint32_t max_blocks, int16_t *coef, uint32_t *frame_status,

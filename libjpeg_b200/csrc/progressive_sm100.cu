@@ -87,8 +87,8 @@ progressive_scan_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, co
     if (g >= total_intervals) return;
     const uint32_t j = (uint32_t)(g / p.intervals_per_scan), iv = (uint32_t)(g % p.intervals_per_scan);
     const uint32_t len_raw = interval_len[g];
-    const uint32_t len_bytes = len_raw & ~kIntervalLenEofFlag;
-    if (len_bytes == 0) return;  // an interval the stream does not contain leaves its blocks as they are
+    const uint32_t len_bytes = len_raw & kIntervalLenMask;
+    if (len_raw & kIntervalLenAbsent) return;  // an interval the stream does not contain leaves its blocks as they are
     const ClassScan &cs = scans[j];
     const uint32_t mcu0 = iv * p.dri;
     const uint32_t nmcu = (p.total_mcus - mcu0 < p.dri) ? (p.total_mcus - mcu0) : p.dri;

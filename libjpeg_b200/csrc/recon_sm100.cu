@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 
 #include "internal.hpp"
@@ -519,6 +520,356 @@ reconstruct_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restr
     }
 }
 
+
+// =====================================================================================================
+// fused reconstruction for 4:2:0 frames: chroma IDCT + luma IDCT + upsampling + colour + store in ONE kernel
+// =====================================================================================================
+// A CTA is one warp. It owns a strip of 32 luma block columns (256 pixels) and walks a segment of the frame top to bottom,
+// two luma block rows per chroma block row:
+//     [C(r0-1)]  C(r0)   L(2 r0)  C(r0+1)  L(2 r0 + 1)  L(2 r0 + 2)  C(r0+2)  L(2 r0 + 3) ...
+// C(k): the 16 Cb + 16 Cr blocks under the strip -- one per lane, the same two compact IDCT loops as a luma row -- go as
+// int16 samples into a two-slot ring in shared memory (slot k & 1: eight sample rows of 128 columns per component plus the
+// one column either side that the upsampling window of the strip's first / last luma block needs).  Those two halo columns
+// belong to the neighbouring strips' blocks; only that one column of them is computed: per (component, side) eight single
+// outputs of the row pass -- one dot product per lane, the row pass is linear before its rounding shift -- and one column
+// pass.  L(j): exactly the luma row of reconstruct_kernel, with the chroma window read from the ring instead of from planes
+// in HBM.  Nothing but coefficients is read from and nothing but pixels is written to HBM: the sample planes, the kernel that
+// wrote them and their 16.5 MB per 4K frame round trip are gone.  A segment recomputes one chroma block row of its upper
+// neighbour (1 / seg_rows of the chroma work); the host picks seg_rows so that the grid fills the chip.
+// Frames whose chroma samples do not fit int16 are flagged `narrow` and redone by the int32 instance (list-driven), as before.
+// ring: [slot 2][component 2][row 8][128 columns] of T, followed by the halo columns [slot][component][row][left, right]
+template <typename T>
+struct RingOf {
+    static constexpr int kRowBytes = 128 * (int)sizeof(T);
+    static constexpr int kCompBytes = 8 * kRowBytes;
+    static constexpr int kSlotBytes = 2 * kCompBytes;
+    static constexpr int kMainBytes = 2 * kSlotBytes;
+    static constexpr int kHaloRowBytes = 2 * (int)sizeof(T);
+    static constexpr int kHaloCompBytes = 8 * kHaloRowBytes;
+    static constexpr int kHaloSlotBytes = 2 * kHaloCompBytes;
+    static constexpr int kBytes = kMainBytes + 2 * kHaloSlotBytes;
+};
+
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_s16(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, int v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// one ring sample (T = short / int) at a shared-space byte address
+template <typename T>
+__device__ __forceinline__ int ring_load(uint32_t a) {
+    return sizeof(T) == 2 ? lds_s16(a) : (int)lds32(a);
+}
+template <typename T>
+__device__ __forceinline__ void ring_store(uint32_t a, int v) {
+    if (sizeof(T) == 2) sts16(a, v);
+    else sts32(a, v);
+}
+
+// The warp's 32 blocks of coefficients (`src_a` for pieces 0..127 = blocks 0..15, `src_b` for blocks 16..31; a luma row passes
+// one run of 4 KB as both) -> tile `ys` [coefficient][lane] after the row pass and the column pass (dct/idct.cpp:237-334).
+// have(block) says whether block b of the 32 exists. Returns this lane's block's min / max sample in mn / mx.
+template <typename Have>
+__device__ __forceinline__ void idct_warp_tile(int *ys, const uint4 *__restrict__ src_a, const uint4 *__restrict__ src_b, Have have, int &mn, int &mx) {
+    const uint32_t lane = threadIdx.x & 31;
+    int *my = ys + lane;
+    const uint32_t wseg = (uint32_t)__cvta_generic_to_shared(ys);
+    const uint32_t prow = lane & 7u, sub = lane >> 3;
+    uint4 pc[8];
+#pragma unroll
+    for (uint32_t i = 0; i < 8; i++) {
+        const uint32_t blk = 4u * i + sub;
+        const uint4 *p = (i < 4) ? src_a + (i * 32u + lane) : src_b + ((i - 4u) * 32u + lane);
+        pc[i] = have(blk) ? __ldg(p) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < 8; i++) {
+        const uint32_t blk = 4u * i + sub;
+        const uint32_t dst = wseg + 128u * (32u + 4u * prow + (blk >> 3)) + 16u * ((blk & 7u) ^ prow);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pc[i].x), "r"(pc[i].y), "r"(pc[i].z), "r"(pc[i].w) : "memory");
+    }
+    __syncwarp();
+    const uint32_t mine = wseg + 128u * (32u + (lane >> 3));
+    auto piece = [&](int r) { return lds128(mine + 512u * (uint32_t)r + 16u * ((lane & 7u) ^ (uint32_t)r)); };
+    uint4 q = piece(0);
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+        const uint4 qn = piece((r < 7) ? r + 1 : r);
+        int v[8];
+        unpack_row(q, v);
+        if (r == 0) v[0] = WADD(v[0], 128 << 7);  // dcoffset << (preshift + 3), idct.cpp:233,244
+        idct8<256, 9>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) my[(8 * r + k) * 32] = v[k];
+        q = qn;
+    }
+    mx = 0, mn = 0;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        int v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = my[(8 * r + k) * 32];
+        idct8<2048, 12>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int r = 0; r < 8; r++) my[(8 * r + k) * 32] = v[r];
+        mx = __vimax3_s32(__vimax3_s32(mx, v[0], v[1]), v[2], v[3]);
+        mx = __vimax3_s32(__vimax3_s32(mx, v[4], v[5]), v[6], v[7]);
+        mn = __vimin3_s32(__vimin3_s32(mn, v[0], v[1]), v[2], v[3]);
+        mn = __vimin3_s32(__vimin3_s32(mn, v[4], v[5]), v[6], v[7]);
+    }
+}
+
+template <typename T, bool kListed>
+__device__ __forceinline__ void reconstruct420_strip(const FrameRecon &f, int *ys, uint32_t ring, const int16_t *__restrict__ coef,
+                                                     uint32_t *__restrict__ narrow_flags, uint8_t *__restrict__ out, uint32_t seg_rows) {
+    using R = RingOf<T>;
+    const uint32_t W = f.width, H = f.height;
+    const uint32_t vbw = (W + 7) >> 3, vbh = (H + 7) >> 3;  // luma blocks that carry visible pixels
+    const int cw = (int)f.cw, ch = (int)f.ch;
+    const uint32_t vch = ((uint32_t)ch + 7u) >> 3;          // chroma block rows that carry real lines
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t sx = blockIdx.x, bx0 = sx * 32u, bx = bx0 + lane;
+    const uint32_t r0 = blockIdx.y * seg_rows;
+    const uint32_t rows_all = (vbh + 1u) >> 1;              // chroma block rows that have luma rows to serve
+    if (r0 >= rows_all || bx0 >= vbw) return;
+    const uint32_t r1 = (r0 + seg_rows < rows_all) ? r0 + seg_rows : rows_all;
+    const uint32_t bwc = f.bw[1];
+    int *my = ys + lane;
+    uint32_t wide_slot[2] = {0u, 0u};  // warp-uniform: a chroma sample of that ring slot lies outside the 32-bit colour range
+
+    // ---- C(k): chroma block row k -> ring slot k & 1
+    auto chroma_row = [&](uint32_t k) {
+        const uint32_t slot = k & 1u;
+        const uint32_t comp = lane >> 4, bl = lane & 15u;  // this lane's block: Cb / Cr, column 16 sx + bl
+        const uint32_t cbx0 = 16u * sx;
+        const uint4 *src_a = reinterpret_cast<const uint4 *>(coef + f.coef_base[1] + ((uint64_t)k * bwc + cbx0) * 64u);
+        const uint4 *src_b = reinterpret_cast<const uint4 *>(coef + f.coef_base[2] + ((uint64_t)k * bwc + cbx0) * 64u);
+        int mn, mx;
+        __syncwarp();
+        idct_warp_tile(ys, src_a, src_b, [&](uint32_t blk) { return cbx0 + (blk & 15u) < bwc; }, mn, mx);
+        // samples -> ring (column-wise: the tile is [sample][lane])
+        const uint32_t base = ring + slot * R::kSlotBytes + comp * R::kCompBytes + (8u * bl) * (uint32_t)sizeof(T);
+#pragma unroll 1
+        for (int r = 0; r < 8; r++) {
+            int v[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) v[c] = my[(8 * r + c) * 32];
+            const uint32_t a = base + (uint32_t)r * R::kRowBytes;
+            if (sizeof(T) == 2) {
+                uint4 w;
+                w.x = ((uint32_t)v[0] & 0xffffu) | ((uint32_t)v[1] << 16);
+                w.y = ((uint32_t)v[2] & 0xffffu) | ((uint32_t)v[3] << 16);
+                w.z = ((uint32_t)v[4] & 0xffffu) | ((uint32_t)v[5] << 16);
+                w.w = ((uint32_t)v[6] & 0xffffu) | ((uint32_t)v[7] << 16);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+            } else {
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a + 16u), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+            }
+        }
+        // ---- halo columns: lane (h, r) = (lane >> 3, lane & 7); h & 1 = side (0: column 7 of the block to the left, 1: column 0
+        // of the block to the right), h >> 1 = component. Output 0 / 7 of the row pass over coefficient row r is one dot
+        // product (the butterfly is linear in front of its rounding shift):
+        //   out0 = 512 v0 + 710 v1 + 669 v2 + 602 v3 + 512 v4 + 402 v5 + 277 v6 + 141 v7,  out7 = the same with the odd terms negated
+        {
+            const uint32_t h = lane >> 3, r = lane & 7u, side = h & 1u, hc = h >> 1;
+            const int nb = side ? (int)(cbx0 + 16u) : (int)cbx0 - 1;
+            const bool exists = nb >= 0 && nb < (int)bwc;
+            int v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (exists) unpack_row(__ldg(reinterpret_cast<const uint4 *>(coef + f.coef_base[1 + hc] + ((uint64_t)k * bwc + (uint32_t)nb) * 64u) + r), v);
+            if (r == 0) v[0] = WADD(v[0], 128 << 7);
+            const int even = WADD(WADD(WMUL(v[0], 512), WMUL(v[2], 669)), WADD(WMUL(v[4], 512), WMUL(v[6], 277)));
+            const int odd = WADD(WADD(WMUL(v[1], 710), WMUL(v[3], 602)), WADD(WMUL(v[5], 402), WMUL(v[7], 141)));
+            const int inter = WADD(side ? WADD(even, odd) : WSUB(even, odd), 256) >> 9;
+            int c[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) c[i] = __shfl_sync(0xffffffffu, inter, (int)((lane & ~7u) + (uint32_t)i));
+            idct8<2048, 12>(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
+            int mine = c[0];
+#pragma unroll
+            for (int i = 1; i < 8; i++) mine = (r == (uint32_t)i) ? c[i] : mine;
+            ring_store<T>(ring + R::kMainBytes + slot * R::kHaloSlotBytes + hc * R::kHaloCompBytes + r * R::kHaloRowBytes + side * (uint32_t)sizeof(T), mine);
+            if (exists) {
+                mx = mine > mx ? mine : mx;
+                mn = mine < mn ? mine : mn;
+            }
+        }
+        if (sizeof(T) == 2) {
+            if (mx > 32767 || mn < -32768) atomicOr(narrow_flags + f.status_idx, 1u);  // `narrow`: the frame needs the int32 ring
+        } else {
+            wide_slot[slot] = __any_sync(0xffffffffu, mx > kWide || mn < -kWide) ? 1u : 0u;
+        }
+        __syncwarp();
+    };
+
+    // ---- L(by): one row of 32 luma blocks -> pixels
+    const uint32_t opitch = W * 3u;
+    const bool valid = bx < vbw;
+    const int X = 8 * (int)bx;
+    const int xmax = (X + 7 < (int)W) ? 7 : (int)((W - 1) & 7);
+    const int cx0 = X / 2 - 1;
+    // this lane's six window columns lie inside the plane: own four by one 8-byte (int16) load, the neighbours by one load each
+    const bool fastx = valid && cx0 >= 0 && cx0 + 6 <= cw;
+    const uint32_t own_off = (4u * lane) * (uint32_t)sizeof(T);
+    const uint32_t left_off = (4u * lane - 1u) * (uint32_t)sizeof(T), right_off = (4u * lane + 4u) * (uint32_t)sizeof(T);
+    auto luma_row = [&](uint32_t by) {
+        const int Y = 8 * (int)by;
+        int mn, mx;
+        const uint4 *src = reinterpret_cast<const uint4 *>(coef + f.coef_base[0] + ((uint64_t)by * f.bw[0] + bx0) * 64u);
+        __syncwarp();
+        idct_warp_tile(ys, src, src + 128, [&](uint32_t blk) { return bx0 + blk < f.bw[0]; }, mn, mx);
+        if (!valid) return;
+        const int ymax = (Y + 7 < (int)H) ? 7 : (int)((H - 1) & 7);
+        uint8_t *obase = out + f.out_base + (uint64_t)Y * opitch + (uint64_t)X * 3u;
+        const int cy0 = Y / 2;
+        const bool ycbcr = f.ycbcr != 0;
+        const bool wide = (sizeof(T) == 4 && (wide_slot[0] | wide_slot[1]) != 0u) || mx > kWide || mn < -kWide;
+        // chroma line y (clamped to the plane = the duplicated first / last line, upsampler.cpp:100-106) of both components
+        auto fetch = [&](int y, int (&d1)[6], int (&d2)[6]) {
+            const int yc = clampi(y, 0, ch - 1);
+            const uint32_t slot = ((uint32_t)yc >> 3) & 1u, rr = (uint32_t)yc & 7u;
+            const uint32_t rowa = ring + slot * R::kSlotBytes + rr * R::kRowBytes;
+            const uint32_t haloa = ring + R::kMainBytes + slot * R::kHaloSlotBytes + rr * R::kHaloRowBytes;  // {left, right} of the row
+            if (fastx) {
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    int (&d)[6] = c ? d2 : d1;
+                    const uint32_t a = rowa + (uint32_t)c * R::kCompBytes, ha = haloa + (uint32_t)c * R::kHaloCompBytes;
+                    if (sizeof(T) == 2) {
+                        const uint2 o = lds64(a + own_off);
+                        d[1] = (int)(short)(o.x & 0xffffu), d[2] = (int)o.x >> 16, d[3] = (int)(short)(o.y & 0xffffu), d[4] = (int)o.y >> 16;
+                    } else {
+                        const uint4 o = lds128(a + own_off);
+                        d[1] = (int)o.x, d[2] = (int)o.y, d[3] = (int)o.z, d[4] = (int)o.w;
+                    }
+                    d[0] = ring_load<T>(lane == 0 ? ha : a + left_off);
+                    d[5] = ring_load<T>(lane == 31 ? ha + (uint32_t)sizeof(T) : a + right_off);
+                }
+            } else {
+                // at the frame edge: dest[-1] = dest[0], dest[width] = dest[width-1] at the TRUE subsampled width
+                // (upsamplerbase.cpp:322-323) = clamped addressing; a clamped column is a strip column or one of its halos
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    const int local = clampi(cx0 + j, 0, cw - 1) - 128 * (int)sx;
+                    const bool in_halo = local < 0 || local > 127;
+                    const uint32_t a = in_halo ? haloa + (local < 0 ? 0u : (uint32_t)sizeof(T)) : rowa + (uint32_t)local * (uint32_t)sizeof(T);
+                    d1[j] = ring_load<T>(a);
+                    d2[j] = ring_load<T>(a + (in_halo ? R::kHaloCompBytes : R::kCompBytes));
+                }
+            }
+        };
+        int top1[6], cur1[6], bot1[6], top2[6], cur2[6], bot2[6];
+        fetch(cy0 - 1, top1, top2);
+        fetch(cy0 + 1, bot1, bot2);
+        fetch(cy0, cur1, cur2);
+        auto lines = [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
+            auto one_line = [&](int r, auto odd_tag) {
+                constexpr bool odd = decltype(odd_tag)::value;
+                constexpr int ra = odd ? 1 : 2, rb = odd ? 2 : 1;  // rounding of even / odd window columns (upsampler.cpp:136-168)
+                int w1[6], w2[6];
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    const int n1 = odd ? bot1[j] : top1[j], n2 = odd ? bot2[j] : top2[j];
+                    w1[j] = WADD(WADD(n1, WMUL(3, cur1[j])), (j & 1) ? rb : ra) >> 2;
+                    w2[j] = WADD(WADD(n2, WMUL(3, cur2[j])), (j & 1) ? rb : ra) >> 2;
+                }
+                int c1[8], c2[8];
+                hfilter2(w1, c1);
+                hfilter2(w2, c2);
+                int px[24];
+#pragma unroll
+                for (int x = 0; x < 8; x++) {
+                    int Rr, G, B;
+                    to_rgb<MODE>(my[(8 * r + x) * 32], c1[x], c2[x], Rr, G, B);
+                    px[3 * x] = Rr, px[3 * x + 1] = G, px[3 * x + 2] = B;
+                }
+                uint32_t wd[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) wd[k] = pack_sat4(px[4 * k], px[4 * k + 1], px[4 * k + 2], px[4 * k + 3]);
+                uint8_t *o = obase + (uint64_t)r * opitch;
+                if (xmax == 7 && ((reinterpret_cast<uintptr_t>(o) & 7u) == 0)) {
+                    uint2 *o2 = reinterpret_cast<uint2 *>(o);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) o2[k] = make_uint2(wd[2 * k], wd[2 * k + 1]);
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 8; x++) {
+                        if (x <= xmax) {
+#pragma unroll
+                            for (int i = 3 * x; i < 3 * x + 3; i++) o[i] = (uint8_t)(wd[i >> 2] >> (8 * (i & 3)));
+                        }
+                    }
+                }
+            };
+#pragma unroll 1
+            for (int r = 0; r < 8; r += 2) {
+                if (r > ymax) break;
+                one_line(r, std::false_type());
+                if (r + 1 <= ymax) one_line(r + 1, std::true_type());
+#pragma unroll
+                for (int j = 0; j < 6; j++) {  // advance the line window after every odd output line (upsampler.cpp:160-165)
+                    top1[j] = cur1[j], cur1[j] = bot1[j];
+                    top2[j] = cur2[j], cur2[j] = bot2[j];
+                }
+                if (r < 6) fetch(cy0 + (r >> 1) + 2, bot1, bot2);
+            }
+        };
+        if (!ycbcr) lines(std::integral_constant<int, 2>());
+        else if (wide) lines(std::integral_constant<int, 1>());
+        else lines(std::integral_constant<int, 0>());
+    };
+
+    if (r0 > 0) chroma_row(r0 - 1);
+    chroma_row(r0);
+    for (uint32_t k = r0; k < r1; k++) {
+        luma_row(2u * k);
+        if (k + 1u < vch) chroma_row(k + 1u);
+        if (2u * k + 1u < vbh) luma_row(2u * k + 1u);
+    }
+}
+
+#ifndef B200JPG_FUSED_CTAS
+#define B200JPG_FUSED_CTAS 13
+#endif
+// grid (strips of 32 luma block columns, segments of seg_rows chroma block rows, frames or kWideSlots); one warp per CTA
+template <typename T, bool kListed>
+__global__ void __launch_bounds__(32, (sizeof(T) == 2) ? B200JPG_FUSED_CTAS : 8)
+reconstruct420_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, uint32_t *__restrict__ narrow_flags,
+                      const uint32_t *__restrict__ list, uint8_t *__restrict__ out, uint32_t seg_rows) {
+    __shared__ int ys[64 * 32];
+    __shared__ __align__(16) uint8_t ring_mem[RingOf<T>::kBytes];
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(ring_mem);
+    if (!kListed) {
+        reconstruct420_strip<T, kListed>(frames[blockIdx.z], ys, ring, coef, narrow_flags, out, seg_rows);
+    } else {
+        const uint32_t n = list[0];
+        for (uint32_t k = blockIdx.z; k < n; k += gridDim.z) {
+            reconstruct420_strip<T, kListed>(frames[list[1 + k]], ys, ring, coef, narrow_flags, out, seg_rows);
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace
 
 template <typename T, bool kListed>
@@ -536,9 +887,34 @@ static void launch_b2(const ReconLaunch &l, dim3 grid, const T *samples, cudaStr
     }
 }
 
+// seg_rows: chroma block rows per CTA of the fused kernel -- as long as possible (a segment recomputes one chroma block row
+// of its upper neighbour) while the grid still holds several waves of CTAs
+static uint32_t fused_seg_rows(const ReconLaunch &l, uint32_t strips, uint32_t rows_all) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t want = (uint64_t)sms * B200JPG_FUSED_CTAS * 6u;  // six waves
+    uint32_t seg = 16;
+    while (seg > 1 && (uint64_t)strips * ((rows_all + seg - 1) / seg) * l.n_frames < want) seg >>= 1;
+    return seg;
+}
+
+static int launch_recon_fused420(const ReconLaunch &l, cudaStream_t s, int *launches) {
+    const uint32_t strips = (l.max_bw0 + 31) / 32, rows_all = (l.max_bh0 + 1) / 2;
+    const uint32_t seg = fused_seg_rows(l, strips, rows_all);
+    const uint32_t gy = (rows_all + seg - 1) / seg;
+    reconstruct420_kernel<int16_t, false><<<dim3(strips, gy, l.n_frames), 32, 0, s>>>(l.frames, l.coef, l.narrow_flags, nullptr, l.out, seg);
+    // the exact pass over the frames flagged `narrow` (none for real images: two near-empty launches)
+    narrow_list_kernel<<<1, 256, 0, s>>>(l.frames, l.n_frames, l.narrow_flags, l.narrow_list);
+    reconstruct420_kernel<int32_t, true><<<dim3(strips, gy, kWideSlots), 32, 0, s>>>(l.frames, l.coef, l.narrow_flags, l.narrow_list, l.out, seg);
+    if (launches) *launches = 3;
+    return (int)cudaGetLastError();
+}
+
 int launch_recon(const ReconLaunch &l, void *stream, int *launches) {
     cudaStream_t s = (cudaStream_t)stream;
     int n = 0;
+    static const bool no_fused = getenv("B200JPG_NO_FUSED") != nullptr;  // A/B switch: the two-kernel path through sample planes
+    if (l.ncomp == 3 && l.subx == 2 && l.suby == 2 && !no_fused) return launch_recon_fused420(l, s, launches);
     const uint32_t cblocks = (l.max_bwc * l.max_bhc + kThreadsB - 1) / kThreadsB;
     const uint32_t gx = (l.max_bw0 + 31) / 32, gy = (l.max_bh0 + kThreadsB / 32 - 1) / (kThreadsB / 32);
     // every frame through the int16 planes
