@@ -30,6 +30,11 @@ inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+static void set_thread_error(int code, const std::string &msg) {
+    g_tls_code = code;
+    g_tls_error = msg;
+}
+
 // Device / pinned-host buffers are recycled through the context: a streaming caller creates and destroys one batch per
 // chunk of frames, and cudaMalloc / cudaHostAlloc per chunk would dominate the host side of the pipeline.
 struct PoolBuf {
@@ -83,8 +88,12 @@ struct b200jpg_ctx {
         pool.clear();
     }
     int fail(int c, const std::string &m) {
-        code = c;
-        error = m;
+        {
+            std::lock_guard<std::mutex> lock(pool_mutex);  // contexts are shared between threads (the JPEG shim)
+            code = c;
+            error = m;
+        }
+        set_thread_error(c, m);  // b200jpg_last_error(NULL, ...) on the failing thread always sees its own failure
         return c;
     }
     int fail_cuda(cudaError_t e, const char *what) {

@@ -12,6 +12,7 @@
 // Pixels come from b200jpg_decode_to_host (CUDA); there is no CPU decode in here.
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -172,12 +173,14 @@ struct JPEG::Impl {
     std::vector<uint8_t> stream;  // the codestream as pulled through the I/O hook
     bool have_image;
     b200jpg_frame_info info;
-    std::vector<uint8_t> pixels;  // decoded frame, interleaved, info.ncomp bytes per pixel
+    // decoded frame, interleaved, info.ncomp bytes per pixel (allocated uninitialised: the decode overwrites every byte)
+    std::unique_ptr<uint8_t[]> pixels;
+    size_t pixel_bytes;
     bool decoded;
     JPG_LONG err_code;
     std::string err_msg;
 
-    Impl() : device(-1), have_image(false), decoded(false), err_code(0) { memset(&info, 0, sizeof(info)); }
+    Impl() : device(-1), have_image(false), pixel_bytes(0), decoded(false), err_code(0) { memset(&info, 0, sizeof(info)); }
     JPG_LONG fail(JPG_LONG code, const std::string &msg) {
         err_code = code;
         err_msg = msg;
@@ -332,15 +335,17 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
         std::string msg;
         int rc = shared_context(s.device, &ctx, msg);
         if (rc) return s.fail(rc, msg);
-        s.pixels.assign((size_t)s.info.width * s.info.height * s.info.ncomp + 256, 0);
+        s.pixel_bytes = (size_t)s.info.width * s.info.height * s.info.ncomp + 256;
+        s.pixels.reset(new (std::nothrow) uint8_t[s.pixel_bytes]);
+        if (!s.pixels) return s.fail(JPGERR_OUT_OF_MEMORY, "out of memory for the decoded frame");
         const uint8_t *frames[1] = {s.stream.data()};
         size_t lens[1] = {s.stream.size()};
-        std::lock_guard<std::mutex> lock(g_ctx_mutex);  // one decode at a time per process-wide context
-        rc = b200jpg_decode_to_host(ctx, frames, lens, 1, s.pixels.data(), s.pixels.size());
+        // JPEG objects decode concurrently: a batch owns its buffers and its stream, the context's buffer pool locks itself
+        rc = b200jpg_decode_to_host(ctx, frames, lens, 1, s.pixels.get(), s.pixel_bytes);
         if (rc) {
             const char *m = 0;
-            b200jpg_last_error(ctx, &m);
-            return s.fail(rc, m ? m : "decoding failed");
+            b200jpg_last_error(0, &m);  // this thread's failure (the context is shared with other JPEG objects)
+            return s.fail(rc, (m && *m) ? m : "decoding failed");
         }
         s.decoded = true;
     }
@@ -403,6 +408,11 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
 
     // ---- copy, block by block like the reference walks the region (PushReconstructedData / ReconstructUnsampled)
     const uint32_t W = s.info.width;
+    // the usual client bitmap -- one interleaved canvas, component c at base + c -- is copied run-wise instead of bytewise
+    bool interleaved = nc > 1;
+    for (int c = 0; c < nc; c++)
+        interleaved = interleaved && lay[c].mem && lay[c].pixel_type && lay[c].mem == lay[0].mem + c && lay[c].bytes_per_pixel == nc &&
+                      lay[c].bytes_per_row == lay[0].bytes_per_row && lay[c].width == lay[0].width && lay[c].height == lay[0].height;
     // block rows up to min(MaxY >> 3, (smallest BIO_HEIGHT >> 3) - 1) are reconstructed (blockbitmaprequester.cpp:1166-1167)
     long long last_by = (long long)(maxy >> 3);
     if ((long long)max_block_row < last_by) last_by = (long long)max_block_row;
@@ -418,9 +428,13 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
                 // or pixel type 0 leave the component unwritten (imagebitmap.cpp:78-110)
                 if (!l.mem || !l.pixel_type || l.width <= (JPG_ULONG)x0 || l.height <= (JPG_ULONG)y0) continue;
                 for (JPG_LONG y = y0; y <= y1; y++) {
-                    const uint8_t *src = s.pixels.data() + ((size_t)y * W + (size_t)x0) * nc + c;
+                    const uint8_t *src = s.pixels.get() + ((size_t)y * W + (size_t)x0) * nc + c;
                     uint8_t *dst = l.mem + (ptrdiff_t)x0 * l.bytes_per_pixel + (ptrdiff_t)y * l.bytes_per_row;
-                    for (JPG_LONG x = x0; x <= x1; x++, src += nc, dst += l.bytes_per_pixel) *dst = *src;
+                    if (interleaved) {  // all components of the run in one go (the other components skip this block)
+                        if (c == 0) memcpy(dst, src, (size_t)(x1 - x0 + 1) * nc);
+                    } else {
+                        for (JPG_LONG x = x0; x <= x1; x++, src += nc, dst += l.bytes_per_pixel) *dst = *src;
+                    }
                 }
             }
         }

@@ -372,3 +372,46 @@ def test_progressive_4k_frames_match_oracle(built, oracle):
     for c in range(s.ncomp):
         q = np.array(s.quant[s.tq[c]], dtype=np.int32).reshape(8, 8)
         assert np.array_equal(dec.coefficients(0, c).astype(np.int32), planes[c] * q), "component %d" % c
+
+
+def test_reference_cli_linked_against_the_b200_library(built, golden_pixels, tmp_path):
+    """SURVEY 8b's acceptance test: the reference's OWN command line client (cmd/main.cpp, reconstruct.cpp, bitmaphook.cpp,
+    filehook.cpp -- compiled unmodified by oracle/Makefile) linked against libb200jpg.so instead of the reference library:
+    `jpeg_b200 in.jpg out.ppm` = Read with DECODER_STOP flags, PeekMarker, GetInformation, 8-row DisplayRectangle stripes
+    with the reference's BitMapHook. Its output files must hold the reference's pixels."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "jpeg_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/jpeg_b200 is built where /root/reference exists (oracle/Makefile)")
+    for name in NAMES:
+        out = str(tmp_path / (name + ".pnm"))
+        r = subprocess.run([exe, os.path.join(GOLDEN, name + ".jpg"), out], capture_output=True, text=True)
+        assert r.returncode == 0 and "failed" not in r.stdout + r.stderr, (name, r.stdout[-300:], r.stderr[-300:])
+        data = open(out, "rb").read()
+        magic, dims, maxv, rest = data.split(b"\n", 3)
+        w, h = map(int, dims.split())
+        px = np.frombuffer(rest, dtype=np.uint8).reshape(h, w, 3 if magic == b"P6" else 1)
+        want = golden_pixels[name]
+        assert np.array_equal(px.reshape(want.shape), want), name
+
+
+def test_region_client_matches_reference_fixtures(built, tmp_path):
+    """horizontal crops (DECODER_MINX / MAXX), planar client bitmaps (BytesPerPixel = 1) and a BitMapHook that
+    returns an error, through tests/client/region_client.cpp linked against libb200jpg.so -- byte for byte the canvas, and the
+    same report line (ok flag, LastError code, number of hook requests), that the same client got from the unmodified
+    reference (tests/golden/regions.npz, make_regions.py)."""
+    import subprocess
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_regions
+    fx = np.load(os.path.join(GOLDEN, "regions.npz"))
+    lib_dir = os.path.join(ROOT, "libjpeg_b200")
+    exe = str(tmp_path / "region_b200")
+    subprocess.run(["g++", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "client", "region_client.cpp"),
+                    "-L" + lib_dir, "-lb200jpg", "-Wl,-rpath," + lib_dir, "-o", exe], check=True)
+    for key, name, args in make_regions.CASES:
+        raw = str(tmp_path / "o.raw")
+        r = subprocess.run([exe, os.path.join(GOLDEN, name + ".jpg"), raw] + args, capture_output=True, text=True)
+        assert r.returncode == 0, (key, r.stderr)
+        assert r.stdout.strip() == bytes(fx[key + "__report"]).decode(), key
+        assert np.array_equal(np.fromfile(raw, dtype=np.uint8), fx[key]), key
