@@ -584,22 +584,25 @@ __device__ __forceinline__ void ring_store(uint32_t a, int v) {
     else sts32(a, v);
 }
 
-// The warp's 32 blocks of coefficients (`src_a` for pieces 0..127 = blocks 0..15, `src_b` for blocks 16..31; a luma row passes
-// one run of 4 KB as both) -> tile `ys` [coefficient][lane] after the row pass and the column pass (dct/idct.cpp:237-334).
-// have(block) says whether block b of the 32 exists. Returns this lane's block's min / max sample in mn / mx.
+// The warp's 32 blocks of coefficients come in as 4 KB of 16-byte pieces, eight per lane (piece i * 32 + lane): a luma row is
+// one contiguous run, a chroma row two runs of 2 KB (Cb blocks 0..15, Cr blocks 16..31). tile_fetch only ISSUES the loads --
+// the strip walk calls it for the NEXT unit before it computes the current one, so HBM latency hides behind a whole unit of
+// arithmetic --, tile_idct parks the pieces in the upper half of the tile (piece (block, row) at row segment 32 + 4 row +
+// block / 8, slot (block % 8) ^ row: conflict-free both ways), hands every lane its own block and runs the row pass and the
+// column pass (dct/idct.cpp:237-334) as two compact loops over the tile [sample][lane].
 template <typename Have>
-__device__ __forceinline__ void idct_warp_tile(int *ys, const uint4 *__restrict__ src_a, const uint4 *__restrict__ src_b, Have have, int &mn, int &mx) {
-    const uint32_t lane = threadIdx.x & 31;
-    int *my = ys + lane;
-    const uint32_t wseg = (uint32_t)__cvta_generic_to_shared(ys);
-    const uint32_t prow = lane & 7u, sub = lane >> 3;
-    uint4 pc[8];
+__device__ __forceinline__ void tile_fetch(uint4 (&pc)[8], const uint4 *__restrict__ src_a, const uint4 *__restrict__ src_b, Have have) {
+    const uint32_t lane = threadIdx.x & 31, sub = lane >> 3;
 #pragma unroll
     for (uint32_t i = 0; i < 8; i++) {
-        const uint32_t blk = 4u * i + sub;
         const uint4 *p = (i < 4) ? src_a + (i * 32u + lane) : src_b + ((i - 4u) * 32u + lane);
-        pc[i] = have(blk) ? __ldg(p) : make_uint4(0u, 0u, 0u, 0u);
+        pc[i] = have(4u * i + sub) ? __ldg(p) : make_uint4(0u, 0u, 0u, 0u);
     }
+}
+
+__device__ __forceinline__ void tile_stash(int *ys, const uint4 (&pc)[8]) {
+    const uint32_t lane = threadIdx.x & 31, prow = lane & 7u, sub = lane >> 3;
+    const uint32_t wseg = (uint32_t)__cvta_generic_to_shared(ys);
 #pragma unroll
     for (uint32_t i = 0; i < 8; i++) {
         const uint32_t blk = 4u * i + sub;
@@ -607,6 +610,13 @@ __device__ __forceinline__ void idct_warp_tile(int *ys, const uint4 *__restrict_
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pc[i].x), "r"(pc[i].y), "r"(pc[i].z), "r"(pc[i].w) : "memory");
     }
     __syncwarp();
+}
+
+// Returns this lane's block's min / max sample in mn / mx.
+__device__ __forceinline__ void tile_idct(int *ys, int &mn, int &mx) {
+    const uint32_t lane = threadIdx.x & 31;
+    int *my = ys + lane;
+    const uint32_t wseg = (uint32_t)__cvta_generic_to_shared(ys);
     const uint32_t mine = wseg + 128u * (32u + (lane >> 3));
     auto piece = [&](int r) { return lds128(mine + 512u * (uint32_t)r + 16u * ((lane & 7u) ^ (uint32_t)r)); };
     uint4 q = piece(0);
@@ -661,11 +671,8 @@ __device__ __forceinline__ void reconstruct420_strip(const FrameRecon &f, int *y
         const uint32_t slot = k & 1u;
         const uint32_t comp = lane >> 4, bl = lane & 15u;  // this lane's block: Cb / Cr, column 16 sx + bl
         const uint32_t cbx0 = 16u * sx;
-        const uint4 *src_a = reinterpret_cast<const uint4 *>(coef + f.coef_base[1] + ((uint64_t)k * bwc + cbx0) * 64u);
-        const uint4 *src_b = reinterpret_cast<const uint4 *>(coef + f.coef_base[2] + ((uint64_t)k * bwc + cbx0) * 64u);
         int mn, mx;
-        __syncwarp();
-        idct_warp_tile(ys, src_a, src_b, [&](uint32_t blk) { return cbx0 + (blk & 15u) < bwc; }, mn, mx);
+        tile_idct(ys, mn, mx);
         // samples -> ring (column-wise: the tile is [sample][lane])
         const uint32_t base = ring + slot * R::kSlotBytes + comp * R::kCompBytes + (8u * bl) * (uint32_t)sizeof(T);
 #pragma unroll 1
@@ -734,9 +741,7 @@ __device__ __forceinline__ void reconstruct420_strip(const FrameRecon &f, int *y
     auto luma_row = [&](uint32_t by) {
         const int Y = 8 * (int)by;
         int mn, mx;
-        const uint4 *src = reinterpret_cast<const uint4 *>(coef + f.coef_base[0] + ((uint64_t)by * f.bw[0] + bx0) * 64u);
-        __syncwarp();
-        idct_warp_tile(ys, src, src + 128, [&](uint32_t blk) { return bx0 + blk < f.bw[0]; }, mn, mx);
+        tile_idct(ys, mn, mx);
         if (!valid) return;
         const int ymax = (Y + 7 < (int)H) ? 7 : (int)((H - 1) & 7);
         uint8_t *obase = out + f.out_base + (uint64_t)Y * opitch + (uint64_t)X * 3u;
@@ -839,12 +844,79 @@ __device__ __forceinline__ void reconstruct420_strip(const FrameRecon &f, int *y
         else lines(std::integral_constant<int, 0>());
     };
 
-    if (r0 > 0) chroma_row(r0 - 1);
-    chroma_row(r0);
-    for (uint32_t k = r0; k < r1; k++) {
-        luma_row(2u * k);
-        if (k + 1u < vch) chroma_row(k + 1u);
-        if (2u * k + 1u < vbh) luma_row(2u * k + 1u);
+    // ---- the walk: [C(r0-1)] C(r0) { L(2k) [C(k+1)] [L(2k+1)] } for k = r0 .. r1-1, the coefficients of unit n+1 in flight
+    // (32 registers per lane) while unit n is computed
+    uint32_t kk = r0;
+    int phase = 0;
+    auto next_unit = [&](int &kind, uint32_t &idx) {  // kind 0: none, 1: chroma block row idx, 2: luma block row idx
+        for (;;) {
+            switch (phase) {
+            case 0:
+                phase = 1;
+                if (r0 > 0) {
+                    kind = 1, idx = r0 - 1;
+                    return;
+                }
+                break;
+            case 1:
+                phase = 2;
+                kind = 1, idx = r0;
+                return;
+            case 2:
+                if (kk >= r1) {
+                    phase = 5;
+                    break;
+                }
+                phase = 3;
+                kind = 2, idx = 2u * kk;
+                return;
+            case 3:
+                phase = 4;
+                if (kk + 1u < vch) {
+                    kind = 1, idx = kk + 1u;
+                    return;
+                }
+                break;
+            case 4: {
+                const uint32_t odd = 2u * kk + 1u;
+                phase = 2;
+                kk++;
+                if (odd < vbh) {
+                    kind = 2, idx = odd;
+                    return;
+                }
+                break;
+            }
+            default:
+                kind = 0, idx = 0;
+                return;
+            }
+        }
+    };
+    uint4 pc[8];
+    auto fetch_unit = [&](int kind, uint32_t idx) {
+        if (kind == 1) {
+            const uint32_t cbx0 = 16u * sx;
+            const uint4 *src_a = reinterpret_cast<const uint4 *>(coef + f.coef_base[1] + ((uint64_t)idx * bwc + cbx0) * 64u);
+            const uint4 *src_b = reinterpret_cast<const uint4 *>(coef + f.coef_base[2] + ((uint64_t)idx * bwc + cbx0) * 64u);
+            tile_fetch(pc, src_a, src_b, [&](uint32_t blk) { return cbx0 + (blk & 15u) < bwc; });
+        } else if (kind == 2) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(coef + f.coef_base[0] + ((uint64_t)idx * f.bw[0] + bx0) * 64u);
+            tile_fetch(pc, src, src + 128, [&](uint32_t blk) { return bx0 + blk < f.bw[0]; });
+        }
+    };
+    int kind, nkind;
+    uint32_t idx, nidx;
+    next_unit(kind, idx);
+    fetch_unit(kind, idx);
+    while (kind) {
+        next_unit(nkind, nidx);
+        __syncwarp();  // every lane is done with the tile (and, before a chroma unit, with the ring slot it replaces)
+        tile_stash(ys, pc);
+        fetch_unit(nkind, nidx);
+        if (kind == 1) chroma_row(idx);
+        else luma_row(idx);
+        kind = nkind, idx = nidx;
     }
 }
 
