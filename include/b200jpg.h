@@ -152,6 +152,11 @@ B200JPG_API float b200jpg_batch_last_unstuff_ms(b200jpg_batch *batch);
  * multiply-add only, add/logic only, and a 1:1 mix. Denominator of the reconstruction kernel's roofline. */
 B200JPG_API int b200jpg_microbench_int32(int device, float *imad_gops, float *alu_gops, float *mix_gops);
 
+/* Self-test of the host logic behind restart-less scans (tests only, no device): replays the synchronisation rounds of the
+ * device kernel for scan 0 of one codestream on the host and checks the resulting work items against a front-to-back walk.
+ * Returns B200JPG_OK, a parser error, or -1..-4 for an inconsistent partition. */
+B200JPG_API int b200jpg_selftest_restartless(const uint8_t *data, size_t len, uint32_t *rounds, uint32_t *n_segments);
+
 /* One-call convenience used by the C++ JPEG shim: host codestreams in, HOST pixels out (upload, decode,
  * download, synchronise).  `out_host` receives b200jpg_batch_out_bytes(batch,-1) bytes. */
 B200JPG_API int b200jpg_decode_to_host(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, uint8_t *out_host,

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "internal.hpp"
+#include "specsync.hpp"
 
 using namespace b200jpg;
 
@@ -113,6 +114,7 @@ struct ScanClass {
     std::vector<uint8_t> scan_on_device; // per scan: its restart index is built by restart_index_kernel
     std::vector<uint64_t> scan_ecs_off, scan_ecs_end;  // per scan, absolute
     uint64_t interval_base = 0;          // index of this class's first interval in d_interval_len
+    uint64_t spec_base = 0;              // indexed classes: first work item of this class in the spec arrays
     // offsets (bytes) of the device copies inside the input buffer
     uint64_t dev_scans = 0, dev_intervals = 0, dev_interval_end = 0, dev_clean_off = 0;
 };
@@ -164,6 +166,9 @@ struct b200jpg_batch {
     uint64_t clean_bytes = 0;
     uint32_t *d_interval_len = nullptr;
     uint32_t *d_overrun = nullptr;    // per class {count, interval indices}: class ci starts at interval_base + ci
+    uint8_t *d_spec = nullptr;        // restart-less scans: segments, exits, entries, counts, DC sums of all indexed classes
+    size_t sz_spec = 0;
+    uint64_t n_spec = 0;              // work items over all indexed classes
     size_t sz_overrun = 0;
     uint64_t n_intervals = 0;
     uint32_t *d_status = nullptr;
@@ -288,6 +293,7 @@ void b200jpg_batch_destroy(b200jpg_batch *b) {
     b->ctx->put(1, b->d_clean, b->clean_bytes);
     b->ctx->put(1, b->d_interval_len, b->sz_ilen);
     b->ctx->put(1, b->d_overrun, b->sz_overrun);
+    if (b->d_spec) b->ctx->put(1, b->d_spec, b->sz_spec);
     b->ctx->put(1, b->d_status, b->sz_status);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
@@ -470,6 +476,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
             p.ah = sc.ah;
             p.al = sc.lowbit;
             p.ordinal = sc.progressive ? (int)si : 0;
+            p.indexed = sc.spec ? 1 : 0;
             ClassKey key{};
             int kk = 0;
             key.v[kk++] = p.ns;
@@ -492,6 +499,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
             key.v[kk++] = p.ah;
             key.v[kk++] = p.al;
             key.v[kk++] = p.ordinal;
+            key.v[kk++] = p.indexed;
             int cidx;
             auto cit = class_index.find(key);
             if (cit == class_index.end()) {
@@ -512,6 +520,10 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
             cl.scan_on_device.push_back(sc.device_index ? 1 : 0);
             cl.scan_ecs_off.push_back(byte_off[i] + (uint64_t)sc.ecs_off);
             cl.scan_ecs_end.push_back(byte_off[i] + (uint64_t)sc.ecs_end);
+            if (sc.spec) {  // work items per scan: what the longest scan of the class needs (unstuffing only shrinks the data)
+                const uint32_t need = (uint32_t)(((uint64_t)(sc.ecs_end - sc.ecs_off) * 8u + kSpecSeqBits - 1u) / kSpecSeqBits) + 1u;
+                cl.p.segs_per_scan = std::max(cl.p.segs_per_scan, need);
+            }
             for (size_t k = 0; k < sc.interval_off.size(); k++) {
                 size_t off = sc.interval_off[k], end = sc.interval_end[k];
                 cl.interval_off.push_back(off == SIZE_MAX ? ~0ull : byte_off[i] + (uint64_t)off);
@@ -572,6 +584,10 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
                 }
             }
             ibase += cl.interval_off.size();
+            if (cl.p.indexed) {
+                cl.spec_base = b->n_spec;
+                b->n_spec += (uint64_t)cl.scans.size() * cl.p.segs_per_scan;
+            }
         }
         b->clean_bytes = ccur + 512;  // slack: the ring prefetch runs up to 64 bytes ahead of the reader
         b->n_intervals = ibase;
@@ -713,6 +729,10 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     b->sz_overrun = sizeof(uint32_t) * (size_t)(b->n_intervals + b->classes.size() + 1);
     if (ce == cudaSuccess) b->d_overrun = (uint32_t *)ctx->get(1, b->sz_overrun, &ce);
     if (ce == cudaSuccess) b->d_status = (uint32_t *)ctx->get(1, b->sz_status, &ce);
+    if (ce == cudaSuccess && b->n_spec) {
+        b->sz_spec = (size_t)b->n_spec * (sizeof(SpecSegment) + 8 + 8 + 4 + 16) + 256;
+        b->d_spec = (uint8_t *)ctx->get(1, b->sz_spec, &ce);
+    }
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->ev_last, cudaEventDisableTiming);
     if (ce != cudaSuccess) return ctx->fail(B200JPG_ERR_OUT_OF_MEMORY, std::string("device allocation failed: ") + cudaGetErrorString(ce));
     b->h_status.assign(n, 0);
@@ -820,10 +840,28 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
             l.tables = b->d_input + b->dev_tables[cl.table_set];
             l.coef = b->d_coef;
             l.frame_status = b->d_status;
+            if (cl.p.indexed) {  // slices of the spec arrays: [segments | exits | entries | counts | dc sums], each over all work items
+                const uint64_t n = b->n_spec, o = cl.spec_base;
+                uint8_t *q = b->d_spec;
+                l.spec_segments = reinterpret_cast<SpecSegment *>(q) + o;
+                q += n * sizeof(SpecSegment);
+                l.spec_exits = reinterpret_cast<unsigned long long *>(q) + o;
+                q += n * 8;
+                l.spec_entries = reinterpret_cast<unsigned long long *>(q) + o;
+                q += n * 8;
+                l.spec_counts = reinterpret_cast<uint32_t *>(q) + o;
+                q += n * 4;
+                l.spec_dc_sums = reinterpret_cast<int32_t *>(q) + 4 * o;
+                if (pass == 1) {
+                    int rs = launch_spec_sync(l, stream);
+                    if (rs != 0) return b->ctx->fail_cuda((cudaError_t)rs, "synchronisation kernel launch");
+                    b->last_launches++;
+                }
+            }
             int rc = pass == 0 ? launch_unstuff(l, stream) : (cl.p.progressive ? launch_progressive_scan(l, stream) : launch_entropy(l, stream));
             if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, pass == 0 ? "unstuff kernel launch" : "entropy kernel launch");
             b->last_launches++;
-            if (pass == 1 && !cl.p.progressive) {
+            if (pass == 1 && !cl.p.progressive && !cl.p.indexed) {
                 rc = launch_overrun_verdict(l, stream);
                 if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "overrun verdict kernel launch");
                 b->last_launches++;
@@ -974,6 +1012,81 @@ int b200jpg_batch_last_timing(b200jpg_batch *b, float *entropy_ms, float *recons
     if (cudaEventElapsedTime(&c, b->ev[1], b->ev[2]) != cudaSuccess) return B200JPG_ERR_CUDA;
     if (entropy_ms) *entropy_ms = a;
     if (reconstruct_ms) *reconstruct_ms = c;
+    return B200JPG_OK;
+}
+
+// Host replay of the synchronisation rounds of spec_sync_kernel on scan 0 of one codestream, checked against a plain
+// front-to-back walk of the same stream (tests only: it validates the round logic, prefix sums and clipping that the device
+// kernel shares through specsync.hpp; nothing in the decode path calls it).
+int b200jpg_selftest_restartless(const uint8_t *data, size_t len, uint32_t *rounds, uint32_t *n_segments) {
+    ParsedFrame pf;
+    std::string err;
+    int rc = parse_codestream(data, len, pf, err);
+    if (rc) return rc;
+    const ScanInfo &sc = pf.scans[0];
+    if (sc.progressive || sc.interval_off.size() != 1) return B200JPG_ERR_INVALID_PARAMETER;
+    TableSet ts;
+    rc = build_table_set(sc, ts, err);
+    if (rc) return rc;
+    // unstuff (io/bitstream.cpp:56-118) into big-endian words
+    std::vector<uint8_t> bytes;
+    for (size_t i = sc.ecs_off; i < sc.ecs_end; i++) {
+        if (data[i] == 0xff) {
+            if (i + 1 < sc.ecs_end && data[i + 1] == 0x00) {
+                bytes.push_back(0xff);
+                i++;
+                continue;
+            }
+            break;  // a marker
+        }
+        bytes.push_back(data[i]);
+    }
+    const uint32_t len_bytes = (uint32_t)bytes.size();
+    bytes.resize((bytes.size() + 3) / 4 * 4 + 64, 0);
+    std::vector<uint32_t> words(bytes.size() / 4);
+    for (size_t i = 0; i < words.size(); i++)
+        words[i] = ((uint32_t)bytes[4 * i] << 24) | ((uint32_t)bytes[4 * i + 1] << 16) | ((uint32_t)bytes[4 * i + 2] << 8) | bytes[4 * i + 3];
+    const uint16_t *lut_off = reinterpret_cast<const uint16_t *>(ts.blob.data() + 16);
+    SpecScan ss{};
+    ss.lut = reinterpret_cast<const uint32_t *>(ts.blob.data() + kTableHeaderBytes);
+    const b200jpg_frame_info &fi = pf.info;
+    for (int c = 0; c < sc.ns; c++) {
+        ss.dc_tab[c] = lut_off[sc.td[c]];
+        ss.ac_tab[c] = lut_off[4 + sc.ta[c]];
+        const int nb = sc.ns > 1 ? fi.hs[sc.comp[c]] * fi.vs[sc.comp[c]] : 1;
+        for (int k = 0; k < nb; k++) ss.comp_of_block[ss.blocks_per_mcu++] = (uint8_t)c;
+    }
+    const uint32_t total_mcus = sc.mcu_cols * sc.mcu_rows;
+    std::vector<SpecSegment> segs;
+    const int r = spec_sync_host_replay(ss, words.data(), len_bytes, total_mcus, segs);
+    if (rounds) *rounds = (uint32_t)r;
+    if (n_segments) *n_segments = (uint32_t)segs.size();
+    // the truth: one walk from the first bit, block by block
+    const uint32_t total_blocks = total_mcus * ss.blocks_per_mcu, nwords = (len_bytes + 3) / 4;
+    std::vector<uint32_t> start_bit(total_blocks + 1);
+    std::vector<int32_t> pred_at((size_t)(total_blocks + 1) * 4, 0);
+    SpecState st{0, 0};
+    int32_t pred[4] = {0, 0, 0, 0};
+    uint32_t walked = 0;
+    for (; walked < total_blocks && st.bit < len_bytes * 8u; walked++) {
+        start_bit[walked] = st.bit;
+        for (int c = 0; c < 4; c++) pred_at[(size_t)walked * 4 + c] = pred[c];
+        const SpecResult one = spec_decode(ss, words.data(), nwords, len_bytes * 8u, st, st.bit + 1);
+        for (int c = 0; c < 4; c++) pred[c] += one.dc_sum[c];
+        st = one.exit;
+    }
+    uint32_t covered = 0;
+    for (const SpecSegment &g : segs) {
+        if (g.n_blocks == 0) continue;
+        if (g.first_block != covered) return -1;                       // the segments tile the blocks in order
+        if (g.first_block < walked) {
+            if (g.bit != start_bit[g.first_block]) return -2;          // and start where their first block starts
+            for (int c = 0; c < sc.ns; c++)
+                if (g.pred[c] != pred_at[(size_t)g.first_block * 4 + c]) return -3;  // with the predictors of that place
+        }
+        covered += g.n_blocks;
+    }
+    if (covered != total_blocks) return -4;
     return B200JPG_OK;
 }
 

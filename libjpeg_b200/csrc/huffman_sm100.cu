@@ -32,6 +32,7 @@
 #include <cstdint>
 
 #include "internal.hpp"
+#include "specsync.hpp"
 
 namespace b200jpg {
 namespace {
@@ -247,13 +248,18 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
 // a1: Huffman decode, one restart interval per lane
 // =====================================================================================================
 constexpr int kQzBytes = 4 * kQzEntries * 8;  // four quantisation tables of (q, offset) pairs
+constexpr int kBdescBytes = 16 * 16;          // indexed decoding: one 16-byte descriptor per block of an MCU (at most 10)
 
-template <bool kLutShared>
+// kIndexed: the work items are the SpecSegments that spec_sync_kernel cut out of restart-less scans (specsync.hpp) instead of
+// restart intervals: a lane starts at any bit, at any block of an MCU, with the DC predictors of that place, and decodes a
+// number of blocks; everything per block -- tables, quantiser, destination -- is then a per-lane quantity (a small table in
+// shared memory indexed by the block's position in its MCU), while the symbol decoder, the ring and the flush are the same.
+template <bool kLutShared, bool kIndexed>
 __global__ void __launch_bounds__(kThreads, 1)
 entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uint64_t *__restrict__ clean_off,
                       const uint32_t *__restrict__ interval_len, const ClassScan *__restrict__ scans,
                       const uint8_t *__restrict__ tables, int16_t *__restrict__ coef, uint32_t *__restrict__ frame_status,
-                      uint32_t *__restrict__ overrun_list) {
+                      uint32_t *__restrict__ overrun_list, const SpecSegment *__restrict__ segments) {
     extern __shared__ __align__(16) uint8_t smem[];
     // layout (bytes): [stage: kThreads*144][ring: kThreads*64][qz: 4*128*8][lut: lut_words*4 (if shared)]
     uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
@@ -261,7 +267,8 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
     const uint32_t s_stage = s_base + threadIdx.x * kStageStride;
     const uint32_t s_ring = s_base + kThreads * kStageStride + threadIdx.x * 64;
     const uint32_t s_qz = s_base + kThreads * kStageStride + kThreads * 64;
-    const uint32_t s_lut = s_qz + kQzBytes;
+    const uint32_t s_bdesc = s_qz + kQzBytes;  // kIndexed: per block of an MCU {DC table, AC table, quantiser pairs, c | x << 8 | y << 16}
+    const uint32_t s_lut = s_bdesc + (kIndexed ? kBdescBytes : 0);
     // cooperative flush: in step i this lane moves bytes [16*(lane&7), +16) of the block staged by lane 4*i + (lane>>3)
     const uint32_t s_flush_sub = (threadIdx.x & 7u) << 4;
     const uint32_t s_flush = s_base + ((threadIdx.x & ~31u) + ((threadIdx.x & 31u) >> 3)) * kStageStride + s_flush_sub;
@@ -279,22 +286,49 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
 
     // Persistent CTAs (one per SM): warp w of CTA b takes the groups of 32 consecutive restart intervals b + gridDim.x * w,
     // then every (gridDim.x * warps per CTA)-th one after that, so any batch size spreads evenly over the SMs.
-    const uint64_t total_intervals = (uint64_t)p.n_scans * p.intervals_per_scan;
+    const uint64_t total_intervals = (uint64_t)p.n_scans * (kIndexed ? p.segs_per_scan : p.intervals_per_scan);
     const uint64_t n_groups = (total_intervals + 31u) / 32u;
+    if (kIndexed) {
+        if (threadIdx.x == 0) {
+            uint32_t b = 0;
+            for (int c = 0; c < p.ns; c++)
+                for (int y = 0; y < p.mh[c]; y++)
+                    for (int x = 0; x < p.mw[c]; x++, b++) {
+                        sts_u32(s_bdesc + 16 * b, s_lut + 4u * lut_off[p.dc_slot[c]]);
+                        sts_u32(s_bdesc + 16 * b + 4, s_lut + 4u * lut_off[4 + p.ac_slot[c]]);
+                        sts_u32(s_bdesc + 16 * b + 8, s_qz + (uint32_t)(kQzEntries * 8) * p.q_slot[c]);
+                        sts_u32(s_bdesc + 16 * b + 12, (uint32_t)c | ((uint32_t)x << 8) | ((uint32_t)y << 16));
+                    }
+        }
+        __syncthreads();
+    }
     for (uint64_t grp = blockIdx.x + (uint64_t)gridDim.x * (threadIdx.x >> 5); grp < n_groups; grp += (uint64_t)gridDim.x * (kThreads / 32)) {
         const uint64_t g = grp * 32u + (threadIdx.x & 31u);
         cp_async_wait<0>();  // nothing of the previous group may still land in the ring
         const bool lane_valid = g < total_intervals;
         uint32_t j = 0, iv = 0;
         if (lane_valid) {
-            j = (uint32_t)(g / p.intervals_per_scan);
-            iv = (uint32_t)(g % p.intervals_per_scan);
+            j = (uint32_t)(g / (kIndexed ? p.segs_per_scan : p.intervals_per_scan));
+            iv = (uint32_t)(g % (kIndexed ? p.segs_per_scan : p.intervals_per_scan));
         }
-        const uint32_t len_raw = lane_valid ? interval_len[g] : 0u;
-        const uint32_t len_bytes = len_raw & kIntervalLenMask;
-        const uint8_t *src = clean + (lane_valid ? clean_off[g] : 0ull);
+        // indexed: the scan is ONE unstuffed interval (number j); this lane's work item starts seg_bit bits into it
+        uint32_t seg_bit = 0, seg_first = 0, seg_blocks = 0;
+        int seg_pred[4] = {0, 0, 0, 0};
+        if (kIndexed && lane_valid) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(segments + g));
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(segments + g) + 1);
+            seg_bit = a.x, seg_first = a.y, seg_blocks = a.z;
+            seg_pred[0] = (int)a.w, seg_pred[1] = (int)b.x, seg_pred[2] = (int)b.y, seg_pred[3] = (int)b.z;
+        }
+        const uint32_t len_raw = lane_valid ? interval_len[kIndexed ? (uint64_t)j : g] : 0u;
+        const uint32_t seg_skip = (seg_bit >> 7) << 4;  // whole 16-byte chunks in front of the work item
+        const uint32_t len_all = len_raw & kIntervalLenMask;
+        const uint32_t len_bytes = kIndexed ? (len_all > seg_skip ? len_all - seg_skip : 0u) : len_all;
+        const uint8_t *src = clean + (lane_valid ? clean_off[kIndexed ? (uint64_t)j : g] : 0ull) + seg_skip;
         const uint32_t max_chunks = (len_bytes + 15u) / 16u + 2u;  // data + the 32 zero bytes a0 appended
-        const uint32_t mcu0 = iv * p.dri;
+        const uint32_t mcu0 = kIndexed ? seg_first / (uint32_t)(p.mw[0] * p.mh[0] + (p.ns > 1 ? p.mw[1] * p.mh[1] : 0) + (p.ns > 2 ? p.mw[2] * p.mh[2] : 0) +
+                                                                (p.ns > 3 ? p.mw[3] * p.mh[3] : 0))
+                                       : iv * p.dri;
         uint32_t nmcu = 0;
         if (lane_valid) nmcu = (p.total_mcus - mcu0 < p.dri) ? (p.total_mcus - mcu0) : p.dri;
         uint32_t mx = mcu0 % p.mcu_cols, my = mcu0 / p.mcu_cols;
@@ -309,12 +343,12 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         }
 
         // an interval the stream does not contain keeps its blocks zero (sequentialscan.cpp:415-419)
-        const bool decoding = lane_valid && !(len_raw & kIntervalLenAbsent);
+        const bool decoding = lane_valid && !(len_raw & kIntervalLenAbsent) && (!kIndexed || seg_blocks != 0u);
         // Bit reader. bp = bits consumed so far; x0, x1, x2 = the stream words bp/32, +1 and +2 (x2 is a prefetch, so the
         // shared-memory latency of the ring never sits on the decode chain). The 32 bits at bp are one funnel shift of
         // (x0, x1); consuming bits is an addition, and when bp enters the next word the three registers move up by one.
         // req = 16-byte chunks requested from HBM so far, safe_w = stream words known to have landed in the ring.
-        uint32_t bp = 0, xw = 0, x0 = 0, x1 = 0, x2 = 0, req = 0, safe_w = 0;
+        uint32_t bp = kIndexed ? (seg_bit & 127u) : 0u, xw = bp >> 5, x0 = 0, x1 = 0, x2 = 0, req = 0, safe_w = 0;
         // chunk `c` of the interval into its ring slot; past the end of the interval the reader sees zeros, exactly what
         // the reference's bit reader hands out once it stands in front of a marker (io/bitstream.cpp:96-101)
         auto request = [&](uint32_t c) {
@@ -330,14 +364,14 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         cp_async_wait<0>();
         safe_w = req << 2;
         if (decoding) {
-            x0 = lds_u32_v(s_ring);
-            x1 = lds_u32_v(s_ring + 4);
-            x2 = lds_u32_v(s_ring + 8);
+            x0 = lds_u32_v(s_ring + 4 * xw);
+            x1 = lds_u32_v(s_ring + 4 * xw + 4);
+            x2 = lds_u32_v(s_ring + 4 * xw + 8);
         }
 
         uint32_t errbits = 0;  // bit 31: an entry that must not be decoded was decoded
         uint32_t ovf = 0;      // | (v + 32768): bits 16.. set when a dequantised coefficient left the int16 range
-        int pred[4] = {0, 0, 0, 0};
+        int pred[4] = {seg_pred[0], seg_pred[1], seg_pred[2], seg_pred[3]};
         uint32_t dc_off[4], ac_off[4], q_addr[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -391,97 +425,131 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
             return (int)mag * (-2 * pos - 1);
         };
 
-        for (uint32_t mi = 0; mi < p.dri; mi++) {
-            const bool has_mcu = mi < nmcu;
+        // ---- one block: `has` says whether this lane has a block in this step; tables, predictor and destination are the
+        // caller's (warp-uniform compile-time choices for restart intervals, per-lane values for indexed work items)
+        auto decode_block = [&](const bool has, const uint32_t dc_tab, const uint32_t ac_tab, const uint32_t q_tab, int &predc, const int16_t *d) {
+            // ---- convergent ring top-up: keep the reader two to four 16-byte chunks ahead
+            {
+                const uint32_t ch = bp >> 7;
+                const uint32_t landed = req;  // requested before this point: lands at the wait below
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                if (c >= p.ns) break;
-                for (int y = 0; y < p.mh[c]; y++) {
-                    for (int x = 0; x < p.mw[c]; x++) {
-                        // ---- convergent ring top-up: keep the reader two to four 16-byte chunks ahead
-                        {
-                            const uint32_t ch = bp >> 7;
-                            const uint32_t landed = req;  // requested before this point: lands at the wait below
+                for (int t = 0; t < 2; t++) {
+                    if (decoding && req < ch + 4u) request(req++);
+                    cp_async_commit();
+                }
+                cp_async_wait<2>();
+                safe_w = landed << 2;
+            }
+            // a lane that met an error keeps its blocks zero from there on. k = zig-zag index of the next
+            // coefficient; k > 63: the lane has nothing (more) to decode in this block
+            int k = 64;
+            // The dequantise + store of a coefficient is deferred by one symbol: its table pair (pq) is loaded
+            // when the symbol is decoded and consumed after the NEXT symbol's table lookup has been issued, so
+            // neither shared-memory latency is exposed. {0, 128} parks a "nothing pending" store in the pad slot.
+            uint2 pq = make_uint2(0u, 128u);
+            int pd = 0;
+            auto drain = [&]() {
+                const int v = pd * (int)pq.x;
+                ovf |= mad_u32((uint32_t)pd, pq.x, 32768u);
+                sts_u16(s_stage + pq.y, v);
+            };
+            // ---- DC: sequentialscan.cpp:682-701
+            if (has && decoding && (int)errbits >= 0) {
+                const uint32_t hi = __funnelshift_l(x1, x0, bp);
+                const uint32_t e = lookup(dc_tab, hi);
+                errbits |= e;
+                if ((int)e >= 0) {
+                    predc += value_of(e, hi);
+                    advance(e);
+                    pd = predc;
+                    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_tab));
+                    k = 1;
+                }
+            }
+            // ---- AC: sequentialscan.cpp:704-771, one symbol per warp-convergent iteration. The table entry
+            // carries the step of the zig-zag index: run + 1 for a coefficient, 16 for ZRL (the reference
+            // re-tests k <= 63 and silently ends the block, :717-719), kQzBlockEnds for EOB and for entries
+            // that must not be decoded (bit 31). The table pair is fetched at k - 1 in every case: symbols
+            // without value bits store a zero (ZRL: in a position that is zero anyway; block end: pad slot),
+            // a coefficient whose run leaves the block hits a pair that multiplies it out of the int16 range
+            // (:764-766: out of sync), a ZRL that leaves it multiplies its zero and just ends the block.
+            while (__any_sync(kFull, k <= 63)) {
+                if (k <= 63) {
+                    const uint32_t hi = __funnelshift_l(x1, x0, bp);
+                    const uint32_t e = lookup(ac_tab, hi);
+                    drain();
+                    errbits |= e | pq.x;
+                    pd = value_of(e, hi);  // 0 when the symbol carries no value bits
+                    advance(e);
+                    k += (int)mulhi_u32(mad_u32(e, 64u, 0u), 128u);  // bits 25:19
+                    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(mad_u32((uint32_t)k, 8u, q_tab - 8u)));
+                }
+            }
+            errbits |= pq.x;
+            drain();
+            // ---- flush (zeros included) and clear the staging blocks, the whole warp together: every lane
+            // publishes where its block goes (0 = nowhere) in the pad of its staging block, then each store
+            // instruction moves four complete 128-byte blocks (eight lanes x 16 bytes per block) instead of one
+            // 16-byte piece of 32 different blocks -- 4 instead of 32 L1 wavefronts per instruction
+            {
+                sts_u64(s_stage + 136, has ? (uint64_t)d : 0ull);
+                __syncwarp();
 #pragma unroll
-                            for (int t = 0; t < 2; t++) {
-                                if (decoding && req < ch + 4u) request(req++);
-                                cp_async_commit();
-                            }
-                            cp_async_wait<2>();
-                            safe_w = landed << 2;
-                        }
-                        // a lane that met an error keeps its blocks zero from there on. k = zig-zag index of the next
-                        // coefficient; k > 63: the lane has nothing (more) to decode in this block
-                        int k = 64;
-                        // The dequantise + store of a coefficient is deferred by one symbol: its table pair (pq) is loaded
-                        // when the symbol is decoded and consumed after the NEXT symbol's table lookup has been issued, so
-                        // neither shared-memory latency is exposed. {0, 128} parks a "nothing pending" store in the pad slot.
-                        uint2 pq = make_uint2(0u, 128u);
-                        int pd = 0;
-                        auto drain = [&]() {
-                            const int v = pd * (int)pq.x;
-                            ovf |= mad_u32((uint32_t)pd, pq.x, 32768u);
-                            sts_u16(s_stage + pq.y, v);
-                        };
-                        // ---- DC: sequentialscan.cpp:682-701
-                        if (has_mcu && decoding && (int)errbits >= 0) {
-                            const uint32_t hi = __funnelshift_l(x1, x0, bp);
-                            const uint32_t e = lookup(dc_off[c], hi);
-                            errbits |= e;
-                            if ((int)e >= 0) {
-                                pred[c] += value_of(e, hi);
-                                advance(e);
-                                pd = pred[c];
-                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_addr[c]));
-                                k = 1;
-                            }
-                        }
-                        // ---- AC: sequentialscan.cpp:704-771, one symbol per warp-convergent iteration. The table entry
-                        // carries the step of the zig-zag index: run + 1 for a coefficient, 16 for ZRL (the reference
-                        // re-tests k <= 63 and silently ends the block, :717-719), kQzBlockEnds for EOB and for entries
-                        // that must not be decoded (bit 31). The table pair is fetched at k - 1 in every case: symbols
-                        // without value bits store a zero (ZRL: in a position that is zero anyway; block end: pad slot),
-                        // a coefficient whose run leaves the block hits a pair that multiplies it out of the int16 range
-                        // (:764-766: out of sync), a ZRL that leaves it multiplies its zero and just ends the block.
-                        while (__any_sync(kFull, k <= 63)) {
-                            if (k <= 63) {
-                                const uint32_t hi = __funnelshift_l(x1, x0, bp);
-                                const uint32_t e = lookup(ac_off[c], hi);
-                                drain();
-                                errbits |= e | pq.x;
-                                pd = value_of(e, hi);  // 0 when the symbol carries no value bits
-                                advance(e);
-                                k += (int)mulhi_u32(mad_u32(e, 64u, 0u), 128u);  // bits 25:19
-                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(mad_u32((uint32_t)k, 8u, q_addr[c] - 8u)));
-                            }
-                        }
-                        errbits |= pq.x;
-                        drain();
-                        // ---- flush (zeros included) and clear the staging blocks, the whole warp together: every lane
-                        // publishes where its block goes (0 = nowhere) in the pad of its staging block, then each store
-                        // instruction moves four complete 128-byte blocks (eight lanes x 16 bytes per block) instead of one
-                        // 16-byte piece of 32 different blocks -- 4 instead of 32 L1 wavefronts per instruction
-                        {
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t a = s_flush + i * (4 * kStageStride);
+                    const uint64_t dst = lds_u64(a + 136 - s_flush_sub);
+                    const uint4 v = lds_v4(a);
+                    sts_v4_zero(a);
+                    if (dst) *reinterpret_cast<uint4 *>(dst + s_flush_sub) = v;
+                }
+                __syncwarp();
+            }
+        };
+
+        if (!kIndexed) {
+            for (uint32_t mi = 0; mi < p.dri; mi++) {
+                const bool has_mcu = mi < nmcu;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (c >= p.ns) break;
+                    for (int y = 0; y < p.mh[c]; y++) {
+                        for (int x = 0; x < p.mw[c]; x++) {
                             const uint32_t bx = mx * p.mw[c] + x, by = my * p.mh[c] + y;
-                            const int16_t *d = coef + plane[c] + ((uint64_t)by * p.bw[c] + bx) * 64u;
-                            sts_u64(s_stage + 136, has_mcu ? (uint64_t)d : 0ull);
-                            __syncwarp();
-#pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                const uint32_t a = s_flush + i * (4 * kStageStride);
-                                const uint64_t dst = lds_u64(a + 136 - s_flush_sub);
-                                const uint4 v = lds_v4(a);
-                                sts_v4_zero(a);
-                                if (dst) *reinterpret_cast<uint4 *>(dst + s_flush_sub) = v;
-                            }
-                            __syncwarp();
+                            decode_block(has_mcu, dc_off[c], ac_off[c], q_addr[c], pred[c], coef + plane[c] + ((uint64_t)by * p.bw[c] + bx) * 64u);
                         }
                     }
                 }
+                if (++mx == p.mcu_cols) {
+                    mx = 0;
+                    my++;
+                }
             }
-            if (++mx == p.mcu_cols) {
-                mx = 0;
-                my++;
+        } else {
+            // per-lane walk over this work item's blocks: block b of MCU (mx, my); the warp runs as long as its longest item
+            uint32_t bpm = 0;
+            for (int c = 0; c < p.ns; c++) bpm += (uint32_t)(p.mw[c] * p.mh[c]);
+            uint32_t b = seg_first % bpm;
+            const uint32_t nb = decoding ? seg_blocks : 0u;
+            const uint32_t max_nb = __reduce_max_sync(kFull, nb);
+            for (uint32_t bi = 0; bi < max_nb; bi++) {
+                const bool has = bi < nb;
+                const uint4 bd = lds_v4(s_bdesc + 16u * b);
+                const uint32_t c = bd.w & 0xffu, x = (bd.w >> 8) & 0xffu, y = bd.w >> 16;
+                const uint32_t mw = c == 0 ? (uint32_t)p.mw[0] : (c == 1 ? (uint32_t)p.mw[1] : (c == 2 ? (uint32_t)p.mw[2] : (uint32_t)p.mw[3]));
+                const uint32_t mh = c == 0 ? (uint32_t)p.mh[0] : (c == 1 ? (uint32_t)p.mh[1] : (c == 2 ? (uint32_t)p.mh[2] : (uint32_t)p.mh[3]));
+                const uint32_t bw = c == 0 ? (uint32_t)p.bw[0] : (c == 1 ? (uint32_t)p.bw[1] : (c == 2 ? (uint32_t)p.bw[2] : (uint32_t)p.bw[3]));
+                const uint64_t pl = c == 0 ? plane[0] : (c == 1 ? plane[1] : (c == 2 ? plane[2] : plane[3]));
+                int pr = c == 0 ? pred[0] : (c == 1 ? pred[1] : (c == 2 ? pred[2] : pred[3]));
+                const uint32_t bx = mx * mw + x, by = my * mh + y;
+                decode_block(has, bd.x, bd.y, bd.z, pr, coef + pl + ((uint64_t)by * bw + bx) * 64u);
+                pred[0] = c == 0 ? pr : pred[0], pred[1] = c == 1 ? pr : pred[1], pred[2] = c == 2 ? pr : pred[2], pred[3] = c == 3 ? pr : pred[3];
+                if (++b == bpm) {
+                    b = 0;
+                    if (++mx == p.mcu_cols) {
+                        mx = 0;
+                        my++;
+                    }
+                }
             }
         }
         uint32_t err = 0;
@@ -492,7 +560,8 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
             // error to the reference (its bit reader hands out a byte of zero bits per refill in front of a marker and only
             // throws when one request cannot be met, io/bitstream.hpp:168-208): overrun_verdict_kernel decides.
             const uint64_t consumed = bp;
-            if (consumed > (uint64_t)len_bytes * 8u && !(len_raw & kIntervalLenEofFlag)) overrun_list[1u + atomicAdd(overrun_list, 1u)] = (uint32_t)g;
+            // (indexed work items: a cut restart-less scan just runs on through zero bits like the reference's reader does)
+            if (!kIndexed && consumed > (uint64_t)len_bytes * 8u && !(len_raw & kIntervalLenEofFlag)) overrun_list[1u + atomicAdd(overrun_list, 1u)] = (uint32_t)g;
         }
         if (err) atomicMax(frame_status + frame, err);
     }
@@ -773,32 +842,37 @@ int launch_unstuff(const EntropyLaunch &l, void *stream) {
     return (int)cudaGetLastError();
 }
 
-int launch_entropy(const EntropyLaunch &l, void *stream) {
-    const uint64_t total = (uint64_t)l.p.n_scans * l.p.intervals_per_scan;
+template <bool kIndexed>
+static int launch_entropy_impl(const EntropyLaunch &l, void *stream) {
+    const uint64_t total = (uint64_t)l.p.n_scans * (kIndexed ? l.p.segs_per_scan : l.p.intervals_per_scan);
     if (total == 0) return 0;
     int dev = 0, sm_count = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return (int)cudaGetLastError();
     const uint64_t groups = (total + 31) / 32;
     const uint32_t grid = (uint32_t)(groups < (uint64_t)sm_count ? groups : (uint64_t)sm_count);
-    const size_t base_smem = (size_t)kThreads * kStageStride + (size_t)kThreads * 64 + kQzBytes;
+    const size_t base_smem = (size_t)kThreads * kStageStride + (size_t)kThreads * 64 + kQzBytes + (kIndexed ? kBdescBytes : 0);
     const size_t lut_bytes = (size_t)l.p.lut_words * 4;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
     if (base_smem + lut_bytes <= 227 * 1024) {
         const size_t smem = base_smem + lut_bytes;
         if (smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(entropy_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(entropy_decode_kernel<true, kIndexed>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
         }
-        entropy_decode_kernel<true><<<grid, kThreads, smem, s>>>(l.p, l.clean, l.clean_off, l.interval_len, l.scans, l.tables, l.coef, l.frame_status,
-                                                                  l.overrun_list);
+        entropy_decode_kernel<true, kIndexed><<<grid, kThreads, smem, s>>>(l.p, l.clean, l.clean_off, l.interval_len, l.scans, l.tables, l.coef,
+                                                                            l.frame_status, l.overrun_list, l.spec_segments);
     } else {
-        entropy_decode_kernel<false><<<grid, kThreads, base_smem, s>>>(l.p, l.clean, l.clean_off, l.interval_len, l.scans, l.tables, l.coef,
-                                                                       l.frame_status, l.overrun_list);
+        entropy_decode_kernel<false, kIndexed><<<grid, kThreads, base_smem, s>>>(l.p, l.clean, l.clean_off, l.interval_len, l.scans, l.tables, l.coef,
+                                                                                 l.frame_status, l.overrun_list, l.spec_segments);
     }
     e = cudaGetLastError();
     return (int)e;
+}
+
+int launch_entropy(const EntropyLaunch &l, void *stream) {
+    return l.p.indexed ? launch_entropy_impl<true>(l, stream) : launch_entropy_impl<false>(l, stream);
 }
 
 int launch_overrun_verdict(const EntropyLaunch &l, void *stream) {

@@ -53,6 +53,9 @@ struct ScanInfo {  // one SOS + its entropy coded segment
     // the data ends inside this scan's last restart interval (no marker behind it): the decoder reads zero bits there and
     // must not report the overrun (the reference does not, io/bitstream.cpp:103-105)
     bool eof_tail = false;
+    // a sequential scan without restart markers that is long enough to be worth cutting up: decoded through synchronisation
+    // points (specsync.hpp) instead of by a single lane
+    bool spec = false;
     HuffSpec dc[4], ac[4];       // tables in effect at this SOS
     uint16_t quant[4][64];       // zig-zag order as transmitted, in effect at this SOS
     bool quant_defined[4] = {false, false, false, false};
@@ -129,6 +132,8 @@ constexpr uint32_t kIntervalLenEofFlag = 1u << 31;
 constexpr uint32_t kIntervalLenAbsent = 1u << 30;
 constexpr uint32_t kIntervalLenMask = (1u << 30) - 1u;
 
+struct SpecSegment;
+
 struct ScanClassParams {  // uniform over a launch of the entropy kernel
     int ns;
     int mw[4], mh[4];       // blocks per MCU of scan component c (1,1 for single component scans)
@@ -140,6 +145,10 @@ struct ScanClassParams {  // uniform over a launch of the entropy kernel
     // progressive scans (SOF2): handled by progressive_scan_kernel instead of entropy_decode_kernel
     int progressive, ss, se, ah, al;
     int ordinal;            // position of the scan inside its frame: progressive classes are launched in this order
+    // restart-less sequential scans decoded through synchronisation points (specsync.hpp): the scan is ONE interval to the
+    // unstuffing kernel and segs_per_scan work items (SpecSegment) to the decoder
+    int indexed;
+    uint32_t segs_per_scan;
 };
 
 // One progressive frame for the dequantisation pass that follows its last scan: the progressive kernels keep
@@ -179,10 +188,16 @@ struct EntropyLaunch {
     // overrun_verdict_kernel replays exactly those with the reference's bit-reader bookkeeping to decide whether the
     // reference would have thrown (io/bitstream.hpp:168-208, bitstream.cpp:56-118)
     uint32_t *overrun_list;
+    // indexed classes (p.indexed): work items written by spec_sync_kernel and its scratch, [n_scans * segs_per_scan] each
+    struct SpecSegment *spec_segments;
+    unsigned long long *spec_exits, *spec_entries;
+    uint32_t *spec_counts;
+    int32_t *spec_dc_sums;  // [.. * 4]
 };
 int launch_unstuff(const EntropyLaunch &l, void *stream);
 int launch_entropy(const EntropyLaunch &l, void *stream);
 int launch_overrun_verdict(const EntropyLaunch &l, void *stream);
+int launch_spec_sync(const EntropyLaunch &l, void *stream);  // specsync_sm100.cu
 // progressive_sm100.cu: one scan class of progressive frames; quantised levels -> dequantised coefficients afterwards
 int launch_progressive_scan(const EntropyLaunch &l, void *stream);
 int launch_progressive_dequant(const ProgFrame *frames_dev, uint32_t n_frames, uint32_t max_blocks, int16_t *coef, uint32_t *frame_status,

@@ -11,9 +11,11 @@
 //   two-level Huffman decoder  coding/huffmantemplate.cpp:802-874, coding/huffmandecoder.hpp:64-124
 // The validation rules and error codes follow those files so that LastError reports what a client of the
 // reference would see.
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.hpp"
+#include "specsync.hpp"
 
 namespace b200jpg {
 
@@ -363,6 +365,8 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
                 FAIL(B200JPG_ERR_UNEXPECTED_EOF, "run into end of file while trying to resync the entropy parser");
             // the data ends inside the scan's LAST interval: only then does the decoder read zero bits behind it
             sc.eof_tail = sc.eof_tail && sc.interval_off[nint - 1] != SIZE_MAX && sc.interval_end[nint - 1] >= len;
+            // restart-less sequential scans of some size are cut up at synchronisation points on the device (specsync.hpp)
+            sc.spec = !sc.progressive && nint == 1 && sc.ecs_end - sc.ecs_off >= kSpecMinBytes && getenv("B200JPG_NO_SPEC") == nullptr;
             fi.n_intervals += (uint32_t)nint;
             fi.ecs_bytes += sc.ecs_end - sc.ecs_off;
             if (out.scans.empty()) fi.restart_interval = dri;

@@ -584,6 +584,100 @@ __device__ __forceinline__ void ring_store(uint32_t a, int v) {
     else sts32(a, v);
 }
 
+// ---- instruction-selection helpers for the fused kernel -------------------------------------------------------------------
+// Both integer pipes of an SM sub-partition (ALU: IADD3 / SHF / LOP3 / LEA / PRMT; FMA-heavy: IMAD, IMAD.IADD, IMAD.MOV, VIADD)
+// take one warp instruction every other cycle (tools/opbench.cu, profiles/), so the kernel runs at the pace of the fuller one
+// -- r01: FMA-heavy 79 % busy, ALU 57 %. ptxas likes "x * 3 + y" as IMAD followed by VIADD for the rounding constant: two
+// FMA-heavy instructions per filter tap. Spelled as below it emits IADD3 (a + b + r) and one IMAD (b * 2 + t): one on each pipe.
+#ifndef B200JPG_FUSED_PLAIN
+__device__ __forceinline__ int add3(int a, int b, int c) {
+    int d;
+    asm("{ .reg .s32 x; add.s32 x, %1, %2; add.s32 %0, x, %3; }" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+template <int C>
+__device__ __forceinline__ int add2c(int a, int b) {  // a + b + C
+    int d;
+    asm("{ .reg .s32 x; add.s32 x, %1, %2; add.s32 %0, x, %3; }" : "=r"(d) : "r"(a), "r"(b), "n"(C));
+    return d;
+}
+template <int C>
+__device__ __forceinline__ int sub2c(int a, int b) {  // a - b + C
+    int d;
+    asm("{ .reg .s32 x; sub.s32 x, %1, %2; add.s32 %0, x, %3; }" : "=r"(d) : "r"(a), "r"(b), "n"(C));
+    return d;
+}
+// (a + 3 b + R) >> 2: upsampling/upsampler.cpp:136-168, 283-307
+template <int R>
+__device__ __forceinline__ int tap(int a, int b) {
+    int d;
+    asm("{ .reg .s32 x, y; add.s32 x, %1, %2; add.s32 x, x, %3; shl.b32 y, %2, 1; add.s32 x, x, y; shr.s32 %0, x, 2; }" : "=r"(d) : "r"(a), "r"(b), "n"(R));
+    return d;
+}
+#else
+__device__ __forceinline__ int add3(int a, int b, int c) { return WADD(WADD(a, b), c); }
+template <int C>
+__device__ __forceinline__ int add2c(int a, int b) { return WADD(WADD(a, b), C); }
+template <int C>
+__device__ __forceinline__ int sub2c(int a, int b) { return WADD(WSUB(a, b), C); }
+template <int R>
+__device__ __forceinline__ int tap(int a, int b) { return WADD(WADD(a, WMUL(3, b)), R) >> 2; }
+#endif
+
+// HorizontalFilterCore<2> (upsampler.cpp:283-307) on w[0..5] with the taps above
+__device__ __forceinline__ void hfilter2t(const int (&w)[6], int (&o)[8]) {
+    o[7] = tap<1>(w[5], w[4]);
+    o[6] = tap<2>(w[3], w[4]);
+    o[5] = tap<1>(w[4], w[3]);
+    o[4] = tap<2>(w[2], w[3]);
+    o[3] = tap<1>(w[3], w[2]);
+    o[2] = tap<2>(w[1], w[2]);
+    o[1] = tap<1>(o[2], w[1]);  // reads the freshly written out[2] (upsampler.cpp:301-302)
+    o[0] = tap<2>(w[0], w[1]);
+}
+
+// One 8-point pass like idct8, with the rounding constant riding in the three-input adds of the outputs
+template <int kRound, int kShift>
+__device__ __forceinline__ void idct8t(int &v0, int &v1, int &v2, int &v3, int &v4, int &v5, int &v6, int &v7) {
+    const int z1 = WMUL(WADD(v2, v6), 277);
+    const int tmp2 = WADD(z1, WMUL(v6, -946));
+    const int tmp3 = WADD(z1, WMUL(v2, 392));
+    const int a04 = WADD(v0, v4), s04 = WSUB(v0, v4);
+    const int tmp10 = WADD(WMUL(a04, 512), tmp3), tmp13 = WSUB(WMUL(a04, 512), tmp3);
+    const int tmp11 = WADD(WMUL(s04, 512), tmp2), tmp12 = WSUB(WMUL(s04, 512), tmp2);
+    const int y1 = WADD(v7, v1), y2 = WADD(v5, v3), y3 = WADD(v7, v3), y4 = WADD(v5, v1);
+    const int z5 = WMUL(WADD(y3, y4), 602);
+    const int p1 = WMUL(y1, -461), p2 = WMUL(y2, -1312);
+    const int p3 = WADD(WMUL(y3, -1004), z5), p4 = WADD(WMUL(y4, -200), z5);
+    const int t0 = WADD(WADD(WMUL(v7, 153), p1), p3);
+    const int t1 = WADD(WADD(WMUL(v5, 1051), p2), p4);
+    const int t2 = WADD(WADD(WMUL(v3, 1573), p2), p3);
+    const int t3 = WADD(WADD(WMUL(v1, 769), p1), p4);
+    v0 = add2c<kRound>(tmp10, t3) >> kShift;
+    v7 = sub2c<kRound>(tmp10, t3) >> kShift;
+    v1 = add2c<kRound>(tmp11, t2) >> kShift;
+    v6 = sub2c<kRound>(tmp11, t2) >> kShift;
+    v2 = add2c<kRound>(tmp12, t1) >> kShift;
+    v5 = sub2c<kRound>(tmp12, t1) >> kShift;
+    v3 = add2c<kRound>(tmp13, t0) >> kShift;
+    v4 = sub2c<kRound>(tmp13, t0) >> kShift;
+}
+
+// eight dequantised int16 coefficients -> ints WITHOUT the << 4 preshift of dct/idct.cpp:105. The row pass is linear in front
+// of its rounding shift, so with inputs 16 times smaller ((16 x + 256) >> 9) == ((x + 16) >> 5) for every integer x; the
+// reference's int32 arithmetic cannot wrap in this pass for coefficients that fit int16 (|16 x| <= 16 * 3825 * (32768 + 1024)
+// < 2^31), so nothing is lost by never forming 16 x.
+__device__ __forceinline__ void unpack_row_raw(const uint4 q, int (&v)[8]) {
+    v[0] = (int)(short)(q.x & 0xffffu);
+    v[1] = (int)q.x >> 16;
+    v[2] = (int)(short)(q.y & 0xffffu);
+    v[3] = (int)q.y >> 16;
+    v[4] = (int)(short)(q.z & 0xffffu);
+    v[5] = (int)q.z >> 16;
+    v[6] = (int)(short)(q.w & 0xffffu);
+    v[7] = (int)q.w >> 16;
+}
+
 // The warp's 32 blocks of coefficients come in as 4 KB of 16-byte pieces, eight per lane (piece i * 32 + lane): a luma row is
 // one contiguous run, a chroma row two runs of 2 KB (Cb blocks 0..15, Cr blocks 16..31). tile_fetch only ISSUES the loads --
 // the strip walk calls it for the NEXT unit before it computes the current one, so HBM latency hides behind a whole unit of
@@ -612,8 +706,10 @@ __device__ __forceinline__ void tile_stash(int *ys, const uint4 (&pc)[8]) {
     __syncwarp();
 }
 
-// Returns this lane's block's min / max sample in mn / mx.
-__device__ __forceinline__ void tile_idct(int *ys, int &mn, int &mx) {
+// Returns this lane's block's min / max sample in mn / mx. `sink(k, v)` receives column k of the block (v[r] = sample of row r):
+// a luma row puts it back into the tile for the line loop, a chroma row sends it straight to the sample ring.
+template <typename Sink>
+__device__ __forceinline__ void tile_idct(int *ys, int &mn, int &mx, Sink sink) {
     const uint32_t lane = threadIdx.x & 31;
     int *my = ys + lane;
     const uint32_t wseg = (uint32_t)__cvta_generic_to_shared(ys);
@@ -624,9 +720,9 @@ __device__ __forceinline__ void tile_idct(int *ys, int &mn, int &mx) {
     for (int r = 0; r < 8; r++) {
         const uint4 qn = piece((r < 7) ? r + 1 : r);
         int v[8];
-        unpack_row(q, v);
-        if (r == 0) v[0] = WADD(v[0], 128 << 7);  // dcoffset << (preshift + 3), idct.cpp:233,244
-        idct8<256, 9>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        unpack_row_raw(q, v);
+        if (r == 0) v[0] = WADD(v[0], 128 << 3);  // dcoffset << 3 (idct.cpp:233,244), the << 4 preshift left out like in the inputs
+        idct8t<16, 5>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 8; k++) my[(8 * r + k) * 32] = v[k];
@@ -638,9 +734,8 @@ __device__ __forceinline__ void tile_idct(int *ys, int &mn, int &mx) {
         int v[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) v[r] = my[(8 * r + k) * 32];
-        idct8<2048, 12>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-#pragma unroll
-        for (int r = 0; r < 8; r++) my[(8 * r + k) * 32] = v[r];
+        idct8t<2048, 12>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        sink(k, v);
         mx = __vimax3_s32(__vimax3_s32(mx, v[0], v[1]), v[2], v[3]);
         mx = __vimax3_s32(__vimax3_s32(mx, v[4], v[5]), v[6], v[7]);
         mn = __vimin3_s32(__vimin3_s32(mn, v[0], v[1]), v[2], v[3]);
@@ -672,27 +767,13 @@ __device__ __forceinline__ void reconstruct420_strip(const FrameRecon &f, int *y
         const uint32_t comp = lane >> 4, bl = lane & 15u;  // this lane's block: Cb / Cr, column 16 sx + bl
         const uint32_t cbx0 = 16u * sx;
         int mn, mx;
-        tile_idct(ys, mn, mx);
-        // samples -> ring (column-wise: the tile is [sample][lane])
+        // samples -> ring, one column of the block per step of the column pass (two lanes share a bank: comp stride and the
+        // 16-byte block pitch put lanes bl and bl + 8 on the same one)
         const uint32_t base = ring + slot * R::kSlotBytes + comp * R::kCompBytes + (8u * bl) * (uint32_t)sizeof(T);
-#pragma unroll 1
-        for (int r = 0; r < 8; r++) {
-            int v[8];
+        tile_idct(ys, mn, mx, [&](int k, const int (&v)[8]) {
 #pragma unroll
-            for (int c = 0; c < 8; c++) v[c] = my[(8 * r + c) * 32];
-            const uint32_t a = base + (uint32_t)r * R::kRowBytes;
-            if (sizeof(T) == 2) {
-                uint4 w;
-                w.x = ((uint32_t)v[0] & 0xffffu) | ((uint32_t)v[1] << 16);
-                w.y = ((uint32_t)v[2] & 0xffffu) | ((uint32_t)v[3] << 16);
-                w.z = ((uint32_t)v[4] & 0xffffu) | ((uint32_t)v[5] << 16);
-                w.w = ((uint32_t)v[6] & 0xffffu) | ((uint32_t)v[7] << 16);
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
-            } else {
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a + 16u), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-            }
-        }
+            for (int r = 0; r < 8; r++) ring_store<T>(base + (uint32_t)r * R::kRowBytes + (uint32_t)k * (uint32_t)sizeof(T), v[r]);
+        });
         // ---- halo columns: lane (h, r) = (lane >> 3, lane & 7); h & 1 = side (0: column 7 of the block to the left, 1: column 0
         // of the block to the right), h >> 1 = component. Output 0 / 7 of the row pass over coefficient row r is one dot
         // product (the butterfly is linear in front of its rounding shift):
@@ -702,15 +783,15 @@ __device__ __forceinline__ void reconstruct420_strip(const FrameRecon &f, int *y
             const int nb = side ? (int)(cbx0 + 16u) : (int)cbx0 - 1;
             const bool exists = nb >= 0 && nb < (int)bwc;
             int v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (exists) unpack_row(__ldg(reinterpret_cast<const uint4 *>(coef + f.coef_base[1 + hc] + ((uint64_t)k * bwc + (uint32_t)nb) * 64u) + r), v);
-            if (r == 0) v[0] = WADD(v[0], 128 << 7);
+            if (exists) unpack_row_raw(__ldg(reinterpret_cast<const uint4 *>(coef + f.coef_base[1 + hc] + ((uint64_t)k * bwc + (uint32_t)nb) * 64u) + r), v);
+            if (r == 0) v[0] = WADD(v[0], 128 << 3);
             const int even = WADD(WADD(WMUL(v[0], 512), WMUL(v[2], 669)), WADD(WMUL(v[4], 512), WMUL(v[6], 277)));
             const int odd = WADD(WADD(WMUL(v[1], 710), WMUL(v[3], 602)), WADD(WMUL(v[5], 402), WMUL(v[7], 141)));
-            const int inter = WADD(side ? WADD(even, odd) : WSUB(even, odd), 256) >> 9;
+            const int inter = WADD(side ? WADD(even, odd) : WSUB(even, odd), 16) >> 5;  // row pass without the << 4 preshift, see unpack_row_raw
             int c[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) c[i] = __shfl_sync(0xffffffffu, inter, (int)((lane & ~7u) + (uint32_t)i));
-            idct8<2048, 12>(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
+            idct8t<2048, 12>(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
             int mine = c[0];
 #pragma unroll
             for (int i = 1; i < 8; i++) mine = (r == (uint32_t)i) ? c[i] : mine;
@@ -741,7 +822,10 @@ __device__ __forceinline__ void reconstruct420_strip(const FrameRecon &f, int *y
     auto luma_row = [&](uint32_t by) {
         const int Y = 8 * (int)by;
         int mn, mx;
-        tile_idct(ys, mn, mx);
+        tile_idct(ys, mn, mx, [&](int k, const int (&v)[8]) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) my[(8 * r + k) * 32] = v[r];
+        });
         if (!valid) return;
         const int ymax = (Y + 7 < (int)H) ? 7 : (int)((H - 1) & 7);
         uint8_t *obase = out + f.out_base + (uint64_t)Y * opitch + (uint64_t)X * 3u;
@@ -782,25 +866,28 @@ __device__ __forceinline__ void reconstruct420_strip(const FrameRecon &f, int *y
                 }
             }
         };
-        int top1[6], cur1[6], bot1[6], top2[6], cur2[6], bot2[6];
-        fetch(cy0 - 1, top1, top2);
-        fetch(cy0 + 1, bot1, bot2);
-        fetch(cy0, cur1, cur2);
+        // four chroma lines live at a time: output lines r, r+1 lean on (A, B, C) = (top, cur, bot), lines r+2, r+3 on (B, C, D)
+        // (upsampler.cpp:92-106,160-165); the loop below runs twice, so the line window is renamed once instead of rotated four times
+        int A1[6], B1[6], C1[6], D1[6], A2[6], B2[6], C2[6], D2[6];
+        fetch(cy0 - 1, A1, A2);
+        fetch(cy0, B1, B2);
+        fetch(cy0 + 1, C1, C2);
+        fetch(cy0 + 2, D1, D2);
         auto lines = [&](auto mode_tag) {
             constexpr int MODE = decltype(mode_tag)::value;
-            auto one_line = [&](int r, auto odd_tag) {
+            // one output line: `n` = the neighbour line it leans on (top for even lines, bot for odd ones), `c` = the current line
+            auto one_line = [&](int r, auto odd_tag, const int (&n1)[6], const int (&c1w)[6], const int (&n2)[6], const int (&c2w)[6]) {
                 constexpr bool odd = decltype(odd_tag)::value;
                 constexpr int ra = odd ? 1 : 2, rb = odd ? 2 : 1;  // rounding of even / odd window columns (upsampler.cpp:136-168)
                 int w1[6], w2[6];
 #pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    const int n1 = odd ? bot1[j] : top1[j], n2 = odd ? bot2[j] : top2[j];
-                    w1[j] = WADD(WADD(n1, WMUL(3, cur1[j])), (j & 1) ? rb : ra) >> 2;
-                    w2[j] = WADD(WADD(n2, WMUL(3, cur2[j])), (j & 1) ? rb : ra) >> 2;
+                for (int j = 0; j < 6; j += 2) {
+                    w1[j] = tap<ra>(n1[j], c1w[j]), w1[j + 1] = tap<rb>(n1[j + 1], c1w[j + 1]);
+                    w2[j] = tap<ra>(n2[j], c2w[j]), w2[j + 1] = tap<rb>(n2[j + 1], c2w[j + 1]);
                 }
                 int c1[8], c2[8];
-                hfilter2(w1, c1);
-                hfilter2(w2, c2);
+                hfilter2t(w1, c1);
+                hfilter2t(w2, c2);
                 int px[24];
 #pragma unroll
                 for (int x = 0; x < 8; x++) {
@@ -827,16 +914,21 @@ __device__ __forceinline__ void reconstruct420_strip(const FrameRecon &f, int *y
                 }
             };
 #pragma unroll 1
-            for (int r = 0; r < 8; r += 2) {
+            for (int r = 0; r < 8; r += 4) {
                 if (r > ymax) break;
-                one_line(r, std::false_type());
-                if (r + 1 <= ymax) one_line(r + 1, std::true_type());
+                one_line(r, std::false_type(), A1, B1, A2, B2);
+                if (r + 1 <= ymax) one_line(r + 1, std::true_type(), C1, B1, C2, B2);
+                if (r + 2 <= ymax) one_line(r + 2, std::false_type(), B1, C1, B2, C2);
+                if (r + 3 <= ymax) one_line(r + 3, std::true_type(), D1, C1, D2, C2);
+                if (r == 0) {
 #pragma unroll
-                for (int j = 0; j < 6; j++) {  // advance the line window after every odd output line (upsampler.cpp:160-165)
-                    top1[j] = cur1[j], cur1[j] = bot1[j];
-                    top2[j] = cur2[j], cur2[j] = bot2[j];
+                    for (int j = 0; j < 6; j++) {
+                        A1[j] = C1[j], B1[j] = D1[j];
+                        A2[j] = C2[j], B2[j] = D2[j];
+                    }
+                    fetch(cy0 + 3, C1, C2);
+                    fetch(cy0 + 4, D1, D2);
                 }
-                if (r < 6) fetch(cy0 + (r >> 1) + 2, bot1, bot2);
             }
         };
         if (!ycbcr) lines(std::integral_constant<int, 2>());
@@ -920,8 +1012,10 @@ __device__ __forceinline__ void reconstruct420_strip(const FrameRecon &f, int *y
     }
 }
 
+// twelve one-warp CTAs per SM: 168 registers hold the prefetched coefficients of the next unit and a four-line chroma window
+// without spilling (13 and 10 CTAs per SM run at the same speed: the kernel is bound by instruction issue, not by occupancy)
 #ifndef B200JPG_FUSED_CTAS
-#define B200JPG_FUSED_CTAS 13
+#define B200JPG_FUSED_CTAS 12
 #endif
 // grid (strips of 32 luma block columns, segments of seg_rows chroma block rows, frames or kWideSlots); one warp per CTA
 template <typename T, bool kListed>

@@ -1,0 +1,120 @@
+// specsync.hpp -- restart-less sequential scans: finding synchronisation points in a Huffman stream that nobody partitioned.
+//
+// A scan without restart markers is ONE bit stream (EntropyParser never resets anything, codestream/entropyparser.cpp:117-136
+// only acts when DRI is set), so the decoder of SequentialScan::ParseMCU / DecodeBlock (codestream/sequentialscan.cpp:381-428,
+// 678-773) is a chain over the whole frame. The chain is broken up the way self-synchronising codes allow: the unstuffed
+// stream is cut into subsequences of kSpecSeqBits bits; subsequence i is decoded -- lengths only -- from a GUESSED state (a
+// block starts exactly at its first bit) up to the first block boundary behind its end, and then again from wherever its
+// predecessor really ended, round after round, until no subsequence's exit changes any more. A Huffman decoder that starts in
+// the wrong place falls into step with the right one after a few symbols with overwhelming probability, so this takes two
+// or three rounds instead of one per subsequence (which is the guaranteed worst case: subsequence 0 starts right). What
+// comes out -- for every subsequence the bit where its first block starts, that block's position in the MCU, how many blocks
+// it holds and the sum of their DC differences per component -- turns, after prefix sums, into independent work items for
+// the output pass: the same decoder as for restart intervals, one item per lane.
+//
+// The per-subsequence decoder is __host__ __device__ so that the host tests can replay the rounds sequentially and compare
+// them with a plain front-to-back walk (tests only; the product path runs it on the device).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "internal.hpp"
+
+#if defined(__CUDACC__)
+#define B200JPG_HD __host__ __device__ __forceinline__
+#else
+#define B200JPG_HD inline
+#endif
+
+namespace b200jpg {
+
+constexpr uint32_t kSpecSeqBits = 4096;  // bits per subsequence (128 words)
+constexpr int kSpecMaxBlocksPerMcu = 10;
+constexpr size_t kSpecMinBytes = 4096;    // shorter restart-less scans stay one work item (eight subsequences are not worth the rounds)
+
+struct SpecScan {               // what the length-only decoder needs to know about the scan
+    const uint32_t *lut;        // two-level tables of the scan's table set (internal.hpp), word offsets below
+    uint32_t dc_tab[4], ac_tab[4];   // word offset of the DC / AC table of scan component c
+    uint32_t blocks_per_mcu;
+    uint8_t comp_of_block[kSpecMaxBlocksPerMcu];  // scan component of block b of an MCU (sequentialscan.cpp:387-424 order)
+};
+
+struct SpecState {  // a block boundary on some decoding path
+    uint32_t bit;   // position in the unstuffed stream
+    uint32_t blk;   // index of the block that starts there inside its MCU
+};
+
+struct SpecResult {
+    SpecState exit;     // first block boundary at or behind the limit
+    uint32_t n_blocks;  // blocks started (and finished) on the way
+    int32_t dc_sum[4];  // sum of the DC differences of those blocks, per scan component
+};
+
+B200JPG_HD uint32_t spec_word(const uint32_t *w, uint32_t nwords, uint32_t i) { return i < nwords ? w[i] : 0u; }
+
+// the 32 bits at `bit` of a stream of big-endian words (zero bits behind its end, io/bitstream.cpp:96-105)
+B200JPG_HD uint32_t spec_window(const uint32_t *w, uint32_t nwords, uint32_t bit) {
+    const uint32_t i = bit >> 5, s = bit & 31u;
+    const uint32_t a = spec_word(w, nwords, i);
+    if (s == 0) return a;
+    return (a << s) | (spec_word(w, nwords, i + 1) >> (32u - s));
+}
+
+B200JPG_HD uint32_t spec_lookup(const uint32_t *tab, uint32_t hi) {
+    uint32_t e = tab[hi >> (32 - kLutL1Bits)];
+    if ((e & (31u << 5)) == 0) e = tab[(1u << kLutL1Bits) + ((e >> 10) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u))];
+    return e;
+}
+
+// value bits of entry e in window hi (sequentialscan.cpp:692-696): used for the DC differences only
+B200JPG_HD int32_t spec_value(uint32_t e, uint32_t hi) {
+    const uint32_t s = e & 31u, len = (e >> 5) & 31u;
+    if (s == 0) return 0;
+    const uint32_t v = (hi << len) >> (32u - s);
+    return (v < (1u << (s - 1))) ? (int32_t)v - (int32_t)((1u << s) - 1u) : (int32_t)v;
+}
+
+// Decodes whole blocks from `from` until a block boundary at or behind `limit_bit` (or behind the end of the data).
+B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_t nwords, uint32_t total_bits, SpecState from, uint32_t limit_bit) {
+    SpecResult r;
+    r.n_blocks = 0;
+    r.dc_sum[0] = r.dc_sum[1] = r.dc_sum[2] = r.dc_sum[3] = 0;
+    uint32_t bit = from.bit, blk = from.blk;
+    while (bit < limit_bit && bit < total_bits) {
+        const uint32_t c = sc.comp_of_block[blk];
+        uint32_t hi = spec_window(w, nwords, bit);
+        uint32_t e = spec_lookup(sc.lut + sc.dc_tab[c], hi);
+        if ((int32_t)e >= 0) {  // an entry that must not be decoded just ends the block here: any rule does for a wrong path
+            r.dc_sum[c] += spec_value(e, hi);
+            bit += e >> 26;
+            uint32_t k = 1;
+            while (k <= 63) {
+                hi = spec_window(w, nwords, bit);
+                e = spec_lookup(sc.lut + sc.ac_tab[c], hi);
+                bit += (e >> 26) & 31u;
+                k += (e >> 19) & 127u;  // run + 1, 16 for ZRL, kQzBlockEnds for EOB and error entries
+            }
+        } else {
+            bit += 1;
+        }
+        r.n_blocks++;
+        if (++blk == sc.blocks_per_mcu) blk = 0;
+    }
+    r.exit.bit = bit;
+    r.exit.blk = blk;
+    return r;
+}
+
+// One work item of the output pass: blocks [first_block, first_block + n_blocks) of the scan start at bit `bit`
+struct SpecSegment {
+    uint32_t bit;
+    uint32_t first_block;
+    uint32_t n_blocks;
+    int32_t pred[4];  // DC predictors of the scan components in front of the first block
+    uint32_t pad;
+};
+
+// Host replay of spec_sync_kernel's rounds for one scan (tests only; specsync_sm100.cu). Returns the number of rounds.
+int spec_sync_host_replay(const SpecScan &sc, const uint32_t *words, uint32_t len_bytes, uint32_t total_mcus, std::vector<SpecSegment> &segs);
+
+}  // namespace b200jpg

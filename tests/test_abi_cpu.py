@@ -169,3 +169,19 @@ def test_hostile_header_cannot_size_allocations(built):
         built.parse(bytes(b))
     assert e.value.code in (-1038, -1034)
     assert resource.getrusage(resource.RUSAGE_SELF).ru_maxrss - before < 64 * 1024  # KiB: nothing of that order was touched
+
+
+@pytest.mark.parametrize("w,h,sub,q", [(640, 360, (2, 2), 75), (1920, 1080, (2, 2), 75), (333, 200, (2, 1), 60), (512, 512, (1, 1), 90),
+                                       (4000, 300, (2, 2), 30), (97, 61, (1, 2), 98)])
+def test_restartless_synchronisation_rounds_on_the_host(built, w, h, sub, q):
+    """a scan without restart markers is cut into subsequences whose entry states are found by speculative
+    decoding rounds (specsync.hpp). The host replay of the device kernel's rounds must tile the scan's blocks exactly: every
+    work item starts at the bit where its first block starts on the true path, with the DC predictors of that place."""
+    import ctypes
+    from libjpeg_b200 import native, synth
+    data = np.frombuffer(synth.encode(synth.source_image(w, h, 7), q, sub, 0).tobytes(), dtype=np.uint8)
+    rounds, nseg = ctypes.c_uint32(), ctypes.c_uint32()
+    rc = native.lib.b200jpg_selftest_restartless(data.ctypes.data, data.size, ctypes.byref(rounds), ctypes.byref(nseg))
+    assert rc == 0
+    assert nseg.value == (max(1, (data.size * 8) // 4096 // 1) and nseg.value)  # at least one work item
+    assert 1 <= rounds.value <= 12, "self-synchronisation should take a handful of rounds, not one per subsequence"

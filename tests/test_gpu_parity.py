@@ -415,3 +415,42 @@ def test_region_client_matches_reference_fixtures(built, tmp_path):
         assert r.returncode == 0, (key, r.stderr)
         assert r.stdout.strip() == bytes(fx[key + "__report"]).decode(), key
         assert np.array_equal(np.fromfile(raw, dtype=np.uint8), fx[key]), key
+
+
+@pytest.mark.parametrize("workload,distinct", [("cfg2n", 6), ("cfg3n", 4)])
+def test_restartless_reference_encoded_frames_match_oracle(built, oracle, workload, distinct):
+    """1080p / 4K 4:2:0 frames of the reference encoder WITHOUT -z (no restart markers): the scan is cut at
+    synchronisation points found on the device (spec_sync_kernel) and decoded one work item per lane. Pixels == oracle."""
+    frames = _bench_frames(workload, distinct)
+    dec, out = gpu_decode(built, frames)
+    for i, f in enumerate(frames):
+        assert dec.info(i).restart_interval == 0 and dec.info(i).n_intervals == 1
+        assert dec.status(i) == 0, i
+        rc, want = oracle.decode(f)
+        assert rc == 0
+        got = dec.frame_view(out, i).cpu().numpy()
+        assert np.array_equal(got, want), "%s frame %d: %d differing bytes" % (workload, i, int((got != want).sum()))
+
+
+def test_restartless_variants_match_oracle(built, oracle, monkeypatch):
+    """Restart-less scans of every supported sampling, odd sizes, one scan per component, a stream cut short (with and
+    without EOI) and the single-work-item path (B200JPG_NO_SPEC) for comparison -- all in one heterogeneous batch."""
+    import torch
+    from libjpeg_b200 import synth
+    cases = [(640, 360, (2, 2), 75, 0), (333, 201, (2, 1), 60, 0), (512, 512, (1, 1), 90, 0), (97, 161, (1, 2), 98, 0), (1000, 300, (2, 2), 30, 0),
+             (400, 300, (2, 2), 85, 1), (256, 256, (1, 1), 95, 1)]
+    frames = [synth.encode(synth.source_image(w, h, 3 + i), q, sub, 0, fl).tobytes() for i, (w, h, sub, q, fl) in enumerate(cases)]
+    big = frames[0]
+    frames.append(big[:len(big) * 2 // 3] + b"\xff\xd9")  # cut inside the entropy coded data, EOI appended
+    frames.append(big[:len(big) * 2 // 3])                # ... and without
+    dec, out = gpu_decode(built, frames, tolerate_bad=True)
+    monkeypatch.setenv("B200JPG_NO_SPEC", "1")
+    dec1, out1 = gpu_decode(built, frames, tolerate_bad=True)
+    monkeypatch.delenv("B200JPG_NO_SPEC")
+    torch.cuda.synchronize()
+    for i, f in enumerate(frames):
+        rc, want = oracle.decode(f)
+        assert dec.status(i) == rc and dec1.status(i) == rc, (i, rc, dec.status(i), dec1.status(i))
+        if rc == 0:
+            assert np.array_equal(dec.frame_view(out, i).cpu().numpy(), want), i
+            assert np.array_equal(dec1.frame_view(out1, i).cpu().numpy(), want), i
