@@ -115,6 +115,8 @@ struct ScanClass {
     std::vector<uint64_t> scan_ecs_off, scan_ecs_end;  // per scan, absolute
     uint64_t interval_base = 0;          // index of this class's first interval in d_interval_len
     uint64_t spec_base = 0;              // indexed classes: first work item of this class in the spec arrays
+    bool fused = false;                  // progressive class decoded by the component-fused kernels (its frames form a PfGroupHost)
+    int frame_comp0 = 0;                 // frame component of the scan's first component
     // offsets (bytes) of the device copies inside the input buffer
     uint64_t dev_scans = 0, dev_intervals = 0, dev_interval_end = 0, dev_clean_off = 0;
 };
@@ -124,6 +126,13 @@ struct ReconGroup {
     std::vector<FrameRecon> frames;
     uint32_t max_bw0 = 0, max_bh0 = 0, max_bwc = 0, max_bhc = 0;
     uint64_t dev_frames = 0;
+};
+
+// progressive frames whose scan script lets a component be decoded in one go (progfused_sm100.cu): the classes of its scans
+struct PfGroupHost {
+    std::vector<int> dc;       // interleaved DC scans, file order
+    std::vector<int> ac[4];    // single-component AC scans per frame component, file order
+    int comp_of_ac[4] = {0, 0, 0, 0};
 };
 
 struct ClassKey {
@@ -146,7 +155,10 @@ struct b200jpg_batch {
     std::vector<ReconGroup> groups;
     std::vector<IndexScan> index_scans;  // scans whose restart index is built on the device, at upload
     uint64_t dev_index_scans = 0;
-    std::vector<ProgFrame> prog_frames;  // progressive frames: dequantised after their last scan
+    std::vector<PfGroupHost> pf_groups;  // progressive frames decoded component by component
+    std::vector<uint16_t> pf_dc_quant;   // per group: quantiser of coefficient 0 per frame component (4 each)
+    int16_t *d_dcplane = nullptr;        // fused progressive groups: one DC level per block
+    std::vector<ProgFrame> prog_frames;  // progressive frames of the scan-by-scan path: dequantised after their last scan
     uint64_t dev_prog_frames = 0;
     uint32_t prog_max_blocks = 0;
     uint64_t ecs_bytes = 0, stored_blocks = 0;
@@ -294,6 +306,7 @@ void b200jpg_batch_destroy(b200jpg_batch *b) {
     b->ctx->put(1, b->d_interval_len, b->sz_ilen);
     b->ctx->put(1, b->d_overrun, b->sz_overrun);
     if (b->d_spec) b->ctx->put(1, b->d_spec, b->sz_spec);
+    if (b->d_dcplane) b->ctx->put(1, b->d_dcplane, b->coef_elems / 64 * sizeof(int16_t));
     b->ctx->put(1, b->d_status, b->sz_status);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
@@ -513,6 +526,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
                 cidx = cit->second;
             }
             ScanClass &cl = b->classes[cidx];
+            cl.frame_comp0 = sc.comp[0];
             ClassScan cs{};
             for (int k = 0; k < sc.ns; k++) cs.coef_base[k] = coef_base[i][sc.comp[k]];
             cs.frame = (uint32_t)i;
@@ -536,8 +550,58 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     }
     // the scans of a progressive frame build on each other: launch order = scan order (sequential classes: ordinal 0)
     std::stable_sort(b->classes.begin(), b->classes.end(), [](const ScanClass &x, const ScanClass &y) { return x.p.ordinal < y.p.ordinal; });
+    // ---- component-fused progressive groups: classes that hold exactly the same frames in the same order and whose scans are
+    // either interleaved DC scans of all components or single-component AC scans with equal restart intervals per group
+    std::vector<uint8_t> frame_fused(n, 0);
+    if (getenv("B200JPG_NO_PFUSE") == nullptr) {
+        std::map<std::vector<uint32_t>, std::vector<int>> by_frames;
+        for (size_t ci = 0; ci < b->classes.size(); ci++) {
+            const ScanClass &cl = b->classes[ci];
+            if (!cl.p.progressive) continue;
+            std::vector<uint32_t> ids;
+            for (auto &cs : cl.scans) ids.push_back(cs.frame);
+            by_frames[ids].push_back((int)ci);
+        }
+        for (auto &kv : by_frames) {
+            const std::vector<uint32_t> &ids = kv.first;
+            std::vector<int> cls = kv.second;  // ascending ordinal (the classes are sorted)
+            bool ok = !ids.empty();
+            for (uint32_t id : ids) ok = ok && b->frames[id].scans.size() == cls.size();
+            PfGroupHost grp;
+            const b200jpg_frame_info &fi0 = b->frames[ids[0]].info;
+            for (int ci : cls) {
+                const ScanClassParams &p = b->classes[(size_t)ci].p;
+                if (!ok) break;
+                if (p.ss == 0) {
+                    ok = p.ns == (int)fi0.ncomp && (grp.dc.empty() ? p.ah == 0 : p.ah != 0);
+                    if (ok && !grp.dc.empty()) {
+                        const ScanClassParams &q = b->classes[(size_t)grp.dc[0]].p;
+                        ok = q.dri == p.dri && q.intervals_per_scan == p.intervals_per_scan && q.total_mcus == p.total_mcus;
+                    }
+                    grp.dc.push_back(ci);
+                } else {
+                    const int c = b->classes[(size_t)ci].frame_comp0;
+                    ok = p.ns == 1 && c < 4;
+                    if (ok && !grp.ac[c].empty()) {
+                        const ScanClassParams &q = b->classes[(size_t)grp.ac[c][0]].p;
+                        ok = q.dri == p.dri && q.intervals_per_scan == p.intervals_per_scan && q.total_mcus == p.total_mcus && q.mcu_cols == p.mcu_cols;
+                    }
+                    if (ok) grp.ac[c].push_back(ci);
+                }
+            }
+            ok = ok && !grp.dc.empty() && grp.dc.size() <= (size_t)kPfMaxScans;
+            for (int c = 0; c < 4; c++) ok = ok && grp.ac[c].size() <= (size_t)kPfMaxScans;
+            if (!ok) continue;
+            for (int ci : cls) b->classes[(size_t)ci].fused = true;
+            for (uint32_t id : ids) frame_fused[id] = 1;
+            const ParsedFrame &pf0 = b->frames[ids[0]];
+            for (int c = 0; c < 4; c++)
+                b->pf_dc_quant.push_back(c < fi0.ncomp && pf0.scans[0].quant_defined[fi0.tq[c]] ? pf0.scans[0].quant[fi0.tq[c]][0] : 0);
+            b->pf_groups.push_back(std::move(grp));
+        }
+    }
     for (int i = 0; i < n; i++) {
-        if (b->parse_status[i] != 0 || b->frames[i].info.frame_type != 2) continue;
+        if (b->parse_status[i] != 0 || b->frames[i].info.frame_type != 2 || frame_fused[i]) continue;
         const ParsedFrame &pf = b->frames[i];
         ProgFrame f{};
         f.frame = (uint32_t)i;
@@ -715,11 +779,13 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     b->sz_status = sizeof(uint32_t) * (5 * (size_t)n + 1);  // status words, wide flags, narrow flags, narrow list, index status
     b->d_input = (uint8_t *)ctx->get(1, b->input_bytes, &ce);
     if (ce == cudaSuccess && b->coef_elems) b->d_coef = (int16_t *)ctx->get(1, b->coef_elems * sizeof(int16_t), &ce);
-    // sample planes only for the reconstruction groups that still go through them: 4:2:0 frames are reconstructed by the fused
-    // kernel (coefficients -> pixels, chroma samples live in shared memory)
+    // sample planes only for the reconstruction groups that go through them (with B200JPG_FUSED=1, 4:2:0 frames are reconstructed
+    // by the fused kernel: coefficients -> pixels, chroma samples live in shared memory)
     {
-        bool need_planes = getenv("B200JPG_NO_FUSED") != nullptr;
-        for (auto &g : b->groups) need_planes = need_planes || (g.ncomp > 1 && !(g.ncomp == 3 && g.subx == 2 && g.suby == 2));
+        const char *fused = getenv("B200JPG_FUSED");
+        const bool use_fused = fused && fused[0] == '1';
+        bool need_planes = false;
+        for (auto &g : b->groups) need_planes = need_planes || (g.ncomp > 1 && !(use_fused && g.ncomp == 3 && g.subx == 2 && g.suby == 2));
         if (!need_planes) b->sample_elems = 0;
     }
     if (ce == cudaSuccess && b->sample_elems) b->d_samples = (int32_t *)ctx->get(1, b->sample_elems * sizeof(int32_t), &ce);
@@ -729,6 +795,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     b->sz_overrun = sizeof(uint32_t) * (size_t)(b->n_intervals + b->classes.size() + 1);
     if (ce == cudaSuccess) b->d_overrun = (uint32_t *)ctx->get(1, b->sz_overrun, &ce);
     if (ce == cudaSuccess) b->d_status = (uint32_t *)ctx->get(1, b->sz_status, &ce);
+    if (ce == cudaSuccess && !b->pf_groups.empty()) b->d_dcplane = (int16_t *)ctx->get(1, b->coef_elems / 64 * sizeof(int16_t), &ce);
     if (ce == cudaSuccess && b->n_spec) {
         b->sz_spec = (size_t)b->n_spec * (sizeof(SpecSegment) + 8 + 8 + 4 + 16) + 256;
         b->d_spec = (uint8_t *)ctx->get(1, b->sz_spec, &ce);
@@ -840,6 +907,7 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
             l.tables = b->d_input + b->dev_tables[cl.table_set];
             l.coef = b->d_coef;
             l.frame_status = b->d_status;
+            if (pass == 1 && cl.fused) continue;  // decoded by the component-fused launches below
             if (cl.p.indexed) {  // slices of the spec arrays: [segments | exits | entries | counts | dc sums], each over all work items
                 const uint64_t n = b->n_spec, o = cl.spec_base;
                 uint8_t *q = b->d_spec;
@@ -866,6 +934,62 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
                 if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "overrun verdict kernel launch");
                 b->last_launches++;
             }
+        }
+    }
+    // ---- progressive frames decoded component by component: the DC scans into the side plane, then every component's AC scans
+    for (size_t gi = 0; gi < b->pf_groups.size(); gi++) {
+        const PfGroupHost &grp = b->pf_groups[gi];
+        auto fill_scan = [&](PfScan &ps, const ScanClass &cl) {
+            ps.tables = b->d_input + b->dev_tables[cl.table_set];
+            ps.clean_off = reinterpret_cast<const uint64_t *>(b->d_input + cl.dev_clean_off);
+            ps.interval_len = b->d_interval_len + cl.interval_base;
+            ps.ss = cl.p.ss, ps.se = cl.p.se, ps.ah = cl.p.ah, ps.al = cl.p.al;
+            for (int k = 0; k < 4; k++) ps.dc_slot[k] = cl.p.dc_slot[k];
+            ps.ac_slot = cl.p.ac_slot[0];
+            ps.q_slot = cl.p.q_slot[0];
+            ps.lut_words = cl.p.lut_words;
+        };
+        auto fill_geometry = [&](PfLaunch &L, const ScanClass &cl) {
+            L.ns = cl.p.ns;
+            for (int k = 0; k < 4; k++) L.mw[k] = cl.p.mw[k], L.mh[k] = cl.p.mh[k], L.bw[k] = cl.p.bw[k];
+            L.mcu_cols = cl.p.mcu_cols, L.total_mcus = cl.p.total_mcus, L.dri = cl.p.dri, L.intervals = cl.p.intervals_per_scan;
+            L.n_frames = (uint32_t)cl.scans.size();
+            L.frames = reinterpret_cast<const ClassScan *>(b->d_input + cl.dev_scans);
+            L.clean = b->d_clean, L.coef = b->d_coef, L.dcplane = b->d_dcplane, L.frame_status = b->d_status;
+        };
+        {
+            PfLaunch L{};
+            L.n_scans = (int)grp.dc.size();
+            for (size_t s = 0; s < grp.dc.size(); s++) fill_scan(L.scan[s], b->classes[(size_t)grp.dc[s]]);
+            const ScanClass &dc0 = b->classes[(size_t)grp.dc[0]];
+            fill_geometry(L, dc0);
+            // scan component k of the DC scans is frame component comp[k] of the SOS: its quantiser and the block grid that
+            // component's own AC scans cover (a component without AC scans is completed by the DC kernel alone)
+            const ParsedFrame &pf0 = b->frames[dc0.scans[0].frame];
+            for (int k = 0; k < L.ns; k++) {
+                const int ci = pf0.scans[(size_t)dc0.p.ordinal].comp[k];
+                L.ac_cols[k] = L.ac_rows[k] = 0;
+                L.dc_quant[k] = b->pf_dc_quant[4 * gi + (size_t)ci];
+                if (!grp.ac[ci].empty()) {
+                    const ScanClassParams &ap = b->classes[(size_t)grp.ac[ci][0]].p;
+                    L.ac_cols[k] = ap.mcu_cols;
+                    L.ac_rows[k] = ap.total_mcus / ap.mcu_cols;
+                }
+            }
+            int rc = launch_pf_dc(L, stream);
+            if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "progressive DC kernel launch");
+            b->last_launches++;
+        }
+        for (int c = 0; c < 4; c++) {
+            if (grp.ac[c].empty()) continue;
+            PfLaunch L{};
+            L.n_scans = (int)grp.ac[c].size();
+            for (size_t s = 0; s < grp.ac[c].size(); s++) fill_scan(L.scan[s], b->classes[(size_t)grp.ac[c][s]]);
+            fill_geometry(L, b->classes[(size_t)grp.ac[c][0]]);
+            L.dc_quant[0] = b->pf_dc_quant[4 * gi + (size_t)c];
+            int rc = launch_pf_ac(L, stream);
+            if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "progressive AC kernel launch");
+            b->last_launches++;
         }
     }
     if (!b->prog_frames.empty()) {  // quantised levels -> the dequantised coefficients stage b expects

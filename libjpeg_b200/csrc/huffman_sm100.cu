@@ -245,6 +245,122 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
 }
 
 // =====================================================================================================
+// a0 for restart-less scans: one CTA per interval
+// =====================================================================================================
+// The whole entropy coded segment of a frame is ONE interval when the stream has no restart markers (megabytes at 4K): a
+// single warp walking it would take longer than everything else together. Here the 32 warps of a CTA split it into 32
+// byte ranges and run the classification twice -- once to count the bytes every range keeps (and to find the first
+// "marker" inside the data, which ends it for the bit reader: io/bitstream.cpp:96-101), then, after a prefix sum over the 32
+// counts, to put every kept byte where it belongs. The second pass stores single bytes (at i ^ 3: big-endian words, like the
+// warp-per-interval kernel writes them): a warp's bytes are consecutive, so they coalesce, and nothing has to be merged
+// where two ranges meet in the middle of a word.
+constexpr int kLongThreads = 1024;
+
+__global__ void __launch_bounds__(kLongThreads)
+unstuff_long_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ interval_off,
+                    const uint64_t *__restrict__ interval_end, const uint64_t *__restrict__ clean_off, uint8_t *__restrict__ clean,
+                    uint32_t *__restrict__ interval_len) {
+    __shared__ uint32_t s_count[32];
+    __shared__ unsigned long long s_marker;  // offset of the first FF xx (xx != 0) inside the data, ~0 = none
+    const uint32_t g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (g >= n_intervals) return;
+    const uint64_t src0 = interval_off[g];
+    if (src0 == ~0ull) {
+        if (threadIdx.x == 0) interval_len[g] = kIntervalLenAbsent;
+        return;
+    }
+    const uint64_t src1_raw = interval_end[g];
+    const uint64_t src1 = src1_raw & ~kIntervalEofFlag;
+    const uint32_t eof_flag = (src1_raw & kIntervalEofFlag) ? kIntervalLenEofFlag : 0u;
+    if (threadIdx.x == 0) s_marker = ~0ull;
+    __syncthreads();
+    // byte ranges of the warps: multiples of 128 bytes counted from the aligned start
+    const uint64_t base0 = src0 & ~3ull;
+    const uint64_t steps = (src1 - base0 + 127) / 128;
+    const uint64_t per = (steps + 31) / 32;
+    const uint64_t lo = base0 + 128 * per * warp;
+    uint64_t hi = lo + 128 * per;
+    if (hi > src1) hi = src1;
+    uint8_t *dst = clean + clean_off[g];
+    // one step of 128 bytes: keep[k] = byte k of this lane's word is data; returns the number of bytes the warp keeps
+    auto classify = [&](uint64_t base, uint64_t limit, uint32_t &cur, uint32_t (&keep)[4]) -> uint32_t {
+        const uint64_t wo = base + 4ull * lane;
+        cur = 0;
+        uint32_t nxt = 0, prv = 0;
+        if (wo < src1) cur = __ldg(reinterpret_cast<const uint32_t *>(bytes + wo));
+        if (wo + 4 < src1 + 2) nxt = __ldg(reinterpret_cast<const uint32_t *>(bytes + wo + 4));
+        if (wo >= src0 + 1) prv = bytes[wo - 1];
+        uint32_t pb = prv, n = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint64_t q = wo + k;
+            const uint32_t v = (cur >> (8 * k)) & 0xffu;
+            const uint32_t nb = (k < 3) ? ((cur >> (8 * k + 8)) & 0xffu) : (nxt & 0xffu);
+            const bool in = q >= src0 && q < limit;
+            if (in && v == 0xffu && nb != 0u) atomicMin(&s_marker, (unsigned long long)q);  // rare: data that runs into a marker
+            keep[k] = (in && !(v == 0u && pb == 0xffu && q > src0)) ? 1u : 0u;  // the 00 of FF 00 goes (io/bitstream.cpp:87-95)
+            n += keep[k];
+            pb = v;
+        }
+        return n;
+    };
+    // ---- pass 1: count
+    uint32_t mine = 0;
+    for (uint64_t base = lo; base < hi; base += 128) {
+        uint32_t cur, keep[4];
+        mine += classify(base, hi, cur, keep);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(kFull, mine, d);
+    if (lane == 0) s_count[warp] = mine;
+    __syncthreads();
+    const uint64_t marker = s_marker;
+    if (marker != ~0ull) {
+        // a marker inside the data: everything from it on is not data. Recount with the ranges clipped (rare path).
+        const uint64_t lim = hi < marker ? hi : marker;
+        mine = 0;
+        for (uint64_t base = lo; base < lim; base += 128) {
+            uint32_t cur, keep[4];
+            mine += classify(base, lim, cur, keep);
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(kFull, mine, d);
+        __syncthreads();
+        if (lane == 0) s_count[warp] = mine;
+        __syncthreads();
+        if (hi > marker) hi = marker;
+    }
+    uint32_t before = 0, total = 0;
+    for (int i = 0; i < 32; i++) {
+        const uint32_t c = s_count[i];
+        if (i < (int)warp) before += c;
+        total += c;
+    }
+    // ---- pass 2: place
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t out = before;
+    for (uint64_t base = lo; base < hi; base += 128) {
+        uint32_t cur, keep[4];
+        classify(base, hi, cur, keep);
+        const uint32_t b0 = __ballot_sync(kFull, keep[0]), b1 = __ballot_sync(kFull, keep[1]);
+        const uint32_t b2 = __ballot_sync(kFull, keep[2]), b3 = __ballot_sync(kFull, keep[3]);
+        uint32_t o = out + __popc(b0 & lt_mask) + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (keep[k]) {
+                dst[o ^ 3u] = (uint8_t)(cur >> (8 * k));
+                o++;
+            }
+        }
+        out += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+    }
+    // ---- tail: zero up to the next 16-byte boundary + 32 bytes (the decoder reads zeros behind the data, :96-105)
+    const uint32_t end_pad = ((total + 15u) & ~15u) + 32u;
+    for (uint32_t i = total + threadIdx.x; i < end_pad; i += kLongThreads) dst[i ^ 3u] = 0;
+    if (threadIdx.x == 0) interval_len[g] = total | eof_flag;
+}
+
+// =====================================================================================================
 // a1: Huffman decode, one restart interval per lane
 // =====================================================================================================
 constexpr int kQzBytes = 4 * kQzEntries * 8;  // four quantisation tables of (q, offset) pairs
@@ -836,6 +952,11 @@ int launch_restart_index(const IndexScan *scans_dev, uint32_t n_scans, uint8_t *
 int launch_unstuff(const EntropyLaunch &l, void *stream) {
     const uint64_t total = (uint64_t)l.p.n_scans * l.p.intervals_per_scan;
     if (total == 0) return 0;
+    if (l.p.indexed) {  // restart-less scans: the interval is the whole entropy coded segment of a frame
+        unstuff_long_kernel<<<(uint32_t)total, kLongThreads, 0, (cudaStream_t)stream>>>((uint32_t)total, l.bytes, l.interval_off, l.interval_end,
+                                                                                           l.clean_off, l.clean, l.interval_len);
+        return (int)cudaGetLastError();
+    }
     const uint32_t grid = (uint32_t)((total + kUnstuffWarps - 1) / kUnstuffWarps);
     unstuff_kernel<<<grid, kUnstuffWarps * 32, 0, (cudaStream_t)stream>>>((uint32_t)total, l.bytes, l.interval_off, l.interval_end, l.clean_off,
                                                                            l.clean, l.interval_len);

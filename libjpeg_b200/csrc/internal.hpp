@@ -160,6 +160,34 @@ struct ProgFrame {
     uint32_t frame, pad;
 };
 
+// Component-fused progressive decoding (progfused_sm100.cu): one launch runs a restart interval through ALL scans of a group
+// -- the interleaved DC scans of a frame, or the AC scans of one component -- in file order.
+constexpr int kPfMaxScans = 6;
+struct PfScan {                    // one scan of the group, uniform over the launch
+    const uint8_t *tables;         // device copy of the scan's table-set blob
+    const uint64_t *clean_off;     // [n_frames * intervals] offsets of the unstuffed intervals of this scan
+    const uint32_t *interval_len;  // [..] unstuffed lengths (flags: kIntervalLenAbsent / kIntervalLenEofFlag)
+    int ss, se, ah, al;
+    int dc_slot[4], ac_slot, q_slot;
+    uint32_t lut_words;
+};
+struct PfLaunch {
+    int n_scans;
+    PfScan scan[kPfMaxScans];
+    int ns;                        // components in the group's scans (DC group: all of the frame; AC group: 1)
+    int mw[4], mh[4], bw[4];       // blocks per MCU and plane pitch of scan component c
+    uint32_t ac_cols[4], ac_rows[4];  // DC group: the block grid the component's own (single-component) scans cover
+    uint16_t dc_quant[4];          // quantiser of coefficient 0 of scan component c
+    uint32_t mcu_cols, total_mcus, dri, intervals, n_frames;
+    const ClassScan *frames;       // [n_frames] coefficient plane of every scan component + frame index
+    const uint8_t *clean;
+    int16_t *coef;
+    int16_t *dcplane;              // one quantised DC level per block, indexed like the coefficient store / 64
+    uint32_t *frame_status;
+};
+int launch_pf_dc(const PfLaunch &L, void *stream);
+int launch_pf_ac(const PfLaunch &L, void *stream);
+
 struct FrameRecon {       // per frame, for the reconstruction kernels
     uint64_t coef_base[4];    // int16 element offsets
     uint64_t sample_base[4];  // element offsets into the sample planes (subsampled components only)

@@ -217,7 +217,28 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
             fi.height = (uint32_t)((s[1] << 8) | s[2]);
             fi.width = (uint32_t)((s[3] << 8) | s[4]);
             if (fi.width == 0) FAIL(B200JPG_ERR_MALFORMED_STREAM, "image width must not be zero");
-            if (fi.height == 0) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "frame height defined by a DNL marker is not supported by the B200 path");
+            if (fi.height == 0) {
+                // The height follows the first scan in a DNL marker (EntropyParser::ParseDNLMarker codestream/entropyparser.cpp:
+                // 204-249, looked for in front of every MCU, entropyparser.hpp:147-152). The kernels want the geometry up front,
+                // so the marker is looked up now: tables up to the first SOS, that scan's entropy coded segment, FF DC.
+                size_t q = pos + (size_t)seglen;
+                while (q + 3 < len && data[q] == 0xff && data[q + 1] != 0xda) {
+                    if (data[q + 1] == 0xff) {
+                        q++;
+                        continue;
+                    }
+                    q += 2 + (size_t)c.u16(q + 2);
+                }
+                int hgt = -1;
+                if (q + 3 < len && data[q] == 0xff && data[q + 1] == 0xda) {
+                    std::vector<size_t> at;
+                    std::vector<uint8_t> id;
+                    const size_t e = index_ecs(c, q + 2 + (size_t)c.u16(q + 2), at, id);
+                    if (e + 5 < len && data[e] == 0xff && data[e + 1] == 0xdc && c.u16(e + 2) == 4) hgt = c.u16(e + 4);
+                }
+                if (hgt <= 0) FAIL(B200JPG_ERR_MALFORMED_STREAM, "frame height is zero and no DNL marker follows the first scan");
+                fi.height = (uint32_t)hgt;
+            }
             int nc = s[5];
             if (nc < 1) FAIL(B200JPG_ERR_MALFORMED_STREAM, "number of components must be between 1 and 255");
             if (seglen - 8 != 3 * nc) FAIL(B200JPG_ERR_MALFORMED_STREAM, "frame header marker size is invalid");

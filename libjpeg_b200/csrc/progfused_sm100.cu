@@ -1,0 +1,397 @@
+// progfused_sm100.cu -- progressive (SOF2) frames decoded COMPONENT BY COMPONENT instead of scan by scan.
+//
+// The scans of a progressive frame build on each other, but only inside one 8x8 block: what a scan does to a block depends on
+// what the earlier scans left in THAT block and on nothing else (RefinementScan::DecodeBlock codestream/refinementscan.cpp:
+// 584-690 looks at the block's own coefficients; the EOB runs and DC predictors of SequentialScan::DecodeBlock codestream/
+// sequentialscan.cpp:678-773 are per scan). Every scan is its own bit stream. So instead of ten launches that each drag the
+// whole coefficient store through HBM (one restart interval per lane, read-modify-write in place), a lane here owns a restart
+// interval of ONE component and carries one bit reader per scan of that component: block after block it runs the block through
+// all of the component's AC scans in file order -- in a 128-byte staging block in shared memory, already dequantised (the scans
+// only ever add multiples of 1 << Al, so value x quantiser can be accumulated directly) --, adds the DC value and hands the
+// finished block to the same warp-cooperative flush as the sequential kernel. The coefficient store is written exactly once
+// and never read; there is no dequantisation pass and no memset.
+//   pf_dc_kernel : the interleaved DC scans (first pass + refinements, sequentialscan.cpp:682-701, refinementscan.cpp:588-592)
+//                  -> one int16 level per block in a dense side plane (1/64 of the coefficient store); blocks of the MCU-padded
+//                  grid that no AC scan covers are completed here (DC + zeros).
+//   pf_ac_kernel : per component, all its AC scans (first passes with EOB runs :704-772, refinements with correction bits
+//                  refinementscan.cpp:594-690).
+// The host uses this path when the frame's scan script has that shape -- every scan either an interleaved DC scan of all
+// components or a single-component AC scan, restart intervals equal within each group (the reference encoder's `-v` script, and
+// the usual ones) -- and the scan-by-scan kernels of progressive_sm100.cu otherwise.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "internal.hpp"
+
+namespace b200jpg {
+namespace {
+
+constexpr int kPfThreads = 256;
+constexpr int kStage = 144;  // bytes per lane: 128 + 16 pad -> conflict-free 16-byte accesses (like the sequential kernel)
+constexpr uint32_t kErrMalformed = 1038u;
+
+// Bit reader over the unstuffed big-endian words of one interval (L1-cached global loads, one word of lookahead); behind the
+// end it hands out zero bits like the reference's reader in front of a marker (io/bitstream.cpp:96-105).
+struct Bits {
+    const uint32_t *w;
+    uint32_t nwords, bp, xw, x0, x1, x2;
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return i < nwords ? __ldg(w + i) : 0u; }
+    __device__ __forceinline__ void open(const uint8_t *p, uint32_t len_bytes) {
+        w = reinterpret_cast<const uint32_t *>(p);
+        nwords = (len_bytes + 3u) / 4u;
+        bp = 0, xw = 0;
+        x0 = word(0), x1 = word(1), x2 = word(2);
+    }
+    __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(x1, x0, bp); }
+    __device__ __forceinline__ void skip(uint32_t n) {  // n < 32
+        bp += n;
+        const uint32_t wi = bp >> 5;
+        if (wi != xw) x0 = x1, x1 = x2, x2 = word(wi + 2u), xw = wi;
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t n) {  // n <= 24
+        const uint32_t v = n ? (window() >> (32u - n)) : 0u;
+        skip(n);
+        return v;
+    }
+};
+
+__device__ __forceinline__ uint32_t lut_entry(const uint32_t *lut, uint32_t hi) {
+    uint32_t e = lut[hi >> (32 - kLutL1Bits)];
+    if ((e & (31u << 5)) == 0) e = lut[(1u << kLutL1Bits) + ((e >> 10) << (16 - kLutL1Bits)) + ((hi >> 16) & ((1u << (16 - kLutL1Bits)) - 1u))];
+    return e;
+}
+__device__ __forceinline__ int extend(uint32_t v, uint32_t s) {  // sequentialscan.cpp:692-696 / 757-762
+    return (v < (1u << (s - 1))) ? (int)v + (int)((~0u) << s) + 1 : (int)v;
+}
+
+__device__ __forceinline__ void sts_zero16(uint32_t a) { asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory"); }
+__device__ __forceinline__ uint4 lds16(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_h(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory"); }
+__device__ __forceinline__ int lds_h(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_q(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ uint64_t lds_q(uint32_t a) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// =====================================================================================================
+// DC scans: one restart interval of the interleaved DC scans per lane
+// =====================================================================================================
+__global__ void __launch_bounds__(kPfThreads)
+pf_dc_kernel(PfLaunch L) {
+    extern __shared__ uint32_t s_lut[];  // tables of the first DC scan (the refinements read raw bits)
+    const PfScan &first = L.scan[0];
+    const uint32_t *g_lut = reinterpret_cast<const uint32_t *>(first.tables + kTableHeaderBytes);
+    for (uint32_t i = threadIdx.x; i < first.lut_words; i += kPfThreads) s_lut[i] = g_lut[i];
+    __syncthreads();
+    const uint16_t *lut_off = reinterpret_cast<const uint16_t *>(first.tables + 16);
+    const uint64_t g = (uint64_t)blockIdx.x * kPfThreads + threadIdx.x;
+    if (g >= (uint64_t)L.n_frames * L.intervals) return;
+    const uint32_t j = (uint32_t)(g / L.intervals), iv = (uint32_t)(g % L.intervals);
+    const ClassScan &cs = L.frames[j];
+    Bits b[kPfMaxScans];
+    bool present[kPfMaxScans];
+#pragma unroll
+    for (int s = 0; s < kPfMaxScans; s++) {
+        present[s] = false;
+        if (s < L.n_scans) {
+            const uint32_t raw = L.scan[s].interval_len[g];
+            present[s] = !(raw & kIntervalLenAbsent);
+            b[s].open(L.clean + L.scan[s].clean_off[g], raw & kIntervalLenMask);
+        }
+    }
+    const uint32_t mcu0 = iv * L.dri;
+    const uint32_t nmcu = (L.total_mcus - mcu0 < L.dri) ? (L.total_mcus - mcu0) : L.dri;
+    uint32_t mx = mcu0 % L.mcu_cols, my = mcu0 / L.mcu_cols;
+    int pred[4] = {0, 0, 0, 0};
+    bool bad = false;
+    for (uint32_t mi = 0; mi < nmcu; mi++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (c >= L.ns) break;
+            const uint32_t *dc = s_lut + lut_off[first.dc_slot[c]];
+            for (int y = 0; y < L.mh[c]; y++)
+                for (int x = 0; x < L.mw[c]; x++) {
+                    int level = 0;
+                    if (present[0] && !bad) {  // first pass: sequentialscan.cpp:682-701
+                        const uint32_t e = lut_entry(dc, b[0].window());
+                        if ((int)e < 0) {
+                            bad = true;
+                        } else {
+                            b[0].skip((e >> 5) & 31u);
+                            const uint32_t sz = e & 31u;
+                            if (sz) pred[c] += extend(b[0].get(sz), sz);
+                        }
+                        level = (int)((uint32_t)pred[c] << first.al);
+                    }
+#pragma unroll
+                    for (int s = 1; s < kPfMaxScans; s++)  // refinements: one raw bit per block, refinementscan.cpp:588-592
+                        if (s < L.n_scans && present[s]) level |= (int)(b[s].get(1) << L.scan[s].al);
+                    const uint32_t bx = mx * L.mw[c] + x, by = my * L.mh[c] + y;
+                    const uint64_t blk = cs.coef_base[c] / 64u + (uint64_t)by * L.bw[c] + bx;
+                    L.dcplane[blk] = (int16_t)level;
+                    if (bx >= L.ac_cols[c] || by >= L.ac_rows[c]) {
+                        // a block of the MCU-padded grid that the component's own (non-interleaved) scans never visit:
+                        // complete it here -- the dequantised DC and 63 zeros
+                        const int v = level * (int)L.dc_quant[c];
+                        if (v > 32767 || v < -32768) bad = true;
+                        uint4 *d = reinterpret_cast<uint4 *>(L.coef + cs.coef_base[c] + ((uint64_t)by * L.bw[c] + bx) * 64u);
+                        d[0] = make_uint4((uint32_t)v & 0xffffu, 0u, 0u, 0u);
+#pragma unroll
+                        for (int i = 1; i < 8; i++) d[i] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+        }
+        if (++mx == L.mcu_cols) mx = 0, my++;
+    }
+    if (bad) atomicMax(L.frame_status + cs.frame, kErrMalformed);
+}
+
+// =====================================================================================================
+// AC scans of one component: one restart interval (of that component's block grid) per lane
+// =====================================================================================================
+// shared memory: [staging: kPfThreads * kStage][per scan: qz pairs (kQzEntries * 8 bytes) + LUT]
+__global__ void __launch_bounds__(kPfThreads)
+pf_ac_kernel(PfLaunch L) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t s_stage = s_base + threadIdx.x * kStage;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t s_flush_sub = (lane & 7u) << 4;
+    const uint32_t s_flush = s_base + ((threadIdx.x & ~31u) + (lane >> 3)) * kStage + s_flush_sub;
+    // per scan: the (q, byte offset) pairs of the component's quantiser (already << Al, parse.cpp build_table_set) and the AC table
+    uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem + kPfThreads * kStage);
+    uint32_t tab_off[kPfMaxScans], lut_at[kPfMaxScans];  // word offsets inside s_tab: pairs, LUT of the scan's AC table
+    {
+        uint32_t at = 0;
+#pragma unroll
+        for (int s = 0; s < kPfMaxScans; s++) {
+            tab_off[s] = lut_at[s] = 0;
+            if (s < L.n_scans) {
+                const PfScan &sc = L.scan[s];
+                const uint32_t *g_qz = reinterpret_cast<const uint32_t *>(sc.tables + 32) + (uint32_t)(kQzEntries * 2) * sc.q_slot;
+                const uint32_t *g_lut = reinterpret_cast<const uint32_t *>(sc.tables + kTableHeaderBytes);
+                const uint16_t *lut_off = reinterpret_cast<const uint16_t *>(sc.tables + 16);
+                tab_off[s] = at;
+                for (uint32_t i = threadIdx.x; i < 128u; i += kPfThreads) s_tab[at + i] = g_qz[i];  // the pairs of k = 0..63
+                at += 128u;
+                lut_at[s] = at + lut_off[4 + sc.ac_slot];
+                for (uint32_t i = threadIdx.x; i < sc.lut_words; i += kPfThreads) s_tab[at + i] = g_lut[i];
+                at += sc.lut_words;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; i++) sts_zero16(s_stage + 16 * i);
+    }
+    __syncthreads();
+    const uint64_t total = (uint64_t)L.n_frames * L.intervals;
+    const uint64_t g = (uint64_t)blockIdx.x * kPfThreads + threadIdx.x;
+    const bool lane_valid = g < total;
+    const uint64_t gg = lane_valid ? g : 0;
+    const uint32_t j = (uint32_t)(gg / L.intervals), iv = (uint32_t)(gg % L.intervals);
+    const ClassScan &cs = L.frames[j];
+    Bits b[kPfMaxScans];
+    bool present[kPfMaxScans];
+    uint32_t skip[kPfMaxScans];
+#pragma unroll
+    for (int s = 0; s < kPfMaxScans; s++) {
+        present[s] = false;
+        skip[s] = 0;
+        if (s < L.n_scans) {
+            const uint32_t raw = lane_valid ? L.scan[s].interval_len[gg] : kIntervalLenAbsent;
+            present[s] = !(raw & kIntervalLenAbsent);
+            b[s].open(L.clean + L.scan[s].clean_off[gg], present[s] ? (raw & kIntervalLenMask) : 0u);
+        }
+    }
+    const uint32_t mcu0 = iv * L.dri;
+    uint32_t nblk = 0;
+    if (lane_valid) nblk = (L.total_mcus - mcu0 < L.dri) ? (L.total_mcus - mcu0) : L.dri;
+    uint32_t bx = mcu0 % L.mcu_cols, by = mcu0 / L.mcu_cols;
+    const uint64_t plane = cs.coef_base[0];
+    const int dcq = (int)L.dc_quant[0];
+    uint32_t ovf = 0;   // | (v + 32768): bits 16.. set when a dequantised coefficient left the int16 range
+    bool bad = false;
+
+    for (uint32_t bi = 0; bi < L.dri; bi++) {
+        const bool has = bi < nblk;
+        unsigned long long H = 0ull;  // bit k: coefficient k (zig-zag) of this block is non-zero so far
+        if (has && !bad) {
+#pragma unroll
+            for (int s = 0; s < kPfMaxScans; s++) {
+                if (s >= L.n_scans) break;
+                if (!present[s]) continue;  // an interval the stream does not contain leaves the block as the other scans make it
+                const PfScan &sc = L.scan[s];
+                const uint32_t *lut = s_tab + lut_at[s];
+                const uint32_t qz = s_base + kPfThreads * kStage + 4u * tab_off[s];  // shared-space address of the pairs
+                const int ss = sc.ss, se = sc.se;
+                Bits &r = b[s];
+                if (sc.ah == 0) {
+                    // ---- first pass of the band: sequentialscan.cpp:704-772
+                    if (skip[s] > 0) {
+                        skip[s]--;
+                        continue;
+                    }
+                    int k = ss;
+                    do {
+                        const uint32_t e = lut_entry(lut, r.window());
+                        if ((int)e < 0) {
+                            bad = true;
+                            break;
+                        }
+                        r.skip((e >> 5) & 31u);
+                        const uint32_t run = (e >> 10) & 15u, sz = e & 31u;
+                        if (sz == 0) {
+                            if (run == 15) {
+                                k += 16;
+                                continue;
+                            }
+                            skip[s] = ((1u << run) | r.get(run)) - 1u;  // EOBn; this block is part of the run
+                            break;
+                        }
+                        k += (int)run;
+                        const int v = extend(r.get(sz), sz);
+                        if (k >= 64) {  // the reference tests against 64, not against Se
+                            bad = true;
+                            break;
+                        }
+                        uint2 pq;
+                        asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)k));
+                        const int d = v * (int)pq.x;
+                        ovf |= (uint32_t)(d + 32768);
+                        sts_h(s_stage + pq.y, d);
+                        H |= 1ull << k;
+                        k++;
+                    } while (k <= se);
+                } else {
+                    // ---- refinement of the band: refinementscan.cpp:594-690. The walk over the band is done on the mask of
+                    // non-zero coefficients instead of coefficient by coefficient: a symbol (run r, size 0 / 1) places its
+                    // value on the (r+1)-th still-zero position at or behind k; every non-zero position passed on the way
+                    // takes one correction bit, in order.
+                    const unsigned long long band = ((se >= 63) ? ~0ull : ((1ull << (se + 1)) - 1ull)) & ~((1ull << ss) - 1ull);
+                    int k = ss;
+                    auto correct = [&](unsigned long long m) {  // one bit for every set position of m, ascending
+                        while (m) {
+                            const int p = __ffsll((long long)m) - 1;
+                            m &= m - 1ull;
+                            if (r.get(1)) {
+                                uint2 pq;
+                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)p));
+                                const int cur = lds_h(s_stage + pq.y);
+                                const int d = cur + (cur > 0 ? (int)pq.x : -(int)pq.x);  // away from zero by 1 << Al, dequantised
+                                ovf |= (uint32_t)(d + 32768);
+                                sts_h(s_stage + pq.y, d);
+                            }
+                        }
+                    };
+                    if (skip[s] == 0) {
+                        while (k <= se) {
+                            const uint32_t e = lut_entry(lut, r.window());
+                            if ((int)e < 0) {
+                                bad = true;
+                                break;
+                            }
+                            r.skip((e >> 5) & 31u);
+                            uint32_t run = (e >> 10) & 15u;
+                            const uint32_t sz = e & 31u;
+                            int sign = 0;  // +1 / -1: a new coefficient of magnitude 1 << Al; 0: nothing to place
+                            if (sz == 0) {
+                                if (run != 15) {  // EOBn: the rest of this block (and of the next skip-1 blocks) only takes correction bits
+                                    skip[s] = (1u << run) | r.get(run);
+                                    break;
+                                }
+                            } else if (sz != 1) {  // the reference warns and goes on with a zero amplitude and no run (:659-668)
+                                run = 0;
+                            } else {
+                                sign = r.get(1) ? 1 : -1;
+                            }
+                            // the (run+1)-th zero position at or behind k inside the band
+                            unsigned long long zeros = ~H & band & ~((1ull << k) - 1ull);
+                            for (uint32_t i = 0; i < run && zeros; i++) zeros &= zeros - 1ull;
+                            const int target = zeros ? __ffsll((long long)zeros) - 1 : se + 1;
+                            const unsigned long long upto = (target >= 64) ? ~0ull : ((1ull << target) - 1ull);
+                            correct(H & band & ~((1ull << k) - 1ull) & upto);
+                            if (target <= se && sign) {
+                                uint2 pq;
+                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)target));
+                                sts_h(s_stage + pq.y, sign * (int)pq.x);
+                                H |= 1ull << target;
+                            }
+                            k = target + 1;
+                        }
+                    }
+                    if (skip[s] > 0 && !bad) {
+                        if (k <= se) correct(H & band & ~((1ull << k) - 1ull));
+                        skip[s]--;
+                    }
+                }
+                if (bad) break;
+            }
+            // ---- the DC value from the side plane, dequantised
+            {
+                const int level = L.dcplane[plane / 64u + (uint64_t)by * L.bw[0] + bx];
+                const int d = level * dcq;
+                ovf |= (uint32_t)(d + 32768);
+                sts_h(s_stage, d);
+            }
+        }
+        // ---- flush (zeros included) and clear the staging blocks, the whole warp together (see entropy_decode_kernel)
+        {
+            const int16_t *d = L.coef + plane + ((uint64_t)by * L.bw[0] + bx) * 64u;
+            sts_q(s_stage + 136, has ? (uint64_t)d : 0ull);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t a = s_flush + i * (4 * kStage);
+                const uint64_t dst = lds_q(a + 136 - s_flush_sub);
+                const uint4 v = lds16(a);
+                sts_zero16(a);
+                if (dst) *reinterpret_cast<uint4 *>(dst + s_flush_sub) = v;
+            }
+            __syncwarp();
+        }
+        if (++bx == L.mcu_cols) bx = 0, by++;
+    }
+    uint32_t err = 0;
+    if (bad || (ovf >> 16) != 0u) err = kErrMalformed;
+    if (err && lane_valid) atomicMax(L.frame_status + cs.frame, err);
+}
+
+}  // namespace
+
+int launch_pf_dc(const PfLaunch &L, void *stream) {
+    const uint64_t total = (uint64_t)L.n_frames * L.intervals;
+    if (total == 0 || L.n_scans == 0) return 0;
+    const size_t smem = (size_t)L.scan[0].lut_words * 4;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(pf_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    pf_dc_kernel<<<(uint32_t)((total + kPfThreads - 1) / kPfThreads), kPfThreads, smem, (cudaStream_t)stream>>>(L);
+    return (int)cudaGetLastError();
+}
+
+int launch_pf_ac(const PfLaunch &L, void *stream) {
+    const uint64_t total = (uint64_t)L.n_frames * L.intervals;
+    if (total == 0 || L.n_scans == 0) return 0;
+    size_t smem = (size_t)kPfThreads * kStage;
+    for (int s = 0; s < L.n_scans; s++) smem += (128u + (size_t)L.scan[s].lut_words) * 4;
+    if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(pf_ac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    pf_ac_kernel<<<(uint32_t)((total + kPfThreads - 1) / kPfThreads), kPfThreads, smem, (cudaStream_t)stream>>>(L);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace b200jpg

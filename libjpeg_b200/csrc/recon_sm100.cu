@@ -88,6 +88,100 @@ __device__ __forceinline__ void unpack_row(const uint4 q, int (&v)[8]) {
     v[7] = (int)(short)(q.w >> 16) << 4;
 }
 
+// ---- instruction-selection helpers ---------------------------------------------------------------------------------------
+// Both integer pipes of an SM sub-partition (ALU: IADD3 / SHF / LOP3 / LEA / PRMT; FMA-heavy: IMAD, IMAD.IADD, IMAD.MOV, VIADD)
+// take one warp instruction every other cycle (tools/opbench.cu, profiles/), so the kernel runs at the pace of the fuller one
+// -- r01: FMA-heavy 79 % busy, ALU 57 %. ptxas likes "x * 3 + y" as IMAD followed by VIADD for the rounding constant: two
+// FMA-heavy instructions per filter tap. Spelled as below it emits IADD3 (a + b + r) and one IMAD (b * 2 + t): one on each pipe.
+#ifndef B200JPG_FUSED_PLAIN
+__device__ __forceinline__ int add3(int a, int b, int c) {
+    int d;
+    asm("{ .reg .s32 x; add.s32 x, %1, %2; add.s32 %0, x, %3; }" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+template <int C>
+__device__ __forceinline__ int add2c(int a, int b) {  // a + b + C
+    int d;
+    asm("{ .reg .s32 x; add.s32 x, %1, %2; add.s32 %0, x, %3; }" : "=r"(d) : "r"(a), "r"(b), "n"(C));
+    return d;
+}
+template <int C>
+__device__ __forceinline__ int sub2c(int a, int b) {  // a - b + C
+    int d;
+    asm("{ .reg .s32 x; sub.s32 x, %1, %2; add.s32 %0, x, %3; }" : "=r"(d) : "r"(a), "r"(b), "n"(C));
+    return d;
+}
+// (a + 3 b + R) >> 2: upsampling/upsampler.cpp:136-168, 283-307
+template <int R>
+__device__ __forceinline__ int tap(int a, int b) {
+    int d;
+    asm("{ .reg .s32 x, y; add.s32 x, %1, %2; add.s32 x, x, %3; shl.b32 y, %2, 1; add.s32 x, x, y; shr.s32 %0, x, 2; }" : "=r"(d) : "r"(a), "r"(b), "n"(R));
+    return d;
+}
+#else
+__device__ __forceinline__ int add3(int a, int b, int c) { return WADD(WADD(a, b), c); }
+template <int C>
+__device__ __forceinline__ int add2c(int a, int b) { return WADD(WADD(a, b), C); }
+template <int C>
+__device__ __forceinline__ int sub2c(int a, int b) { return WADD(WSUB(a, b), C); }
+template <int R>
+__device__ __forceinline__ int tap(int a, int b) { return WADD(WADD(a, WMUL(3, b)), R) >> 2; }
+#endif
+
+// HorizontalFilterCore<2> (upsampler.cpp:283-307) on w[0..5] with the taps above
+__device__ __forceinline__ void hfilter2t(const int (&w)[6], int (&o)[8]) {
+    o[7] = tap<1>(w[5], w[4]);
+    o[6] = tap<2>(w[3], w[4]);
+    o[5] = tap<1>(w[4], w[3]);
+    o[4] = tap<2>(w[2], w[3]);
+    o[3] = tap<1>(w[3], w[2]);
+    o[2] = tap<2>(w[1], w[2]);
+    o[1] = tap<1>(o[2], w[1]);  // reads the freshly written out[2] (upsampler.cpp:301-302)
+    o[0] = tap<2>(w[0], w[1]);
+}
+
+// One 8-point pass like idct8, with the rounding constant riding in the three-input adds of the outputs
+template <int kRound, int kShift>
+__device__ __forceinline__ void idct8t(int &v0, int &v1, int &v2, int &v3, int &v4, int &v5, int &v6, int &v7) {
+    const int z1 = WMUL(WADD(v2, v6), 277);
+    const int tmp2 = WADD(z1, WMUL(v6, -946));
+    const int tmp3 = WADD(z1, WMUL(v2, 392));
+    const int a04 = WADD(v0, v4), s04 = WSUB(v0, v4);
+    const int tmp10 = WADD(WMUL(a04, 512), tmp3), tmp13 = WSUB(WMUL(a04, 512), tmp3);
+    const int tmp11 = WADD(WMUL(s04, 512), tmp2), tmp12 = WSUB(WMUL(s04, 512), tmp2);
+    const int y1 = WADD(v7, v1), y2 = WADD(v5, v3), y3 = WADD(v7, v3), y4 = WADD(v5, v1);
+    const int z5 = WMUL(WADD(y3, y4), 602);
+    const int p1 = WMUL(y1, -461), p2 = WMUL(y2, -1312);
+    const int p3 = WADD(WMUL(y3, -1004), z5), p4 = WADD(WMUL(y4, -200), z5);
+    const int t0 = WADD(WADD(WMUL(v7, 153), p1), p3);
+    const int t1 = WADD(WADD(WMUL(v5, 1051), p2), p4);
+    const int t2 = WADD(WADD(WMUL(v3, 1573), p2), p3);
+    const int t3 = WADD(WADD(WMUL(v1, 769), p1), p4);
+    v0 = add2c<kRound>(tmp10, t3) >> kShift;
+    v7 = sub2c<kRound>(tmp10, t3) >> kShift;
+    v1 = add2c<kRound>(tmp11, t2) >> kShift;
+    v6 = sub2c<kRound>(tmp11, t2) >> kShift;
+    v2 = add2c<kRound>(tmp12, t1) >> kShift;
+    v5 = sub2c<kRound>(tmp12, t1) >> kShift;
+    v3 = add2c<kRound>(tmp13, t0) >> kShift;
+    v4 = sub2c<kRound>(tmp13, t0) >> kShift;
+}
+
+// eight dequantised int16 coefficients -> ints WITHOUT the << 4 preshift of dct/idct.cpp:105. The row pass is linear in front
+// of its rounding shift, so with inputs 16 times smaller ((16 x + 256) >> 9) == ((x + 16) >> 5) for every integer x; the
+// reference's int32 arithmetic cannot wrap in this pass for coefficients that fit int16 (|16 x| <= 16 * 3825 * (32768 + 1024)
+// < 2^31), so nothing is lost by never forming 16 x.
+__device__ __forceinline__ void unpack_row_raw(const uint4 q, int (&v)[8]) {
+    v[0] = (int)(short)(q.x & 0xffffu);
+    v[1] = (int)q.x >> 16;
+    v[2] = (int)(short)(q.y & 0xffffu);
+    v[3] = (int)q.y >> 16;
+    v[4] = (int)(short)(q.z & 0xffffu);
+    v[5] = (int)q.z >> 16;
+    v[6] = (int)(short)(q.w & 0xffffu);
+    v[7] = (int)q.w >> 16;
+}
+
 // ---- b1: non-luma components -> sample planes ---------------------------------------------------------
 // Samples of real images fit 16 bits with room to spare, so the planes that every frame goes through are int16
 // (half the HBM traffic of this memory-bound kernel). A frame in which any sample does not fit is flagged `narrow`
@@ -104,14 +198,14 @@ __device__ __forceinline__ void idct_planes_block(const FrameRecon &f, int c, ui
     int s[8][8];
     const uint4 *src = reinterpret_cast<const uint4 *>(coef + f.coef_base[c] + (uint64_t)t * 64u);
 #pragma unroll
-    for (int r = 0; r < 8; r++) unpack_row(__ldg(src + r), s[r]);
-    s[0][0] = WADD(s[0][0], 128 << 7);  // dcoffset << (preshift + 3), idct.cpp:233,244
+    for (int r = 0; r < 8; r++) unpack_row_raw(__ldg(src + r), s[r]);
+    s[0][0] = WADD(s[0][0], 128 << 3);  // dcoffset << 3 (idct.cpp:233,244); the << 4 preshift is folded into the row pass' rounding
 #pragma unroll
-    for (int r = 0; r < 8; r++) idct8<256, 9>(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7]);
+    for (int r = 0; r < 8; r++) idct8t<16, 5>(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7]);
     int mx = 0, mn = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        idct8<2048, 12>(s[0][k], s[1][k], s[2][k], s[3][k], s[4][k], s[5][k], s[6][k], s[7][k]);
+        idct8t<2048, 12>(s[0][k], s[1][k], s[2][k], s[3][k], s[4][k], s[5][k], s[6][k], s[7][k]);
 #pragma unroll
         for (int r = 0; r < 8; r += 2) {
             mx = __vimax3_s32(mx, s[r][k], s[r + 1][k]);
@@ -310,9 +404,9 @@ __device__ __forceinline__ void reconstruct_tile(const FrameRecon &f, int *ys, c
         for (int r = 0; r < 8; r++) {
             const uint4 qn = piece((r < 7) ? r + 1 : r);
             int v[8];
-            unpack_row(q, v);
-            if (r == 0) v[0] = WADD(v[0], 128 << 7);  // dcoffset << (preshift + 3), idct.cpp:233,244
-            idct8<256, 9>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+            unpack_row_raw(q, v);
+            if (r == 0) v[0] = WADD(v[0], 128 << 3);  // dcoffset << 3 (idct.cpp:233,244), preshift folded into the rounding (unpack_row_raw)
+            idct8t<16, 5>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 8; k++) my[(8 * r + k) * kThreadsB] = v[k];
@@ -326,7 +420,7 @@ __device__ __forceinline__ void reconstruct_tile(const FrameRecon &f, int *ys, c
         int v[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) v[r] = my[(8 * r + k) * kThreadsB];
-        idct8<2048, 12>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        idct8t<2048, 12>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
 #pragma unroll
         for (int r = 0; r < 8; r++) my[(8 * r + k) * kThreadsB] = v[r];
         mx = __vimax3_s32(__vimax3_s32(mx, v[0], v[1]), v[2], v[3]);
@@ -407,10 +501,9 @@ __device__ __forceinline__ void reconstruct_tile(const FrameRecon &f, int *ys, c
                 if (SY == 2) {  // VerticalFilterCore<2>, upsampler.cpp:136-168: even lines lean on top, odd lines on bot
                     constexpr int ra = odd ? 1 : 2, rb = odd ? 2 : 1;  // rounding of even / odd window columns
 #pragma unroll
-                    for (int j = 0; j < NW; j++) {
-                        const int n1 = odd ? bot1[j] : top1[j], n2 = odd ? bot2[j] : top2[j];
-                        v1[j] = WADD(WADD(n1, WMUL(3, cur1[j])), (j & 1) ? rb : ra) >> 2;
-                        v2[j] = WADD(WADD(n2, WMUL(3, cur2[j])), (j & 1) ? rb : ra) >> 2;
+                    for (int j = 0; j < NW; j += 2) {
+                        v1[j] = tap<ra>(odd ? bot1[j] : top1[j], cur1[j]), v1[j + 1] = tap<rb>(odd ? bot1[j + 1] : top1[j + 1], cur1[j + 1]);
+                        v2[j] = tap<ra>(odd ? bot2[j] : top2[j], cur2[j]), v2[j + 1] = tap<rb>(odd ? bot2[j + 1] : top2[j + 1], cur2[j + 1]);
                     }
                 } else {
 #pragma unroll
@@ -427,8 +520,8 @@ __device__ __forceinline__ void reconstruct_tile(const FrameRecon &f, int *ys, c
                         w1[j] = v1[j];
                         w2[j] = v2[j];
                     }
-                    hfilter2(w1, c1);
-                    hfilter2(w2, c2);
+                    hfilter2t(w1, c1);
+                    hfilter2t(w2, c2);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
@@ -582,100 +675,6 @@ template <typename T>
 __device__ __forceinline__ void ring_store(uint32_t a, int v) {
     if (sizeof(T) == 2) sts16(a, v);
     else sts32(a, v);
-}
-
-// ---- instruction-selection helpers for the fused kernel -------------------------------------------------------------------
-// Both integer pipes of an SM sub-partition (ALU: IADD3 / SHF / LOP3 / LEA / PRMT; FMA-heavy: IMAD, IMAD.IADD, IMAD.MOV, VIADD)
-// take one warp instruction every other cycle (tools/opbench.cu, profiles/), so the kernel runs at the pace of the fuller one
-// -- r01: FMA-heavy 79 % busy, ALU 57 %. ptxas likes "x * 3 + y" as IMAD followed by VIADD for the rounding constant: two
-// FMA-heavy instructions per filter tap. Spelled as below it emits IADD3 (a + b + r) and one IMAD (b * 2 + t): one on each pipe.
-#ifndef B200JPG_FUSED_PLAIN
-__device__ __forceinline__ int add3(int a, int b, int c) {
-    int d;
-    asm("{ .reg .s32 x; add.s32 x, %1, %2; add.s32 %0, x, %3; }" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-template <int C>
-__device__ __forceinline__ int add2c(int a, int b) {  // a + b + C
-    int d;
-    asm("{ .reg .s32 x; add.s32 x, %1, %2; add.s32 %0, x, %3; }" : "=r"(d) : "r"(a), "r"(b), "n"(C));
-    return d;
-}
-template <int C>
-__device__ __forceinline__ int sub2c(int a, int b) {  // a - b + C
-    int d;
-    asm("{ .reg .s32 x; sub.s32 x, %1, %2; add.s32 %0, x, %3; }" : "=r"(d) : "r"(a), "r"(b), "n"(C));
-    return d;
-}
-// (a + 3 b + R) >> 2: upsampling/upsampler.cpp:136-168, 283-307
-template <int R>
-__device__ __forceinline__ int tap(int a, int b) {
-    int d;
-    asm("{ .reg .s32 x, y; add.s32 x, %1, %2; add.s32 x, x, %3; shl.b32 y, %2, 1; add.s32 x, x, y; shr.s32 %0, x, 2; }" : "=r"(d) : "r"(a), "r"(b), "n"(R));
-    return d;
-}
-#else
-__device__ __forceinline__ int add3(int a, int b, int c) { return WADD(WADD(a, b), c); }
-template <int C>
-__device__ __forceinline__ int add2c(int a, int b) { return WADD(WADD(a, b), C); }
-template <int C>
-__device__ __forceinline__ int sub2c(int a, int b) { return WADD(WSUB(a, b), C); }
-template <int R>
-__device__ __forceinline__ int tap(int a, int b) { return WADD(WADD(a, WMUL(3, b)), R) >> 2; }
-#endif
-
-// HorizontalFilterCore<2> (upsampler.cpp:283-307) on w[0..5] with the taps above
-__device__ __forceinline__ void hfilter2t(const int (&w)[6], int (&o)[8]) {
-    o[7] = tap<1>(w[5], w[4]);
-    o[6] = tap<2>(w[3], w[4]);
-    o[5] = tap<1>(w[4], w[3]);
-    o[4] = tap<2>(w[2], w[3]);
-    o[3] = tap<1>(w[3], w[2]);
-    o[2] = tap<2>(w[1], w[2]);
-    o[1] = tap<1>(o[2], w[1]);  // reads the freshly written out[2] (upsampler.cpp:301-302)
-    o[0] = tap<2>(w[0], w[1]);
-}
-
-// One 8-point pass like idct8, with the rounding constant riding in the three-input adds of the outputs
-template <int kRound, int kShift>
-__device__ __forceinline__ void idct8t(int &v0, int &v1, int &v2, int &v3, int &v4, int &v5, int &v6, int &v7) {
-    const int z1 = WMUL(WADD(v2, v6), 277);
-    const int tmp2 = WADD(z1, WMUL(v6, -946));
-    const int tmp3 = WADD(z1, WMUL(v2, 392));
-    const int a04 = WADD(v0, v4), s04 = WSUB(v0, v4);
-    const int tmp10 = WADD(WMUL(a04, 512), tmp3), tmp13 = WSUB(WMUL(a04, 512), tmp3);
-    const int tmp11 = WADD(WMUL(s04, 512), tmp2), tmp12 = WSUB(WMUL(s04, 512), tmp2);
-    const int y1 = WADD(v7, v1), y2 = WADD(v5, v3), y3 = WADD(v7, v3), y4 = WADD(v5, v1);
-    const int z5 = WMUL(WADD(y3, y4), 602);
-    const int p1 = WMUL(y1, -461), p2 = WMUL(y2, -1312);
-    const int p3 = WADD(WMUL(y3, -1004), z5), p4 = WADD(WMUL(y4, -200), z5);
-    const int t0 = WADD(WADD(WMUL(v7, 153), p1), p3);
-    const int t1 = WADD(WADD(WMUL(v5, 1051), p2), p4);
-    const int t2 = WADD(WADD(WMUL(v3, 1573), p2), p3);
-    const int t3 = WADD(WADD(WMUL(v1, 769), p1), p4);
-    v0 = add2c<kRound>(tmp10, t3) >> kShift;
-    v7 = sub2c<kRound>(tmp10, t3) >> kShift;
-    v1 = add2c<kRound>(tmp11, t2) >> kShift;
-    v6 = sub2c<kRound>(tmp11, t2) >> kShift;
-    v2 = add2c<kRound>(tmp12, t1) >> kShift;
-    v5 = sub2c<kRound>(tmp12, t1) >> kShift;
-    v3 = add2c<kRound>(tmp13, t0) >> kShift;
-    v4 = sub2c<kRound>(tmp13, t0) >> kShift;
-}
-
-// eight dequantised int16 coefficients -> ints WITHOUT the << 4 preshift of dct/idct.cpp:105. The row pass is linear in front
-// of its rounding shift, so with inputs 16 times smaller ((16 x + 256) >> 9) == ((x + 16) >> 5) for every integer x; the
-// reference's int32 arithmetic cannot wrap in this pass for coefficients that fit int16 (|16 x| <= 16 * 3825 * (32768 + 1024)
-// < 2^31), so nothing is lost by never forming 16 x.
-__device__ __forceinline__ void unpack_row_raw(const uint4 q, int (&v)[8]) {
-    v[0] = (int)(short)(q.x & 0xffffu);
-    v[1] = (int)q.x >> 16;
-    v[2] = (int)(short)(q.y & 0xffffu);
-    v[3] = (int)q.y >> 16;
-    v[4] = (int)(short)(q.z & 0xffffu);
-    v[5] = (int)q.z >> 16;
-    v[6] = (int)(short)(q.w & 0xffffu);
-    v[7] = (int)q.w >> 16;
 }
 
 // The warp's 32 blocks of coefficients come in as 4 KB of 16-byte pieces, eight per lane (piece i * 32 + lane): a luma row is
@@ -1079,8 +1078,11 @@ static int launch_recon_fused420(const ReconLaunch &l, cudaStream_t s, int *laun
 int launch_recon(const ReconLaunch &l, void *stream, int *launches) {
     cudaStream_t s = (cudaStream_t)stream;
     int n = 0;
-    static const bool no_fused = getenv("B200JPG_NO_FUSED") != nullptr;  // A/B switch: the two-kernel path through sample planes
-    if (l.ncomp == 3 && l.subx == 2 && l.suby == 2 && !no_fused) return launch_recon_fused420(l, s, launches);
+    // B200JPG_FUSED=1 selects the single-kernel reconstruction of 4:2:0 frames (no sample planes: 51 instead of 66 MB of DRAM
+    // traffic per 4K frame and 25 MB less memory per frame, but 19 % more time: the stage is bound by instruction issue, not by
+    // HBM, and the fused kernel issues more -- profiles/README.md); the default is the two-kernel path through int16 planes.
+    const char *fused = getenv("B200JPG_FUSED");
+    if (l.ncomp == 3 && l.subx == 2 && l.suby == 2 && fused && fused[0] == '1') return launch_recon_fused420(l, s, launches);
     const uint32_t cblocks = (l.max_bwc * l.max_bhc + kThreadsB - 1) / kThreadsB;
     const uint32_t gx = (l.max_bw0 + 31) / 32, gy = (l.max_bh0 + kThreadsB / 32 - 1) / (kThreadsB / 32);
     // every frame through the int16 planes

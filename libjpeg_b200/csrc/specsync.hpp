@@ -75,33 +75,44 @@ B200JPG_HD int32_t spec_value(uint32_t e, uint32_t hi) {
 }
 
 // Decodes whole blocks from `from` until a block boundary at or behind `limit_bit` (or behind the end of the data).
+// ONE flat loop, one symbol per iteration (the DC symbol of a block when k == 0, else an AC symbol): the threads of a warp
+// run the same few instructions whatever their blocks look like, and only diverge where they finish.
 B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_t nwords, uint32_t total_bits, SpecState from, uint32_t limit_bit) {
-    SpecResult r;
-    r.n_blocks = 0;
-    r.dc_sum[0] = r.dc_sum[1] = r.dc_sum[2] = r.dc_sum[3] = 0;
-    uint32_t bit = from.bit, blk = from.blk;
-    while (bit < limit_bit && bit < total_bits) {
-        const uint32_t c = sc.comp_of_block[blk];
-        uint32_t hi = spec_window(w, nwords, bit);
-        uint32_t e = spec_lookup(sc.lut + sc.dc_tab[c], hi);
-        if ((int32_t)e >= 0) {  // an entry that must not be decoded just ends the block here: any rule does for a wrong path
-            r.dc_sum[c] += spec_value(e, hi);
-            bit += e >> 26;
-            uint32_t k = 1;
-            while (k <= 63) {
-                hi = spec_window(w, nwords, bit);
-                e = spec_lookup(sc.lut + sc.ac_tab[c], hi);
-                bit += (e >> 26) & 31u;
-                k += (e >> 19) & 127u;  // run + 1, 16 for ZRL, kQzBlockEnds for EOB and error entries
+    uint32_t comp_bits = 0;  // two bits per block of an MCU: no indexed local array in the loop
+    for (uint32_t b = 0; b < sc.blocks_per_mcu; b++) comp_bits |= (uint32_t)sc.comp_of_block[b] << (2u * b);
+    const uint32_t bpm = sc.blocks_per_mcu;
+    uint32_t bit = from.bit, blk = from.blk, k = 0, n = 0;
+    int32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    while ((k != 0 || bit < limit_bit) && (k != 0 || bit < total_bits)) {
+        const uint32_t c = (comp_bits >> (2u * blk)) & 3u;
+        const uint32_t hi = spec_window(w, nwords, bit);
+        const uint32_t dct = c == 0 ? sc.dc_tab[0] : (c == 1 ? sc.dc_tab[1] : (c == 2 ? sc.dc_tab[2] : sc.dc_tab[3]));
+        const uint32_t act = c == 0 ? sc.ac_tab[0] : (c == 1 ? sc.ac_tab[1] : (c == 2 ? sc.ac_tab[2] : sc.ac_tab[3]));
+        const uint32_t e = spec_lookup(sc.lut + (k == 0 ? dct : act), hi);
+        if (k == 0) {
+            if ((int32_t)e >= 0) {
+                const int32_t v = spec_value(e, hi);
+                s0 += c == 0 ? v : 0, s1 += c == 1 ? v : 0, s2 += c == 2 ? v : 0, s3 += c == 3 ? v : 0;
+                bit += e >> 26;
+                k = 1;
+            } else {  // an entry that must not be decoded ends the block here: any rule does for a path that is wrong anyway
+                bit += 1;
+                k = 64;
             }
         } else {
-            bit += 1;
+            bit += (e >> 26) & 31u;
+            k += (e >> 19) & 127u;  // run + 1, 16 for ZRL, kQzBlockEnds for EOB and error entries
         }
-        r.n_blocks++;
-        if (++blk == sc.blocks_per_mcu) blk = 0;
+        if (k > 63) {
+            k = 0;
+            n++;
+            blk = blk + 1 == bpm ? 0 : blk + 1;
+        }
     }
-    r.exit.bit = bit;
-    r.exit.blk = blk;
+    SpecResult r;
+    r.exit.bit = bit, r.exit.blk = blk;
+    r.n_blocks = n;
+    r.dc_sum[0] = s0, r.dc_sum[1] = s1, r.dc_sum[2] = s2, r.dc_sum[3] = s3;
     return r;
 }
 

@@ -467,7 +467,23 @@ static int walk(const uint8_t *d, size_t n, jpgo_info *info, decoder_tables *tab
             info->width = rd16(d, n, p + 3);
             info->ncomp = d[p + 5];
             if (info->width == 0) return JPGO_ERR_MALFORMED_STREAM;
-            if (info->height == 0) return JPGO_ERR_NOT_IMPLEMENTED; /* DNL-defined height: out of scope */
+            if (info->height == 0) { /* the height follows the first scan in a DNL marker (entropyparser.cpp:204-249, entropyparser.hpp:147-152) */
+                size_t q = pos + (size_t)len, e;
+                int hgt = -1;
+                while (q + 3 < n && d[q] == 0xff && d[q + 1] != 0xda) { /* tables up to the first SOS */
+                    if (d[q + 1] == 0xff) {
+                        q++;
+                        continue;
+                    }
+                    q += 2 + (size_t)rd16(d, n, q + 2);
+                }
+                if (q + 3 < n && d[q + 1] == 0xda) {
+                    e = find_ecs_end(d, n, q + 2 + (size_t)rd16(d, n, q + 2));
+                    if (e + 5 < n && d[e] == 0xff && d[e + 1] == 0xdc && rd16(d, n, e + 2) == 4) hgt = rd16(d, n, e + 4);
+                }
+                if (hgt <= 0) return JPGO_ERR_MALFORMED_STREAM;
+                info->height = hgt;
+            }
             if (info->ncomp < 1) return JPGO_ERR_MALFORMED_STREAM;
             if (info->ncomp > JPGO_MAX_COMP) return JPGO_ERR_NOT_IMPLEMENTED;
             if (len - 8 != 3 * info->ncomp) return JPGO_ERR_MALFORMED_STREAM;

@@ -454,3 +454,38 @@ def test_restartless_variants_match_oracle(built, oracle, monkeypatch):
         if rc == 0:
             assert np.array_equal(dec.frame_view(out, i).cpu().numpy(), want), i
             assert np.array_equal(dec1.frame_view(out1, i).cpu().numpy(), want), i
+
+
+def test_dnl_streams_match_reference_fixtures(built):
+    """frame height in a DNL marker behind the first scan (tests/golden/dnl, make_dnl.py)."""
+    d = os.path.join(GOLDEN, "dnl")
+    px = np.load(os.path.join(d, "dnl_pixels.npz"))
+    names = sorted(n for n in px.files if not n.endswith("__ref_dnl"))
+    dec, out = gpu_decode(built, [open(os.path.join(d, n + ".jpg"), "rb").read() for n in names])
+    for i, n in enumerate(names):
+        assert dec.status(i) == 0, n
+        got = dec.frame_view(out, i).cpu().numpy()
+        assert np.array_equal(got, px[n]), n
+        assert np.array_equal(got[:-1], px[n + "__ref_dnl"][:-1]), n
+
+
+def test_fused_420_reconstruction_matches_oracle(built, oracle, golden_pixels, monkeypatch):
+    """The single-kernel reconstruction of 4:2:0 frames (B200JPG_FUSED=1: chroma IDCT into a shared-memory ring, no sample
+    planes) on the 4:2:0 goldens, odd sizes, frames whose samples leave the int16 / 32-bit colour ranges, and benchmark frames."""
+    from libjpeg_b200 import synth
+    from tests import oracle_binding
+    monkeypatch.setenv("B200JPG_FUSED", "1")
+    names = [n for n in NAMES if n.startswith("c420")]
+    frames = [open(os.path.join(GOLDEN, n + ".jpg"), "rb").read() for n in names]
+    want = [golden_pixels[n] for n in names]
+    for (w, h, z, dcq) in [(641, 479, 13, 0), (96, 80, 3, 255), (640, 360, 40, 160), (1920, 1080, 120, 0), (3840, 2160, 240, 0), (260, 20, 0, 0)]:
+        f = synth.encode(synth.source_image(w, h, 5), 75, (2, 2), z)
+        f = oracle_binding.with_dc_quantiser(f, dcq) if dcq else f.tobytes()
+        rc, px = oracle.decode(f)
+        assert rc == 0
+        frames.append(f)
+        want.append(px)
+    dec, out = gpu_decode(built, frames)
+    for i in range(len(frames)):
+        assert dec.status(i) == 0, i
+        assert np.array_equal(dec.frame_view(out, i).cpu().numpy().reshape(want[i].shape), want[i]), i

@@ -237,3 +237,18 @@ def test_zrl_that_steps_over_position_63_ends_the_block_silently(oracle, tmp_pat
     assert ref is not None
     rc, px = oracle.decode(data)
     assert rc == 0 and np.array_equal(px.reshape(ref.shape), ref)
+
+
+DNL = os.path.join(GOLDEN, "dnl")
+DNLNAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(DNL, "*.jpg")))
+
+
+@pytest.mark.parametrize("name", DNLNAMES)
+def test_oracle_reads_the_height_from_the_dnl_marker(oracle, name):
+    """SOF height 0 + DNL behind the first scan (entropyparser.cpp:204-249): the pixels the reference delivers for the same
+    image with the height in the SOF; the reference's own decode of the DNL stream differs from that in its last pixel row
+    only (its upsampler is sized before the DNL arrives -- make_dnl.py), which is not restated."""
+    px = np.load(os.path.join(DNL, "dnl_pixels.npz"))
+    rc, got = oracle.decode(open(os.path.join(DNL, name + ".jpg"), "rb").read())
+    assert rc == 0 and np.array_equal(got, px[name])
+    assert np.array_equal(got[:-1], px[name + "__ref_dnl"][:-1])
