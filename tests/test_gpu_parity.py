@@ -489,3 +489,14 @@ def test_fused_420_reconstruction_matches_oracle(built, oracle, golden_pixels, m
     for i in range(len(frames)):
         assert dec.status(i) == 0, i
         assert np.array_equal(dec.frame_view(out, i).cpu().numpy().reshape(want[i].shape), want[i]), i
+
+
+def test_progressive_scan_by_scan_path_matches_fixtures(built, monkeypatch):
+    """The progressive goldens again with the component-fused kernels switched off (B200JPG_NO_PFUSE): the scan-by-scan kernels
+    of progressive_sm100.cu serve scan scripts the fused path does not take, and stay pinned on the same reference pixels."""
+    monkeypatch.setenv("B200JPG_NO_PFUSE", "1")
+    px = np.load(os.path.join(PROGRESSIVE, "progressive_pixels.npz"))
+    dec, out = gpu_decode(built, [open(os.path.join(PROGRESSIVE, n + ".jpg"), "rb").read() for n in PNAMES])
+    for i, n in enumerate(PNAMES):
+        assert dec.status(i) == 0, n
+        assert np.array_equal(dec.frame_view(out, i).cpu().numpy().reshape(px[n].shape), px[n]), n
