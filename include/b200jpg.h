@@ -99,6 +99,12 @@ typedef struct b200jpg_batch b200jpg_batch;
  * skipped and reported through b200jpg_batch_frame_status. */
 B200JPG_API int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad,
                          b200jpg_batch **batch);
+/* The same with request flags -- what a RectangleRequest carries besides the rectangle (codestream/rectanglerequest.cpp:
+ * 93-165): B200JPG_FLAG_NO_COLOR_TRANSFORM = JPGTAG_MATRIX_LTRAFO set to JPGFLAG_MATRIX_COLORTRANSFORMATION_NONE: the
+ * components are upsampled and delivered as they are (YCbCr frames come out as Y, Cb, Cr). */
+#define B200JPG_FLAG_NO_COLOR_TRANSFORM 1u
+B200JPG_API int b200jpg_batch_create_ex(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad,
+                            unsigned flags, b200jpg_batch **batch);
 /* Waits for the work last enqueued for this batch (its buffers return to the context's pool for reuse by the
  * next batch; b200jpg_destroy frees the pool). The caller must have consumed `out_dev` before reusing it. */
 B200JPG_API void b200jpg_batch_destroy(b200jpg_batch *batch);
@@ -161,6 +167,8 @@ B200JPG_API int b200jpg_selftest_restartless(const uint8_t *data, size_t len, ui
  * download, synchronise).  `out_host` receives b200jpg_batch_out_bytes(batch,-1) bytes. */
 B200JPG_API int b200jpg_decode_to_host(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, uint8_t *out_host,
                            uint64_t out_capacity);
+B200JPG_API int b200jpg_decode_to_host_ex(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, uint8_t *out_host,
+                              uint64_t out_capacity, unsigned flags);
 
 #ifdef __cplusplus
 }

@@ -123,6 +123,7 @@ struct ScanClass {
 
 struct ReconGroup {
     uint32_t ncomp = 0, subx = 1, suby = 1;
+    bool generic = false;
     std::vector<FrameRecon> frames;
     uint32_t max_bw0 = 0, max_bh0 = 0, max_bwc = 0, max_bhc = 0;
     uint64_t dev_frames = 0;
@@ -134,6 +135,14 @@ struct PfGroupHost {
     std::vector<int> ac[4];    // single-component AC scans per frame component, file order
     int comp_of_ac[4] = {0, 0, 0, 0};
 };
+
+// the tuned reconstruction kernels cover grey frames and three-component frames whose first component is not subsampled and
+// whose two other components share factors of 1 or 2; everything else goes through the generic kernels
+static bool frame_is_generic(const b200jpg_frame_info &fi) {
+    if (fi.ncomp == 1) return fi.subx[0] != 1 || fi.suby[0] != 1;
+    if (fi.ncomp != 3) return true;
+    return fi.subx[0] != 1 || fi.suby[0] != 1 || fi.subx[1] != fi.subx[2] || fi.suby[1] != fi.suby[2] || fi.subx[1] > 2 || fi.suby[1] > 2;
+}
 
 struct ClassKey {
     int v[40];
@@ -313,13 +322,19 @@ void b200jpg_batch_destroy(b200jpg_batch *b) {
     delete b;
 }
 
-static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad, b200jpg_batch **out);
+static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad, unsigned flags,
+                             b200jpg_batch **out);
 
 int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad,
                          b200jpg_batch **out) {
+    return b200jpg_batch_create_ex(ctx, frames, lens, n, tolerate_bad, 0u, out);
+}
+
+int b200jpg_batch_create_ex(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad, unsigned flags,
+                            b200jpg_batch **out) {
     if (!ctx) return B200JPG_ERR_INVALID_PARAMETER;
     try {  // no exception crosses the C ABI
-        return batch_create_impl(ctx, frames, lens, n, tolerate_bad, out);
+        return batch_create_impl(ctx, frames, lens, n, tolerate_bad, flags, out);
     } catch (const std::bad_alloc &) {
         if (out) *out = nullptr;
         return ctx->fail(B200JPG_ERR_OUT_OF_MEMORY, "out of host memory while preparing the batch");
@@ -329,7 +344,8 @@ int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *frames, const s
     }
 }
 
-static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad, b200jpg_batch **out) {
+static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad, unsigned flags,
+                             b200jpg_batch **out) {
     if (!out || !frames || !lens || n <= 0) return ctx->fail(B200JPG_ERR_INVALID_PARAMETER, "invalid batch arguments");
     *out = nullptr;
     cudaError_t ce = cudaSetDevice(ctx->device);
@@ -372,15 +388,11 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
         int &st = b->parse_status[i];
         if (st == 0) {  // what the kernels cover
             const b200jpg_frame_info &fi = pf.info;
-            if (fi.ncomp != 1 && fi.ncomp != 3) {
+            bool factors_ok = fi.ncomp >= 1 && fi.ncomp <= 4;
+            for (int c = 0; c < fi.ncomp; c++) factors_ok = factors_ok && fi.subx[c] >= 1 && fi.subx[c] <= 4 && fi.suby[c] >= 1 && fi.suby[c] <= 4;
+            if (!factors_ok) {  // the reference's upsampler cores exist for factors 1..4 (upsampling/upsamplerbase.cpp:CreateUpsampler)
                 st = B200JPG_ERR_NOT_IMPLEMENTED;
-                errs[i] = "only one and three component frames are supported by the B200 path";
-            } else if (fi.subx[0] != 1 || fi.suby[0] != 1) {
-                st = B200JPG_ERR_NOT_IMPLEMENTED;
-                errs[i] = "a subsampled first component is not supported by the B200 path";
-            } else if (fi.ncomp == 3 && (fi.subx[1] != fi.subx[2] || fi.suby[1] != fi.suby[2] || fi.subx[1] > 2 || fi.suby[1] > 2)) {
-                st = B200JPG_ERR_NOT_IMPLEMENTED;
-                errs[i] = "only 1x1, 2x1, 1x2 and 2x2 chroma subsampling (equal for both chroma components) is supported";
+                errs[i] = "only frames of one to four components with subsampling factors of one to four are supported";
             } else {
                 // A sequential frame codes a component at most once. A component no scan codes (the stream ends early: the
                 // reference just stops at the EOI / the end of the data, Frame::ParseTrailer marker/frame.cpp:1062-1092)
@@ -433,7 +445,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
         for (int c = 0; c < fi.ncomp; c++) {
             coef_base[i][c] = coef_cur;
             coef_cur += (uint64_t)fi.blocks_w[c] * fi.blocks_h[c] * 64;
-            if (c > 0) {
+            if (c > 0 || frame_is_generic(fi)) {  // generic reconstruction keeps a sample plane of every component
                 sample_base[i][c] = sample_cur;
                 sample_cur += (uint64_t)fi.blocks_w[c] * fi.blocks_h[c] * 64;
             }
@@ -661,16 +673,19 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     for (int i = 0; i < n; i++) {
         if (b->parse_status[i] != 0) continue;
         const b200jpg_frame_info &fi = b->frames[i].info;
+        const bool generic = frame_is_generic(fi);
         uint32_t sx = fi.ncomp > 1 ? fi.subx[1] : 1, sy = fi.ncomp > 1 ? fi.suby[1] : 1;
+        if (generic) sx = sy = 0;  // one group per component count: the generic kernels read the factors per frame
         ReconGroup *g = nullptr;
         for (auto &gg : b->groups)
-            if (gg.ncomp == fi.ncomp && gg.subx == sx && gg.suby == sy) g = &gg;
+            if (gg.ncomp == fi.ncomp && gg.subx == sx && gg.suby == sy && gg.generic == generic) g = &gg;
         if (!g) {
             b->groups.emplace_back();
             g = &b->groups.back();
             g->ncomp = fi.ncomp;
             g->subx = sx;
             g->suby = sy;
+            g->generic = generic;
         }
         FrameRecon fr{};
         for (int c = 0; c < fi.ncomp; c++) {
@@ -678,12 +693,14 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
             fr.sample_base[c] = sample_base[i][c];
             fr.bw[c] = fi.blocks_w[c];
             fr.bh[c] = fi.blocks_h[c];
+            fr.csx[c] = fi.subx[c];
+            fr.csy[c] = fi.suby[c];
         }
         fr.out_base = b->out_off[i];
         fr.width = fi.width;
         fr.height = fi.height;
         fr.ncomp = fi.ncomp;
-        fr.ycbcr = fi.ycbcr;
+        fr.ycbcr = (flags & B200JPG_FLAG_NO_COLOR_TRANSFORM) ? 0 : fi.ycbcr;  // JPGTAG_MATRIX_LTRAFO = ..._NONE (rectanglerequest.cpp:150-152)
         fr.subx = sx;
         fr.suby = sy;
         fr.cw = (fi.width + sx - 1) / sx;
@@ -692,7 +709,10 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
         g->frames.push_back(fr);
         g->max_bw0 = std::max(g->max_bw0, (fi.width + 7) / 8);
         g->max_bh0 = std::max(g->max_bh0, (fi.height + 7) / 8);
-        if (fi.ncomp > 1) {
+        if (generic) {  // the largest block grid of any component: the extent of the generic IDCT launch
+            for (int c = 0; c < fi.ncomp; c++)
+                if ((uint64_t)fi.blocks_w[c] * fi.blocks_h[c] > (uint64_t)g->max_bwc * g->max_bhc) g->max_bwc = fi.blocks_w[c], g->max_bhc = fi.blocks_h[c];
+        } else if (fi.ncomp > 1) {
             g->max_bwc = std::max(g->max_bwc, fi.blocks_w[1]);
             g->max_bhc = std::max(g->max_bhc, fi.blocks_h[1]);
         }
@@ -785,7 +805,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
         const char *fused = getenv("B200JPG_FUSED");
         const bool use_fused = fused && fused[0] == '1';
         bool need_planes = false;
-        for (auto &g : b->groups) need_planes = need_planes || (g.ncomp > 1 && !(use_fused && g.ncomp == 3 && g.subx == 2 && g.suby == 2));
+        for (auto &g : b->groups) need_planes = need_planes || g.generic || (g.ncomp > 1 && !(use_fused && g.ncomp == 3 && g.subx == 2 && g.suby == 2));
         if (!need_planes) b->sample_elems = 0;
     }
     if (ce == cudaSuccess && b->sample_elems) b->d_samples = (int32_t *)ctx->get(1, b->sample_elems * sizeof(int32_t), &ce);
@@ -797,7 +817,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     if (ce == cudaSuccess) b->d_status = (uint32_t *)ctx->get(1, b->sz_status, &ce);
     if (ce == cudaSuccess && !b->pf_groups.empty()) b->d_dcplane = (int16_t *)ctx->get(1, b->coef_elems / 64 * sizeof(int16_t), &ce);
     if (ce == cudaSuccess && b->n_spec) {
-        b->sz_spec = (size_t)b->n_spec * (sizeof(SpecSegment) + 8 + 8 + 4 + 16) + 256;
+        b->sz_spec = (size_t)b->n_spec * (sizeof(SpecSegment) + 8 + 8 + 4 + 16 + sizeof(SpecLog)) + 256;
         b->d_spec = (uint8_t *)ctx->get(1, b->sz_spec, &ce);
     }
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->ev_last, cudaEventDisableTiming);
@@ -920,6 +940,8 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
                 l.spec_counts = reinterpret_cast<uint32_t *>(q) + o;
                 q += n * 4;
                 l.spec_dc_sums = reinterpret_cast<int32_t *>(q) + 4 * o;
+                q += n * 16;
+                l.spec_logs = reinterpret_cast<SpecLog *>(q) + o;
                 if (pass == 1) {
                     int rs = launch_spec_sync(l, stream);
                     if (rs != 0) return b->ctx->fail_cuda((cudaError_t)rs, "synchronisation kernel launch");
@@ -1016,6 +1038,7 @@ static int run_recon(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
         l.ncomp = g.ncomp;
         l.subx = g.subx;
         l.suby = g.suby;
+        l.generic = g.generic;
         l.coef = b->d_coef;
         l.samples16 = b->d_samples16;
         l.samples32 = b->d_samples;
@@ -1216,9 +1239,14 @@ int b200jpg_selftest_restartless(const uint8_t *data, size_t len, uint32_t *roun
 
 int b200jpg_decode_to_host(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, uint8_t *out_host,
                            uint64_t out_capacity) {
+    return b200jpg_decode_to_host_ex(ctx, frames, lens, n, out_host, out_capacity, 0u);
+}
+
+int b200jpg_decode_to_host_ex(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, uint8_t *out_host,
+                              uint64_t out_capacity, unsigned flags) {
     if (!ctx) return B200JPG_ERR_INVALID_PARAMETER;
     b200jpg_batch *b = nullptr;
-    int rc = b200jpg_batch_create(ctx, frames, lens, n, 0, &b);
+    int rc = b200jpg_batch_create_ex(ctx, frames, lens, n, 0, flags, &b);
     if (rc) return rc;
     uint8_t *d_out = nullptr;
     cudaStream_t s = nullptr;

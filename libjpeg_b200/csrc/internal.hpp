@@ -133,6 +133,7 @@ constexpr uint32_t kIntervalLenAbsent = 1u << 30;
 constexpr uint32_t kIntervalLenMask = (1u << 30) - 1u;
 
 struct SpecSegment;
+struct SpecLog;
 
 struct ScanClassParams {  // uniform over a launch of the entropy kernel
     int ns;
@@ -197,6 +198,7 @@ struct FrameRecon {       // per frame, for the reconstruction kernels
     uint32_t ncomp, ycbcr, subx, suby;  // subx/suby of the subsampled (chroma) components
     uint32_t cw, ch;                    // true subsampled size ceil(W/subx), ceil(H/suby)
     uint32_t status_idx, pad;
+    uint8_t csx[4], csy[4];             // generic reconstruction: subsampling factors of every component (1..4)
 };
 
 // kernel launchers (huffman_sm100.cu, recon_sm100.cu). All asynchronous on `stream`.
@@ -221,6 +223,7 @@ struct EntropyLaunch {
     unsigned long long *spec_exits, *spec_entries;
     uint32_t *spec_counts;
     int32_t *spec_dc_sums;  // [.. * 4]
+    struct SpecLog *spec_logs;
 };
 int launch_unstuff(const EntropyLaunch &l, void *stream);
 int launch_entropy(const EntropyLaunch &l, void *stream);
@@ -237,6 +240,7 @@ struct ReconLaunch {
     uint32_t max_bw0, max_bh0;     // largest luma block grid in the group
     uint32_t max_bwc, max_bhc;     // largest chroma block grid in the group
     uint32_t ncomp, subx, suby;    // uniform over the group
+    bool generic;                  // formats outside the tuned kernels: any component count / factors, per-frame parameters
     const int16_t *coef;
     int16_t *samples16;            // chroma sample planes every frame goes through
     int32_t *samples32;            // the same planes for the exact pass over frames flagged `narrow`

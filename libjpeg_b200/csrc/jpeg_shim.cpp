@@ -177,10 +177,11 @@ struct JPEG::Impl {
     std::unique_ptr<uint8_t[]> pixels;
     size_t pixel_bytes;
     bool decoded;
+    unsigned decoded_flags;  // request flags the cached pixels were decoded with (colour transformation on / off)
     JPG_LONG err_code;
     std::string err_msg;
 
-    Impl() : device(-1), have_image(false), pixel_bytes(0), decoded(false), err_code(0) { memset(&info, 0, sizeof(info)); }
+    Impl() : device(-1), have_image(false), pixel_bytes(0), decoded(false), decoded_flags(0), err_code(0) { memset(&info, 0, sizeof(info)); }
     JPG_LONG fail(JPG_LONG code, const std::string &msg) {
         err_code = code;
         err_msg = msg;
@@ -324,13 +325,12 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
     }
     if (maxx < minx || maxy < miny) return s.fail(JPGERR_INVALID_PARAMETER, "the requested rectangle is empty");
     if (!upsample) return s.fail(JPGERR_NOT_IMPLEMENTED, "reconstruction without upsampling is not supported by the B200 path");
-    if (!colortrafo && s.info.ycbcr)
-        return s.fail(JPGERR_NOT_IMPLEMENTED, "disabling the colour transformation is not supported by the B200 path");
     if (firstc != 0 || lastc != s.info.ncomp - 1)
         return s.fail(JPGERR_NOT_IMPLEMENTED, "reconstructing a subset of the components is not supported by the B200 path");
 
     // ---- decode on first use (CUDA; the whole frame, kept for later rectangles)
-    if (!s.decoded) {
+    const unsigned want_flags = (!colortrafo && s.info.ycbcr) ? B200JPG_FLAG_NO_COLOR_TRANSFORM : 0u;
+    if (!s.decoded || s.decoded_flags != want_flags) {
         b200jpg_ctx *ctx = 0;
         std::string msg;
         int rc = shared_context(s.device, &ctx, msg);
@@ -341,13 +341,14 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
         const uint8_t *frames[1] = {s.stream.data()};
         size_t lens[1] = {s.stream.size()};
         // JPEG objects decode concurrently: a batch owns its buffers and its stream, the context's buffer pool locks itself
-        rc = b200jpg_decode_to_host(ctx, frames, lens, 1, s.pixels.get(), s.pixel_bytes);
+        rc = b200jpg_decode_to_host_ex(ctx, frames, lens, 1, s.pixels.get(), s.pixel_bytes, want_flags);
         if (rc) {
             const char *m = 0;
             b200jpg_last_error(0, &m);  // this thread's failure (the context is shared with other JPEG objects)
             return s.fail(rc, (m && *m) ? m : "decoding failed");
         }
         s.decoded = true;
+        s.decoded_flags = want_flags;
     }
 
     // ---- REQUEST per component (bitmaphook.cpp:130-209), pixel types must agree (bitmapctrl.cpp:152-158)

@@ -291,6 +291,11 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
                 if (sc.td[i] > 3) FAIL(B200JPG_ERR_MALFORMED_STREAM, "DC table index in SOS marker is out of range, must be at most 4");
                 if (sc.ta[i] > 3) FAIL(B200JPG_ERR_MALFORMED_STREAM, "AC table index in SOS marker is out of range, must be at most 4");
             }
+            if (sc.ns > 1) {  // T.81 B.2.3: an interleaved MCU holds at most ten blocks (the kernels' per-MCU tables rely on it)
+                int blocks = 0;
+                for (int i = 0; i < sc.ns; i++) blocks += fi.hs[sc.comp[i]] * fi.vs[sc.comp[i]];
+                if (blocks > 10) FAIL(B200JPG_ERR_MALFORMED_STREAM, "more than ten blocks per MCU in an interleaved scan");
+            }
             const uint8_t *t = s + 1 + 2 * sc.ns;
             sc.progressive = fi.frame_type == 2;
             sc.ss = t[0];

@@ -225,117 +225,136 @@ pf_ac_kernel(PfLaunch L) {
     for (uint32_t bi = 0; bi < L.dri; bi++) {
         const bool has = bi < nblk;
         unsigned long long H = 0ull;  // bit k: coefficient k (zig-zag) of this block is non-zero so far
-        if (has && !bad) {
+        // The scans of the script are the same for every lane, so the walk over them is uniform; inside a scan every lane is
+        // somewhere else in ITS block, so the symbol loops are voted: one Huffman symbol per warp-convergent iteration (like the
+        // sequential kernel), lanes that are through wait for the others in the vote, not in divergent code.
 #pragma unroll
-            for (int s = 0; s < kPfMaxScans; s++) {
-                if (s >= L.n_scans) break;
-                if (!present[s]) continue;  // an interval the stream does not contain leaves the block as the other scans make it
-                const PfScan &sc = L.scan[s];
-                const uint32_t *lut = s_tab + lut_at[s];
-                const uint32_t qz = s_base + kPfThreads * kStage + 4u * tab_off[s];  // shared-space address of the pairs
-                const int ss = sc.ss, se = sc.se;
-                Bits &r = b[s];
-                if (sc.ah == 0) {
-                    // ---- first pass of the band: sequentialscan.cpp:704-772
-                    if (skip[s] > 0) {
-                        skip[s]--;
-                        continue;
-                    }
-                    int k = ss;
-                    do {
+        for (int s = 0; s < kPfMaxScans; s++) {
+            if (s >= L.n_scans) break;
+            const PfScan &sc = L.scan[s];
+            const uint32_t *lut = s_tab + lut_at[s];
+            const uint32_t qz = s_base + kPfThreads * kStage + 4u * tab_off[s];  // shared-space address of the pairs
+            const int ss = sc.ss, se = sc.se;
+            Bits &r = b[s];
+            // an interval the stream does not contain leaves the block as the other scans make it
+            bool active = has && !bad && present[s];
+            int k = ss;
+            if (sc.ah == 0) {
+                // ---- first pass of the band: sequentialscan.cpp:704-772
+                if (active && skip[s] > 0) {
+                    skip[s]--;
+                    active = false;
+                }
+                while (__any_sync(0xffffffffu, active)) {
+                    if (active) {
                         const uint32_t e = lut_entry(lut, r.window());
                         if ((int)e < 0) {
                             bad = true;
-                            break;
-                        }
-                        r.skip((e >> 5) & 31u);
-                        const uint32_t run = (e >> 10) & 15u, sz = e & 31u;
-                        if (sz == 0) {
-                            if (run == 15) {
-                                k += 16;
-                                continue;
+                            active = false;
+                        } else {
+                            r.skip((e >> 5) & 31u);
+                            const uint32_t run = (e >> 10) & 15u, sz = e & 31u;
+                            if (sz == 0) {
+                                if (run == 15) {
+                                    k += 16;
+                                } else {
+                                    skip[s] = ((1u << run) | r.get(run)) - 1u;  // EOBn; this block is part of the run
+                                    active = false;
+                                }
+                            } else {
+                                k += (int)run;
+                                const int v = extend(r.get(sz), sz);
+                                if (k >= 64) {  // the reference tests against 64, not against Se
+                                    bad = true;
+                                    active = false;
+                                } else {
+                                    uint2 pq;
+                                    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)k));
+                                    const int d = v * (int)pq.x;
+                                    ovf |= (uint32_t)(d + 32768);
+                                    sts_h(s_stage + pq.y, d);
+                                    H |= 1ull << k;
+                                    k++;
+                                }
                             }
-                            skip[s] = ((1u << run) | r.get(run)) - 1u;  // EOBn; this block is part of the run
-                            break;
+                            if (k > se) active = false;
                         }
-                        k += (int)run;
-                        const int v = extend(r.get(sz), sz);
-                        if (k >= 64) {  // the reference tests against 64, not against Se
+                    }
+                }
+            } else {
+                // ---- refinement of the band: refinementscan.cpp:594-690. The walk over the band is done on the mask of
+                // non-zero coefficients instead of coefficient by coefficient: a symbol (run r, size 0 / 1) places its value on
+                // the (r+1)-th still-zero position at or behind k; every non-zero position passed on the way takes one
+                // correction bit, in order. `pending` collects the positions that still owe a correction bit; they are paid
+                // one per voted iteration as well, before the lane decodes its next symbol.
+                const unsigned long long band = ((se >= 63) ? ~0ull : ((1ull << (se + 1)) - 1ull)) & ~((1ull << ss) - 1ull);
+                unsigned long long pending = 0ull;
+                bool tail = active && skip[s] > 0;  // inside an EOB run: the whole band only takes correction bits
+                if (tail) {
+                    pending = H & band;
+                    active = false;
+                }
+                while (__any_sync(0xffffffffu, active || pending != 0ull)) {
+                    if (pending != 0ull) {
+                        const int p = __ffsll((long long)pending) - 1;
+                        pending &= pending - 1ull;
+                        if (r.get(1)) {
+                            uint2 pq;
+                            asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)p));
+                            const int cur = lds_h(s_stage + pq.y);
+                            const int d = cur + (cur > 0 ? (int)pq.x : -(int)pq.x);  // away from zero by 1 << Al, dequantised
+                            ovf |= (uint32_t)(d + 32768);
+                            sts_h(s_stage + pq.y, d);
+                        }
+                    } else if (active) {
+                        const uint32_t e = lut_entry(lut, r.window());
+                        if ((int)e < 0) {
                             bad = true;
-                            break;
-                        }
-                        uint2 pq;
-                        asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)k));
-                        const int d = v * (int)pq.x;
-                        ovf |= (uint32_t)(d + 32768);
-                        sts_h(s_stage + pq.y, d);
-                        H |= 1ull << k;
-                        k++;
-                    } while (k <= se);
-                } else {
-                    // ---- refinement of the band: refinementscan.cpp:594-690. The walk over the band is done on the mask of
-                    // non-zero coefficients instead of coefficient by coefficient: a symbol (run r, size 0 / 1) places its
-                    // value on the (r+1)-th still-zero position at or behind k; every non-zero position passed on the way
-                    // takes one correction bit, in order.
-                    const unsigned long long band = ((se >= 63) ? ~0ull : ((1ull << (se + 1)) - 1ull)) & ~((1ull << ss) - 1ull);
-                    int k = ss;
-                    auto correct = [&](unsigned long long m) {  // one bit for every set position of m, ascending
-                        while (m) {
-                            const int p = __ffsll((long long)m) - 1;
-                            m &= m - 1ull;
-                            if (r.get(1)) {
-                                uint2 pq;
-                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)p));
-                                const int cur = lds_h(s_stage + pq.y);
-                                const int d = cur + (cur > 0 ? (int)pq.x : -(int)pq.x);  // away from zero by 1 << Al, dequantised
-                                ovf |= (uint32_t)(d + 32768);
-                                sts_h(s_stage + pq.y, d);
-                            }
-                        }
-                    };
-                    if (skip[s] == 0) {
-                        while (k <= se) {
-                            const uint32_t e = lut_entry(lut, r.window());
-                            if ((int)e < 0) {
-                                bad = true;
-                                break;
-                            }
+                            active = false;
+                        } else {
                             r.skip((e >> 5) & 31u);
                             uint32_t run = (e >> 10) & 15u;
                             const uint32_t sz = e & 31u;
                             int sign = 0;  // +1 / -1: a new coefficient of magnitude 1 << Al; 0: nothing to place
+                            bool eob = false;
                             if (sz == 0) {
                                 if (run != 15) {  // EOBn: the rest of this block (and of the next skip-1 blocks) only takes correction bits
                                     skip[s] = (1u << run) | r.get(run);
-                                    break;
+                                    eob = true;
                                 }
                             } else if (sz != 1) {  // the reference warns and goes on with a zero amplitude and no run (:659-668)
                                 run = 0;
                             } else {
                                 sign = r.get(1) ? 1 : -1;
                             }
-                            // the (run+1)-th zero position at or behind k inside the band
-                            unsigned long long zeros = ~H & band & ~((1ull << k) - 1ull);
-                            for (uint32_t i = 0; i < run && zeros; i++) zeros &= zeros - 1ull;
-                            const int target = zeros ? __ffsll((long long)zeros) - 1 : se + 1;
-                            const unsigned long long upto = (target >= 64) ? ~0ull : ((1ull << target) - 1ull);
-                            correct(H & band & ~((1ull << k) - 1ull) & upto);
-                            if (target <= se && sign) {
-                                uint2 pq;
-                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)target));
-                                sts_h(s_stage + pq.y, sign * (int)pq.x);
-                                H |= 1ull << target;
+                            const unsigned long long from_k = ~((1ull << k) - 1ull);
+                            if (eob) {
+                                pending = H & band & from_k;
+                                tail = true;
+                                active = false;
+                            } else {
+                                // the (run+1)-th zero position at or behind k inside the band
+                                unsigned long long zeros = ~H & band & from_k;
+                                for (uint32_t i = 0; i < run && zeros; i++) zeros &= zeros - 1ull;
+                                const int target = zeros ? __ffsll((long long)zeros) - 1 : se + 1;
+                                const unsigned long long upto = (target >= 64) ? ~0ull : ((1ull << target) - 1ull);
+                                pending = H & band & from_k & upto;
+                                if (target <= se && sign) {  // (its position is behind every position that still owes a bit)
+                                    uint2 pq;
+                                    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)target));
+                                    sts_h(s_stage + pq.y, sign * (int)pq.x);
+                                    H |= 1ull << target;
+                                }
+                                k = target + 1;
+                                if (k > se) active = false;
                             }
-                            k = target + 1;
                         }
                     }
-                    if (skip[s] > 0 && !bad) {
-                        if (k <= se) correct(H & band & ~((1ull << k) - 1ull));
-                        skip[s]--;
-                    }
                 }
-                if (bad) break;
+                if (tail && !bad) skip[s]--;
             }
+        }
+        if (has && !bad) {
             // ---- the DC value from the side plane, dequantised
             {
                 const int level = L.dcplane[plane / 64u + (uint64_t)by * L.bw[0] + bx];

@@ -240,8 +240,8 @@ __device__ __forceinline__ void idct_planes_block(const FrameRecon &f, int c, ui
 template <typename T, bool kListed>
 __global__ void __launch_bounds__(kThreadsB)
 idct_planes_kernel(const FrameRecon *__restrict__ frames, const int16_t *__restrict__ coef, T *__restrict__ samples, uint32_t *__restrict__ flags,
-                   const uint32_t *__restrict__ list) {
-    const int c = 1 + blockIdx.z;
+                   const uint32_t *__restrict__ list, int first_comp) {
+    const int c = first_comp + blockIdx.z;
     const uint32_t t = blockIdx.x * kThreadsB + threadIdx.x;
     if (!kListed) {
         const FrameRecon &f = frames[blockIdx.y];
@@ -1035,6 +1035,157 @@ reconstruct420_kernel(const FrameRecon *__restrict__ frames, const int16_t *__re
     }
 }
 
+
+// =====================================================================================================
+// generic reconstruction: any number of components (1..4), any subsampling factors (1..4, per component)
+// =====================================================================================================
+// The formats outside the tuned kernels -- chroma factors 3 and 4, components with different factors, a subsampled first
+// component, two or four components -- are rare, so this path is written for exactness, not for speed: every
+// component goes through idct_planes_kernel into an int32 sample plane, then one thread per 8x8 OUTPUT block follows
+// Upsampler<sx,sy>::UpsampleRegion to the letter (upsampling/upsampler.cpp:83-112, VerticalFilterCore<1..4> :114-268,
+// HorizontalFilterCore<1..4> :270-386 -- including the in-place stores of the horizontal cores, whose order is part of the
+// result) and the colour transformation in 64 bits (ycbcrtrafo.cpp:842-850 / identity numerics.hpp:69).
+__device__ __forceinline__ int gmix(int a, int wa, int b, int wb, int rnd, int sh) {
+    return (int)((unsigned)wa * (unsigned)a + (unsigned)wb * (unsigned)b + (unsigned)rnd) >> sh;
+}
+
+// one 8x8 block of component samples at output position (X, Y), upsampled by (sx, sy); plane = IDCT output, pitch in samples,
+// (w, h) = true subsampled size; edge replication dest[-1] = dest[0], dest[w] = dest[w-1] (upsamplerbase.cpp:322-323) by clamping
+__device__ void generic_upsample_block(const int32_t *__restrict__ plane, uint32_t pitch, int w, int h, int sx, int sy, int X, int Y, int *out) {
+    const int y = Y / sy;
+    const int x0 = X / sx - ((sx > 1) ? 1 : 0);
+    int top = (y > 0) ? y - 1 : y, cur = y, bot = (y + 1 < h) ? y + 1 : y;
+    int ymod = Y % sy;
+    const int xmod = X % sx;
+    auto at = [&](int x, int yy) { return plane[(size_t)yy * pitch + (size_t)clampi(x, 0, w - 1)]; };
+    for (int row = 0; row < 8; row++) {
+        int *o = out + 8 * row;
+        int advance = 0;
+        if (sy == 1) {
+            for (int j = 0; j < 8; j++) o[j] = at(x0 + j, cur);
+            if (cur + 1 < h) cur++;
+        } else if (sy == 2) {
+            const int nb = (ymod == 0) ? top : bot;
+            for (int j = 0; j < 8; j++) o[j] = gmix(at(x0 + j, nb), 1, at(x0 + j, cur), 3, ((j & 1) == ymod) ? 2 : 1, 2);
+            advance = (ymod == 1);
+        } else if (sy == 3) {
+            if (ymod == 1) {
+                for (int j = 0; j < 8; j++) o[j] = at(x0 + j, cur);
+            } else {
+                const int nb = (ymod == 0) ? top : bot;
+                for (int j = 0; j < 8; j++) o[j] = gmix(at(x0 + j, nb), 1, at(x0 + j, cur), 3, (((j & 1) == 0) == (ymod == 0)) ? 2 : 1, 2);
+            }
+            advance = (ymod == 2);
+        } else {
+            const int nb = (ymod < 2) ? top : bot;
+            const bool far = (ymod == 0 || ymod == 3);  // far from the sample line: weights 3:5, else 1:7
+            for (int j = 0; j < 8; j++) {
+                int rnd;
+                if (ymod == 0 || ymod == 2 || ymod == 3) rnd = (j & 1) ? 3 : 4;
+                else rnd = (j & 1) ? 4 : 3;
+                o[j] = gmix(at(x0 + j, nb), far ? 3 : 1, at(x0 + j, cur), far ? 5 : 7, rnd, 3);
+            }
+            advance = (ymod == 3);
+        }
+        if (sy > 1) {
+            if (advance) {
+                ymod = 0;
+                top = cur;
+                cur = bot;
+                if (bot + 1 < h) bot++;
+            } else {
+                ymod++;
+            }
+        }
+        // horizontal, in place, in the reference's store order (src[i] = o[i + 1])
+        if (sx == 2) {
+            int *src = o + 1, t;
+            o[7] = gmix(src[4], 1, src[3], 3, 1, 2);
+            o[6] = gmix(src[2], 1, src[3], 3, 2, 2);
+            o[5] = gmix(src[3], 1, src[2], 3, 1, 2);
+            o[4] = gmix(src[1], 1, src[2], 3, 2, 2);
+            o[3] = gmix(src[2], 1, src[1], 3, 1, 2);
+            o[2] = gmix(src[0], 1, src[1], 3, 2, 2);
+            t = src[0];
+            o[1] = gmix(src[1], 1, t, 3, 1, 2);  // src[1] is the NEW o[2]
+            o[0] = gmix(src[-1], 1, t, 3, 2, 2);
+        } else if (sx == 3) {
+            int *src = o + 1, t;
+            if (xmod == 0) {
+                o[7] = src[2];
+                o[6] = gmix(src[1], 1, src[2], 3, 2, 2);
+                o[5] = gmix(src[2], 1, src[1], 3, 1, 2);
+                o[4] = src[1];
+                o[3] = gmix(src[0], 1, src[1], 3, 2, 2);
+                o[2] = gmix(src[1], 1, src[0], 3, 1, 2);
+                o[0] = gmix(src[-1], 1, src[0], 3, 2, 2);
+                o[1] = src[0];
+            } else if (xmod == 1) {
+                o[7] = gmix(src[3], 1, src[2], 3, 1, 2);
+                o[6] = src[2];
+                o[5] = gmix(src[1], 1, src[2], 3, 2, 2);
+                o[4] = gmix(src[2], 1, src[1], 3, 1, 2);
+                o[3] = src[1];
+                t = src[0];
+                o[2] = gmix(t, 1, src[1], 3, 2, 2);
+                o[1] = gmix(src[1], 1, t, 3, 1, 2);
+                o[0] = t;
+            } else {
+                o[7] = gmix(src[2], 1, src[3], 3, 2, 2);
+                o[6] = gmix(src[3], 1, src[2], 3, 1, 2);
+                o[5] = src[2];
+                o[4] = gmix(src[1], 1, src[2], 3, 2, 2);
+                o[3] = gmix(src[2], 1, src[1], 3, 1, 2);
+                o[2] = src[1];
+                t = src[0];
+                o[1] = gmix(t, 1, src[1], 3, 2, 2);
+                o[0] = gmix(src[1], 1, t, 3, 1, 2);
+            }
+        } else if (sx == 4) {
+            int *src = o + 1, t;
+            o[7] = gmix(src[2], 3, src[1], 5, 1, 3);
+            o[6] = gmix(src[2], 1, src[1], 7, 2, 3);
+            o[5] = gmix(src[0], 1, src[1], 7, 1, 3);
+            o[4] = gmix(src[0], 3, src[1], 5, 2, 3);
+            t = src[0];
+            o[3] = gmix(src[1], 3, t, 5, 1, 3);
+            o[2] = gmix(src[1], 1, t, 7, 2, 3);
+            o[1] = gmix(src[-1], 1, t, 7, 1, 3);
+            o[0] = gmix(src[-1], 3, t, 5, 2, 3);
+        }
+    }
+}
+
+// grid (output block columns / 64, output block rows, frames)
+__global__ void __launch_bounds__(64)
+generic_reconstruct_kernel(const FrameRecon *__restrict__ frames, const int32_t *__restrict__ samples, uint8_t *__restrict__ out) {
+    const FrameRecon &f = frames[blockIdx.z];
+    const uint32_t W = f.width, H = f.height, nc = f.ncomp;
+    const uint32_t bx = blockIdx.x * 64 + threadIdx.x, by = blockIdx.y;
+    if (bx >= (W + 7) / 8 || by >= (H + 7) / 8) return;
+    const int X = 8 * (int)bx, Y = 8 * (int)by;
+    int buf[4][64];  // 64 upsampled samples per component (local memory: this path is not tuned)
+    for (uint32_t c = 0; c < nc; c++) {
+        const int sx = f.csx[c], sy = f.csy[c];
+        const int w = (int)((W + sx - 1) / sx), h = (int)((H + sy - 1) / sy);
+        generic_upsample_block(samples + f.sample_base[c], 8u * f.bw[c], w, h, sx, sy, X, Y, buf[c]);
+    }
+    const int xmax = (X + 7 < (int)W) ? 7 : (int)((W - 1) & 7), ymax = (Y + 7 < (int)H) ? 7 : (int)((H - 1) & 7);
+    for (int y = 0; y <= ymax; y++) {
+        uint8_t *o = out + f.out_base + ((uint64_t)(Y + y) * W + (uint64_t)X) * nc;
+        for (int x = 0; x <= xmax; x++) {
+            if (nc == 3 && f.ycbcr) {
+                const long long yv = buf[0][8 * y + x], cb = (long long)buf[1][8 * y + x] - (128 << 4), cr = (long long)buf[2][8 * y + x] - (128 << 4);
+                o[3 * x] = (uint8_t)sat_u8_64((yv * 8192 + cr * 11485 + 65536) >> 17);
+                o[3 * x + 1] = (uint8_t)sat_u8_64((yv * 8192 - cb * 2819 - cr * 5850 + 65536) >> 17);
+                o[3 * x + 2] = (uint8_t)sat_u8_64((yv * 8192 + cb * 14516 + 65536) >> 17);
+            } else {
+                for (uint32_t c = 0; c < nc; c++) o[nc * x + c] = (uint8_t)sat_u8_64(((long long)buf[c][8 * y + x] + 8) >> 4);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 template <typename T, bool kListed>
@@ -1075,9 +1226,20 @@ static int launch_recon_fused420(const ReconLaunch &l, cudaStream_t s, int *laun
     return (int)cudaGetLastError();
 }
 
+static int launch_recon_generic(const ReconLaunch &l, cudaStream_t s, int *launches) {
+    uint32_t mb = 0;
+    mb = l.max_bwc * l.max_bhc;  // the largest component block grid of the group (set by the host for generic groups)
+    const uint32_t cblocks = (mb + kThreadsB - 1) / kThreadsB;
+    idct_planes_kernel<int32_t, false><<<dim3(cblocks, l.n_frames, l.ncomp), kThreadsB, 0, s>>>(l.frames, l.coef, l.samples32, l.wide_flags, nullptr, 0);
+    generic_reconstruct_kernel<<<dim3((l.max_bw0 + 63) / 64, l.max_bh0, l.n_frames), 64, 0, s>>>(l.frames, l.samples32, l.out);
+    if (launches) *launches = 2;
+    return (int)cudaGetLastError();
+}
+
 int launch_recon(const ReconLaunch &l, void *stream, int *launches) {
     cudaStream_t s = (cudaStream_t)stream;
     int n = 0;
+    if (l.generic) return launch_recon_generic(l, s, launches);
     // B200JPG_FUSED=1 selects the single-kernel reconstruction of 4:2:0 frames (no sample planes: 51 instead of 66 MB of DRAM
     // traffic per 4K frame and 25 MB less memory per frame, but 19 % more time: the stage is bound by instruction issue, not by
     // HBM, and the fused kernel issues more -- profiles/README.md); the default is the two-kernel path through int16 planes.
@@ -1087,7 +1249,7 @@ int launch_recon(const ReconLaunch &l, void *stream, int *launches) {
     const uint32_t gx = (l.max_bw0 + 31) / 32, gy = (l.max_bh0 + kThreadsB / 32 - 1) / (kThreadsB / 32);
     // every frame through the int16 planes
     if (l.ncomp > 1) {
-        idct_planes_kernel<int16_t, false><<<dim3(cblocks, l.n_frames, l.ncomp - 1), kThreadsB, 0, s>>>(l.frames, l.coef, l.samples16, l.narrow_flags, nullptr);
+        idct_planes_kernel<int16_t, false><<<dim3(cblocks, l.n_frames, l.ncomp - 1), kThreadsB, 0, s>>>(l.frames, l.coef, l.samples16, l.narrow_flags, nullptr, 1);
         n++;
     }
     launch_b2<int16_t, false>(l, dim3(gx, gy, l.n_frames), l.samples16, s);
@@ -1095,7 +1257,7 @@ int launch_recon(const ReconLaunch &l, void *stream, int *launches) {
     // the exact pass over the frames that were flagged `narrow` (none for real images: three near-empty launches)
     if (l.ncomp > 1) {
         narrow_list_kernel<<<1, 256, 0, s>>>(l.frames, l.n_frames, l.narrow_flags, l.narrow_list);
-        idct_planes_kernel<int32_t, true><<<dim3(cblocks, kWideSlots, l.ncomp - 1), kThreadsB, 0, s>>>(l.frames, l.coef, l.samples32, l.wide_flags, l.narrow_list);
+        idct_planes_kernel<int32_t, true><<<dim3(cblocks, kWideSlots, l.ncomp - 1), kThreadsB, 0, s>>>(l.frames, l.coef, l.samples32, l.wide_flags, l.narrow_list, 1);
         launch_b2<int32_t, true>(l, dim3(gx, gy, kWideSlots), l.samples32, s);
         n += 3;
     }

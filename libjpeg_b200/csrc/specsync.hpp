@@ -74,16 +74,57 @@ B200JPG_HD int32_t spec_value(uint32_t e, uint32_t hi) {
     return (v < (1u << (s - 1))) ? (int32_t)v - (int32_t)((1u << s) - 1u) : (int32_t)v;
 }
 
+// Where a subsequence's decoding path stood at the first block boundary behind each of kSpecMarks evenly spaced marks, and
+// what was still in front of it there (blocks, DC differences up to the exit). A later round that starts from a corrected
+// entry state walks until it stands on one of these states -- the paths have merged -- and takes the rest from the log
+// instead of decoding it again: the suffix quantities do not depend on how the path got there.
+constexpr int kSpecMarks = 7;
+constexpr uint32_t kSpecMarkBits = kSpecSeqBits / (kSpecMarks + 1);
+struct SpecLog {
+    unsigned long long state[kSpecMarks];  // bit | blk << 32; ~0: not reached
+    uint32_t n_after[kSpecMarks];
+    int32_t dc_after[kSpecMarks][4];
+};
+
 // Decodes whole blocks from `from` until a block boundary at or behind `limit_bit` (or behind the end of the data).
 // ONE flat loop, one symbol per iteration (the DC symbol of a block when k == 0, else an AC symbol): the threads of a warp
 // run the same few instructions whatever their blocks look like, and only diverge where they finish.
-B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_t nwords, uint32_t total_bits, SpecState from, uint32_t limit_bit) {
+// With a log: `log` holds the marks of this subsequence's previous path (states ~0 before the first round) and receives
+// those of the new one; `merged` tells that the walk ended on an old mark (the exit of the previous round stands) and the
+// returned counts already include the logged rest.
+B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_t nwords, uint32_t total_bits, SpecState from, uint32_t limit_bit,
+                                  SpecLog *log = nullptr, uint32_t first_mark_bit = 0, bool *merged = nullptr) {
     uint32_t comp_bits = 0;  // two bits per block of an MCU: no indexed local array in the loop
     for (uint32_t b = 0; b < sc.blocks_per_mcu; b++) comp_bits |= (uint32_t)sc.comp_of_block[b] << (2u * b);
     const uint32_t bpm = sc.blocks_per_mcu;
     uint32_t bit = from.bit, blk = from.blk, k = 0, n = 0;
     int32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int mark = 0, merge_at = -1;   // next mark to pass; the mark the path merged at
+    uint32_t next_mark = first_mark_bit;
+    if (merged) *merged = false;
+    if (log) {  // a path that starts behind marks leaves them unreached
+        while (mark < kSpecMarks && bit > next_mark) {
+            log->state[mark] = ~0ull;
+            mark++;
+            next_mark += kSpecMarkBits;
+        }
+    }
     while ((k != 0 || bit < limit_bit) && (k != 0 || bit < total_bits)) {
+        if (log && k == 0) {  // at a block boundary: marks passed since the last one
+            const unsigned long long here = (unsigned long long)bit | ((unsigned long long)blk << 32);
+            while (mark < kSpecMarks && bit >= next_mark && merge_at < 0) {
+                if (log->state[mark] == here) {
+                    merge_at = mark;
+                } else {
+                    log->state[mark] = here;
+                    log->n_after[mark] = n;  // cumulative for now: turned into "still in front" below
+                    log->dc_after[mark][0] = s0, log->dc_after[mark][1] = s1, log->dc_after[mark][2] = s2, log->dc_after[mark][3] = s3;
+                    mark++;
+                    next_mark += kSpecMarkBits;
+                }
+            }
+            if (merge_at >= 0) break;
+        }
         const uint32_t c = (comp_bits >> (2u * blk)) & 3u;
         const uint32_t hi = spec_window(w, nwords, bit);
         const uint32_t dct = c == 0 ? sc.dc_tab[0] : (c == 1 ? sc.dc_tab[1] : (c == 2 ? sc.dc_tab[2] : sc.dc_tab[3]));
@@ -107,6 +148,20 @@ B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_
             k = 0;
             n++;
             blk = blk + 1 == bpm ? 0 : blk + 1;
+        }
+    }
+    if (log) {
+        if (merge_at >= 0) {  // the rest of the way is the logged one
+            n += log->n_after[merge_at];
+            s0 += log->dc_after[merge_at][0], s1 += log->dc_after[merge_at][1], s2 += log->dc_after[merge_at][2], s3 += log->dc_after[merge_at][3];
+            if (merged) *merged = true;
+        } else {  // marks behind the exit were not reached on this path
+            for (int m = mark; m < kSpecMarks; m++) log->state[m] = ~0ull;
+        }
+        for (int m = 0; m < mark && m < (merge_at >= 0 ? merge_at : kSpecMarks); m++) {  // cumulative -> what was still in front
+            log->n_after[m] = n - log->n_after[m];
+            log->dc_after[m][0] = s0 - log->dc_after[m][0], log->dc_after[m][1] = s1 - log->dc_after[m][1];
+            log->dc_after[m][2] = s2 - log->dc_after[m][2], log->dc_after[m][3] = s3 - log->dc_after[m][3];
         }
     }
     SpecResult r;

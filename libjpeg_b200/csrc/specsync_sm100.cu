@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(kSyncThreads)
 spec_sync_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uint64_t *__restrict__ clean_off,
                  const uint32_t *__restrict__ interval_len, const uint8_t *__restrict__ tables, SpecSegment *__restrict__ segs,
                  unsigned long long *__restrict__ exits, unsigned long long *__restrict__ entries, uint32_t *__restrict__ counts,
-                 int32_t *__restrict__ dc_sums) {
+                 int32_t *__restrict__ dc_sums, SpecLog *__restrict__ logs) {
     extern __shared__ uint32_t s_lut[];
     __shared__ int s_changed;
     const uint32_t j = blockIdx.x;  // scan
@@ -51,10 +51,12 @@ spec_sync_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uin
     unsigned long long *ex = exits + (size_t)j * cap, *en = entries + (size_t)j * cap;
     uint32_t *cnt = counts + (size_t)j * cap;
     int32_t *ds = dc_sums + (size_t)j * cap * 4u;
+    SpecLog *lg = logs + (size_t)j * cap;
     if (tid == 0) s_changed = 1;
     for (uint32_t i = tid; i < nseq; i += kSyncThreads) {
         ex[i] = ~0ull;
         en[i] = ~0ull;
+        for (int m = 0; m < kSpecMarks; m++) lg[i].state[m] = ~0ull;
     }
     __syncthreads();
     for (uint32_t round = 0; s_changed; round++) {
@@ -72,9 +74,11 @@ spec_sync_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uin
             SpecState from;
             from.bit = (uint32_t)entry;
             from.blk = (uint32_t)(entry >> 32);
-            const SpecResult r = spec_decode(sc, w, nwords, total_bits, from, (i + 1u) * kSpecSeqBits);
+            bool merged;
+            const SpecResult r = spec_decode(sc, w, nwords, total_bits, from, (i + 1u) * kSpecSeqBits, lg + i, i * kSpecSeqBits + kSpecMarkBits, &merged);
             cnt[i] = r.n_blocks;
             ds[4 * i + 0] = r.dc_sum[0], ds[4 * i + 1] = r.dc_sum[1], ds[4 * i + 2] = r.dc_sum[2], ds[4 * i + 3] = r.dc_sum[3];
+            if (merged) continue;  // the path joined the previous round's: its exit stands
             const unsigned long long out = (unsigned long long)r.exit.bit | ((unsigned long long)r.exit.blk << 32);
             if (out != ex[i]) {
                 *reinterpret_cast<volatile unsigned long long *>(ex + i) = out;
@@ -121,7 +125,7 @@ int launch_spec_sync(const EntropyLaunch &l, void *stream) {
         if (e != cudaSuccess) return (int)e;
     }
     spec_sync_kernel<<<l.p.n_scans, kSyncThreads, smem, (cudaStream_t)stream>>>(l.p, l.clean, l.clean_off, l.interval_len, l.tables, l.spec_segments,
-                                                                                 l.spec_exits, l.spec_entries, l.spec_counts, l.spec_dc_sums);
+                                                                                 l.spec_exits, l.spec_entries, l.spec_counts, l.spec_dc_sums, l.spec_logs);
     return (int)cudaGetLastError();
 }
 
@@ -132,6 +136,9 @@ int spec_sync_host_replay(const SpecScan &sc, const uint32_t *w, uint32_t len_by
     std::vector<unsigned long long> ex(nseq, ~0ull), en(nseq, ~0ull);
     std::vector<uint32_t> cnt(nseq, 0);
     std::vector<int32_t> ds(4 * (size_t)nseq, 0);
+    std::vector<SpecLog> logs(nseq);
+    for (auto &l : logs)
+        for (int m = 0; m < kSpecMarks; m++) l.state[m] = ~0ull;
     int rounds = 0;
     for (bool changed = true; changed; rounds++) {
         changed = false;
@@ -142,9 +149,11 @@ int spec_sync_host_replay(const SpecScan &sc, const uint32_t *w, uint32_t len_by
             en[i] = entry;
             SpecState from;
             from.bit = (uint32_t)entry, from.blk = (uint32_t)(entry >> 32);
-            const SpecResult r = spec_decode(sc, w, nwords, total_bits, from, (i + 1u) * kSpecSeqBits);
+            bool merged;
+            const SpecResult r = spec_decode(sc, w, nwords, total_bits, from, (i + 1u) * kSpecSeqBits, &logs[i], i * kSpecSeqBits + kSpecMarkBits, &merged);
             cnt[i] = r.n_blocks;
             for (int c = 0; c < 4; c++) ds[4 * i + c] = r.dc_sum[c];
+            if (merged) continue;
             const unsigned long long out = (unsigned long long)r.exit.bit | ((unsigned long long)r.exit.blk << 32);
             if (out != ex[i]) ex[i] = out, changed = true;
         }

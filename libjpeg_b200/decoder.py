@@ -87,7 +87,7 @@ class Context:
 class BatchDecoder:
     """One batch of codestreams: parse + pack on construction, then upload() / decode() on a CUDA stream."""
 
-    def __init__(self, frames, device=-1, tolerate_bad=False, ctx=None):
+    def __init__(self, frames, device=-1, tolerate_bad=False, ctx=None, color_transform=True):
         self.ctx = ctx or Context(device)
         self._keep = []
         n = len(frames)
@@ -99,7 +99,8 @@ class BatchDecoder:
             lens[i] = ln
             self._keep.append(keep)
         self.handle = ctypes.c_void_p()
-        rc = lib.b200jpg_batch_create(self.ctx.handle, ptrs, lens, n, int(tolerate_bad), ctypes.byref(self.handle))
+        flags = 0 if color_transform else 1  # B200JPG_FLAG_NO_COLOR_TRANSFORM (JPGTAG_MATRIX_LTRAFO = none)
+        rc = lib.b200jpg_batch_create_ex(self.ctx.handle, ptrs, lens, n, int(tolerate_bad), flags, ctypes.byref(self.handle))
         native.check(rc, self.ctx.handle)
         self._keep = []  # the batch holds its own pinned copy
         self.n = n

@@ -80,6 +80,19 @@ class Oracle:
         rc = self.lib.jpgo_decode_coefficients(data.ctypes.data, data.size, ctypes.byref(s), ptrs)
         return rc, s, planes
 
+    def decode_without_color_transform(self, data):
+        """-> (rc, pixels): the components upsampled and delivered as they are (JPGTAG_MATRIX_LTRAFO = none)"""
+        rc, s, planes = self.coefficients(data)
+        if rc != 0:
+            return rc, None
+        s.ycbcr = 0
+        out = np.zeros((s.height, s.width, s.ncomp), dtype=np.uint8)
+        ptrs = (ctypes.c_void_p * 4)(*[p.ctypes.data for p in planes] + [None] * (4 - s.ncomp))
+        self.lib.jpgo_reconstruct.restype = ctypes.c_int
+        self.lib.jpgo_reconstruct.argtypes = [ctypes.POINTER(InfoStruct), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]
+        rc = self.lib.jpgo_reconstruct(ctypes.byref(s), ptrs, out.ctypes.data)
+        return rc, (out if rc == 0 else None)
+
     def idct(self, block_raster_int32, delta_raster_u16, dcoffset=128):
         src = np.ascontiguousarray(block_raster_int32, dtype=np.int32)
         q = np.ascontiguousarray(delta_raster_u16, dtype=np.uint16)
@@ -231,3 +244,32 @@ def with_restart_damage(data, damage):
     else:
         raise ValueError(damage)
     return bytes(b)
+
+
+def with_fourth_component(data):
+    """A four-component codestream made from a three-component one whose components are coded in separate scans
+    (synth.NON_INTERLEAVED): the third component's frame entry and scan are duplicated under a new component id. Four
+    components have no colour transformation in the reference (identity, colortrafo/ycbcrtrafo.cpp:834-892)."""
+    b = bytes(data.tobytes() if hasattr(data, "tobytes") else data)
+    sof = b.find(b"\xff\xc0")
+    seglen = (b[sof + 2] << 8) | b[sof + 3]
+    assert b[sof + 9] == 3
+    last = b[sof + 10 + 6:sof + 10 + 9]  # (id, HV, Tq) of the third component
+    new_id = max(b[sof + 10], b[sof + 13], b[sof + 16]) + 1
+    sof_new = b[sof:sof + 2] + (seglen + 3).to_bytes(2, "big") + b[sof + 4:sof + 9] + bytes([4]) + b[sof + 10:sof + 2 + seglen] + bytes([new_id]) + last[1:]
+    head = b[:sof] + sof_new
+    rest = b[sof + 2 + seglen:]
+    # the last SOS (third component) up to EOI
+    pos, sos_at = 0, []
+    while True:
+        i = rest.find(b"\xff\xda", pos)
+        if i < 0:
+            break
+        sos_at.append(i)
+        pos = i + 2
+    assert len(sos_at) == 3
+    eoi = rest.rfind(b"\xff\xd9")
+    scan3 = bytearray(rest[sos_at[2]:eoi])
+    assert scan3[4] == 1  # one component in the scan
+    scan3[5] = new_id
+    return head + rest[:eoi] + bytes(scan3) + b"\xff\xd9"

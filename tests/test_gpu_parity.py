@@ -500,3 +500,50 @@ def test_progressive_scan_by_scan_path_matches_fixtures(built, monkeypatch):
     for i, n in enumerate(PNAMES):
         assert dec.status(i) == 0, n
         assert np.array_equal(dec.frame_view(out, i).cpu().numpy().reshape(px[n].shape), px[n]), n
+
+
+SUBSAMPLING = os.path.join(GOLDEN, "subsampling")
+SNAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(SUBSAMPLING, "*.jpg")))
+
+
+def test_unusual_subsampling_matches_reference_fixtures(built):
+    """chroma factors 3 and 4, components with different factors, 4:1:1 / 4:1:0 (upsampler.cpp:171-268,310-386) --
+    streams of the reference encoder, pixels of the reference decoder (tests/golden/subsampling, make_subsampling.py), through
+    the generic reconstruction kernels; all of them in one batch next to an ordinary 4:2:0 frame."""
+    want = np.load(os.path.join(SUBSAMPLING, "subsampling_pixels.npz"))
+    frames = [open(os.path.join(SUBSAMPLING, n + ".jpg"), "rb").read() for n in SNAMES]
+    frames.append(open(os.path.join(GOLDEN, "c420_96x80_z6_q75.jpg"), "rb").read())
+    dec, out = gpu_decode(built, frames)
+    assert len(SNAMES) >= 7
+    for i, n in enumerate(SNAMES):
+        assert dec.status(i) == 0, n
+        got = dec.frame_view(out, i).cpu().numpy()
+        assert np.array_equal(got.reshape(want[n].shape), want[n]), n
+    assert np.array_equal(dec.frame_view(out, len(SNAMES)).cpu().numpy(), np.load(os.path.join(GOLDEN, "golden_pixels.npz"))["c420_96x80_z6_q75"])
+
+
+@pytest.mark.parametrize("w,h,sub,z", [(64, 48, (1, 1), 4), (70, 50, (2, 2), 5), (100, 37, (2, 1), 0), (33, 90, (1, 2), 3)])
+def test_four_component_frames_match_oracle(built, oracle, w, h, sub, z):
+    """four components (no colour transformation, ycbcrtrafo.cpp:834-892). The streams are three-component ones
+    with the third component's scan duplicated under a fourth id (oracle_binding.with_fourth_component; the oracle is pinned on
+    the reference for exactly these in tests/test_oracle.py)."""
+    from libjpeg_b200 import synth
+    from tests import oracle_binding
+    data = oracle_binding.with_fourth_component(synth.encode(synth.source_image(w, h, 5), 80, sub, z, 1))
+    dec, out = gpu_decode(built, [data])
+    assert dec.status(0) == 0 and dec.info(0).ncomp == 4
+    rc, px = oracle.decode(data)
+    assert rc == 0 and px.shape[2] == 4
+    assert np.array_equal(dec.frame_view(out, 0).cpu().numpy(), px)
+
+
+def test_color_transform_can_be_switched_off(built, oracle):
+    """JPGTAG_MATRIX_LTRAFO = ..._NONE (rectanglerequest.cpp:150-152) through the request flags of the C ABI: YCbCr frames come
+    out as upsampled Y, Cb, Cr (the oracle's untransformed reconstruction, pinned on `jpeg -c` in tests/test_oracle.py)."""
+    names = ["c420_96x80_z6_q75", "c444_64x64_z16_q90", "c422_100x60_z5_q80", "c440_100x61_z3_q80", "c420_127x255_z7_q30"]
+    frames = [open(os.path.join(GOLDEN, n + ".jpg"), "rb").read() for n in names]
+    dec, out = gpu_decode(built, frames, color_transform=False)
+    for i, f in enumerate(frames):
+        rc, want = oracle.decode_without_color_transform(f)
+        assert rc == 0 and dec.status(i) == 0
+        assert np.array_equal(dec.frame_view(out, i).cpu().numpy(), want), names[i]

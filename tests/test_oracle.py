@@ -252,3 +252,33 @@ def test_oracle_reads_the_height_from_the_dnl_marker(oracle, name):
     rc, got = oracle.decode(open(os.path.join(DNL, name + ".jpg"), "rb").read())
     assert rc == 0 and np.array_equal(got, px[name])
     assert np.array_equal(got[:-1], px[name + "__ref_dnl"][:-1])
+
+
+@pytest.mark.skipif(not oracle_binding.have_reference(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("w,h,sub,z", [(64, 48, (1, 1), 4), (70, 50, (2, 2), 5), (100, 37, (2, 1), 0), (33, 90, (1, 2), 3)])
+def test_oracle_matches_reference_on_four_component_streams(oracle, built, tmp_path, w, h, sub, z):
+    from libjpeg_b200 import synth
+    data = oracle_binding.with_fourth_component(synth.encode(synth.source_image(w, h, 5), 80, sub, z, 1))
+    jpg = tmp_path / "f4.jpg"
+    jpg.write_bytes(data)
+    ref = oracle_binding.reference_decode(str(jpg), str(tmp_path / "f4.raw"))
+    assert ref is not None and ref.shape[2] == 4
+    rc, px = oracle.decode(data)
+    assert rc == 0 and np.array_equal(px, ref)
+
+
+@pytest.mark.skipif(not oracle_binding.have_reference(), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("name", ["c420_96x80_z6_q75", "c444_64x64_z16_q90", "c422_100x60_z5_q80"])
+def test_oracle_without_color_transform_matches_reference_cli(oracle, tmp_path, name):
+    """JPGTAG_MATRIX_LTRAFO = none (`jpeg -c` on decoding, cmd/main.cpp / reconstruct.cpp:336): Y, Cb, Cr upsampled, untransformed."""
+    import subprocess
+    src = os.path.join(GOLDEN, name + ".jpg")
+    ppm = tmp_path / "o.ppm"
+    r = subprocess.run([oracle_binding.REF_CLI, "-c", src, str(ppm)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = ppm.read_bytes()
+    magic, dims, maxv, rest = raw.split(b"\n", 3)
+    w, h = map(int, dims.split())
+    ref = np.frombuffer(rest, dtype=np.uint8).reshape(h, w, 3)
+    rc, px = oracle.decode_without_color_transform(open(src, "rb").read())
+    assert rc == 0 and np.array_equal(px, ref)
