@@ -703,8 +703,8 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
         fr.ycbcr = (flags & B200JPG_FLAG_NO_COLOR_TRANSFORM) ? 0 : fi.ycbcr;  // JPGTAG_MATRIX_LTRAFO = ..._NONE (rectanglerequest.cpp:150-152)
         fr.subx = sx;
         fr.suby = sy;
-        fr.cw = (fi.width + sx - 1) / sx;
-        fr.ch = (fi.height + sy - 1) / sy;
+        fr.cw = sx ? (fi.width + sx - 1) / sx : fi.width;  // (generic groups carry the factors per component: csx / csy)
+        fr.ch = sy ? (fi.height + sy - 1) / sy : fi.height;
         fr.status_idx = (uint32_t)i;
         g->frames.push_back(fr);
         g->max_bw0 = std::max(g->max_bw0, (fi.width + 7) / 8);
@@ -1205,7 +1205,11 @@ int b200jpg_selftest_restartless(const uint8_t *data, size_t len, uint32_t *roun
     }
     const uint32_t total_mcus = sc.mcu_cols * sc.mcu_rows;
     std::vector<SpecSegment> segs;
+    extern unsigned long long g_spec_replay_bits;
+    g_spec_replay_bits = 0;
     const int r = spec_sync_host_replay(ss, words.data(), len_bytes, total_mcus, segs);
+    if (getenv("B200JPG_SPEC_STATS"))
+        fprintf(stderr, "restart-less replay: %u rounds, %.2f x the stream walked\n", (unsigned)r, (double)g_spec_replay_bits / (8.0 * len_bytes + 1));
     if (rounds) *rounds = (uint32_t)r;
     if (n_segments) *n_segments = (uint32_t)segs.size();
     // the truth: one walk from the first bit, block by block

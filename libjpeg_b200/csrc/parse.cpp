@@ -291,10 +291,12 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
                 if (sc.td[i] > 3) FAIL(B200JPG_ERR_MALFORMED_STREAM, "DC table index in SOS marker is out of range, must be at most 4");
                 if (sc.ta[i] > 3) FAIL(B200JPG_ERR_MALFORMED_STREAM, "AC table index in SOS marker is out of range, must be at most 4");
             }
-            if (sc.ns > 1) {  // T.81 B.2.3: an interleaved MCU holds at most ten blocks (the kernels' per-MCU tables rely on it)
-                int blocks = 0;
-                for (int i = 0; i < sc.ns; i++) blocks += fi.hs[sc.comp[i]] * fi.vs[sc.comp[i]];
-                if (blocks > 10) FAIL(B200JPG_ERR_MALFORMED_STREAM, "more than ten blocks per MCU in an interleaved scan");
+            // T.81 B.2.3 limits an interleaved MCU to ten blocks; the reference does not insist (its encoder writes 4x4 luma
+            // sampling happily), so neither does this parser -- only the synchronisation path's per-MCU tables do (below)
+            int blocks_per_mcu = 1;
+            if (sc.ns > 1) {
+                blocks_per_mcu = 0;
+                for (int i = 0; i < sc.ns; i++) blocks_per_mcu += fi.hs[sc.comp[i]] * fi.vs[sc.comp[i]];
             }
             const uint8_t *t = s + 1 + 2 * sc.ns;
             sc.progressive = fi.frame_type == 2;
@@ -392,7 +394,8 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
             // the data ends inside the scan's LAST interval: only then does the decoder read zero bits behind it
             sc.eof_tail = sc.eof_tail && sc.interval_off[nint - 1] != SIZE_MAX && sc.interval_end[nint - 1] >= len;
             // restart-less sequential scans of some size are cut up at synchronisation points on the device (specsync.hpp)
-            sc.spec = !sc.progressive && nint == 1 && sc.ecs_end - sc.ecs_off >= kSpecMinBytes && getenv("B200JPG_NO_SPEC") == nullptr;
+            sc.spec = !sc.progressive && nint == 1 && sc.ecs_end - sc.ecs_off >= kSpecMinBytes && blocks_per_mcu <= kSpecMaxBlocksPerMcu &&
+                      getenv("B200JPG_NO_SPEC") == nullptr;
             fi.n_intervals += (uint32_t)nint;
             fi.ecs_bytes += sc.ecs_end - sc.ecs_off;
             if (out.scans.empty()) fi.restart_interval = dri;

@@ -30,6 +30,7 @@ namespace b200jpg {
 
 constexpr uint32_t kSpecSeqBits = 4096;  // bits per subsequence (128 words)
 constexpr int kSpecMaxBlocksPerMcu = 10;
+constexpr uint32_t kSpecRunUpBits = 2048;   // the first round starts this far in front of a subsequence (see spec_decode)
 constexpr size_t kSpecMinBytes = 4096;    // shorter restart-less scans stay one work item (eight subsequences are not worth the rounds)
 
 struct SpecScan {               // what the length-only decoder needs to know about the scan
@@ -92,8 +93,13 @@ struct SpecLog {
 // With a log: `log` holds the marks of this subsequence's previous path (states ~0 before the first round) and receives
 // those of the new one; `merged` tells that the walk ended on an old mark (the exit of the previous round stands) and the
 // returned counts already include the logged rest.
+// With a run-up (count_from > from.bit): the walk starts somewhere IN FRONT of the subsequence, on a guess; blocks that start in
+// front of `count_from` are decoded but not counted, and `*entered` receives the first block boundary at or behind count_from
+// -- the subsequence's entry state as this path sees it. A path that has fallen into step during the run-up reports the true
+// entry, and its counts and its exit are the true ones without a second walk.
 B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_t nwords, uint32_t total_bits, SpecState from, uint32_t limit_bit,
-                                  SpecLog *log = nullptr, uint32_t first_mark_bit = 0, bool *merged = nullptr) {
+                                  SpecLog *log = nullptr, uint32_t first_mark_bit = 0, bool *merged = nullptr, uint32_t count_from = 0,
+                                  SpecState *entered = nullptr) {
     uint32_t comp_bits = 0;  // two bits per block of an MCU: no indexed local array in the loop
     for (uint32_t b = 0; b < sc.blocks_per_mcu; b++) comp_bits |= (uint32_t)sc.comp_of_block[b] << (2u * b);
     const uint32_t bpm = sc.blocks_per_mcu;
@@ -109,8 +115,15 @@ B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_
             next_mark += kSpecMarkBits;
         }
     }
+    bool counting = entered == nullptr || bit >= count_from;
+    if (entered && counting) entered->bit = bit, entered->blk = blk;
     while ((k != 0 || bit < limit_bit) && (k != 0 || bit < total_bits)) {
-        if (log && k == 0) {  // at a block boundary: marks passed since the last one
+        if (!counting && k == 0 && bit >= count_from) {  // the run-up is over: this boundary is the entry, counting starts here
+            counting = true;
+            entered->bit = bit, entered->blk = blk;
+            n = 0, s0 = s1 = s2 = s3 = 0;
+        }
+        if (log && k == 0 && counting) {  // at a block boundary: marks passed since the last one
             const unsigned long long here = (unsigned long long)bit | ((unsigned long long)blk << 32);
             while (mark < kSpecMarks && bit >= next_mark && merge_at < 0) {
                 if (log->state[mark] == here) {
@@ -149,6 +162,10 @@ B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_
             n++;
             blk = blk + 1 == bpm ? 0 : blk + 1;
         }
+    }
+    if (!counting) {  // the walk ended inside the run-up (end of the data): nothing of the subsequence is there
+        entered->bit = bit, entered->blk = blk;
+        n = 0, s0 = s1 = s2 = s3 = 0;
     }
     if (log) {
         if (merge_at >= 0) {  // the rest of the way is the logged one

@@ -66,16 +66,19 @@ spec_sync_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uin
         bool changed = false;
         for (uint32_t i = tid; i < nseq; i += kSyncThreads) {
             unsigned long long entry;
+            const bool run_up = round == 0 && i != 0;
             if (i == 0) entry = 0ull;                                         // the scan starts with block 0 of MCU 0 at bit 0
-            else if (round == 0) entry = (unsigned long long)(i * kSpecSeqBits);  // the guess: (bit, block 0)
+            else if (round == 0) entry = (unsigned long long)(i * kSpecSeqBits - kSpecRunUpBits);  // the guess: a block starts here
             else entry = *reinterpret_cast<volatile unsigned long long *>(ex + i - 1);
-            if (entry == en[i] || entry == ~0ull) continue;
-            en[i] = entry;
-            SpecState from;
+            if (!run_up && (entry == en[i] || entry == ~0ull)) continue;
+            SpecState from, entered;
             from.bit = (uint32_t)entry;
             from.blk = (uint32_t)(entry >> 32);
             bool merged;
-            const SpecResult r = spec_decode(sc, w, nwords, total_bits, from, (i + 1u) * kSpecSeqBits, lg + i, i * kSpecSeqBits + kSpecMarkBits, &merged);
+            const SpecResult r = spec_decode(sc, w, nwords, total_bits, from, (i + 1u) * kSpecSeqBits, lg + i, i * kSpecSeqBits + kSpecMarkBits, &merged,
+                                             run_up ? i * kSpecSeqBits : 0u, run_up ? &entered : nullptr);
+            // the entry this walk really had: after a run-up, the first block boundary inside the subsequence as the walk found it
+            en[i] = run_up ? ((unsigned long long)entered.bit | ((unsigned long long)entered.blk << 32)) : entry;
             cnt[i] = r.n_blocks;
             ds[4 * i + 0] = r.dc_sum[0], ds[4 * i + 1] = r.dc_sum[1], ds[4 * i + 2] = r.dc_sum[2], ds[4 * i + 3] = r.dc_sum[3];
             if (merged) continue;  // the path joined the previous round's: its exit stands
@@ -129,6 +132,10 @@ int launch_spec_sync(const EntropyLaunch &l, void *stream) {
     return (int)cudaGetLastError();
 }
 
+}  // namespace b200jpg
+unsigned long long g_spec_replay_bits = 0;
+namespace b200jpg {  // host replay only: bits walked (a merged walk counts up to the merge)
+
 // Host replay of the same rounds (tests only): fills `segs` for one scan given its unstuffed words; returns the rounds used.
 int spec_sync_host_replay(const SpecScan &sc, const uint32_t *w, uint32_t len_bytes, uint32_t total_mcus, std::vector<SpecSegment> &segs) {
     const uint32_t total_bits = len_bytes * 8u, nwords = (len_bytes + 3u) / 4u;
@@ -144,13 +151,16 @@ int spec_sync_host_replay(const SpecScan &sc, const uint32_t *w, uint32_t len_by
         changed = false;
         const std::vector<unsigned long long> prev = ex;  // a synchronous round: everybody sees last round's exits
         for (uint32_t i = 0; i < nseq; i++) {
-            unsigned long long entry = i == 0 ? 0ull : (rounds == 0 ? (unsigned long long)(i * kSpecSeqBits) : prev[i - 1]);
-            if (entry == en[i] || entry == ~0ull) continue;
-            en[i] = entry;
-            SpecState from;
+            const bool run_up = rounds == 0 && i != 0;
+            unsigned long long entry = i == 0 ? 0ull : (rounds == 0 ? (unsigned long long)(i * kSpecSeqBits - kSpecRunUpBits) : prev[i - 1]);
+            if (!run_up && (entry == en[i] || entry == ~0ull)) continue;
+            SpecState from, entered;
             from.bit = (uint32_t)entry, from.blk = (uint32_t)(entry >> 32);
             bool merged;
-            const SpecResult r = spec_decode(sc, w, nwords, total_bits, from, (i + 1u) * kSpecSeqBits, &logs[i], i * kSpecSeqBits + kSpecMarkBits, &merged);
+            const SpecResult r = spec_decode(sc, w, nwords, total_bits, from, (i + 1u) * kSpecSeqBits, &logs[i], i * kSpecSeqBits + kSpecMarkBits, &merged,
+                                             run_up ? i * kSpecSeqBits : 0u, run_up ? &entered : nullptr);
+            en[i] = run_up ? ((unsigned long long)entered.bit | ((unsigned long long)entered.blk << 32)) : entry;
+            ::g_spec_replay_bits += r.exit.bit > from.bit ? r.exit.bit - from.bit : 0;
             cnt[i] = r.n_blocks;
             for (int c = 0; c < 4; c++) ds[4 * i + c] = r.dc_sum[c];
             if (merged) continue;
