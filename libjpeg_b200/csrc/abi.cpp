@@ -817,7 +817,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     if (ce == cudaSuccess) b->d_status = (uint32_t *)ctx->get(1, b->sz_status, &ce);
     if (ce == cudaSuccess && !b->pf_groups.empty()) b->d_dcplane = (int16_t *)ctx->get(1, b->coef_elems / 64 * sizeof(int16_t), &ce);
     if (ce == cudaSuccess && b->n_spec) {
-        b->sz_spec = (size_t)b->n_spec * (sizeof(SpecSegment) + 8 + 8 + 4 + 16 + sizeof(SpecLog)) + 256;
+        b->sz_spec = (size_t)align_up(b->n_spec, 4) * (sizeof(SpecSegment) + 8 + 8 + 4 + 16 + sizeof(SpecLog)) + 256;
         b->d_spec = (uint8_t *)ctx->get(1, b->sz_spec, &ce);
     }
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->ev_last, cudaEventDisableTiming);
@@ -929,7 +929,7 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
             l.frame_status = b->d_status;
             if (pass == 1 && cl.fused) continue;  // decoded by the component-fused launches below
             if (cl.p.indexed) {  // slices of the spec arrays: [segments | exits | entries | counts | dc sums], each over all work items
-                const uint64_t n = b->n_spec, o = cl.spec_base;
+                const uint64_t n = align_up(b->n_spec, 4), o = cl.spec_base;  // (every slice starts 16-byte aligned)
                 uint8_t *q = b->d_spec;
                 l.spec_segments = reinterpret_cast<SpecSegment *>(q) + o;
                 q += n * sizeof(SpecSegment);

@@ -247,37 +247,29 @@ pf_ac_kernel(PfLaunch L) {
                 }
                 while (__any_sync(0xffffffffu, active)) {
                     if (active) {
+                        // one symbol, in one straight line whatever its kind (coefficient, ZRL, EOBn): the lanes of a warp stay
+                        // together inside the iteration
                         const uint32_t e = lut_entry(lut, r.window());
-                        if ((int)e < 0) {
+                        r.skip((e >> 5) & 31u);
+                        const uint32_t run = (e >> 10) & 15u, sz = e & 31u;
+                        const bool eob = sz == 0 && run != 15;
+                        const uint32_t bits = r.get(sz ? sz : (eob ? run : 0u));  // value bits, or the length of an EOB run
+                        const int kk = k + (int)run;                             // ZRL: 15 zeros and the (zero) "coefficient" behind them
+                        if ((int)e < 0 || (sz != 0 && kk >= 64)) {  // undefined code / the reference tests against 64, not against Se
                             bad = true;
                             active = false;
                         } else {
-                            r.skip((e >> 5) & 31u);
-                            const uint32_t run = (e >> 10) & 15u, sz = e & 31u;
-                            if (sz == 0) {
-                                if (run == 15) {
-                                    k += 16;
-                                } else {
-                                    skip[s] = ((1u << run) | r.get(run)) - 1u;  // EOBn; this block is part of the run
-                                    active = false;
-                                }
-                            } else {
-                                k += (int)run;
-                                const int v = extend(r.get(sz), sz);
-                                if (k >= 64) {  // the reference tests against 64, not against Se
-                                    bad = true;
-                                    active = false;
-                                } else {
-                                    uint2 pq;
-                                    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)k));
-                                    const int d = v * (int)pq.x;
-                                    ovf |= (uint32_t)(d + 32768);
-                                    sts_h(s_stage + pq.y, d);
-                                    H |= 1ull << k;
-                                    k++;
-                                }
+                            if (sz != 0) {
+                                uint2 pq;
+                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)kk));
+                                const int d = extend(bits, sz) * (int)pq.x;
+                                ovf |= (uint32_t)(d + 32768);
+                                sts_h(s_stage + pq.y, d);
+                                H |= 1ull << kk;
                             }
-                            if (k > se) active = false;
+                            k = kk + 1;
+                            if (eob) skip[s] = ((1u << run) | bits) - 1u;  // EOBn; this block is part of the run
+                            if (eob || k > se) active = false;
                         }
                     }
                 }
@@ -307,47 +299,38 @@ pf_ac_kernel(PfLaunch L) {
                             sts_h(s_stage + pq.y, d);
                         }
                     } else if (active) {
+                        // one symbol, straight through for every kind (new coefficient, ZRL, EOBn, a size the reference ignores)
                         const uint32_t e = lut_entry(lut, r.window());
+                        r.skip((e >> 5) & 31u);
+                        const uint32_t sz = e & 31u;
+                        const bool eob = sz == 0 && ((e >> 10) & 15u) != 15u;
+                        // the reference warns about sizes other than 0 / 1 and goes on with a zero amplitude and no run (:659-668)
+                        const uint32_t run = (sz > 1) ? 0u : ((e >> 10) & 15u);
+                        const uint32_t bits = r.get(eob ? run : (sz == 1 ? 1u : 0u));  // the sign of a new coefficient / the length of an EOB run
+                        const int sign = (sz == 1) ? (bits ? 1 : -1) : 0;             // 0: nothing to place (ZRL, ignored sizes)
+                        const unsigned long long ahead = band & ~((1ull << k) - 1ull);  // the band from k on
+                        // the (run+1)-th zero position at or behind k inside the band
+                        unsigned long long zeros = ~H & ahead;
+                        for (uint32_t i = 0; i < run && zeros && !eob; i++) zeros &= zeros - 1ull;
+                        const int target = (zeros && !eob) ? __ffsll((long long)zeros) - 1 : se + 1;
+                        const unsigned long long upto = (target >= 64) ? ~0ull : ((1ull << target) - 1ull);
                         if ((int)e < 0) {
                             bad = true;
                             active = false;
                         } else {
-                            r.skip((e >> 5) & 31u);
-                            uint32_t run = (e >> 10) & 15u;
-                            const uint32_t sz = e & 31u;
-                            int sign = 0;  // +1 / -1: a new coefficient of magnitude 1 << Al; 0: nothing to place
-                            bool eob = false;
-                            if (sz == 0) {
-                                if (run != 15) {  // EOBn: the rest of this block (and of the next skip-1 blocks) only takes correction bits
-                                    skip[s] = (1u << run) | r.get(run);
-                                    eob = true;
-                                }
-                            } else if (sz != 1) {  // the reference warns and goes on with a zero amplitude and no run (:659-668)
-                                run = 0;
-                            } else {
-                                sign = r.get(1) ? 1 : -1;
+                            pending = H & ahead & upto;  // EOBn: target = se + 1, the whole rest of the band
+                            if (target <= se && sign) {  // (its position is behind every position that still owes a bit)
+                                uint2 pq;
+                                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)target));
+                                sts_h(s_stage + pq.y, sign * (int)pq.x);
+                                H |= 1ull << target;
                             }
-                            const unsigned long long from_k = ~((1ull << k) - 1ull);
-                            if (eob) {
-                                pending = H & band & from_k;
+                            if (eob) {  // the rest of this block (and of the next skip-1 blocks) only takes correction bits
+                                skip[s] = (1u << run) | bits;
                                 tail = true;
-                                active = false;
-                            } else {
-                                // the (run+1)-th zero position at or behind k inside the band
-                                unsigned long long zeros = ~H & band & from_k;
-                                for (uint32_t i = 0; i < run && zeros; i++) zeros &= zeros - 1ull;
-                                const int target = zeros ? __ffsll((long long)zeros) - 1 : se + 1;
-                                const unsigned long long upto = (target >= 64) ? ~0ull : ((1ull << target) - 1ull);
-                                pending = H & band & from_k & upto;
-                                if (target <= se && sign) {  // (its position is behind every position that still owes a bit)
-                                    uint2 pq;
-                                    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)target));
-                                    sts_h(s_stage + pq.y, sign * (int)pq.x);
-                                    H |= 1ull << target;
-                                }
-                                k = target + 1;
-                                if (k > se) active = false;
                             }
+                            k = target + 1;
+                            if (eob || k > se) active = false;
                         }
                     }
                 }

@@ -103,7 +103,13 @@ B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_
     uint32_t comp_bits = 0;  // two bits per block of an MCU: no indexed local array in the loop
     for (uint32_t b = 0; b < sc.blocks_per_mcu; b++) comp_bits |= (uint32_t)sc.comp_of_block[b] << (2u * b);
     const uint32_t bpm = sc.blocks_per_mcu;
+    // everything the loop needs from the scan description in registers (the struct itself may sit in local memory)
+    const uint32_t *const lut = sc.lut;
+    const uint32_t dc0 = sc.dc_tab[0], dc1 = sc.dc_tab[1], dc2 = sc.dc_tab[2], dc3 = sc.dc_tab[3];
+    const uint32_t ac0 = sc.ac_tab[0], ac1 = sc.ac_tab[1], ac2 = sc.ac_tab[2], ac3 = sc.ac_tab[3];
     uint32_t bit = from.bit, blk = from.blk, k = 0, n = 0;
+    // the stream words around `bit` in registers: a symbol has fewer than 32 bits, so at most one new word per step
+    uint32_t wi = bit >> 5, x0 = spec_word(w, nwords, wi), x1 = spec_word(w, nwords, wi + 1u);
     int32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     int mark = 0, merge_at = -1;   // next mark to pass; the mark the path merged at
     uint32_t next_mark = first_mark_bit;
@@ -139,10 +145,14 @@ B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_
             if (merge_at >= 0) break;
         }
         const uint32_t c = (comp_bits >> (2u * blk)) & 3u;
-        const uint32_t hi = spec_window(w, nwords, bit);
-        const uint32_t dct = c == 0 ? sc.dc_tab[0] : (c == 1 ? sc.dc_tab[1] : (c == 2 ? sc.dc_tab[2] : sc.dc_tab[3]));
-        const uint32_t act = c == 0 ? sc.ac_tab[0] : (c == 1 ? sc.ac_tab[1] : (c == 2 ? sc.ac_tab[2] : sc.ac_tab[3]));
-        const uint32_t e = spec_lookup(sc.lut + (k == 0 ? dct : act), hi);
+#if defined(__CUDA_ARCH__)
+        const uint32_t hi = __funnelshift_l(x1, x0, bit);
+#else
+        const uint32_t hi = (bit & 31u) ? ((x0 << (bit & 31u)) | (x1 >> (32u - (bit & 31u)))) : x0;
+#endif
+        const uint32_t dct = c == 0 ? dc0 : (c == 1 ? dc1 : (c == 2 ? dc2 : dc3));
+        const uint32_t act = c == 0 ? ac0 : (c == 1 ? ac1 : (c == 2 ? ac2 : ac3));
+        const uint32_t e = spec_lookup(lut + (k == 0 ? dct : act), hi);
         if (k == 0) {
             if ((int32_t)e >= 0) {
                 const int32_t v = spec_value(e, hi);
@@ -161,6 +171,11 @@ B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_
             k = 0;
             n++;
             blk = blk + 1 == bpm ? 0 : blk + 1;
+        }
+        if ((bit >> 5) != wi) {  // the window moves up by one word
+            wi = bit >> 5;
+            x0 = x1;
+            x1 = spec_word(w, nwords, wi + 1u);
         }
     }
     if (!counting) {  // the walk ended inside the run-up (end of the data): nothing of the subsequence is there
@@ -188,6 +203,8 @@ B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_
     return r;
 }
 
+static_assert(sizeof(SpecLog) % 8 == 0, "SpecLog arrays keep their 64-bit members aligned");
+
 // One work item of the output pass: blocks [first_block, first_block + n_blocks) of the scan start at bit `bit`
 struct SpecSegment {
     uint32_t bit;
@@ -196,6 +213,8 @@ struct SpecSegment {
     int32_t pred[4];  // DC predictors of the scan components in front of the first block
     uint32_t pad;
 };
+
+static_assert(sizeof(SpecSegment) == 32, "two 16-byte loads per work item (entropy_decode_kernel)");
 
 // Host replay of spec_sync_kernel's rounds for one scan (tests only; specsync_sm100.cu). Returns the number of rounds.
 int spec_sync_host_replay(const SpecScan &sc, const uint32_t *words, uint32_t len_bytes, uint32_t total_mcus, std::vector<SpecSegment> &segs);
