@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: total frames per step, split over the GPUs")
     ap.add_argument("--distinct", type=int, default=64)
     ap.add_argument("--e2e-chunk", type=int, default=32)
+    ap.add_argument("--p2d-chunks", type=int, default=2, help="pinned_to_device_rgb: chunks per step (each: H2D + index + kernels on its own stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -418,7 +419,8 @@ def main():
     peaks, peak_kind = measured_peaks()
     ncu = NCU_DRAM_BYTES_PER_FRAME.get(args.workload, {})
     algo_a = dec.ecs_bytes + 128 * dec.stored_blocks
-    roof_a = {"bound": "hbm", "kernel": "stage a = unstuff_kernel + %s" % ("progressive_scan_kernel x scans + dequant" if PROG else "entropy_decode_kernel"),
+    roof_a = {"bound": "hbm", "kernel": "stage a = unstuff_kernel + %s" % ("pf_dc_kernel + pf_ac_kernel per component (all scans of a block in one pass)" if PROG else
+                                                               ("unstuff_long_kernel + spec_sync_kernel + entropy_decode_kernel<indexed>" if args.workload.endswith("n") else "entropy_decode_kernel")),
               "ms_unstuff": uns, "ms_decode": ent - uns,
               "achieved": algo_a / (ent * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
               "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
@@ -449,7 +451,7 @@ def main():
     # The batch is cut into chunks that were parsed and packed into pinned memory before the timed region; timed per chunk:
     # H2D + restart_index_kernel + unstuff + entropy + reconstruction, chunks rotating over three streams; no D2H.
     p2d = None
-    chunk_frames = max(1, min(nf, max(args.e2e_chunk, (nf + 7) // 8)))
+    chunk_frames = max(1, min(nf, max(args.e2e_chunk, (nf + args.p2d_chunks - 1) // args.p2d_chunks)))
     if not args.no_e2e:
         dec.close()
         dec = None

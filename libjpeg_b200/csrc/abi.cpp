@@ -139,6 +139,7 @@ struct PfGroupHost {
 // the tuned reconstruction kernels cover grey frames and three-component frames whose first component is not subsampled and
 // whose two other components share factors of 1 or 2; everything else goes through the generic kernels
 static bool frame_is_generic(const b200jpg_frame_info &fi) {
+    if (fi.precision != 8) return true;  // 12-bit frames: int32 planes, 16-bit samples out
     if (fi.ncomp == 1) return fi.subx[0] != 1 || fi.suby[0] != 1;
     if (fi.ncomp != 3) return true;
     return fi.subx[0] != 1 || fi.suby[0] != 1 || fi.subx[1] != fi.subx[2] || fi.suby[1] != fi.suby[2] || fi.subx[1] > 2 || fi.suby[1] > 2;
@@ -451,7 +452,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
             }
         }
         b->out_off[i] = out_cur;
-        b->out_bytes[i] = (uint64_t)fi.width * fi.height * fi.ncomp;
+        b->out_bytes[i] = (uint64_t)fi.width * fi.height * fi.ncomp * (fi.precision > 8 ? 2u : 1u);
         out_cur = align_up(out_cur + b->out_bytes[i], 256);
         b->ecs_bytes += fi.ecs_bytes;
         b->stored_blocks += fi.stored_blocks;

@@ -197,7 +197,7 @@ struct FrameRecon {       // per frame, for the reconstruction kernels
     uint32_t bw[4], bh[4];
     uint32_t ncomp, ycbcr, subx, suby;  // subx/suby of the subsampled (chroma) components
     uint32_t cw, ch;                    // true subsampled size ceil(W/subx), ceil(H/suby)
-    uint32_t status_idx, pad;
+    uint32_t status_idx, precision;     // sample precision of the frame (8, or 12: generic reconstruction, 16-bit samples out)
     uint8_t csx[4], csy[4];             // generic reconstruction: subsampling factors of every component (1..4)
 };
 

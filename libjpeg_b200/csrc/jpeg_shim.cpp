@@ -335,7 +335,7 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
         std::string msg;
         int rc = shared_context(s.device, &ctx, msg);
         if (rc) return s.fail(rc, msg);
-        s.pixel_bytes = (size_t)s.info.width * s.info.height * s.info.ncomp + 256;
+        s.pixel_bytes = (size_t)s.info.width * s.info.height * s.info.ncomp * (s.info.precision > 8 ? 2 : 1) + 256;
         s.pixels.reset(new (std::nothrow) uint8_t[s.pixel_bytes]);
         if (!s.pixels) return s.fail(JPGERR_OUT_OF_MEMORY, "out of memory for the decoded frame");
         const uint8_t *frames[1] = {s.stream.data()};
@@ -404,15 +404,21 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
         const JPG_ULONG mr = (l.height >> 3) - 1;  // unsigned, wraps for heights below 8 exactly like the reference
         if (mr < max_block_row) max_block_row = mr;
     }
-    if (common_type != 0 && common_type != CTYP_UBYTE)
-        return s.fail(JPGERR_INVALID_PARAMETER, "8 bit images must be reconstructed into CTYP_UBYTE pixels");
+    // colortransformerfactory.cpp:613-632: bytes only hold 8-bit frames; 16-bit samples hold any precision of this path
+    const bool deep = s.info.precision > 8;
+    if (common_type != 0 && common_type != CTYP_UBYTE && common_type != CTYP_UWORD)
+        return s.fail(JPGERR_INVALID_PARAMETER, "only CTYP_UBYTE and CTYP_UWORD pixels are supported by the B200 path");
+    if (deep && common_type == CTYP_UBYTE)
+        return s.fail(JPGERR_OVERFLOW_PARAMETER, "invalid data type selected for the image, image precision is deeper than 8 bits");
+    const bool wide_out = common_type == CTYP_UWORD;
 
     // ---- copy, block by block like the reference walks the region (PushReconstructedData / ReconstructUnsampled)
     const uint32_t W = s.info.width;
     // the usual client bitmap -- one interleaved canvas, component c at base + c -- is copied run-wise instead of bytewise
     bool interleaved = nc > 1;
     for (int c = 0; c < nc; c++)
-        interleaved = interleaved && lay[c].mem && lay[c].pixel_type && lay[c].mem == lay[0].mem + c && lay[c].bytes_per_pixel == nc &&
+        interleaved = interleaved && deep == wide_out && lay[c].mem && lay[c].pixel_type && lay[c].mem == lay[0].mem + c * (deep ? 2 : 1) &&
+                      lay[c].bytes_per_pixel == nc * (deep ? 2 : 1) &&
                       lay[c].bytes_per_row == lay[0].bytes_per_row && lay[c].width == lay[0].width && lay[c].height == lay[0].height;
     // block rows up to min(MaxY >> 3, (smallest BIO_HEIGHT >> 3) - 1) are reconstructed (blockbitmaprequester.cpp:1166-1167)
     long long last_by = (long long)(maxy >> 3);
@@ -429,12 +435,20 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
                 // or pixel type 0 leave the component unwritten (imagebitmap.cpp:78-110)
                 if (!l.mem || !l.pixel_type || l.width <= (JPG_ULONG)x0 || l.height <= (JPG_ULONG)y0) continue;
                 for (JPG_LONG y = y0; y <= y1; y++) {
-                    const uint8_t *src = s.pixels.get() + ((size_t)y * W + (size_t)x0) * nc + c;
+                    const size_t at = ((size_t)y * W + (size_t)x0) * nc + c;
+                    const uint8_t *src = s.pixels.get() + at * (deep ? 2 : 1);
                     uint8_t *dst = l.mem + (ptrdiff_t)x0 * l.bytes_per_pixel + (ptrdiff_t)y * l.bytes_per_row;
                     if (interleaved) {  // all components of the run in one go (the other components skip this block)
-                        if (c == 0) memcpy(dst, src, (size_t)(x1 - x0 + 1) * nc);
-                    } else {
+                        if (c == 0) memcpy(dst, src, (size_t)(x1 - x0 + 1) * nc * (deep ? 2 : 1));
+                    } else if (!wide_out) {
                         for (JPG_LONG x = x0; x <= x1; x++, src += nc, dst += l.bytes_per_pixel) *dst = *src;
+                    } else if (!deep) {  // 8-bit samples into 16-bit pixels
+                        for (JPG_LONG x = x0; x <= x1; x++, src += nc, dst += l.bytes_per_pixel) {
+                            const uint16_t v = *src;
+                            memcpy(dst, &v, 2);
+                        }
+                    } else {
+                        for (JPG_LONG x = x0; x <= x1; x++, src += 2 * nc, dst += l.bytes_per_pixel) memcpy(dst, src, 2);
                     }
                 }
             }

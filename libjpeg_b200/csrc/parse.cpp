@@ -213,7 +213,6 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
             fi.precision = s[0];
             if (m == 0xc0 && fi.precision != 8) FAIL(B200JPG_ERR_MALFORMED_STREAM, "frame precision in baseline mode must be 8");
             if (fi.precision != 8 && fi.precision != 12) FAIL(B200JPG_ERR_MALFORMED_STREAM, "frame precision in lossy mode must be 8 or 12");
-            if (fi.precision != 8) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, "12 bit frames are not supported by the B200 path");
             fi.height = (uint32_t)((s[1] << 8) | s[2]);
             fi.width = (uint32_t)((s[3] << 8) | s[4]);
             if (fi.width == 0) FAIL(B200JPG_ERR_MALFORMED_STREAM, "image width must not be zero");

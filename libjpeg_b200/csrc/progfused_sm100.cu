@@ -287,18 +287,9 @@ pf_ac_kernel(PfLaunch L) {
                     active = false;
                 }
                 while (__any_sync(0xffffffffu, active || pending != 0ull)) {
-                    if (pending != 0ull) {
-                        const int p = __ffsll((long long)pending) - 1;
-                        pending &= pending - 1ull;
-                        if (r.get(1)) {
-                            uint2 pq;
-                            asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)p));
-                            const int cur = lds_h(s_stage + pq.y);
-                            const int d = cur + (cur > 0 ? (int)pq.x : -(int)pq.x);  // away from zero by 1 << Al, dequantised
-                            ovf |= (uint32_t)(d + 32768);
-                            sts_h(s_stage + pq.y, d);
-                        }
-                    } else if (active) {
+                    // every iteration: a lane that owes no correction bit decodes its next symbol, and then every lane that owes
+                    // one (also the one that has just decoded) pays one -- two straight pieces instead of two diverging ones
+                    if (pending == 0ull && active) {
                         // one symbol, straight through for every kind (new coefficient, ZRL, EOBn, a size the reference ignores)
                         const uint32_t e = lut_entry(lut, r.window());
                         r.skip((e >> 5) & 31u);
@@ -331,6 +322,18 @@ pf_ac_kernel(PfLaunch L) {
                             }
                             k = target + 1;
                             if (eob || k > se) active = false;
+                        }
+                    }
+                    if (pending != 0ull) {
+                        const int p = __ffsll((long long)pending) - 1;
+                        pending &= pending - 1ull;
+                        if (r.get(1)) {
+                            uint2 pq;
+                            asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(qz + 8u * (uint32_t)p));
+                            const int cur = lds_h(s_stage + pq.y);
+                            const int d = cur + (cur > 0 ? (int)pq.x : -(int)pq.x);  // away from zero by 1 << Al, dequantised
+                            ovf |= (uint32_t)(d + 32768);
+                            sts_h(s_stage + pq.y, d);
                         }
                     }
                 }

@@ -199,7 +199,9 @@ __device__ __forceinline__ void idct_planes_block(const FrameRecon &f, int c, ui
     const uint4 *src = reinterpret_cast<const uint4 *>(coef + f.coef_base[c] + (uint64_t)t * 64u);
 #pragma unroll
     for (int r = 0; r < 8; r++) unpack_row_raw(__ldg(src + r), s[r]);
-    s[0][0] = WADD(s[0][0], 128 << 3);  // dcoffset << 3 (idct.cpp:233,244); the << 4 preshift is folded into the row pass' rounding
+    // dcoffset << 3 (idct.cpp:233,244); the << 4 preshift is folded into the row pass' rounding. 12-bit frames only come
+    // through the int32 planes (tables.cpp:1877-1891: the same LONG IDCT, level shift 1 << 11)
+    s[0][0] = WADD(s[0][0], sizeof(T) == 4 ? (int)(8u << (f.precision - 1u)) : (128 << 3));
 #pragma unroll
     for (int r = 0; r < 8; r++) idct8t<16, 5>(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7]);
     int mx = 0, mn = 0;
@@ -1171,16 +1173,28 @@ generic_reconstruct_kernel(const FrameRecon *__restrict__ frames, const int32_t 
         generic_upsample_block(samples + f.sample_base[c], 8u * f.bw[c], w, h, sx, sy, X, Y, buf[c]);
     }
     const int xmax = (X + 7 < (int)W) ? 7 : (int)((W - 1) & 7), ymax = (Y + 7 < (int)H) ? 7 : (int)((H - 1) & 7);
+    // level shift, chroma offset and clamp scale with the precision; 12-bit frames leave as native-endian 16-bit samples
+    // (what the reference writes into CTYP_UWORD bitmaps)
+    const bool deep = f.precision > 8;
+    const long long maxval = (1ll << f.precision) - 1, coff = 16ll << (f.precision - 1u);
     for (int y = 0; y <= ymax; y++) {
-        uint8_t *o = out + f.out_base + ((uint64_t)(Y + y) * W + (uint64_t)X) * nc;
+        const uint64_t at = ((uint64_t)(Y + y) * W + (uint64_t)X) * nc;
+        uint8_t *o8 = out + f.out_base + at;
+        uint16_t *o16 = reinterpret_cast<uint16_t *>(out + f.out_base) + at;
         for (int x = 0; x <= xmax; x++) {
+            long long v[4];
             if (nc == 3 && f.ycbcr) {
-                const long long yv = buf[0][8 * y + x], cb = (long long)buf[1][8 * y + x] - (128 << 4), cr = (long long)buf[2][8 * y + x] - (128 << 4);
-                o[3 * x] = (uint8_t)sat_u8_64((yv * 8192 + cr * 11485 + 65536) >> 17);
-                o[3 * x + 1] = (uint8_t)sat_u8_64((yv * 8192 - cb * 2819 - cr * 5850 + 65536) >> 17);
-                o[3 * x + 2] = (uint8_t)sat_u8_64((yv * 8192 + cb * 14516 + 65536) >> 17);
+                const long long yv = buf[0][8 * y + x], cb = (long long)buf[1][8 * y + x] - coff, cr = (long long)buf[2][8 * y + x] - coff;
+                v[0] = (yv * 8192 + cr * 11485 + 65536) >> 17;
+                v[1] = (yv * 8192 - cb * 2819 - cr * 5850 + 65536) >> 17;
+                v[2] = (yv * 8192 + cb * 14516 + 65536) >> 17;
             } else {
-                for (uint32_t c = 0; c < nc; c++) o[nc * x + c] = (uint8_t)sat_u8_64(((long long)buf[c][8 * y + x] + 8) >> 4);
+                for (uint32_t c = 0; c < nc; c++) v[c] = ((long long)buf[c][8 * y + x] + 8) >> 4;
+            }
+            for (uint32_t c = 0; c < nc; c++) {
+                const long long w = v[c] < 0 ? 0 : (v[c] > maxval ? maxval : v[c]);
+                if (deep) o16[nc * x + c] = (uint16_t)w;
+                else o8[nc * x + c] = (uint8_t)w;
             }
         }
     }
@@ -1247,13 +1261,24 @@ int launch_recon(const ReconLaunch &l, void *stream, int *launches) {
     if (l.ncomp == 3 && l.subx == 2 && l.suby == 2 && fused && fused[0] == '1') return launch_recon_fused420(l, s, launches);
     const uint32_t cblocks = (l.max_bwc * l.max_bhc + kThreadsB - 1) / kThreadsB;
     const uint32_t gx = (l.max_bw0 + 31) / 32, gy = (l.max_bh0 + kThreadsB / 32 - 1) / (kThreadsB / 32);
-    // every frame through the int16 planes
-    if (l.ncomp > 1) {
-        idct_planes_kernel<int16_t, false><<<dim3(cblocks, l.n_frames, l.ncomp - 1), kThreadsB, 0, s>>>(l.frames, l.coef, l.samples16, l.narrow_flags, nullptr, 1);
+    // every frame through the int16 planes, B200JPG_RECON_CHUNK frames at a time (0: all at once): in chunks the planes b1 writes
+    // are still in L2 when b2 reads them
+    uint32_t chunk = l.n_frames;
+    if (const char *e = getenv("B200JPG_RECON_CHUNK")) {
+        const long v = atol(e);
+        if (v > 0 && (uint32_t)v < chunk) chunk = (uint32_t)v;
+    }
+    for (uint32_t f0 = 0; f0 < l.n_frames; f0 += chunk) {
+        const uint32_t nf = (l.n_frames - f0 < chunk) ? (l.n_frames - f0) : chunk;
+        ReconLaunch c = l;
+        c.frames = l.frames + f0;
+        if (l.ncomp > 1) {
+            idct_planes_kernel<int16_t, false><<<dim3(cblocks, nf, l.ncomp - 1), kThreadsB, 0, s>>>(c.frames, l.coef, l.samples16, l.narrow_flags, nullptr, 1);
+            n++;
+        }
+        launch_b2<int16_t, false>(c, dim3(gx, gy, nf), l.samples16, s);
         n++;
     }
-    launch_b2<int16_t, false>(l, dim3(gx, gy, l.n_frames), l.samples16, s);
-    n++;
     // the exact pass over the frames that were flagged `narrow` (none for real images: three near-empty launches)
     if (l.ncomp > 1) {
         narrow_list_kernel<<<1, 256, 0, s>>>(l.frames, l.n_frames, l.narrow_flags, l.narrow_list);

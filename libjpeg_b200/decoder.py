@@ -206,7 +206,10 @@ class BatchDecoder:
         """Frame i of a decoded output tensor as [H, W, C]."""
         fi = self.info(i)
         off = self.out_offset(i)
-        return out[off:off + fi.width * fi.height * fi.ncomp].view(fi.height, fi.width, fi.ncomp)
+        n = fi.width * fi.height * fi.ncomp
+        if fi.precision > 8:  # 12-bit frames: native-endian 16-bit samples
+            return out[off:off + 2 * n].view(torch.int16).view(fi.height, fi.width, fi.ncomp)
+        return out[off:off + n].view(fi.height, fi.width, fi.ncomp)
 
     def close(self):
         if getattr(self, "handle", None):

@@ -35,6 +35,9 @@ def main():
             for k in KEYS:
                 if k in hdr and r[hdr.index(k)] != "":
                     w.writerow([name, k, r[hdr.index(k)], units[hdr.index(k)]])
+            for i, h in enumerate(hdr):  # every execution pipe: share of its peak issue rate while the SM was active
+                if h.startswith("sm__inst_executed_pipe_") and h.endswith(".avg.pct_of_peak_sustained_active") and r[i] not in ("", "0"):
+                    w.writerow([name, h, r[i], units[i]])
             top = sorted(((float(r[i]) if r[i] else 0.0, h) for i, h in stalls), reverse=True)[:8]
             for v, h in top:
                 w.writerow([name, "stall:" + h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", ""), "%.3f" % v, "warps per issue"])
