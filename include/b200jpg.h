@@ -103,6 +103,11 @@ B200JPG_API int b200jpg_batch_create(b200jpg_ctx *ctx, const uint8_t *const *fra
  * 93-165): B200JPG_FLAG_NO_COLOR_TRANSFORM = JPGTAG_MATRIX_LTRAFO set to JPGFLAG_MATRIX_COLORTRANSFORMATION_NONE: the
  * components are upsampled and delivered as they are (YCbCr frames come out as Y, Cb, Cr). */
 #define B200JPG_FLAG_NO_COLOR_TRANSFORM 1u
+/* B200JPG_FLAG_NO_UPSAMPLE = JPGTAG_DECODER_UPSAMPLE false (control/bitmapctrl.cpp:273-293, BlockBitmapRequester::
+ * ReconstructUnsampled control/blockbitmaprequester.cpp:1013-1074): no upsampling and no colour transformation (the reference
+ * refuses one without the other); frame i is written as plane after plane, component c holding ceil(width / subx[c]) x
+ * ceil(height / suby[c]) samples, rows tightly packed.  Samples are bytes, or native-endian 16-bit for 12-bit frames. */
+#define B200JPG_FLAG_NO_UPSAMPLE 2u
 B200JPG_API int b200jpg_batch_create_ex(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad,
                             unsigned flags, b200jpg_batch **batch);
 /* Waits for the work last enqueued for this batch (its buffers return to the context's pool for reuse by the

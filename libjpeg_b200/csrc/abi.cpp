@@ -138,7 +138,8 @@ struct PfGroupHost {
 
 // the tuned reconstruction kernels cover grey frames and three-component frames whose first component is not subsampled and
 // whose two other components share factors of 1 or 2; everything else goes through the generic kernels
-static bool frame_is_generic(const b200jpg_frame_info &fi) {
+static bool frame_is_generic(const b200jpg_frame_info &fi, unsigned flags = 0) {
+    if (flags & B200JPG_FLAG_NO_UPSAMPLE) return true;  // planes of every component, then one sample -> one output value
     if (fi.precision != 8) return true;  // 12-bit frames: int32 planes, 16-bit samples out
     if (fi.ncomp == 1) return fi.subx[0] != 1 || fi.suby[0] != 1;
     if (fi.ncomp != 3) return true;
@@ -155,6 +156,7 @@ struct ClassKey {
 struct b200jpg_batch {
     b200jpg_ctx *ctx = nullptr;
     int n = 0;
+    unsigned flags = 0;  // B200JPG_FLAG_*
     std::vector<ParsedFrame> frames;
     std::vector<int> parse_status;
     std::vector<uint64_t> out_off, out_bytes;
@@ -356,6 +358,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     b200jpg_batch *b = bp.get();
     b->ctx = ctx;
     b->n = n;
+    b->flags = flags;
     b->frames.resize(n);
     b->parse_status.assign(n, 0);
     std::vector<std::string> errs(n);
@@ -446,13 +449,19 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
         for (int c = 0; c < fi.ncomp; c++) {
             coef_base[i][c] = coef_cur;
             coef_cur += (uint64_t)fi.blocks_w[c] * fi.blocks_h[c] * 64;
-            if (c > 0 || frame_is_generic(fi)) {  // generic reconstruction keeps a sample plane of every component
+            if (c > 0 || frame_is_generic(fi, flags)) {  // generic reconstruction keeps a sample plane of every component
                 sample_base[i][c] = sample_cur;
                 sample_cur += (uint64_t)fi.blocks_w[c] * fi.blocks_h[c] * 64;
             }
         }
         b->out_off[i] = out_cur;
-        b->out_bytes[i] = (uint64_t)fi.width * fi.height * fi.ncomp * (fi.precision > 8 ? 2u : 1u);
+        uint64_t samples = (uint64_t)fi.width * fi.height * fi.ncomp;
+        if (flags & B200JPG_FLAG_NO_UPSAMPLE) {  // plane after plane, every component at its own resolution
+            samples = 0;
+            for (int c = 0; c < fi.ncomp; c++)
+                samples += (uint64_t)((fi.width + fi.subx[c] - 1) / fi.subx[c]) * ((fi.height + fi.suby[c] - 1) / fi.suby[c]);
+        }
+        b->out_bytes[i] = samples * (fi.precision > 8 ? 2u : 1u);
         out_cur = align_up(out_cur + b->out_bytes[i], 256);
         b->ecs_bytes += fi.ecs_bytes;
         b->stored_blocks += fi.stored_blocks;
@@ -674,7 +683,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     for (int i = 0; i < n; i++) {
         if (b->parse_status[i] != 0) continue;
         const b200jpg_frame_info &fi = b->frames[i].info;
-        const bool generic = frame_is_generic(fi);
+        const bool generic = frame_is_generic(fi, flags);
         uint32_t sx = fi.ncomp > 1 ? fi.subx[1] : 1, sy = fi.ncomp > 1 ? fi.suby[1] : 1;
         if (generic) sx = sy = 0;  // one group per component count: the generic kernels read the factors per frame
         ReconGroup *g = nullptr;
@@ -1040,6 +1049,7 @@ static int run_recon(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
         l.subx = g.subx;
         l.suby = g.suby;
         l.generic = g.generic;
+        l.planes_out = (b->flags & B200JPG_FLAG_NO_UPSAMPLE) != 0;
         l.coef = b->d_coef;
         l.samples16 = b->d_samples16;
         l.samples32 = b->d_samples;

@@ -324,18 +324,42 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
         }
     }
     if (maxx < minx || maxy < miny) return s.fail(JPGERR_INVALID_PARAMETER, "the requested rectangle is empty");
-    if (!upsample) return s.fail(JPGERR_NOT_IMPLEMENTED, "reconstruction without upsampling is not supported by the B200 path");
-    if (firstc != 0 || lastc != s.info.ncomp - 1)
-        return s.fail(JPGERR_NOT_IMPLEMENTED, "reconstructing a subset of the components is not supported by the B200 path");
+    // without upsampling there is no colour transformation either (rectanglerequest.cpp:155-158), and the components come one
+    // per request, each in its own subsampled coordinates (BitmapCtrl::SubsampledRegion, bitmapctrl.cpp:273-293)
+    if (!upsample) {
+        colortrafo = false;
+        if (firstc != lastc)
+            return s.fail(JPGERR_INVALID_PARAMETER, "if upsampling is disabled, components can only be reconstructed one by one");
+    }
+    // a subset of the components: the identity transformation works component by component; through YCbCr->RGB the reference
+    // feeds zeros for the components left out (blockbitmaprequester.cpp:1046-1051) -- not offered here
+    if ((firstc != 0 || lastc != s.info.ncomp - 1) && colortrafo && s.info.ycbcr)
+        return s.fail(JPGERR_NOT_IMPLEMENTED, "a subset of the components through the colour transformation is not supported by the B200 path");
+    const int sample_bytes = s.info.precision > 8 ? 2 : 1;
+    // planes mode: plane offsets (in samples) and sizes of the components at their own resolution
+    size_t plane_at[B200JPG_MAX_COMPONENTS + 1] = {0};
+    uint32_t plane_w[B200JPG_MAX_COMPONENTS] = {0};
+    for (int c = 0; c < s.info.ncomp; c++) {
+        plane_w[c] = (s.info.width + s.info.subx[c] - 1) / s.info.subx[c];
+        plane_at[c + 1] = plane_at[c] + (size_t)plane_w[c] * ((s.info.height + s.info.suby[c] - 1) / s.info.suby[c]);
+    }
+    // the rectangle the samples are copied for: the request's, or its subsampled image (the hook still sees the request's)
+    JPG_LONG cminx = minx, cmaxx = maxx, cminy = miny, cmaxy = maxy;
+    if (!upsample && firstc <= lastc) {
+        const int sx = s.info.subx[firstc], sy = s.info.suby[firstc];
+        cminx = (minx + sx - 1) / sx, cmaxx = (maxx + sx) / sx - 1;
+        cminy = (miny + sy - 1) / sy, cmaxy = (maxy + sy) / sy - 1;
+    }
 
     // ---- decode on first use (CUDA; the whole frame, kept for later rectangles)
-    const unsigned want_flags = (!colortrafo && s.info.ycbcr) ? B200JPG_FLAG_NO_COLOR_TRANSFORM : 0u;
+    const unsigned want_flags = !upsample ? (B200JPG_FLAG_NO_UPSAMPLE | B200JPG_FLAG_NO_COLOR_TRANSFORM)
+                                          : ((!colortrafo && s.info.ycbcr) ? B200JPG_FLAG_NO_COLOR_TRANSFORM : 0u);
     if (!s.decoded || s.decoded_flags != want_flags) {
         b200jpg_ctx *ctx = 0;
         std::string msg;
         int rc = shared_context(s.device, &ctx, msg);
         if (rc) return s.fail(rc, msg);
-        s.pixel_bytes = (size_t)s.info.width * s.info.height * s.info.ncomp * (s.info.precision > 8 ? 2 : 1) + 256;
+        s.pixel_bytes = (upsample ? (size_t)s.info.width * s.info.height * s.info.ncomp : plane_at[s.info.ncomp]) * sample_bytes + 256;
         s.pixels.reset(new (std::nothrow) uint8_t[s.pixel_bytes]);
         if (!s.pixels) return s.fail(JPGERR_OUT_OF_MEMORY, "out of memory for the decoded frame");
         const uint8_t *frames[1] = {s.stream.data()};
@@ -384,7 +408,7 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
     };
     int common_type = 0;
     JPG_ULONG max_block_row = 0xffffffffu;  // blockbitmaprequester.cpp:1240
-    for (int c = 0; c < nc; c++) {
+    for (int c = (int)firstc; c <= (int)lastc; c++) {
         fill(JPGFLAG_BIO_REQUEST, c, def);
         if (hook) {
             JPG_LONG r = hook->CallLong(bt);
@@ -415,47 +439,49 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
     // ---- copy, block by block like the reference walks the region (PushReconstructedData / ReconstructUnsampled)
     const uint32_t W = s.info.width;
     // the usual client bitmap -- one interleaved canvas, component c at base + c -- is copied run-wise instead of bytewise
-    bool interleaved = nc > 1;
-    for (int c = 0; c < nc; c++)
+    bool interleaved = nc > 1 && upsample && firstc == 0 && lastc == nc - 1;
+    for (int c = 0; c < nc && interleaved; c++)
         interleaved = interleaved && deep == wide_out && lay[c].mem && lay[c].pixel_type && lay[c].mem == lay[0].mem + c * (deep ? 2 : 1) &&
                       lay[c].bytes_per_pixel == nc * (deep ? 2 : 1) &&
                       lay[c].bytes_per_row == lay[0].bytes_per_row && lay[c].width == lay[0].width && lay[c].height == lay[0].height;
     // block rows up to min(MaxY >> 3, (smallest BIO_HEIGHT >> 3) - 1) are reconstructed (blockbitmaprequester.cpp:1166-1167)
-    long long last_by = (long long)(maxy >> 3);
+    long long last_by = (long long)(cmaxy >> 3);
     if ((long long)max_block_row < last_by) last_by = (long long)max_block_row;
-    for (long long by = (long long)(miny >> 3); by <= last_by; by++) {
-        const JPG_LONG y0 = (by == (miny >> 3)) ? miny : (JPG_LONG)(by << 3);
-        const JPG_LONG y1 = ((JPG_LONG)(by << 3) + 7 < maxy) ? (JPG_LONG)(by << 3) + 7 : maxy;
-        for (JPG_LONG bx = minx >> 3; bx <= (maxx >> 3); bx++) {
-            const JPG_LONG x0 = (bx == (minx >> 3)) ? minx : (bx << 3);
-            const JPG_LONG x1 = ((bx << 3) + 7 < maxx) ? (bx << 3) + 7 : maxx;
-            for (int c = 0; c < nc; c++) {
+    for (long long by = (long long)(cminy >> 3); by <= last_by; by++) {
+        const JPG_LONG y0 = (by == (cminy >> 3)) ? cminy : (JPG_LONG)(by << 3);
+        const JPG_LONG y1 = ((JPG_LONG)(by << 3) + 7 < cmaxy) ? (JPG_LONG)(by << 3) + 7 : cmaxy;
+        for (JPG_LONG bx = cminx >> 3; bx <= (cmaxx >> 3); bx++) {
+            const JPG_LONG x0 = (bx == (cminx >> 3)) ? cminx : (bx << 3);
+            const JPG_LONG x1 = ((bx << 3) + 7 < cmaxx) ? (bx << 3) + 7 : cmaxx;
+            for (int c = (int)firstc; c <= (int)lastc; c++) {
                 const BitmapLayout &l = lay[c];
                 // ImageBitMap::ExtractBitMap: a block whose origin lies outside the client bitmap, a NULL base
                 // or pixel type 0 leave the component unwritten (imagebitmap.cpp:78-110)
                 if (!l.mem || !l.pixel_type || l.width <= (JPG_ULONG)x0 || l.height <= (JPG_ULONG)y0) continue;
                 for (JPG_LONG y = y0; y <= y1; y++) {
-                    const size_t at = ((size_t)y * W + (size_t)x0) * nc + c;
-                    const uint8_t *src = s.pixels.get() + at * (deep ? 2 : 1);
+                    // sample (x0, y) of component c: in the interleaved frame, or in the component's own plane
+                    const size_t at = upsample ? ((size_t)y * W + (size_t)x0) * nc + c : plane_at[c] + (size_t)y * plane_w[c] + (size_t)x0;
+                    const size_t step = upsample ? (size_t)nc : 1;
+                    const uint8_t *src = s.pixels.get() + at * sample_bytes;
                     uint8_t *dst = l.mem + (ptrdiff_t)x0 * l.bytes_per_pixel + (ptrdiff_t)y * l.bytes_per_row;
                     if (interleaved) {  // all components of the run in one go (the other components skip this block)
-                        if (c == 0) memcpy(dst, src, (size_t)(x1 - x0 + 1) * nc * (deep ? 2 : 1));
+                        if (c == 0) memcpy(dst, src, (size_t)(x1 - x0 + 1) * nc * sample_bytes);
                     } else if (!wide_out) {
-                        for (JPG_LONG x = x0; x <= x1; x++, src += nc, dst += l.bytes_per_pixel) *dst = *src;
+                        for (JPG_LONG x = x0; x <= x1; x++, src += step, dst += l.bytes_per_pixel) *dst = *src;
                     } else if (!deep) {  // 8-bit samples into 16-bit pixels
-                        for (JPG_LONG x = x0; x <= x1; x++, src += nc, dst += l.bytes_per_pixel) {
+                        for (JPG_LONG x = x0; x <= x1; x++, src += step, dst += l.bytes_per_pixel) {
                             const uint16_t v = *src;
                             memcpy(dst, &v, 2);
                         }
                     } else {
-                        for (JPG_LONG x = x0; x <= x1; x++, src += 2 * nc, dst += l.bytes_per_pixel) memcpy(dst, src, 2);
+                        for (JPG_LONG x = x0; x <= x1; x++, src += 2 * step, dst += l.bytes_per_pixel) memcpy(dst, src, 2);
                     }
                 }
             }
         }
     }
     // ---- RELEASE per component (bitmaphook.cpp:214-248)
-    for (int c = 0; c < nc; c++) {
+    for (int c = (int)firstc; c <= (int)lastc; c++) {
         fill(JPGFLAG_BIO_RELEASE, c, lay[c]);
         if (hook) {
             JPG_LONG r = hook->CallLong(bt);

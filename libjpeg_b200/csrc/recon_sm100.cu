@@ -24,6 +24,7 @@
 //     unrolled register-resident version stalled on instruction fetch).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <type_traits>
@@ -1200,6 +1201,26 @@ generic_reconstruct_kernel(const FrameRecon *__restrict__ frames, const int32_t 
     }
 }
 
+// B200JPG_FLAG_NO_UPSAMPLE: component blockIdx.z of frame blockIdx.y, one thread per sample of its true (subsampled) size:
+// COLOR_TO_INT and the clamp of the identity transformation (tools/numerics.hpp:69), nothing else
+__global__ void __launch_bounds__(256)
+planes_out_kernel(const FrameRecon *__restrict__ frames, const int32_t *__restrict__ samples, uint8_t *__restrict__ out) {
+    const FrameRecon &f = frames[blockIdx.y];
+    const uint32_t c = blockIdx.z;
+    if (c >= f.ncomp) return;
+    uint64_t before = 0;  // samples of the planes in front of this one
+    for (uint32_t k = 0; k < c; k++) before += (uint64_t)((f.width + f.csx[k] - 1) / f.csx[k]) * ((f.height + f.csy[k] - 1) / f.csy[k]);
+    const uint32_t w = (f.width + f.csx[c] - 1) / f.csx[c], h = (f.height + f.csy[c] - 1) / f.csy[c];
+    const int maxval = (1 << f.precision) - 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < (uint64_t)w * h; i += (uint64_t)gridDim.x * 256) {
+        const uint32_t x = (uint32_t)(i % w), y = (uint32_t)(i / w);
+        int v = (samples[f.sample_base[c] + (uint64_t)y * (8u * f.bw[c]) + x] + 8) >> 4;
+        v = v < 0 ? 0 : (v > maxval ? maxval : v);
+        if (f.precision > 8) reinterpret_cast<uint16_t *>(out + f.out_base)[before + i] = (uint16_t)v;
+        else out[f.out_base + before + i] = (uint8_t)v;
+    }
+}
+
 }  // namespace
 
 template <typename T, bool kListed>
@@ -1245,7 +1266,12 @@ static int launch_recon_generic(const ReconLaunch &l, cudaStream_t s, int *launc
     mb = l.max_bwc * l.max_bhc;  // the largest component block grid of the group (set by the host for generic groups)
     const uint32_t cblocks = (mb + kThreadsB - 1) / kThreadsB;
     idct_planes_kernel<int32_t, false><<<dim3(cblocks, l.n_frames, l.ncomp), kThreadsB, 0, s>>>(l.frames, l.coef, l.samples32, l.wide_flags, nullptr, 0);
-    generic_reconstruct_kernel<<<dim3((l.max_bw0 + 63) / 64, l.max_bh0, l.n_frames), 64, 0, s>>>(l.frames, l.samples32, l.out);
+    if (l.planes_out) {
+        const uint32_t gx = std::min<uint32_t>((l.max_bw0 * l.max_bh0 * 64u + 255u) / 256u, 4096u);
+        planes_out_kernel<<<dim3(gx, l.n_frames, l.ncomp), 256, 0, s>>>(l.frames, l.samples32, l.out);
+    } else {
+        generic_reconstruct_kernel<<<dim3((l.max_bw0 + 63) / 64, l.max_bh0, l.n_frames), 64, 0, s>>>(l.frames, l.samples32, l.out);
+    }
     if (launches) *launches = 2;
     return (int)cudaGetLastError();
 }

@@ -87,7 +87,7 @@ class Context:
 class BatchDecoder:
     """One batch of codestreams: parse + pack on construction, then upload() / decode() on a CUDA stream."""
 
-    def __init__(self, frames, device=-1, tolerate_bad=False, ctx=None, color_transform=True):
+    def __init__(self, frames, device=-1, tolerate_bad=False, ctx=None, color_transform=True, upsample=True):
         self.ctx = ctx or Context(device)
         self._keep = []
         n = len(frames)
@@ -100,6 +100,9 @@ class BatchDecoder:
             self._keep.append(keep)
         self.handle = ctypes.c_void_p()
         flags = 0 if color_transform else 1  # B200JPG_FLAG_NO_COLOR_TRANSFORM (JPGTAG_MATRIX_LTRAFO = none)
+        if not upsample:
+            flags = 3  # B200JPG_FLAG_NO_UPSAMPLE (JPGTAG_DECODER_UPSAMPLE = false): planes, no colour transformation
+        self.upsample = bool(upsample)
         rc = lib.b200jpg_batch_create_ex(self.ctx.handle, ptrs, lens, n, int(tolerate_bad), flags, ctypes.byref(self.handle))
         native.check(rc, self.ctx.handle)
         self._keep = []  # the batch holds its own pinned copy
@@ -210,6 +213,19 @@ class BatchDecoder:
         if fi.precision > 8:  # 12-bit frames: native-endian 16-bit samples
             return out[off:off + 2 * n].view(torch.int16).view(fi.height, fi.width, fi.ncomp)
         return out[off:off + n].view(fi.height, fi.width, fi.ncomp)
+
+    def plane_views(self, out, i):
+        """upsample=False: the components of frame i as planes [ceil(H/suby), ceil(W/subx)] at their own resolution."""
+        assert not self.upsample
+        fi = self.info(i)
+        off, deep, planes = self.out_offset(i), fi.precision > 8, []
+        for c in range(fi.ncomp):
+            h, w = (fi.height + fi.suby[c] - 1) // fi.suby[c], (fi.width + fi.subx[c] - 1) // fi.subx[c]
+            n = h * w * (2 if deep else 1)
+            p = out[off:off + n]
+            planes.append(p.view(torch.int16).view(h, w) if deep else p.view(h, w))
+            off += n
+        return planes
 
     def close(self):
         if getattr(self, "handle", None):

@@ -1004,6 +1004,51 @@ int jpgo_reconstruct(const jpgo_info *info, int32_t *const planes[], uint8_t *ou
 
 int jpgo_reconstruct16(const jpgo_info *info, int32_t *const planes[], uint16_t *out) { return reconstruct(info, planes, NULL, out); }
 
+/* JPGTAG_DECODER_UPSAMPLE = false (control/bitmapctrl.cpp:273-293, BlockBitmapRequester::ReconstructUnsampled,
+ * control/blockbitmaprequester.cpp:1013-1074): one component per request at its own resolution, no upsampling, the identity
+ * "colour transformation" (the reference refuses anything else).  Component c is written as a plane of
+ * ceil(W/subx) x ceil(H/suby) native-endian 16-bit samples at out + (sum of the planes before it). */
+int jpgo_reconstruct_planes16(const jpgo_info *info, int32_t *const planes[], uint16_t *out) {
+    const int32_t dcshift = (int32_t)1 << (info->precision - 1);
+    const int64_t maxval = ((int64_t)1 << info->precision) - 1;
+    int c, bx, by, x, y;
+    for (c = 0; c < info->ncomp; c++) {
+        const int w = (info->width + info->subx[c] - 1) / info->subx[c], h = (info->height + info->suby[c] - 1) / info->suby[c];
+        if (!info->quant_defined[info->tq[c]]) return JPGO_ERR_MALFORMED_STREAM;
+        for (by = 0; by < (h + 7) / 8; by++)
+            for (bx = 0; bx < (w + 7) / 8; bx++) {
+                int32_t blk[64];
+                jpgo_idct_block(blk, planes[c] + 64 * ((size_t)by * info->bw[c] + bx), info->quant[info->tq[c]], dcshift);
+                for (y = 0; y < 8 && 8 * by + y < h; y++)
+                    for (x = 0; x < 8 && 8 * bx + x < w; x++) /* COLOR_TO_INT, tools/numerics.hpp:69 */
+                        out[(size_t)(8 * by + y) * w + 8 * bx + x] = (uint16_t)clampmax(((int64_t)blk[8 * y + x] + 8) >> 4, maxval);
+            }
+        out += (size_t)w * h;
+    }
+    return JPGO_OK;
+}
+
+int jpgo_decode_planes16(const uint8_t *data, size_t len, uint16_t *out, size_t cap_samples, jpgo_info *info_out) {
+    jpgo_info info;
+    int32_t *planes[JPGO_MAX_COMP] = {0, 0, 0, 0};
+    size_t need = 0;
+    int rc, c;
+    rc = jpgo_read_info(data, len, &info);
+    if (info_out) *info_out = info;
+    if (rc) return rc;
+    for (c = 0; c < info.ncomp; c++)
+        need += (size_t)((info.width + info.subx[c] - 1) / info.subx[c]) * ((info.height + info.suby[c] - 1) / info.suby[c]);
+    if (cap_samples < need) return JPGO_ERR_INVALID_PARAMETER;
+    for (c = 0; c < info.ncomp; c++) {
+        planes[c] = (int32_t *)malloc(sizeof(int32_t) * 64 * (size_t)info.bw[c] * info.bh[c]);
+        if (!planes[c]) rc = JPGO_ERR_OUT_OF_MEMORY;
+    }
+    if (!rc) rc = jpgo_decode_coefficients(data, len, &info, planes);
+    if (!rc) rc = jpgo_reconstruct_planes16(&info, planes, out);
+    for (c = 0; c < info.ncomp; c++) free(planes[c]);
+    return rc;
+}
+
 static int decode_any(const uint8_t *data, size_t len, uint8_t *out8, uint16_t *out16, size_t cap, jpgo_info *info_out);
 
 int jpgo_decode(const uint8_t *data, size_t len, uint8_t *out, size_t cap, jpgo_info *info_out) {

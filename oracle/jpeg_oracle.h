@@ -75,6 +75,9 @@ int jpgo_decode(const uint8_t *data, size_t len, uint8_t *out, size_t out_capaci
 /* The same into native-endian 16-bit samples (what a CTYP_UWORD client bitmap receives): 8- and 12-bit frames. */
 int jpgo_decode16(const uint8_t *data, size_t len, uint16_t *out, size_t capacity_in_samples, jpgo_info *info_out);
 int jpgo_reconstruct16(const jpgo_info *info, int32_t *const planes[], uint16_t *out);
+/* JPGTAG_DECODER_UPSAMPLE = false: the components as planes at their own resolution, 16-bit samples, no colour transformation */
+int jpgo_reconstruct_planes16(const jpgo_info *info, int32_t *const planes[], uint16_t *out);
+int jpgo_decode_planes16(const uint8_t *data, size_t len, uint16_t *out, size_t capacity_in_samples, jpgo_info *info_out);
 
 /* building blocks, exported so the tests can hit them directly */
 void jpgo_idct_block(int32_t *target, const int32_t *source, const uint16_t *delta_raster, int32_t dcoffset);

@@ -69,6 +69,25 @@ class Oracle:
         rc = self.lib.jpgo_decode16(data.ctypes.data, data.size, out.ctypes.data, out.size, ctypes.byref(s))
         return rc, (out if rc == 0 else None)
 
+    def decode_planes(self, data):
+        """-> (rc, [plane of component c: [ceil(H/suby), ceil(W/subx)] uint16] or None): JPGTAG_DECODER_UPSAMPLE = false"""
+        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        rc, s = self.info(data)
+        if rc != 0:
+            return rc, None
+        dims = [((s.height + s.suby[c] - 1) // s.suby[c], (s.width + s.subx[c] - 1) // s.subx[c]) for c in range(s.ncomp)]
+        out = np.zeros(sum(h * w for h, w in dims), dtype=np.uint16)
+        self.lib.jpgo_decode_planes16.restype = ctypes.c_int
+        self.lib.jpgo_decode_planes16.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(InfoStruct)]
+        rc = self.lib.jpgo_decode_planes16(data.ctypes.data, data.size, out.ctypes.data, out.size, ctypes.byref(s))
+        if rc != 0:
+            return rc, None
+        planes, at = [], 0
+        for h, w in dims:
+            planes.append(out[at:at + h * w].reshape(h, w))
+            at += h * w
+        return rc, planes
+
     def coefficients(self, data):
         """-> (rc, info, [per component int32 [bh,bw,8,8] QUANTIZED raster-order coefficients])"""
         data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))

@@ -282,3 +282,17 @@ def test_oracle_without_color_transform_matches_reference_cli(oracle, tmp_path, 
     ref = np.frombuffer(rest, dtype=np.uint8).reshape(h, w, 3)
     rc, px = oracle.decode_without_color_transform(open(src, "rb").read())
     assert rc == 0 and np.array_equal(px, ref)
+
+
+def test_oracle_planes_match_reference_without_upsampling(oracle):
+    """JPGTAG_DECODER_UPSAMPLE = false (bitmapctrl.cpp:273-293, blockbitmaprequester.cpp:1013-1074): every component as a plane
+    at its own resolution == what `oracle/_ref/jpeg -U -c` wrote (tests/golden/planes.npz, make_planes.py)."""
+    fx = np.load(os.path.join(GOLDEN, "planes.npz"))
+    names = sorted({k.rsplit("__", 1)[0] for k in fx.files})
+    assert len(names) >= 12
+    for name in names:
+        data = open(os.path.join(GOLDEN, name.replace("__", "/") + ".jpg"), "rb").read()
+        rc, planes = oracle.decode_planes(data)
+        assert rc == 0
+        for c, p in enumerate(planes):
+            assert np.array_equal(p, fx["%s__%d" % (name, c)]), (name, c)
