@@ -716,6 +716,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
         fr.cw = sx ? (fi.width + sx - 1) / sx : fi.width;  // (generic groups carry the factors per component: csx / csy)
         fr.ch = sy ? (fi.height + sy - 1) / sy : fi.height;
         fr.status_idx = (uint32_t)i;
+        fr.precision = fi.precision;
         g->frames.push_back(fr);
         g->max_bw0 = std::max(g->max_bw0, (fi.width + 7) / 8);
         g->max_bh0 = std::max(g->max_bh0, (fi.height + 7) / 8);

@@ -363,7 +363,18 @@ unstuff_long_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, con
 // =====================================================================================================
 // a1: Huffman decode, one restart interval per lane
 // =====================================================================================================
-constexpr int kQzBytes = 4 * kQzEntries * 8;  // four quantisation tables of (q, offset) pairs
+// B200JPG_A1_PACKED_PAIR: the (q, byte offset) pair of a zig-zag position as ONE word in shared memory, q << 8 | offset
+// (q < 2^24, parse.cpp; offsets <= 128): a 4-byte load per symbol is one L1 wavefront before bank conflicts, the 8-byte load of
+// the table's global form two. B200JPG_A1_SHFL_DST: the flush learns where the other lanes' blocks go by shuffle (a 32-bit
+// block number) instead of through the pad of the staging blocks (an 8-byte shared load per lane and step).
+#ifndef B200JPG_A1_PACKED_PAIR
+#define B200JPG_A1_PACKED_PAIR 1
+#endif
+#ifndef B200JPG_A1_SHFL_DST
+#define B200JPG_A1_SHFL_DST 1
+#endif
+constexpr int kQzPairBytes = B200JPG_A1_PACKED_PAIR ? 4 : 8;
+constexpr int kQzBytes = 4 * kQzEntries * kQzPairBytes;  // four quantisation tables of (q, offset) pairs
 constexpr int kBdescBytes = 16 * 16;          // indexed decoding: one 16-byte descriptor per block of an MCU (at most 10)
 
 // kIndexed: the work items are the SpecSegments that spec_sync_kernel cut out of restart-less scans (specsync.hpp) instead of
@@ -391,7 +402,11 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
     const uint32_t *g_lut = reinterpret_cast<const uint32_t *>(tables + kTableHeaderBytes);
     {
         const uint32_t *g_qz = reinterpret_cast<const uint32_t *>(tables + 32);
+#if B200JPG_A1_PACKED_PAIR
+        for (uint32_t i = threadIdx.x; i < 4 * kQzEntries; i += kThreads) sts_u32(s_qz + 4 * i, (g_qz[2 * i] << 8) | g_qz[2 * i + 1]);
+#else
         for (uint32_t i = threadIdx.x; i < kQzBytes / 4; i += kThreads) sts_u32(s_qz + 4 * i, g_qz[i]);
+#endif
         if (kLutShared)
             for (uint32_t i = threadIdx.x; i < p.lut_words; i += kThreads) sts_u32(s_lut + 4 * i, g_lut[i]);
 #pragma unroll
@@ -412,7 +427,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                     for (int x = 0; x < p.mw[c]; x++, b++) {
                         sts_u32(s_bdesc + 16 * b, s_lut + 4u * lut_off[p.dc_slot[c]]);
                         sts_u32(s_bdesc + 16 * b + 4, s_lut + 4u * lut_off[4 + p.ac_slot[c]]);
-                        sts_u32(s_bdesc + 16 * b + 8, s_qz + (uint32_t)(kQzEntries * 8) * p.q_slot[c]);
+                        sts_u32(s_bdesc + 16 * b + 8, s_qz + (uint32_t)(kQzEntries * kQzPairBytes) * p.q_slot[c]);
                         sts_u32(s_bdesc + 16 * b + 12, (uint32_t)c | ((uint32_t)x << 8) | ((uint32_t)y << 16));
                     }
         }
@@ -493,7 +508,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
         for (int c = 0; c < 4; c++) {
             dc_off[c] = (c < p.ns) ? s_lut + 4u * lut_off[p.dc_slot[c]] : 0;
             ac_off[c] = (c < p.ns) ? s_lut + 4u * lut_off[4 + p.ac_slot[c]] : 0;
-            q_addr[c] = s_qz + ((c < p.ns) ? (uint32_t)(kQzEntries * 8) * p.q_slot[c] : 0u);
+            q_addr[c] = s_qz + ((c < p.ns) ? (uint32_t)(kQzEntries * kQzPairBytes) * p.q_slot[c] : 0u);
         }
 
         // A symbol has fewer than 32 bits, so bp crosses at most one word boundary. The moves and the load of the new x2
@@ -562,12 +577,24 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
             // The dequantise + store of a coefficient is deferred by one symbol: its table pair (pq) is loaded
             // when the symbol is decoded and consumed after the NEXT symbol's table lookup has been issued, so
             // neither shared-memory latency is exposed. {0, 128} parks a "nothing pending" store in the pad slot.
-            uint2 pq = make_uint2(0u, 128u);
+            uint2 pq = make_uint2(B200JPG_A1_PACKED_PAIR ? 128u : 0u, 128u);
             int pd = 0;
+            auto load_pair = [&](uint32_t k_minus_1_scaled_addr) {
+#if B200JPG_A1_PACKED_PAIR
+                pq.x = lds_u32(k_minus_1_scaled_addr);  // unpacked where it is consumed (drain), not behind the load
+#else
+                asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(k_minus_1_scaled_addr));
+#endif
+            };
             auto drain = [&]() {
-                const int v = pd * (int)pq.x;
-                ovf |= mad_u32((uint32_t)pd, pq.x, 32768u);
-                sts_u16(s_stage + pq.y, v);
+#if B200JPG_A1_PACKED_PAIR
+                const uint32_t q = pq.x >> 8, off = pq.x & 0xffu;
+#else
+                const uint32_t q = pq.x, off = pq.y;
+#endif
+                const int v = pd * (int)q;
+                ovf |= mad_u32((uint32_t)pd, q, 32768u);
+                sts_u16(s_stage + off, v);
             };
             // ---- DC: sequentialscan.cpp:682-701
             if (has && decoding && (int)errbits >= 0) {
@@ -578,7 +605,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                     predc += value_of(e, hi);
                     advance(e);
                     pd = predc;
-                    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(q_tab));
+                    load_pair(q_tab);
                     k = 1;
                 }
             }
@@ -594,20 +621,33 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                     const uint32_t hi = __funnelshift_l(x1, x0, bp);
                     const uint32_t e = lookup(ac_tab, hi);
                     drain();
-                    errbits |= e | pq.x;
+                    errbits |= e;
                     pd = value_of(e, hi);  // 0 when the symbol carries no value bits
                     advance(e);
                     k += (int)mulhi_u32(mad_u32(e, 64u, 0u), 128u);  // bits 25:19
-                    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(pq.x), "=r"(pq.y) : "r"(mad_u32((uint32_t)k, 8u, q_tab - 8u)));
+                    load_pair(mad_u32((uint32_t)k, (uint32_t)kQzPairBytes, q_tab - (uint32_t)kQzPairBytes));
                 }
             }
-            errbits |= pq.x;
             drain();
             // ---- flush (zeros included) and clear the staging blocks, the whole warp together: every lane
             // publishes where its block goes (0 = nowhere) in the pad of its staging block, then each store
             // instruction moves four complete 128-byte blocks (eight lanes x 16 bytes per block) instead of one
             // 16-byte piece of 32 different blocks -- 4 instead of 32 L1 wavefronts per instruction
             {
+#if B200JPG_A1_SHFL_DST
+                // the block's number in the coefficient store + 1 (0 = nowhere): 32 bits are enough for 2^32 blocks of 128 bytes
+                const uint32_t mine = has ? (uint32_t)((d - coef) >> 6) + 1u : 0u;
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t a = s_flush + i * (4 * kStageStride);
+                    const uint32_t blk = __shfl_sync(kFull, mine, 4 * i + (int)((threadIdx.x & 31u) >> 3));
+                    const uint4 v = lds_v4(a);
+                    sts_v4_zero(a);
+                    if (blk) *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(coef) + ((uint64_t)(blk - 1u) << 7) + s_flush_sub) = v;
+                }
+                __syncwarp();
+#else
                 sts_u64(s_stage + 136, has ? (uint64_t)d : 0ull);
                 __syncwarp();
 #pragma unroll
@@ -619,6 +659,7 @@ entropy_decode_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, cons
                     if (dst) *reinterpret_cast<uint4 *>(dst + s_flush_sub) = v;
                 }
                 __syncwarp();
+#endif
             }
         };
 

@@ -300,10 +300,18 @@ pf_ac_kernel(PfLaunch L) {
                         const uint32_t bits = r.get(eob ? run : (sz == 1 ? 1u : 0u));  // the sign of a new coefficient / the length of an EOB run
                         const int sign = (sz == 1) ? (bits ? 1 : -1) : 0;             // 0: nothing to place (ZRL, ignored sizes)
                         const unsigned long long ahead = band & ~((1ull << k) - 1ull);  // the band from k on
-                        // the (run+1)-th zero position at or behind k inside the band
-                        unsigned long long zeros = ~H & ahead;
-                        for (uint32_t i = 0; i < run && zeros && !eob; i++) zeros &= zeros - 1ull;
-                        const int target = (zeros && !eob) ? __ffsll((long long)zeros) - 1 : se + 1;
+                        // the (run+1)-th zero position at or behind k inside the band: whole low word first (one population
+                        // count), then bit by bit in ONE 32-bit word -- two instructions per skipped position; the lanes of a
+                        // warp run this loop together, as long as the longest run among them
+                        const unsigned long long zeros = ~H & ahead;
+                        uint32_t zw = (uint32_t)zeros, zbase = 0u, zn = eob ? 0u : run;
+                        {
+                            const uint32_t c = (uint32_t)__popc(zw);
+                            if (zn >= c) zn -= c, zw = (uint32_t)(zeros >> 32), zbase = 32u;
+                        }
+#pragma unroll 2
+                        for (uint32_t i = 0; i < zn; i++) zw &= zw - 1u;
+                        const int target = (zw && !eob) ? (int)zbase + __ffs((int)zw) - 1 : se + 1;
                         const unsigned long long upto = (target >= 64) ? ~0ull : ((1ull << target) - 1ull);
                         if ((int)e < 0) {
                             bad = true;

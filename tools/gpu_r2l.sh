@@ -4,6 +4,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | grep -v "Warning\|os.fork\|^$\|Docs:" | tail -40 | tee $OUT/pytest_gpu.txt
 echo "== cfg4"; python tools/probe.py --workload cfg4 1024 256 2>&1 | grep frames: | tee -a $OUT/variants.txt
+echo "== a1 variants"; for v in "" a1old a1pk a1sh; do echo "variant [$v]"; if [ -n "$v" ]; then export B200JPG_LIB=$PWD/libjpeg_b200/build/libb200jpg_$v.so; else unset B200JPG_LIB; fi; python tools/probe.py 840 512 2>&1 | grep frames: ; done | tee $OUT/a1_variants.txt; unset B200JPG_LIB
 echo "== p2d chunks"; for c in 2 3 4; do timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --p2d-chunks $c 2>&1 | tail -1 > $OUT/bench_p2d$c.json; python - $OUT/bench_p2d$c.json <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read())

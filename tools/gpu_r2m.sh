@@ -1,0 +1,9 @@
+#!/bin/bash
+TAG=${1:-r2m}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | grep -v "Warning\|os.fork\|^$\|Docs:" | tail -60 | tee $OUT/pytest_gpu.txt
+echo "== cfg4"; python tools/probe.py --workload cfg4 1024 256 2>&1 | grep frames: | tee -a $OUT/variants.txt
+echo "== a1 variants"; for v in "" a1old a1pk a1sh; do echo "variant [$v]"; if [ -n "$v" ]; then export B200JPG_LIB=$PWD/libjpeg_b200/build/libb200jpg_$v.so; else unset B200JPG_LIB; fi; python tools/probe.py 840 512 2>&1 | grep frames: ; done | tee $OUT/a1_variants.txt; unset B200JPG_LIB
+echo "== pf_ac source profile"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pf_ac" -s 3 -c 1 -o $OUT/prof_pf -f python tools/probe.py --workload cfg4 256 > $OUT/ncu_pf.log 2>&1
+ls -la $OUT
