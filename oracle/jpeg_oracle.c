@@ -917,29 +917,22 @@ static int64_t clampmax(int64_t v, int64_t max) { return v < 0 ? 0 : (v > max ? 
  * reference writes for CTYP_UBYTE / CTYP_UWORD client bitmaps. Level shift, chroma offset and clamp scale with the
  * precision (1 << (precision - 1), (1 << precision) - 1); the arithmetic is the same (tables.cpp:1877-1891: the LONG
  * IDCT up to 12 bits).                                                                                  */
-static int reconstruct(const jpgo_info *info, int32_t *const planes[], uint8_t *out8, uint16_t *out16) {
+/* IDCT of every stored block into a sample plane (what PullQData/DefineRegion or the direct IDCT produce), with the edge
+ * columns the upsampler replicates (upsamplerbase.cpp:322-323) */
+static int build_sample_planes(const jpgo_info *info, int32_t *const planes[], splane sp[JPGO_MAX_COMP]) {
     const int32_t dcshift = (int32_t)1 << (info->precision - 1);
-    const int64_t maxval = ((int64_t)1 << info->precision) - 1;
-    splane sp[JPGO_MAX_COMP];
-    int c, rc = JPGO_OK, bx, by, i;
+    int c, bx, by, i;
     int W = info->width, H = info->height, nc = info->ncomp;
-    int any_sub = 0;
-    memset(sp, 0, sizeof(sp));
-    for (c = 0; c < nc; c++) {
+    memset(sp, 0, sizeof(splane) * JPGO_MAX_COMP);
+    for (c = 0; c < nc; c++)
         if (!info->quant_defined[info->tq[c]]) return JPGO_ERR_MALFORMED_STREAM;
-        if (info->subx[c] > 1 || info->suby[c] > 1) any_sub = 1;
-    }
-    /* IDCT every stored block into a sample plane (what PullQData/DefineRegion or the direct IDCT produce) */
     for (c = 0; c < nc; c++) {
         splane *p = &sp[c];
         p->w = (W + info->subx[c] - 1) / info->subx[c];
         p->h = (H + info->suby[c] - 1) / info->suby[c];
         p->pw = 8 * info->bw[c] + 2 + 8;
         p->s = (int32_t *)calloc((size_t)p->pw * 8 * info->bh[c], sizeof(int32_t));
-        if (!p->s) {
-            rc = JPGO_ERR_OUT_OF_MEMORY;
-            goto done;
-        }
+        if (!p->s) return JPGO_ERR_OUT_OF_MEMORY;
         for (by = 0; by < info->bh[c]; by++) {
             for (bx = 0; bx < info->bw[c]; bx++) {
                 int32_t blk[64];
@@ -956,19 +949,35 @@ static int reconstruct(const jpgo_info *info, int32_t *const planes[], uint8_t *
             line[p->w] = line[p->w - 1];
         }
     }
-    (void)any_sub;
+    return JPGO_OK;
+}
+
+/* the 8x8 output block (bx, by) of every component, upsampled to the frame's resolution, 4 fractional bits */
+static void block_samples(const jpgo_info *info, const splane sp[JPGO_MAX_COMP], int bx, int by, int32_t buf[JPGO_MAX_COMP][64]) {
+    int c, x, y;
+    for (c = 0; c < info->ncomp; c++) {
+        if (info->subx[c] > 1 || info->suby[c] > 1) {
+            upsample_block(&sp[c], info->subx[c], info->suby[c], 8 * bx, 8 * by, buf[c]);
+        } else {
+            for (y = 0; y < 8; y++)
+                for (x = 0; x < 8; x++) buf[c][8 * y + x] = sp[c].s[(size_t)(8 * by + y) * sp[c].pw + 1 + 8 * bx + x];
+        }
+    }
+}
+
+static int reconstruct(const jpgo_info *info, int32_t *const planes[], uint8_t *out8, uint16_t *out16) {
+    const int32_t dcshift = (int32_t)1 << (info->precision - 1);
+    const int64_t maxval = ((int64_t)1 << info->precision) - 1;
+    splane sp[JPGO_MAX_COMP];
+    int c, rc, bx, by;
+    int W = info->width, H = info->height, nc = info->ncomp;
+    rc = build_sample_planes(info, planes, sp);
+    if (rc) goto done;
     for (by = 0; by < (H + 7) / 8; by++) {
         for (bx = 0; bx < (W + 7) / 8; bx++) {
             int32_t buf[JPGO_MAX_COMP][64];
             int xmax = (8 * bx + 7 < W) ? 7 : (W - 1) & 7, ymax = (8 * by + 7 < H) ? 7 : (H - 1) & 7, x, y;
-            for (c = 0; c < nc; c++) {
-                if (info->subx[c] > 1 || info->suby[c] > 1) {
-                    upsample_block(&sp[c], info->subx[c], info->suby[c], 8 * bx, 8 * by, buf[c]);
-                } else {
-                    for (y = 0; y < 8; y++)
-                        for (x = 0; x < 8; x++) buf[c][8 * y + x] = sp[c].s[(size_t)(8 * by + y) * sp[c].pw + 1 + 8 * bx + x];
-                }
-            }
+            block_samples(info, sp, bx, by, buf);
             /* YCbCrTrafo<UBYTE,count,ClampFlag,trafo,Zero>::YCbCr2RGB, colortrafo/ycbcrtrafo.cpp:679-1008 */
             for (y = 0; y <= ymax; y++) {
                 for (x = 0; x <= xmax; x++) {
@@ -1059,6 +1068,220 @@ int jpgo_decode16(const uint8_t *data, size_t len, uint16_t *out, size_t cap_sam
     return decode_any(data, len, NULL, out, cap_samples, info_out);
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* JPEG XT (ISO/IEC 18477) residual layer, SURVEY 8f3 -- the integer profile the reference encoder writes with
+ * `-r -q <base> -Q <extension>` for 8-bit images: a second, ordinary DCT codestream in a RESI box of the APP11 markers,
+ * merged pixel by pixel with the base image (YCbCrTrafo::YCbCr2RGB, colortrafo/ycbcrtrafo.cpp:747-880) under the control of
+ * the merging specification box SPEC.  Boxes: boxes/box.cpp:95-205 (APP11: 'JP', enumerator, sequence number, LBox, TBox,
+ * payload; pieces of one box are concatenated), boxes/superbox.cpp (SPEC holds sub-boxes LBox TBox payload),
+ * boxes/outputconversionbox.cpp:92-127, boxes/colortrafobox.cpp:55-78.  Everything outside that profile -- tone mapping
+ * curves, free-form matrices, refinement scans, the lossless / DCT-bypass residuals, alpha, float output -- is reported as
+ * NOT_IMPLEMENTED, never decoded as if it were absent.                                                             */
+typedef struct {
+    int have_spec, have_resi, unsupported;
+    uint8_t *spec, *resi;
+    size_t spec_len, resi_len, spec_size, resi_size; /* collected so far / LBox - 8 */
+    int spec_en, resi_en;
+    int ocon, ltrf, rtrf, ctrf; /* first byte of the sub-box payload, -1 = absent */
+} xt_boxes;
+
+static void xt_free(xt_boxes *x) {
+    free(x->spec);
+    free(x->resi);
+    x->spec = x->resi = NULL;
+}
+
+static uint32_t rd32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+#define XT_ID(a, b, c, d) (((uint32_t)(a) << 24) | ((uint32_t)(b) << 16) | ((uint32_t)(c) << 8) | (uint32_t)(d))
+
+/* collects the SPEC and RESI boxes of the APP11 markers in front of the first scan */
+static int xt_collect(const uint8_t *d, size_t n, xt_boxes *x) {
+    size_t pos = 2;
+    memset(x, 0, sizeof(*x));
+    x->ocon = x->ltrf = x->rtrf = x->ctrf = -1;
+    if (n < 4 || d[0] != 0xff || d[1] != 0xd8) return JPGO_OK;
+    while (pos + 3 < n && d[pos] == 0xff) {
+        int m = d[pos + 1];
+        size_t len;
+        if (m == 0xff) {
+            pos++;
+            continue;
+        }
+        if (m == 0xda || m == 0xd9) break;
+        if (m >= 0xd0 && m <= 0xd7) {
+            pos += 2;
+            continue;
+        }
+        len = ((size_t)d[pos + 2] << 8) | d[pos + 3];
+        if (len < 2 || pos + 2 + len > n) break;
+        if (m == 0xeb && len >= 2 + 2 + 2 + 4 + 4 + 4 && d[pos + 4] == 'J' && d[pos + 5] == 'P') {
+            const uint8_t *b = d + pos + 6;
+            const int en = (b[0] << 8) | b[1];
+            const uint32_t lbox = rd32(b + 6), tbox = rd32(b + 10);
+            const uint8_t *payload = b + 14;
+            const size_t plen = len - 2 - 2 - 2 - 4 - 4 - 4;
+            uint8_t **buf = NULL;
+            size_t *have = NULL, *size = NULL;
+            int *ben = NULL, *flag = NULL;
+            if (tbox == XT_ID('S', 'P', 'E', 'C')) buf = &x->spec, have = &x->spec_len, size = &x->spec_size, ben = &x->spec_en, flag = &x->have_spec;
+            else if (tbox == XT_ID('R', 'E', 'S', 'I')) buf = &x->resi, have = &x->resi_len, size = &x->resi_size, ben = &x->resi_en, flag = &x->have_resi;
+            else if (tbox != XT_ID('f', 't', 'y', 'p') && tbox != XT_ID('L', 'C', 'H', 'K')) x->unsupported = 1; /* refinement, alpha, curves, matrices ... */
+            if (buf) {
+                if (lbox < 8) { /* 1 = XLBox (boxes beyond 4 GB), 0 = to the end of the file */
+                    x->unsupported = 1;
+                } else if (!*flag) {
+                    *flag = 1;
+                    *ben = en;
+                    *size = lbox - 8;
+                    *buf = (uint8_t *)malloc(*size ? *size : 1);
+                    if (!*buf) return JPGO_ERR_OUT_OF_MEMORY;
+                } else if (*ben != en || *size != lbox - 8) {
+                    x->unsupported = 1; /* a second box of this type */
+                    buf = NULL;
+                }
+                if (buf && *buf) {
+                    if (*have + plen > *size) return JPGO_ERR_MALFORMED_STREAM; /* box.cpp:186-188 */
+                    memcpy(*buf + *have, payload, plen);
+                    *have += plen;
+                }
+            }
+        }
+        pos += 2 + len;
+    }
+    if ((x->have_spec && x->spec_len != x->spec_size) || (x->have_resi && x->resi_len != x->resi_size)) return JPGO_ERR_MALFORMED_STREAM;
+    if (x->have_spec) { /* the sub-boxes of the merging specification */
+        size_t p = 0;
+        while (p + 8 <= x->spec_len) {
+            const uint32_t lbox = rd32(x->spec + p), tbox = rd32(x->spec + p + 4);
+            if (lbox < 8 || p + lbox > x->spec_len) return JPGO_ERR_MALFORMED_STREAM;
+            if (tbox == XT_ID('O', 'C', 'O', 'N') && lbox == 11) x->ocon = x->spec[p + 8] | (x->spec[p + 9] << 8) | (x->spec[p + 10] << 16);
+            else if (tbox == XT_ID('L', 'T', 'R', 'F') && lbox == 9) x->ltrf = x->spec[p + 8];
+            else if (tbox == XT_ID('R', 'T', 'R', 'F') && lbox == 9) x->rtrf = x->spec[p + 8];
+            else if (tbox == XT_ID('C', 'T', 'R', 'F') && lbox == 9) x->ctrf = x->spec[p + 8];
+            else x->unsupported = 1;
+            p += lbox;
+        }
+        if (p != x->spec_len) return JPGO_ERR_MALFORMED_STREAM;
+    }
+    return JPGO_OK;
+}
+
+/* Base image + residual image -> pixels.  Parameters of the 8-bit integer profile (colortransformerfactory.cpp:686-705,
+ * 300-352, 425-520): max = rmax = outmax = 255, DC shifts 128; L tables the identity over 0..255 (a lookup clamps its index),
+ * the C transformation the identity, Q tables the identity over the pre-shifted range 0..4095, R2 tables
+ * floor(i / 16 + 0.5) over 0..4095 (ParametricToneMappingBox::ScaledTableOf, boxes/parametrictonemappingbox.cpp:387-426),
+ * clamping output (OCON flag 0x02).                                                                              */
+static int xt_merge(const jpgo_info *bi, int32_t *const bplanes[], const jpgo_info *ri, int32_t *const rplanes[], int l_ycbcr, int r_ycbcr,
+                    uint8_t *out8, uint16_t *out16) {
+    splane bs[JPGO_MAX_COMP], rs[JPGO_MAX_COMP];
+    int c, rc, bx, by;
+    const int W = bi->width, H = bi->height, nc = bi->ncomp;
+    memset(rs, 0, sizeof(rs));
+    rc = build_sample_planes(bi, bplanes, bs);
+    if (!rc) rc = build_sample_planes(ri, rplanes, rs);
+    if (rc) goto done;
+    for (by = 0; by < (H + 7) / 8; by++) {
+        for (bx = 0; bx < (W + 7) / 8; bx++) {
+            int32_t b[JPGO_MAX_COMP][64], r[JPGO_MAX_COMP][64];
+            int xmax = (8 * bx + 7 < W) ? 7 : (W - 1) & 7, ymax = (8 * by + 7 < H) ? 7 : (H - 1) & 7, x, y;
+            block_samples(bi, bs, bx, by, b);
+            block_samples(ri, rs, bx, by, r);
+            for (y = 0; y <= ymax; y++) {
+                for (x = 0; x <= xmax; x++) {
+                    const size_t at = ((size_t)(8 * by + y) * W + (8 * bx + x)) * nc;
+                    const int i = 8 * y + x;
+                    int64_t res[3] = {128, 128, 128}, v[3] = {0, 0, 0};
+                    /* the residual: Q table first (clamped index), then the R transformation, then the R2 table
+                     * (ycbcrtrafo.cpp:757-828) */
+                    if (nc == 3 && r_ycbcr) {
+                        const int64_t yv = clampmax(r[0][i], 4095), cb = clampmax(r[1][i], 4095) - (128 << 4), cr = clampmax(r[2][i], 4095) - (128 << 4);
+                        res[0] = (yv * 8192 + cr * 11485 + 4096) >> 13; /* FIX_COLOR_TO_INTCOLOR, tools/numerics.hpp:67 */
+                        res[1] = (yv * 8192 - cb * 2819 - cr * 5850 + 4096) >> 13;
+                        res[2] = (yv * 8192 + cb * 14516 + 4096) >> 13;
+                    } else {
+                        for (c = 0; c < nc; c++) res[c] = clampmax(r[c][i], 4095);
+                    }
+                    for (c = 0; c < nc; c++) res[c] = (clampmax(res[c], 4095) + 8) >> 4;
+                    /* the base image: L transformation, then the L table (:834-862) */
+                    if (nc == 3 && l_ycbcr) {
+                        const int64_t yv = b[0][i], cb = (int64_t)b[1][i] - (128 << 4), cr = (int64_t)b[2][i] - (128 << 4);
+                        v[0] = (yv * 8192 + cr * 11485 + 65536) >> 17;
+                        v[1] = (yv * 8192 - cb * 2819 - cr * 5850 + 65536) >> 17;
+                        v[2] = (yv * 8192 + cb * 14516 + 65536) >> 17;
+                    } else {
+                        for (c = 0; c < nc; c++) v[c] = ((int64_t)b[c][i] + 8) >> 4;
+                    }
+                    for (c = 0; c < nc; c++) {
+                        /* L table (index clamped), C = identity (FIX_TO_INT(v << 13) = v), merge, clamp (:863-878, :935-947) */
+                        const int64_t o = clampmax(clampmax(v[c], 255) + res[c] - 128, 255);
+                        if (out16) out16[at + c] = (uint16_t)o;
+                        else out8[at + c] = (uint8_t)o;
+                    }
+                }
+            }
+        }
+    }
+done:
+    for (c = 0; c < nc; c++) {
+        free(bs[c].s);
+        free(rs[c].s);
+    }
+    return rc;
+}
+
+static int decode_plain(const uint8_t *data, size_t len, const jpgo_info *info, int32_t *planes[JPGO_MAX_COMP]) {
+    int c, rc = JPGO_OK;
+    for (c = 0; c < info->ncomp; c++) {
+        planes[c] = (int32_t *)malloc(sizeof(int32_t) * 64 * (size_t)info->bw[c] * info->bh[c]);
+        if (!planes[c]) rc = JPGO_ERR_OUT_OF_MEMORY;
+    }
+    if (!rc) rc = jpgo_decode_coefficients(data, len, info, planes);
+    return rc;
+}
+
+static int decode_xt(const uint8_t *data, size_t len, const jpgo_info *info, const xt_boxes *x, uint8_t *out8, uint16_t *out16) {
+    jpgo_info rinfo;
+    int32_t *bp[JPGO_MAX_COMP] = {0, 0, 0, 0}, *rp[JPGO_MAX_COMP] = {0, 0, 0, 0};
+    int rc, c, l_ycbcr, r_ycbcr;
+    const int nc = info->ncomp;
+    /* what this restatement covers of MergingSpecBox / ColorTransformerFactory::BuildColorTransformer */
+    if (x->unsupported || !x->have_resi || info->precision != 8 || (nc != 1 && nc != 3)) return JPGO_ERR_NOT_IMPLEMENTED;
+    if (x->ocon != 0x02) return JPGO_ERR_NOT_IMPLEMENTED;                      /* clamping only: no lossless, float, lookup, extra bits */
+    if (x->ctrf != -1 && x->ctrf != (1 << 4)) return JPGO_ERR_NOT_IMPLEMENTED; /* C: identity */
+    if (nc == 1) {
+        if (x->ltrf != -1) return JPGO_ERR_MALFORMED_STREAM; /* tables.cpp:2001-2003 */
+        if (x->rtrf != -1 && x->rtrf != (1 << 4)) return JPGO_ERR_NOT_IMPLEMENTED;
+        l_ycbcr = r_ycbcr = 0;
+    } else {
+        if (x->ltrf == -1) l_ycbcr = info->ycbcr; /* the JPEG default, tables.cpp:2023-2030 */
+        else if (x->ltrf == (2 << 4)) l_ycbcr = 1;
+        else if (x->ltrf == (1 << 4)) l_ycbcr = 0;
+        else return JPGO_ERR_NOT_IMPLEMENTED;
+        if (x->rtrf == -1 || x->rtrf == (2 << 4)) r_ycbcr = 1; /* tables.cpp:2052-2060 */
+        else if (x->rtrf == (1 << 4)) r_ycbcr = 0;
+        else return JPGO_ERR_NOT_IMPLEMENTED; /* RCT (lossless), free form */
+    }
+    rc = jpgo_read_info(x->resi, x->resi_len, &rinfo); /* residual scan types 0xffb1.. are not ordinary frames: NOT_IMPLEMENTED */
+    if (rc) return rc;
+    if (rinfo.width != info->width || rinfo.height != info->height || rinfo.ncomp != nc || rinfo.precision != 8) return JPGO_ERR_NOT_IMPLEMENTED;
+    rc = decode_plain(data, len, info, bp);
+    if (!rc) rc = decode_plain(x->resi, x->resi_len, &rinfo, rp);
+    if (!rc) rc = xt_merge(info, bp, &rinfo, rp, l_ycbcr, r_ycbcr, out8, out16);
+    for (c = 0; c < nc; c++) {
+        free(bp[c]);
+        free(rp[c]);
+    }
+    return rc;
+}
+
+/* 1: the stream carries a merging specification (the caller decides what to do about it) */
+int jpgo_has_xt_layer(const uint8_t *data, size_t len) {
+    xt_boxes x;
+    int rc = xt_collect(data, len, &x), yes = (rc != JPGO_OK) || x.have_spec || x.have_resi || x.unsupported;
+    xt_free(&x);
+    return yes;
+}
+
 static int decode_any(const uint8_t *data, size_t len, uint8_t *out8, uint16_t *out16, size_t cap, jpgo_info *info_out) {
     jpgo_info info;
     int32_t *planes[JPGO_MAX_COMP] = {0, 0, 0, 0};
@@ -1067,6 +1290,17 @@ static int decode_any(const uint8_t *data, size_t len, uint8_t *out8, uint16_t *
     if (info_out) *info_out = info;
     if (rc) return rc;
     if (cap < (size_t)info.width * info.height * info.ncomp) return JPGO_ERR_INVALID_PARAMETER;
+    {
+        xt_boxes x;
+        rc = xt_collect(data, len, &x);
+        if (!rc && (x.have_spec || x.have_resi || x.unsupported)) {
+            rc = (out8 && info.precision != 8) ? JPGO_ERR_INVALID_PARAMETER : decode_xt(data, len, &info, &x, out8, out16);
+            xt_free(&x);
+            return rc;
+        }
+        xt_free(&x);
+        if (rc) return rc;
+    }
     for (c = 0; c < info.ncomp; c++) {
         planes[c] = (int32_t *)malloc(sizeof(int32_t) * 64 * (size_t)info.bw[c] * info.bh[c]);
         if (!planes[c]) rc = JPGO_ERR_OUT_OF_MEMORY;

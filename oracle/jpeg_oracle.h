@@ -74,6 +74,9 @@ int jpgo_reconstruct(const jpgo_info *info, int32_t *const planes[], uint8_t *ou
 int jpgo_decode(const uint8_t *data, size_t len, uint8_t *out, size_t out_capacity, jpgo_info *info_out);
 /* The same into native-endian 16-bit samples (what a CTYP_UWORD client bitmap receives): 8- and 12-bit frames. */
 int jpgo_decode16(const uint8_t *data, size_t len, uint16_t *out, size_t capacity_in_samples, jpgo_info *info_out);
+/* 1 when the stream carries JPEG XT boxes beyond the file type (merging specification, residual codestream, ...): jpgo_decode then
+ * merges the residual layer (the 8-bit integer profile) or reports NOT_IMPLEMENTED */
+int jpgo_has_xt_layer(const uint8_t *data, size_t len);
 int jpgo_reconstruct16(const jpgo_info *info, int32_t *const planes[], uint16_t *out);
 /* JPGTAG_DECODER_UPSAMPLE = false: the components as planes at their own resolution, 16-bit samples, no colour transformation */
 int jpgo_reconstruct_planes16(const jpgo_info *info, int32_t *const planes[], uint16_t *out);
