@@ -159,6 +159,8 @@ struct b200jpg_batch {
     unsigned flags = 0;  // B200JPG_FLAG_*
     std::vector<ParsedFrame> frames;
     std::vector<int> parse_status;
+    int n_user = 0;                       // frames of the caller; [n_user, n) are residual codestreams of JPEG XT frames
+    std::vector<int> xt_child, xt_parent;  // [n_user] index of a frame's residual frame or -1; [n] the reverse
     std::vector<uint64_t> out_off, out_bytes;
     uint64_t out_total = 0;
     std::vector<TableSet> table_sets;
@@ -209,12 +211,34 @@ struct b200jpg_batch {
 
 extern "C" {
 
+// JPEG XT: the residual codestream of `base` (its RESI box) as a frame of its own; what of it the path covers
+static int parse_residual(const ParsedFrame &base, ParsedFrame &rf, std::string &err, bool device_index) {
+    int rst;
+    try {
+        rst = parse_codestream(base.xt.resi.data(), base.xt.resi.size(), rf, err, device_index);
+    } catch (...) {
+        rst = B200JPG_ERR_MALFORMED_STREAM;
+        err = "could not be parsed";
+    }
+    const b200jpg_frame_info &bi = base.info, &ri = rf.info;
+    if (rst == 0 && (rf.xt.present || ri.width != bi.width || ri.height != bi.height || ri.ncomp != bi.ncomp || ri.precision != 8)) {
+        rst = B200JPG_ERR_NOT_IMPLEMENTED;
+        err = "outside the JPEG XT profile of the B200 path (8-bit DCT residual of the frame's size)";
+    }
+    if (rst != 0) err = "residual codestream: " + err;
+    return rst;
+}
+
 int b200jpg_parse(const uint8_t *data, size_t len, b200jpg_frame_info *info) {
     ParsedFrame pf;
     std::string err;
     int rc;
     try {
         rc = parse_codestream(data, len, pf, err);
+        if (rc == 0 && pf.xt.present) {
+            ParsedFrame rf;
+            rc = parse_residual(pf, rf, err, false);
+        }
     } catch (const std::bad_alloc &) {
         rc = B200JPG_ERR_OUT_OF_MEMORY;
         err = "out of memory while parsing the codestream";
@@ -357,11 +381,13 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     std::unique_ptr<b200jpg_batch, void (*)(b200jpg_batch *)> bp(new b200jpg_batch(), b200jpg_batch_destroy);
     b200jpg_batch *b = bp.get();
     b->ctx = ctx;
-    b->n = n;
+    b->n = b->n_user = n;
     b->flags = flags;
     b->frames.resize(n);
     b->parse_status.assign(n, 0);
     std::vector<std::string> errs(n);
+    std::vector<const uint8_t *> fp(frames, frames + n);  // codestreams of the batch: the caller's, then the residual
+    std::vector<size_t> fl(lens, lens + n);               // codestreams of JPEG XT frames (internal frames behind them)
 
     // ---- parse (host threads). Interleaved scans with restart markers get their restart index on the device (8f1);
     // B200JPG_HOST_INDEX=1 keeps the memchr pass over every entropy coded byte on the host for all of them.
@@ -374,7 +400,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
             pool.emplace_back([&, t]() {
                 for (int i = (int)t; i < n; i += (int)nt) {
                     try {  // an exception must not leave the thread (std::terminate): it fails this frame only
-                        b->parse_status[i] = parse_codestream(frames[i], lens[i], b->frames[i], errs[i], device_index);
+                        b->parse_status[i] = parse_codestream(fp[i], fl[i], b->frames[i], errs[i], device_index);
                     } catch (const std::bad_alloc &) {
                         b->parse_status[i] = B200JPG_ERR_OUT_OF_MEMORY;
                         errs[i] = "out of memory while parsing the codestream";
@@ -386,6 +412,39 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
             });
         for (auto &th : pool) th.join();
     }
+    // ---- JPEG XT: the residual codestream of a frame is one more frame of the batch -- same entropy kernels, same
+    // IDCT -- that owns no output; the parent's reconstruction merges the two (generic_reconstruct_kernel)
+    const int n_user = n;
+    b->xt_child.assign(n_user, -1);
+    for (int i = 0; i < n_user; i++) {
+        if (b->parse_status[i] != 0 || !b->frames[i].xt.present) continue;
+        if (flags & (B200JPG_FLAG_NO_COLOR_TRANSFORM | B200JPG_FLAG_NO_UPSAMPLE)) {
+            b->parse_status[i] = B200JPG_ERR_NOT_IMPLEMENTED;
+            errs[i] = "JPEG XT frames are only reconstructed with upsampling and colour transformation";
+            continue;
+        }
+        ParsedFrame rf;
+        std::string rerr;
+        const int rst = parse_residual(b->frames[i], rf, rerr, device_index);
+        if (rst != 0) {
+            b->parse_status[i] = rst;
+            errs[i] = rerr;
+            continue;
+        }
+        b->xt_child[i] = (int)b->frames.size();
+        fp.push_back(b->frames[i].xt.resi.data());  // (the vectors' buffers stay where they are when b->frames grows: moved, not copied)
+        fl.push_back(b->frames[i].xt.resi.size());
+        b->frames.push_back(std::move(rf));
+        b->parse_status.push_back(0);
+        errs.emplace_back();
+    }
+    for (int i = 0; i < n_user; i++)  // push_back may have moved the frames: take the addresses again
+        if (b->xt_child[i] >= 0) fp[b->xt_child[i]] = b->frames[i].xt.resi.data();
+    n = (int)b->frames.size();
+    b->n = n;
+    b->xt_parent.assign(n, -1);
+    for (int i = 0; i < n_user; i++)
+        if (b->xt_child[i] >= 0) b->xt_parent[b->xt_child[i]] = i;
     std::vector<std::vector<TableSet>> frame_tables(n);
     for (int i = 0; i < n; i++) {
         ParsedFrame &pf = b->frames[i];
@@ -426,15 +485,23 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
                 }
             }
         }
+        if (st != 0 && b->xt_parent[i] >= 0) {  // a residual codestream the kernels do not cover fails its frame
+            const int par = b->xt_parent[i];
+            if (b->parse_status[par] == 0) b->parse_status[par] = st, errs[par] = "residual codestream: " + errs[i];
+            b->xt_child[par] = -1;
+            if (!tolerate_bad) return ctx->fail(st, "frame " + std::to_string(par) + ": " + errs[par]);
+        }
         if (st != 0 && !tolerate_bad) return ctx->fail(st, "frame " + std::to_string(i) + ": " + errs[i]);
     }
+    for (int i = 0; i < n; i++)  // ... and a frame that failed takes its residual codestream with it
+        if (b->xt_parent[i] >= 0 && b->parse_status[b->xt_parent[i]] != 0 && b->parse_status[i] == 0) b->parse_status[i] = b->parse_status[b->xt_parent[i]];
 
     // ---- layout of the packed input buffer: [codestreams][table blobs][per class: scans, intervals][per group: frames]
     std::vector<uint64_t> byte_off(n, 0);
     uint64_t cur = 0;
     for (int i = 0; i < n; i++) {
         byte_off[i] = cur;
-        if (b->parse_status[i] == 0) cur = align_up(cur + lens[i] + 32, 16);
+        if (b->parse_status[i] == 0) cur = align_up(cur + fl[i] + 32, 16);
     }
     b->bytes_region = align_up(cur + 64, 256);
 
@@ -449,7 +516,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
         for (int c = 0; c < fi.ncomp; c++) {
             coef_base[i][c] = coef_cur;
             coef_cur += (uint64_t)fi.blocks_w[c] * fi.blocks_h[c] * 64;
-            if (c > 0 || frame_is_generic(fi, flags)) {  // generic reconstruction keeps a sample plane of every component
+            if (c > 0 || frame_is_generic(fi, flags) || b->xt_parent[i] >= 0 || (i < n_user && b->xt_child[i] >= 0)) {  // generic reconstruction keeps a sample plane of every component
                 sample_base[i][c] = sample_cur;
                 sample_cur += (uint64_t)fi.blocks_w[c] * fi.blocks_h[c] * 64;
             }
@@ -461,7 +528,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
             for (int c = 0; c < fi.ncomp; c++)
                 samples += (uint64_t)((fi.width + fi.subx[c] - 1) / fi.subx[c]) * ((fi.height + fi.suby[c] - 1) / fi.suby[c]);
         }
-        b->out_bytes[i] = samples * (fi.precision > 8 ? 2u : 1u);
+        b->out_bytes[i] = (b->xt_parent[i] >= 0) ? 0 : samples * (fi.precision > 8 ? 2u : 1u);  // a residual codestream has no pixels of its own
         out_cur = align_up(out_cur + b->out_bytes[i], 256);
         b->ecs_bytes += fi.ecs_bytes;
         b->stored_blocks += fi.stored_blocks;
@@ -683,7 +750,8 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     for (int i = 0; i < n; i++) {
         if (b->parse_status[i] != 0) continue;
         const b200jpg_frame_info &fi = b->frames[i].info;
-        const bool generic = frame_is_generic(fi, flags);
+        const int xt_res = (i < n_user) ? b->xt_child[i] : -1;  // JPEG XT: this frame's residual frame
+        const bool generic = frame_is_generic(fi, flags) || xt_res >= 0 || b->xt_parent[i] >= 0;
         uint32_t sx = fi.ncomp > 1 ? fi.subx[1] : 1, sy = fi.ncomp > 1 ? fi.suby[1] : 1;
         if (generic) sx = sy = 0;  // one group per component count: the generic kernels read the factors per frame
         ReconGroup *g = nullptr;
@@ -709,6 +777,17 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
         fr.out_base = b->out_off[i];
         fr.width = fi.width;
         fr.height = fi.height;
+        if (b->xt_parent[i] >= 0) fr.width = fr.height = 0;  // a residual codestream: planes only, its frame's reconstruction reads them
+        if (xt_res >= 0) {
+            const b200jpg_frame_info &ri = b->frames[xt_res].info;
+            fr.xt = 1u | (b->frames[i].xt.l_ycbcr ? 2u : 0u) | (b->frames[i].xt.r_ycbcr ? 4u : 0u);
+            for (int c = 0; c < ri.ncomp; c++) {
+                fr.res_sample_base[c] = sample_base[xt_res][c];
+                fr.res_bw[c] = ri.blocks_w[c];
+                fr.res_csx[c] = ri.subx[c];
+                fr.res_csy[c] = ri.suby[c];
+            }
+        }
         fr.ncomp = fi.ncomp;
         fr.ycbcr = (flags & B200JPG_FLAG_NO_COLOR_TRANSFORM) ? 0 : fi.ycbcr;  // JPGTAG_MATRIX_LTRAFO = ..._NONE (rectanglerequest.cpp:150-152)
         fr.subx = sx;
@@ -775,12 +854,12 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
                 for (int i = (int)t; i < n; i += (int)nt) {
                     if (b->parse_status[i] != 0) continue;
                     uint8_t *dst = b->h_input + byte_off[i];
-                    memcpy(dst, frames[i], lens[i]);
+                    memcpy(dst, fp[i], fl[i]);
                     // sentinel: a damaged segment must still meet a marker before it leaves its codestream
-                    uint64_t pad_end = align_up(byte_off[i] + lens[i] + 32, 16);
-                    memset(dst + lens[i], 0, pad_end - (byte_off[i] + lens[i]));
-                    dst[lens[i]] = 0xff;
-                    dst[lens[i] + 1] = 0xd9;
+                    uint64_t pad_end = align_up(byte_off[i] + fl[i] + 32, 16);
+                    memset(dst + fl[i], 0, pad_end - (byte_off[i] + fl[i]));
+                    dst[fl[i]] = 0xff;
+                    dst[fl[i] + 1] = 0xd9;
                 }
             });
         for (auto &th : pool) th.join();
@@ -789,7 +868,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     {
         uint64_t last_end = 0;
         for (int i = 0; i < n; i++)
-            if (b->parse_status[i] == 0) last_end = align_up(byte_off[i] + lens[i] + 32, 16);
+            if (b->parse_status[i] == 0) last_end = align_up(byte_off[i] + fl[i] + 32, 16);
         memset(b->h_input + last_end, 0, b->bytes_region - last_end);
         b->h_input[last_end] = 0xff;
         b->h_input[last_end + 1] = 0xd9;
@@ -839,16 +918,16 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
 }
 
 int b200jpg_batch_frame_info(const b200jpg_batch *b, int i, b200jpg_frame_info *info) {
-    if (!b || i < 0 || i >= b->n || !info) return B200JPG_ERR_INVALID_PARAMETER;
+    if (!b || i < 0 || i >= b->n_user || !info) return B200JPG_ERR_INVALID_PARAMETER;
     *info = b->frames[i].info;
     return b->parse_status[i];
 }
 
-uint64_t b200jpg_batch_out_offset(const b200jpg_batch *b, int i) { return (b && i >= 0 && i < b->n) ? b->out_off[i] : 0; }
+uint64_t b200jpg_batch_out_offset(const b200jpg_batch *b, int i) { return (b && i >= 0 && i < b->n_user) ? b->out_off[i] : 0; }
 uint64_t b200jpg_batch_out_bytes(const b200jpg_batch *b, int i) {
     if (!b) return 0;
     if (i < 0) return b->out_total;
-    return i < b->n ? b->out_bytes[i] : 0;
+    return i < b->n_user ? b->out_bytes[i] : 0;
 }
 uint64_t b200jpg_batch_ecs_bytes(const b200jpg_batch *b) { return b ? b->ecs_bytes : 0; }
 uint64_t b200jpg_batch_stored_blocks(const b200jpg_batch *b) { return b ? b->stored_blocks : 0; }
@@ -1116,7 +1195,7 @@ int b200jpg_batch_reconstruct(b200jpg_batch *b, uint8_t *out_dev, void *stream) 
 }
 
 int b200jpg_batch_frame_status(b200jpg_batch *b, int i) {
-    if (!b || i < 0 || i >= b->n) return B200JPG_ERR_INVALID_PARAMETER;
+    if (!b || i < 0 || i >= b->n_user) return B200JPG_ERR_INVALID_PARAMETER;
     if (b->parse_status[i] != 0) return b->parse_status[i];
     if (!b->status_fetched) {
         cudaSetDevice(b->ctx->device);
@@ -1124,6 +1203,7 @@ int b200jpg_batch_frame_status(b200jpg_batch *b, int i) {
         if (e != cudaSuccess) return b->ctx->fail_cuda(e, "status download");
         b->status_fetched = true;
     }
+    if (b->h_status[i] == 0 && b->xt_child[i] >= 0) return -(int)b->h_status[b->xt_child[i]];  // JPEG XT: the residual codestream's errors are the frame's
     return -(int)b->h_status[i];
 }
 

@@ -61,9 +61,22 @@ struct ScanInfo {  // one SOS + its entropy coded segment
     bool quant_defined[4] = {false, false, false, false};
 };
 
+// JPEG XT (ISO/IEC 18477) residual layer of a frame, SURVEY 8f3: what the APP11 boxes in front of the first scan say
+// (boxes/box.cpp:95-205, boxes/mergingspecbox.cpp, boxes/outputconversionbox.cpp:92-127, boxes/colortrafobox.cpp:55-78).
+// Covered: the 8-bit integer profile the reference encoder writes with `-r -q -Q` -- an ordinary DCT codestream in the RESI
+// box, merged per pixel (YCbCrTrafo::YCbCr2RGB colortrafo/ycbcrtrafo.cpp:747-880) with default (identity) tables, clamped
+// output.  Anything else that is present makes the frame NOT_IMPLEMENTED; it is never decoded as if the boxes were absent.
+struct XtLayer {
+    bool present = false;      // a merging specification and a residual codestream were found and are covered
+    bool l_ycbcr = false;      // base image: YCbCr -> RGB before the merge
+    bool r_ycbcr = false;      // residual image: YCbCr -> RGB before the merge
+    std::vector<uint8_t> resi;  // the residual codestream, reassembled from its APP11 pieces
+};
+
 struct ParsedFrame {
     b200jpg_frame_info info{};
     std::vector<ScanInfo> scans;
+    XtLayer xt;
 };
 
 // Returns 0 or a negative reference error code; `err` receives a message. With `device_index` a scan that carries all
@@ -199,6 +212,12 @@ struct FrameRecon {       // per frame, for the reconstruction kernels
     uint32_t cw, ch;                    // true subsampled size ceil(W/subx), ceil(H/suby)
     uint32_t status_idx, precision;     // sample precision of the frame (8, or 12: generic reconstruction, 16-bit samples out)
     uint8_t csx[4], csy[4];             // generic reconstruction: subsampling factors of every component (1..4)
+    // JPEG XT (generic reconstruction): bit 0 = merge with the residual image whose int32 sample planes start at
+    // res_sample_base (block grid width res_bw, factors res_csx / res_csy), bit 1 / 2 = YCbCr -> RGB on the base / residual side
+    uint32_t xt, xt_pad;
+    uint64_t res_sample_base[4];
+    uint32_t res_bw[4];
+    uint8_t res_csx[4], res_csy[4];
 };
 
 // kernel launchers (huffman_sm100.cu, recon_sm100.cu). All asynchronous on `stream`.

@@ -134,6 +134,14 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
     bool have_sof = false, adobe_none = false;
     int hmax = 0, vmax = 0;
     size_t pos = 2;
+    // JPEG XT boxes (APP11 'JP'): the merging specification and the residual codestream, collected piece by piece
+    struct XtBox {
+        bool seen = false;
+        int en = 0;
+        uint64_t size = 0;
+        std::vector<uint8_t> bytes;
+    } xt_spec, xt_resi;
+    bool xt_other = false;  // boxes this path does not cover (refinement data, alpha, curves, matrices, ...)
 
     for (;;) {
         // Behind the first scan the reference only warns about a missing EOI or bytes that are no marker and still delivers
@@ -203,6 +211,34 @@ int parse_codestream(const uint8_t *data, size_t len, ParsedFrame &out, std::str
             break;
         case 0xee:  // APP14: Adobe colour information (tables.cpp:2023-2025)
             if (rem >= 12 && memcmp(s, "Adobe", 5) == 0) adobe_none = (s[11] == 0);
+            break;
+        case 0xeb:  // APP11: a piece of a JPEG XT box -- 'JP', enumerator, sequence number, LBox, TBox, payload (boxes/box.cpp:95-205)
+            if (out.scans.empty() && rem >= 2 + 2 + 4 + 4 + 4 && s[0] == 'J' && s[1] == 'P') {
+                const int en = (s[2] << 8) | s[3];
+                const uint32_t lbox = ((uint32_t)s[8] << 24) | ((uint32_t)s[9] << 16) | ((uint32_t)s[10] << 8) | s[11];
+                const uint32_t tbox = ((uint32_t)s[12] << 24) | ((uint32_t)s[13] << 16) | ((uint32_t)s[14] << 8) | s[15];
+                const uint8_t *payload = s + 16;
+                const size_t plen = (size_t)rem - 16;
+                XtBox *box = nullptr;
+                if (tbox == 0x53504543u) box = &xt_spec;       // 'SPEC'
+                else if (tbox == 0x52455349u) box = &xt_resi;  // 'RESI'
+                else if (tbox != 0x66747970u && tbox != 0x4c43484bu) xt_other = true;  // not 'ftyp', not 'LCHK' (checksum: not verified)
+                if (box) {
+                    if (lbox < 8) {  // 1 = XLBox, 0 = up to the end of the file
+                        xt_other = true;
+                    } else if (!box->seen) {
+                        box->seen = true, box->en = en, box->size = lbox - 8;
+                    } else if (box->en != en || box->size != lbox - 8) {
+                        xt_other = true;  // a second box of the type
+                        box = nullptr;
+                    }
+                    if (box && lbox >= 8) {
+                        if (box->bytes.size() + plen > box->size)
+                            FAIL(B200JPG_ERR_MALFORMED_STREAM, "more data in the application marker than indicated by the box contained within");
+                        box->bytes.insert(box->bytes.end(), payload, payload + plen);
+                    }
+                }
+            }
             break;
         case 0xc0:
         case 0xc1:
@@ -414,6 +450,52 @@ parsed:
     if (out.scans.empty()) FAIL(B200JPG_ERR_MALFORMED_STREAM, "codestream contains no scan");
     fi.nscans = (uint32_t)out.scans.size();
     fi.ycbcr = (fi.ncomp == 3 && !adobe_none) ? 1 : 0;  // tables.cpp:2023-2030
+    if (xt_spec.seen || xt_resi.seen || xt_other) {
+        // ---- JPEG XT: what of MergingSpecBox / ColorTransformerFactory::BuildColorTransformer (colortransformerfactory.cpp:
+        // 217-300) this path covers
+        int ocon = -1, ltrf = -1, rtrf = -1, ctrf = -1;
+        if ((xt_spec.seen && xt_spec.bytes.size() != xt_spec.size) || (xt_resi.seen && xt_resi.bytes.size() != xt_resi.size))
+            FAIL(B200JPG_ERR_MALFORMED_STREAM, "JPEG XT box is incomplete");
+        const std::vector<uint8_t> &sp = xt_spec.bytes;
+        size_t p = 0;
+        while (p + 8 <= sp.size()) {  // the sub-boxes of the merging specification: LBox, TBox, payload
+            const uint32_t lbox = ((uint32_t)sp[p] << 24) | ((uint32_t)sp[p + 1] << 16) | ((uint32_t)sp[p + 2] << 8) | sp[p + 3];
+            const uint32_t tbox = ((uint32_t)sp[p + 4] << 24) | ((uint32_t)sp[p + 5] << 16) | ((uint32_t)sp[p + 6] << 8) | sp[p + 7];
+            if (lbox < 8 || p + lbox > sp.size()) FAIL(B200JPG_ERR_MALFORMED_STREAM, "merging specification box is corrupt");
+            if (tbox == 0x4f434f4eu && lbox == 11) ocon = sp[p + 8] | (sp[p + 9] << 8) | (sp[p + 10] << 16);  // 'OCON'
+            else if (tbox == 0x4c545246u && lbox == 9) ltrf = sp[p + 8];                                       // 'LTRF'
+            else if (tbox == 0x52545246u && lbox == 9) rtrf = sp[p + 8];                                       // 'RTRF'
+            else if (tbox == 0x43545246u && lbox == 9) ctrf = sp[p + 8];                                       // 'CTRF'
+            else xt_other = true;
+            p += lbox;
+        }
+        if (p != sp.size()) FAIL(B200JPG_ERR_MALFORMED_STREAM, "merging specification box is corrupt");
+        const char *nimpl = "JPEG XT profile outside the B200 path (covered: 8-bit base + 8-bit DCT residual, default tables, clamped output)";
+        if (xt_other || !xt_spec.seen || fi.precision != 8 || (fi.ncomp != 1 && fi.ncomp != 3)) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, nimpl);
+        if (ocon != 0x02) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, nimpl);                  // clamping only: no lossless, float, lookup, extra range bits
+        if (ctrf != -1 && ctrf != (1 << 4)) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, nimpl);  // C transformation: the identity
+        if (fi.ncomp == 1) {
+            if (ltrf != -1) FAIL(B200JPG_ERR_MALFORMED_STREAM, "Base transformation box exists even though the number of components is one");  // tables.cpp:2001-2003
+            if (rtrf != -1 && rtrf != (1 << 4)) FAIL(B200JPG_ERR_NOT_IMPLEMENTED, nimpl);
+        } else {
+            if (ltrf == -1) out.xt.l_ycbcr = fi.ycbcr != 0;  // the JPEG default, tables.cpp:2023-2030
+            else if (ltrf == (2 << 4)) out.xt.l_ycbcr = true;
+            else if (ltrf == (1 << 4)) out.xt.l_ycbcr = false;
+            else FAIL(B200JPG_ERR_NOT_IMPLEMENTED, nimpl);
+            if (rtrf == -1 || rtrf == (2 << 4)) out.xt.r_ycbcr = true;  // tables.cpp:2052-2060
+            else if (rtrf == (1 << 4)) out.xt.r_ycbcr = false;
+            else FAIL(B200JPG_ERR_NOT_IMPLEMENTED, nimpl);  // RCT (lossless), free form
+        }
+        if (xt_resi.seen) {
+            out.xt.present = true;
+            out.xt.resi = std::move(xt_resi.bytes);
+        } else {
+            // a merging specification without a residual codestream (the reference encoder writes one into every grey file):
+            // Extended | ClampFlag -- L transformation, identity tables, clamp (ycbcrtrafo.cpp:834-878 with rr = the DC shift):
+            // the plain decode with the L transformation the box names
+            if (fi.ncomp == 3) fi.ycbcr = out.xt.l_ycbcr ? 1 : 0;
+        }
+    }
     return B200JPG_OK;
 }
 

@@ -1174,6 +1174,45 @@ generic_reconstruct_kernel(const FrameRecon *__restrict__ frames, const int32_t 
         generic_upsample_block(samples + f.sample_base[c], 8u * f.bw[c], w, h, sx, sy, X, Y, buf[c]);
     }
     const int xmax = (X + 7 < (int)W) ? 7 : (int)((W - 1) & 7), ymax = (Y + 7 < (int)H) ? 7 : (int)((H - 1) & 7);
+    if (f.xt & 1u) {
+        // ---- JPEG XT: base image + residual image, YCbCrTrafo<..., Residual | Extended | ClampFlag, ...>::YCbCr2RGB
+        // colortrafo/ycbcrtrafo.cpp:747-880 with the tables of the 8-bit integer profile (colortransformerfactory.cpp:300-352,
+        // 425-520; ParametricToneMappingBox::ScaledTableOf boxes/parametrictonemappingbox.cpp:387-426): Q = identity over the
+        // pre-shifted range 0..4095, R2 = floor(i / 16 + 0.5), L = identity over 0..255, C = identity; a lookup clamps its index
+        int rbuf[3][64];
+        for (uint32_t c = 0; c < nc; c++) {
+            const int sx = f.res_csx[c], sy = f.res_csy[c];
+            const int w = (int)((W + sx - 1) / sx), h = (int)((H + sy - 1) / sy);
+            generic_upsample_block(samples + f.res_sample_base[c], 8u * f.res_bw[c], w, h, sx, sy, X, Y, rbuf[c]);
+        }
+        auto clamp_to = [](long long v, long long mx) { return v < 0 ? 0ll : (v > mx ? mx : v); };
+        for (int y = 0; y <= ymax; y++) {
+            uint8_t *o = out + f.out_base + ((uint64_t)(Y + y) * W + (uint64_t)X) * nc;
+            for (int x = 0; x <= xmax; x++) {
+                const int i = 8 * y + x;
+                long long res[3] = {128, 128, 128}, v[3] = {0, 0, 0};
+                if (nc == 3 && (f.xt & 4u)) {  // the residual: Q table, R transformation (FIX_COLOR_TO_INTCOLOR), R2 table
+                    const long long yv = clamp_to(rbuf[0][i], 4095), cb = clamp_to(rbuf[1][i], 4095) - (128 << 4), cr = clamp_to(rbuf[2][i], 4095) - (128 << 4);
+                    res[0] = (yv * 8192 + cr * 11485 + 4096) >> 13;
+                    res[1] = (yv * 8192 - cb * 2819 - cr * 5850 + 4096) >> 13;
+                    res[2] = (yv * 8192 + cb * 14516 + 4096) >> 13;
+                } else {
+                    for (uint32_t c = 0; c < nc; c++) res[c] = clamp_to(rbuf[c][i], 4095);
+                }
+                if (nc == 3 && (f.xt & 2u)) {  // the base image: L transformation (FIX_COLOR_TO_INT), L table
+                    const long long yv = buf[0][i], cb = (long long)buf[1][i] - (128 << 4), cr = (long long)buf[2][i] - (128 << 4);
+                    v[0] = (yv * 8192 + cr * 11485 + 65536) >> 17;
+                    v[1] = (yv * 8192 - cb * 2819 - cr * 5850 + 65536) >> 17;
+                    v[2] = (yv * 8192 + cb * 14516 + 65536) >> 17;
+                } else {
+                    for (uint32_t c = 0; c < nc; c++) v[c] = ((long long)buf[c][i] + 8) >> 4;
+                }
+                for (uint32_t c = 0; c < nc; c++)  // merge and clamp (:863-878, :935-947)
+                    o[nc * x + c] = (uint8_t)clamp_to(clamp_to(v[c], 255) + ((clamp_to(res[c], 4095) + 8) >> 4) - 128, 255);
+            }
+        }
+        return;
+    }
     // level shift, chroma offset and clamp scale with the precision; 12-bit frames leave as native-endian 16-bit samples
     // (what the reference writes into CTYP_UWORD bitmaps)
     const bool deep = f.precision > 8;

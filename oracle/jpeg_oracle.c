@@ -1245,7 +1245,7 @@ static int decode_xt(const uint8_t *data, size_t len, const jpgo_info *info, con
     int rc, c, l_ycbcr, r_ycbcr;
     const int nc = info->ncomp;
     /* what this restatement covers of MergingSpecBox / ColorTransformerFactory::BuildColorTransformer */
-    if (x->unsupported || !x->have_resi || info->precision != 8 || (nc != 1 && nc != 3)) return JPGO_ERR_NOT_IMPLEMENTED;
+    if (x->unsupported || !x->have_spec || info->precision != 8 || (nc != 1 && nc != 3)) return JPGO_ERR_NOT_IMPLEMENTED;
     if (x->ocon != 0x02) return JPGO_ERR_NOT_IMPLEMENTED;                      /* clamping only: no lossless, float, lookup, extra bits */
     if (x->ctrf != -1 && x->ctrf != (1 << 4)) return JPGO_ERR_NOT_IMPLEMENTED; /* C: identity */
     if (nc == 1) {
@@ -1260,6 +1260,16 @@ static int decode_xt(const uint8_t *data, size_t len, const jpgo_info *info, con
         if (x->rtrf == -1 || x->rtrf == (2 << 4)) r_ycbcr = 1; /* tables.cpp:2052-2060 */
         else if (x->rtrf == (1 << 4)) r_ycbcr = 0;
         else return JPGO_ERR_NOT_IMPLEMENTED; /* RCT (lossless), free form */
+    }
+    if (!x->have_resi) {
+        /* a merging specification without a residual codestream (the reference encoder writes one into every grey file):
+         * Extended | ClampFlag, rr = the DC shift: the plain decode with the L transformation the box names (:834-878) */
+        jpgo_info plain = *info;
+        if (nc == 3) plain.ycbcr = l_ycbcr;
+        rc = decode_plain(data, len, &plain, bp);
+        if (!rc) rc = reconstruct(&plain, bp, out8, out16);
+        for (c = 0; c < nc; c++) free(bp[c]);
+        return rc;
     }
     rc = jpgo_read_info(x->resi, x->resi_len, &rinfo); /* residual scan types 0xffb1.. are not ordinary frames: NOT_IMPLEMENTED */
     if (rc) return rc;
@@ -1277,7 +1287,7 @@ static int decode_xt(const uint8_t *data, size_t len, const jpgo_info *info, con
 /* 1: the stream carries a merging specification (the caller decides what to do about it) */
 int jpgo_has_xt_layer(const uint8_t *data, size_t len) {
     xt_boxes x;
-    int rc = xt_collect(data, len, &x), yes = (rc != JPGO_OK) || x.have_spec || x.have_resi || x.unsupported;
+    int rc = xt_collect(data, len, &x), yes = (rc != JPGO_OK) || x.have_resi || x.unsupported;
     xt_free(&x);
     return yes;
 }

@@ -185,3 +185,29 @@ def test_restartless_synchronisation_rounds_on_the_host(built, w, h, sub, q):
     assert rc == 0
     assert nseg.value == (max(1, (data.size * 8) // 4096 // 1) and nseg.value)  # at least one work item
     assert 1 <= rounds.value <= 12, "self-synchronisation should take a handful of rounds, not one per subsequence"
+
+
+def test_parser_reads_the_xt_boxes(built):
+    """streams with a JPEG XT residual layer parse (the covered profile) or are refused by name -- they are never
+    taken for plain JPEG (host only, no device)."""
+    import glob
+    from libjpeg_b200 import NativeError
+    xt = os.path.join(GOLDEN, "xt")
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(xt, "*.jpg")))
+    assert len(names) >= 11
+    for name in names:
+        data = open(os.path.join(xt, name + ".jpg"), "rb").read()
+        if name.endswith("__nimpl"):
+            with pytest.raises(NativeError) as e:
+                built.parse(data)
+            assert e.value.code == -1034, name
+        else:
+            fi = built.parse(data)
+            assert fi.precision == 8 and fi.ncomp in (1, 3)
+    # a residual box cut short is malformed, not ignored
+    data = bytearray(open(os.path.join(xt, [n for n in names if not n.endswith("__nimpl")][0] + ".jpg"), "rb").read())
+    at = data.find(b"RESI") - 4
+    data[at:at + 4] = (int.from_bytes(data[at:at + 4], "big") + 100).to_bytes(4, "big")
+    with pytest.raises(NativeError) as e:
+        built.parse(bytes(data))
+    assert e.value.code == -1038
