@@ -1096,7 +1096,22 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
             if (grp.ac[c].empty()) continue;
             PfLaunch L{};
             L.n_scans = (int)grp.ac[c].size();
-            for (size_t s = 0; s < grp.ac[c].size(); s++) fill_scan(L.scan[s], b->classes[(size_t)grp.ac[c][s]]);
+            for (size_t s = 0; s < grp.ac[c].size(); s++) {
+                fill_scan(L.scan[s], b->classes[(size_t)grp.ac[c][s]]);
+                // scans that decode with the same Huffman tables (the usual case: one AC table per component, or the
+                // standard tables) share one copy in shared memory; the quantiser pairs differ with the point transform
+                L.scan[s].lut_share = (int)s;
+                const std::vector<uint8_t> &mine = b->table_sets[(size_t)b->classes[(size_t)grp.ac[c][s]].table_set].blob;
+                for (size_t t = 0; t < s; t++) {
+                    const std::vector<uint8_t> &other = b->table_sets[(size_t)b->classes[(size_t)grp.ac[c][t]].table_set].blob;
+                    if (L.scan[t].lut_share == (int)t && L.scan[t].lut_words == L.scan[s].lut_words && L.scan[t].ac_slot == L.scan[s].ac_slot &&
+                        mine.size() == other.size() && memcmp(mine.data() + 16, other.data() + 16, 16) == 0 &&
+                        memcmp(mine.data() + kTableHeaderBytes, other.data() + kTableHeaderBytes, (size_t)L.scan[s].lut_words * 4) == 0) {
+                        L.scan[s].lut_share = (int)t;
+                        break;
+                    }
+                }
+            }
             fill_geometry(L, b->classes[(size_t)grp.ac[c][0]]);
             L.dc_quant[0] = b->pf_dc_quant[4 * gi + (size_t)c];
             int rc = launch_pf_ac(L, stream);

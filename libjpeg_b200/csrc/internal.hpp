@@ -184,6 +184,7 @@ struct PfScan {                    // one scan of the group, uniform over the la
     int ss, se, ah, al;
     int dc_slot[4], ac_slot, q_slot;
     uint32_t lut_words;
+    int lut_share;                 // AC kernel: the first scan of the launch whose decoder tables are the same words (itself if none)
 };
 struct PfLaunch {
     int n_scans;

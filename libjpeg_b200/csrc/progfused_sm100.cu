@@ -35,19 +35,23 @@ constexpr uint32_t kErrMalformed = 1038u;
 // end it hands out zero bits like the reference's reader in front of a marker (io/bitstream.cpp:96-105).
 struct Bits {
     const uint32_t *w;
-    uint32_t nwords, bp, xw, x0, x1, x2;
+    uint32_t nwords, bp, x0, x1, x2;
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return i < nwords ? __ldg(w + i) : 0u; }
-    __device__ __forceinline__ void open(const uint8_t *p, uint32_t len_bytes) {
+    __device__ __forceinline__ void open(const uint8_t *p, uint32_t len_bytes) { resume(p, (len_bytes + 3u) / 4u, 0u); }
+    // picks the stream up again at bit `at` (the AC kernel parks the readers of the scans it is not in in shared memory)
+    __device__ __forceinline__ void resume(const uint8_t *p, uint32_t words, uint32_t at) {
         w = reinterpret_cast<const uint32_t *>(p);
-        nwords = (len_bytes + 3u) / 4u;
-        bp = 0, xw = 0;
-        x0 = word(0), x1 = word(1), x2 = word(2);
+        nwords = words;
+        bp = at;
+        const uint32_t wi = at >> 5;
+        x0 = word(wi), x1 = word(wi + 1u), x2 = word(wi + 2u);
     }
     __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(x1, x0, bp); }
     __device__ __forceinline__ void skip(uint32_t n) {  // n < 32
+        const uint32_t was = bp >> 5;
         bp += n;
         const uint32_t wi = bp >> 5;
-        if (wi != xw) x0 = x1, x1 = x2, x2 = word(wi + 2u), xw = wi;
+        if (wi != was) x0 = x1, x1 = x2, x2 = word(wi + 2u);
     }
     __device__ __forceinline__ uint32_t get(uint32_t n) {  // n <= 24
         const uint32_t v = n ? (window() >> (32u - n)) : 0u;
@@ -160,8 +164,12 @@ pf_dc_kernel(PfLaunch L) {
 // =====================================================================================================
 // AC scans of one component: one restart interval (of that component's block grid) per lane
 // =====================================================================================================
-// shared memory: [staging: kPfThreads * kStage][per scan: qz pairs (kQzEntries * 8 bytes) + LUT]
-__global__ void __launch_bounds__(kPfThreads)
+// shared memory: [staging: kPfThreads * kStage][parked readers: n_scans * 3 * kPfThreads words][meta: 2 words per scan]
+//                [per scan: qz pairs (128 words)][one LUT per DISTINCT AC table (PfScan::lut_share)]
+// Registers are what limits the warps per SM here, and a lane is inside ONE scan at a time: the bit readers of the other
+// scans are parked in shared memory as (first word, words, bit position) and re-opened -- three L2 loads -- when the walk
+// over the scans of a block comes to them.
+__global__ void __launch_bounds__(kPfThreads, 3)
 pf_ac_kernel(PfLaunch L) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem);
@@ -169,50 +177,59 @@ pf_ac_kernel(PfLaunch L) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t s_flush_sub = (lane & 7u) << 4;
     const uint32_t s_flush = s_base + ((threadIdx.x & ~31u) + (lane >> 3)) * kStage + s_flush_sub;
+    uint32_t *s_park = reinterpret_cast<uint32_t *>(smem + kPfThreads * kStage) + threadIdx.x;  // [scan][4][thread]: first word, words, bit position, blocks left of an EOB run
+    uint32_t *s_meta = reinterpret_cast<uint32_t *>(smem + kPfThreads * kStage) + (uint32_t)L.n_scans * 4u * kPfThreads;
     // per scan: the (q, byte offset) pairs of the component's quantiser (already << Al, parse.cpp build_table_set) and the AC table
-    uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem + kPfThreads * kStage);
-    uint32_t tab_off[kPfMaxScans], lut_at[kPfMaxScans];  // word offsets inside s_tab: pairs, LUT of the scan's AC table
+    uint32_t *s_tab = s_meta + 2 * kPfMaxScans;
     {
         uint32_t at = 0;
+        uint32_t lut_of[kPfMaxScans];
 #pragma unroll
         for (int s = 0; s < kPfMaxScans; s++) {
-            tab_off[s] = lut_at[s] = 0;
+            lut_of[s] = 0;
             if (s < L.n_scans) {
                 const PfScan &sc = L.scan[s];
                 const uint32_t *g_qz = reinterpret_cast<const uint32_t *>(sc.tables + 32) + (uint32_t)(kQzEntries * 2) * sc.q_slot;
                 const uint32_t *g_lut = reinterpret_cast<const uint32_t *>(sc.tables + kTableHeaderBytes);
                 const uint16_t *lut_off = reinterpret_cast<const uint16_t *>(sc.tables + 16);
-                tab_off[s] = at;
                 for (uint32_t i = threadIdx.x; i < 128u; i += kPfThreads) s_tab[at + i] = g_qz[i];  // the pairs of k = 0..63
+                if (threadIdx.x == 0) s_meta[2 * s] = at;
                 at += 128u;
-                lut_at[s] = at + lut_off[4 + sc.ac_slot];
-                for (uint32_t i = threadIdx.x; i < sc.lut_words; i += kPfThreads) s_tab[at + i] = g_lut[i];
-                at += sc.lut_words;
+                if (sc.lut_share == s) {  // the first scan with this table holds the copy
+                    lut_of[s] = at;
+                    for (uint32_t i = threadIdx.x; i < sc.lut_words; i += kPfThreads) s_tab[at + i] = g_lut[i];
+                    at += sc.lut_words;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < kPfMaxScans; t++)
+                        if (t == sc.lut_share) lut_of[s] = lut_of[t];
+                }
+                if (threadIdx.x == 0) s_meta[2 * s + 1] = lut_of[s] + lut_off[4 + sc.ac_slot];
             }
         }
 #pragma unroll
         for (int i = 0; i < 9; i++) sts_zero16(s_stage + 16 * i);
     }
-    __syncthreads();
     const uint64_t total = (uint64_t)L.n_frames * L.intervals;
     const uint64_t g = (uint64_t)blockIdx.x * kPfThreads + threadIdx.x;
     const bool lane_valid = g < total;
     const uint64_t gg = lane_valid ? g : 0;
     const uint32_t j = (uint32_t)(gg / L.intervals), iv = (uint32_t)(gg % L.intervals);
     const ClassScan &cs = L.frames[j];
-    Bits b[kPfMaxScans];
-    bool present[kPfMaxScans];
-    uint32_t skip[kPfMaxScans];
+    uint32_t present = 0;  // bit s: this lane's interval of scan s is in the stream
 #pragma unroll
     for (int s = 0; s < kPfMaxScans; s++) {
-        present[s] = false;
-        skip[s] = 0;
         if (s < L.n_scans) {
             const uint32_t raw = lane_valid ? L.scan[s].interval_len[gg] : kIntervalLenAbsent;
-            present[s] = !(raw & kIntervalLenAbsent);
-            b[s].open(L.clean + L.scan[s].clean_off[gg], present[s] ? (raw & kIntervalLenMask) : 0u);
+            const bool there = !(raw & kIntervalLenAbsent);
+            present |= there ? (1u << s) : 0u;
+            s_park[(4 * s + 0) * kPfThreads] = (uint32_t)(L.scan[s].clean_off[gg] >> 2);  // first word (16-byte aligned offsets)
+            s_park[(4 * s + 1) * kPfThreads] = there ? ((raw & kIntervalLenMask) + 3u) / 4u : 0u;
+            s_park[(4 * s + 2) * kPfThreads] = 0u;
+            s_park[(4 * s + 3) * kPfThreads] = 0u;
         }
     }
+    __syncthreads();
     const uint32_t mcu0 = iv * L.dri;
     uint32_t nblk = 0;
     if (lane_valid) nblk = (L.total_mcus - mcu0 < L.dri) ? (L.total_mcus - mcu0) : L.dri;
@@ -232,17 +249,23 @@ pf_ac_kernel(PfLaunch L) {
         for (int s = 0; s < kPfMaxScans; s++) {
             if (s >= L.n_scans) break;
             const PfScan &sc = L.scan[s];
-            const uint32_t *lut = s_tab + lut_at[s];
-            const uint32_t qz = s_base + kPfThreads * kStage + 4u * tab_off[s];  // shared-space address of the pairs
+            const uint32_t *lut = s_tab + s_meta[2 * s + 1];
+            const uint32_t qz = (uint32_t)__cvta_generic_to_shared(s_tab + s_meta[2 * s]);  // shared-space address of the pairs
             const int ss = sc.ss, se = sc.se;
-            Bits &r = b[s];
             // an interval the stream does not contain leaves the block as the other scans make it
-            bool active = has && !bad && present[s];
+            bool active = has && !bad && ((present >> s) & 1u);
+            // the lane reads bits of this scan in this block unless it sits in an EOB run of a first pass
+            uint32_t run_left = s_park[(4 * s + 3) * kPfThreads];  // blocks of an EOB run still to come (this one included)
+            const uint32_t run_was = run_left;
+            const bool reads = active && !(sc.ah == 0 && run_left > 0);
+            Bits r;
+            r.resume(L.clean, 0u, 0u);
+            if (reads) r.resume(L.clean + 4ull * s_park[(4 * s + 0) * kPfThreads], s_park[(4 * s + 1) * kPfThreads], s_park[(4 * s + 2) * kPfThreads]);
             int k = ss;
             if (sc.ah == 0) {
                 // ---- first pass of the band: sequentialscan.cpp:704-772
-                if (active && skip[s] > 0) {
-                    skip[s]--;
+                if (active && run_left > 0) {
+                    run_left--;
                     active = false;
                 }
                 while (__any_sync(0xffffffffu, active)) {
@@ -268,7 +291,7 @@ pf_ac_kernel(PfLaunch L) {
                                 H |= 1ull << kk;
                             }
                             k = kk + 1;
-                            if (eob) skip[s] = ((1u << run) | bits) - 1u;  // EOBn; this block is part of the run
+                            if (eob) run_left = ((1u << run) | bits) - 1u;  // EOBn; this block is part of the run
                             if (eob || k > se) active = false;
                         }
                     }
@@ -281,7 +304,7 @@ pf_ac_kernel(PfLaunch L) {
                 // one per voted iteration as well, before the lane decodes its next symbol.
                 const unsigned long long band = ((se >= 63) ? ~0ull : ((1ull << (se + 1)) - 1ull)) & ~((1ull << ss) - 1ull);
                 unsigned long long pending = 0ull;
-                bool tail = active && skip[s] > 0;  // inside an EOB run: the whole band only takes correction bits
+                bool tail = active && run_left > 0;  // inside an EOB run: the whole band only takes correction bits
                 if (tail) {
                     pending = H & band;
                     active = false;
@@ -325,7 +348,7 @@ pf_ac_kernel(PfLaunch L) {
                                 H |= 1ull << target;
                             }
                             if (eob) {  // the rest of this block (and of the next skip-1 blocks) only takes correction bits
-                                skip[s] = (1u << run) | bits;
+                                run_left = (1u << run) | bits;
                                 tail = true;
                             }
                             k = target + 1;
@@ -345,8 +368,10 @@ pf_ac_kernel(PfLaunch L) {
                         }
                     }
                 }
-                if (tail && !bad) skip[s]--;
+                if (tail && !bad) run_left--;
             }
+            if (reads) s_park[(4 * s + 2) * kPfThreads] = r.bp;
+            if (run_left != run_was) s_park[(4 * s + 3) * kPfThreads] = run_left;
         }
         if (has && !bad) {
             // ---- the DC value from the side plane, dequantised
@@ -396,8 +421,8 @@ int launch_pf_dc(const PfLaunch &L, void *stream) {
 int launch_pf_ac(const PfLaunch &L, void *stream) {
     const uint64_t total = (uint64_t)L.n_frames * L.intervals;
     if (total == 0 || L.n_scans == 0) return 0;
-    size_t smem = (size_t)kPfThreads * kStage;
-    for (int s = 0; s < L.n_scans; s++) smem += (128u + (size_t)L.scan[s].lut_words) * 4;
+    size_t smem = (size_t)kPfThreads * kStage + (size_t)L.n_scans * 4 * kPfThreads * 4 + 2 * kPfMaxScans * 4;
+    for (int s = 0; s < L.n_scans; s++) smem += (128u + (L.scan[s].lut_share == s ? (size_t)L.scan[s].lut_words : 0u)) * 4;
     if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(pf_ac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -211,11 +211,13 @@ class BatchDecoder:
         off = self.out_offset(i)
         n = fi.width * fi.height * fi.ncomp
         if fi.precision > 8:  # 12-bit frames: native-endian 16-bit samples
+            import torch
             return out[off:off + 2 * n].view(torch.int16).view(fi.height, fi.width, fi.ncomp)
         return out[off:off + n].view(fi.height, fi.width, fi.ncomp)
 
     def plane_views(self, out, i):
         """upsample=False: the components of frame i as planes [ceil(H/suby), ceil(W/subx)] at their own resolution."""
+        import torch
         assert not self.upsample
         fi = self.info(i)
         off, deep, planes = self.out_offset(i), fi.precision > 8, []
