@@ -50,7 +50,7 @@ if ROOT not in sys.path:
 
 from tools import bench_inputs  # noqa: E402
 
-DEFAULT_FRAMES = {"cfg3": 840, "cfg2": 4096, "cfg4": 1024, "cfg3n": 840, "cfg2n": 4096, "cfg1": 8192}
+DEFAULT_FRAMES = {"cfg3": 840, "cfg2": 4096, "cfg4": 1024, "cfg3n": 840, "cfg2n": 4096, "cfg1": 8192, "cfg5": 24}
 # DRAM bytes per cfg3 frame measured with ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum); see profiles/
 NCU_DRAM_BYTES_PER_FRAME = {"cfg3": {"entropy": None, "recon": None}}
 try:
@@ -286,7 +286,7 @@ def main():
     else:
         nf = args.frames_per_gpu or DEFAULT_FRAMES[args.workload]
         global_batch = nf * max(world, 1)
-    mb_codestream = {"cfg2": 0.37, "cfg2n": 0.37, "cfg1": 0.25}.get(args.workload, 1.45)
+    mb_codestream = {"cfg2": 0.37, "cfg2n": 0.37, "cfg1": 0.25, "cfg5": 38.0}.get(args.workload, 1.45)
     config = {"workload": desc, "encoder": bench_inputs.encoder_name(args.workload), "frames_per_gpu": nf, "global_batch": global_batch,
               "distinct_frames": args.distinct, "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
               "l2": "inputs larger than L2 (no flush needed): about %.1f GB codestreams + %.1f GB coefficients per step vs 126 MB L2"
@@ -433,7 +433,8 @@ def main():
     int_peak = max(fi.value, fa.value, fm.value)
     int_ops = INT_OPS_PER_PIXEL_420 * W * H * nf
     algo_b = 128 * dec.stored_blocks + dec.out_bytes
-    roof_b = {"bound": "hbm", "kernel": "stage b = reconstruction kernel(s): IDCT + upsampling + colour + store",
+    roof_b = {"bound": "hbm", "kernel": ("stage b = idct_planes_kernel<int> of base + residual image, generic_reconstruct_kernel: upsampling + JPEG XT merge + store"
+                                         if args.workload == "cfg5" else "stage b = reconstruction kernel(s): IDCT + upsampling + colour + store"),
               "achieved": algo_b / (rec * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
               "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
               "traffic": ncu["recon"] * nf if ncu.get("recon") else None,

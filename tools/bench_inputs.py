@@ -9,6 +9,8 @@ snapshot -- and by the repo's own generator (libjpeg_b200/synth.py) only as a st
     cfg3      3840x2160 4:2:0 q75 DRI=240      jpeg -q 75 -bl -s 1x1,2x2,2x2 -z 240
     cfg4      3840x2160 4:2:0 q75 DRI=240 SOF2 jpeg -q 75 -v  -s 1x1,2x2,2x2 -z 240      (progressive)
     cfg3n     cfg3 without restart markers     jpeg -q 75 -bl -s 1x1,2x2,2x2             (DRI-less streams)
+    cfg5      8192x8192 4:2:0 q75 DRI=512 + XT  jpeg -q 75 -bl -s 1x1,2x2,2x2 -z 512 -r -Q 90  (JPEG XT: 4:4:4 q90 DCT residual in a RESI
+                                                box, 8-bit integer profile -- BASELINE config 5's geometry; its HDR profile is not covered)
 """
 import hashlib
 import os
@@ -30,7 +32,10 @@ WORKLOADS = {
     "cfg4": (3840, 2160, 75, (2, 2), 240, True, "cfg4: 3840x2160 4:2:0 q75 progressive (SOF2, ten scans), DRI=240"),
     "cfg3n": (3840, 2160, 75, (2, 2), 0, False, "cfg3n: 3840x2160 4:2:0 q75 baseline WITHOUT restart markers"),
     "cfg2n": (1920, 1080, 75, (2, 2), 0, False, "cfg2n: 1920x1080 4:2:0 q75 baseline WITHOUT restart markers"),
+    "cfg5": (8192, 8192, 75, (2, 2), 512, False,
+             "cfg5: 8192x8192 4:2:0 q75 baseline + JPEG XT residual layer (4:4:4 q90 DCT codestream in the RESI box, 8-bit integer profile), DRI=512"),
 }
+EXTRA_ARGS = {"cfg5": ["-r", "-Q", "90"]}  # more encoder arguments of a workload
 
 
 def have_reference_encoder():
@@ -40,8 +45,8 @@ def have_reference_encoder():
 def encoder_name(workload):
     w, h, q, sub, z, prog, _ = WORKLOADS[workload]
     if have_reference_encoder():
-        return "reference: oracle/_ref/jpeg " + " ".join(_ref_args(q, sub, z, prog))
-    if prog:
+        return "reference: oracle/_ref/jpeg " + " ".join(_ref_args(q, sub, z, prog) + EXTRA_ARGS.get(workload, []))
+    if prog or workload in EXTRA_ARGS:
         return "unavailable (the progressive workload needs the reference encoder)"
     return "synth fallback: libjpeg_b200/csrc/synth_encoder.cpp (oracle/_ref/jpeg is not in this snapshot)"
 
@@ -67,8 +72,8 @@ def encode_one(args):
     w, h, q, sub, z, prog, _ = WORKLOADS[workload]
     from libjpeg_b200 import synth
     ref = have_reference_encoder()
-    if not ref and prog:
-        raise RuntimeError("the progressive workload needs the reference encoder (oracle/_ref/jpeg)")
+    if not ref and (prog or workload in EXTRA_ARGS):
+        raise RuntimeError("this workload needs the reference encoder (oracle/_ref/jpeg)")
     key = hashlib.sha1(("%s|%d|%s|v2" % (workload, seed, "ref" if ref else "synth")).encode()).hexdigest()[:16]
     path = os.path.join(_cache_dir(), "%s_%d_%s.jpg" % (workload, seed, key))
     if os.path.exists(path):
@@ -80,7 +85,7 @@ def encode_one(args):
             with open(ppm, "wb") as f:
                 f.write(b"P6\n%d %d\n255\n" % (w, h))
                 f.write(img.tobytes())
-            r = subprocess.run([REF_CLI] + _ref_args(q, sub, z, prog) + [ppm, jpg], capture_output=True, text=True)
+            r = subprocess.run([REF_CLI] + _ref_args(q, sub, z, prog) + EXTRA_ARGS.get(workload, []) + [ppm, jpg], capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError("reference encoder failed: " + r.stderr[-300:])
             data = open(jpg, "rb").read()
