@@ -4,6 +4,7 @@
 // tables into launch classes, lays the batch out in HBM (see internal.hpp) and drives the two CUDA stages.
 // There is no CPU decode path in here: without a CUDA device every decode entry point fails.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges show up in Nsight Systems timelines, cost nothing without a tool attached
 
 #include <algorithm>
 #include <array>
@@ -19,6 +20,13 @@
 
 #include "internal.hpp"
 #include "specsync.hpp"
+
+namespace {
+struct NvtxRange {  // one range per stage of the path
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
 
 using namespace b200jpg;
 
@@ -373,6 +381,7 @@ int b200jpg_batch_create_ex(b200jpg_ctx *ctx, const uint8_t *const *frames, cons
 
 static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, int tolerate_bad, unsigned flags,
                              b200jpg_batch **out) {
+    NvtxRange nvtx("b200jpg batch_create: parse + pack");
     if (!out || !frames || !lens || n <= 0) return ctx->fail(B200JPG_ERR_INVALID_PARAMETER, "invalid batch arguments");
     *out = nullptr;
     cudaError_t ce = cudaSetDevice(ctx->device);
@@ -970,6 +979,7 @@ static int run_restart_index(b200jpg_batch *b, void *stream) {
 }
 
 int b200jpg_batch_upload(b200jpg_batch *b, void *stream) {
+    NvtxRange nvtx("b200jpg upload: H2D + restart index");
     if (!b) return B200JPG_ERR_INVALID_PARAMETER;
     cudaSetDevice(b->ctx->device);
     cudaError_t e = cudaMemcpyAsync(b->d_input, b->h_input, b->input_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
@@ -988,6 +998,7 @@ int b200jpg_batch_reindex(b200jpg_batch *b, void *stream) {
 }
 
 static int run_entropy(b200jpg_batch *b, void *stream) {
+    NvtxRange nvtx("b200jpg entropy: unstuff + Huffman decode");
     // the status words start from what the restart index found at upload (out-of-sequence restart markers)
     cudaError_t e = cudaMemcpyAsync(b->d_status, b->d_status + 4 * (size_t)b->n + 1, sizeof(uint32_t) * (size_t)b->n, cudaMemcpyDeviceToDevice,
                                     (cudaStream_t)stream);
@@ -1130,6 +1141,7 @@ static int run_entropy(b200jpg_batch *b, void *stream) {
 }
 
 static int run_recon(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
+    NvtxRange nvtx("b200jpg reconstruction: IDCT + upsampling + colour");
     cudaError_t me = cudaMemsetAsync(b->d_status + b->n, 0, sizeof(uint32_t) * 2 * (size_t)b->n, (cudaStream_t)stream);
     if (me != cudaSuccess) return b->ctx->fail_cuda(me, "flag reset");
     for (auto &g : b->groups) {
