@@ -267,7 +267,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(DEFAULT_FRAMES))
     ap.add_argument("--frames-per-gpu", type=int, default=0, help="frames per GPU per step (default: per workload)")
     ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: total frames per step, split over the GPUs")
-    ap.add_argument("--distinct", type=int, default=64)
+    ap.add_argument("--distinct", type=int, default=0, help="distinct frames cycled through the batch (default 64; cfg5: 2)")
     ap.add_argument("--e2e-chunk", type=int, default=32)
     ap.add_argument("--p2d-chunks", type=int, default=2, help="pinned_to_device_rgb: chunks per step (each: H2D + index + kernels on its own stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -279,6 +279,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ncpu = os.cpu_count() or 8
     W, H, QUALITY, SUB, DRI, PROG, desc = bench_inputs.WORKLOADS[args.workload]
+    if args.distinct <= 0:
+        args.distinct = 2 if args.workload == "cfg5" else 64
     strong = args.global_batch > 0
     if strong:
         nf = (args.global_batch + world - 1) // world
@@ -286,7 +288,7 @@ def main():
     else:
         nf = args.frames_per_gpu or DEFAULT_FRAMES[args.workload]
         global_batch = nf * max(world, 1)
-    mb_codestream = {"cfg2": 0.37, "cfg2n": 0.37, "cfg1": 0.25, "cfg5": 38.0}.get(args.workload, 1.45)
+    mb_codestream = {"cfg2": 0.37, "cfg2n": 0.37, "cfg1": 0.25, "cfg5": 54.0}.get(args.workload, 1.45)
     config = {"workload": desc, "encoder": bench_inputs.encoder_name(args.workload), "frames_per_gpu": nf, "global_batch": global_batch,
               "distinct_frames": args.distinct, "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
               "l2": "inputs larger than L2 (no flush needed): about %.1f GB codestreams + %.1f GB coefficients per step vs 126 MB L2"

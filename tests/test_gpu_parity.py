@@ -337,8 +337,8 @@ def test_zrl_that_steps_over_position_63_ends_the_block_silently(built, oracle):
 
 def _bench_frames(workload, distinct):
     from tools import bench_inputs
-    if bench_inputs.WORKLOADS[workload][5] and not bench_inputs.have_reference_encoder():
-        pytest.skip("progressive inputs need the reference encoder (oracle/_ref/jpeg)")
+    if (bench_inputs.WORKLOADS[workload][5] or workload in bench_inputs.EXTRA_ARGS) and not bench_inputs.have_reference_encoder():
+        pytest.skip("these inputs need the reference encoder (oracle/_ref/jpeg)")
     return bench_inputs.make_frames(workload, distinct, workers=min(16, os.cpu_count() or 1))
 
 
@@ -355,6 +355,18 @@ def test_every_distinct_bench_frame_matches_oracle(built, oracle, workload, dist
         assert rc == 0
         got = dec.frame_view(out, i).cpu().numpy()
         assert np.array_equal(got, want), "%s frame %d (seed %d): %d differing bytes" % (workload, i, i + 1, int((got != want).sum()))
+
+
+def test_xt_8k_bench_frame_matches_oracle(built, oracle):
+    """BASELINE configs[4] geometry: one 8192x8192 frame of bench.py's cfg5 workload (4:2:0 q75 base with restart markers + 4:4:4
+    q90 residual codestream in RESI boxes spread over hundreds of APP11 markers), pixels == oracle."""
+    frames = _bench_frames("cfg5", 1)
+    dec, out = gpu_decode(built, frames)
+    assert dec.status(0) == 0
+    rc, want = oracle.decode(frames[0])
+    assert rc == 0 and want.shape == (8192, 8192, 3)
+    got = dec.frame_view(out, 0).cpu().numpy()
+    assert np.array_equal(got, want), "%d differing bytes" % int((got != want).sum())
 
 
 def test_progressive_4k_frames_match_oracle(built, oracle):
