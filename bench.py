@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: total frames per step, split over the GPUs")
     ap.add_argument("--distinct", type=int, default=0, help="distinct frames cycled through the batch (default 64; cfg5: 2)")
     ap.add_argument("--e2e-chunk", type=int, default=32)
+    ap.add_argument("--e2e-producers", type=int, default=2, help="host threads that prepare chunks (b200jpg_batch_create) ahead of the device")
     ap.add_argument("--p2d-chunks", type=int, default=2, help="pinned_to_device_rgb: chunks per step (each: H2D + index + kernels on its own stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -515,21 +516,23 @@ def main():
                   "host": torch.empty(ob, dtype=torch.uint8).pin_memory()} for _ in range(nslots)]
         counters = {"h2d": 0, "d2h": 0}
 
+        nprod = max(1, args.e2e_producers)
+
         def e2e_step(keep_last=False):
-            q = queue.Queue(maxsize=3)
+            # host preparation (b200jpg_batch_create: parse + pack into pinned memory) runs ahead of the device in `nprod` threads,
+            # thread t building the chunks c = t (mod nprod); the consumer takes them in order
+            qs = [queue.Queue(maxsize=2) for _ in range(nprod)]
 
-            def producer():
-                for c in range(nchunks):
-                    q.put(libjpeg_b200.BatchDecoder(frames[c * chunk:(c + 1) * chunk], ctx=ctx))
-                q.put(None)
+            def producer(t):
+                for c in range(t, nchunks, nprod):
+                    qs[t].put(libjpeg_b200.BatchDecoder(frames[c * chunk:(c + 1) * chunk], ctx=ctx))
 
-            th = threading.Thread(target=producer, daemon=True)
-            th.start()
-            inflight, c = [], 0
-            while True:
-                bd = q.get()
-                if bd is None:
-                    break
+            ths = [threading.Thread(target=producer, args=(t,), daemon=True) for t in range(nprod)]
+            for th in ths:
+                th.start()
+            inflight = []
+            for c in range(nchunks):
+                bd = qs[c % nprod].get()
                 s = slots[c % nslots]
                 with torch.cuda.stream(s["stream"]):
                     bd.upload(s["stream"])
@@ -540,16 +543,31 @@ def main():
                 inflight.append(bd)
                 if len(inflight) > nslots:
                     inflight.pop(0).close()
-                c += 1
             for s in slots:
                 s["stream"].synchronize()
             for bd in inflight[:-1] if keep_last else inflight:
                 bd.close()
-            th.join()
+            for th in ths:
+                th.join()
             return inflight[-1] if keep_last else None
 
         for _ in range(2):
             e2e_step()
+        # the host share of a chunk on its own: b200jpg_batch_create = marker parse + packing into pinned memory
+        tp = []
+        for c in range(min(nchunks, 6)):
+            t0 = time.perf_counter()
+            bd = libjpeg_b200.BatchDecoder(frames[c * chunk:(c + 1) * chunk], ctx=ctx)
+            tp.append((time.perf_counter() - t0) * 1e3)
+            bd.close()
+        host_prepare_ms = statistics.median(tp)
+        # ... and the bare copy of a chunk's pixels, pinned, alone on the link: what the D2H leg can at most deliver
+        s0 = slots[0]
+        t0 = time.perf_counter()
+        for _ in range(4):
+            s0["host"].copy_(s0["out"], non_blocking=True)
+        torch.cuda.synchronize()
+        d2h_gbs = 4 * ob / (time.perf_counter() - t0) / 1e9
         barrier()
         counters["h2d"] = counters["d2h"] = 0
         t0 = time.perf_counter()
@@ -563,10 +581,12 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         e2e = {"value": nframes_all * esteps / dt, "unit": "frames/s", "h2d_bytes_per_step": int(counters["h2d"] // esteps),
-               "d2h_bytes_per_step": int(counters["d2h"] // esteps), "steps": esteps, "chunk_frames": chunk, "streams": nslots,
+               "d2h_bytes_per_step": int(counters["d2h"] // esteps), "steps": esteps, "chunk_frames": chunk, "streams": nslots, "host_threads_preparing": nprod,
+               "host_prepare_ms_per_chunk": host_prepare_ms, "bare_d2h_gbs_this_rank_alone": d2h_gbs,
+               "d2h_ceiling_frames_per_s": d2h_gbs * 1e9 / (ob / chunk) * max(world, 1),
                "timed_region": "per chunk: b200jpg_batch_create on the host codestreams (marker parse, packing into pinned memory) -> H2D "
                                "+ restart index -> unstuff + entropy + reconstruction kernels -> D2H of every pixel into pinned host "
-                               "memory -> batch_destroy; host preparation runs one chunk ahead in a second thread"}
+                               "memory -> batch_destroy; host preparation runs ahead of the device in its own threads"}
         # sanity: what came back is what the device-resident path produced (frame nf-1 is in `out` from the value run)
         fi_last = last_bd.info(last_bd.n - 1)
         nbytes = fi_last.width * fi_last.height * fi_last.ncomp

@@ -1165,14 +1165,19 @@ static int run_recon(b200jpg_batch *b, uint8_t *out_dev, void *stream) {
         l.narrow_list = b->d_status + 3 * (size_t)b->n;
         l.out = out_dev;
         int launches = 0;
-        // grid.y carries the frame index: at most 65535 frames per launch
-        for (uint32_t first = 0; first < l.n_frames; first += 65535u) {
-            ReconLaunch part = l;
-            part.frames = l.frames + first;
-            part.n_frames = std::min<uint32_t>(65535u, l.n_frames - first);
-            int rc = launch_recon(part, stream, &launches);
-            if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "reconstruction kernel launch");
-            b->last_launches += launches;
+        // grid.y carries the frame index: at most 65535 frames per launch. A generic group that is cut runs the IDCT of ALL its
+        // frames first: a JPEG XT frame reads the planes of its residual frame, which may sit in another part
+        const bool cut = l.n_frames > 65535u;
+        for (int phase = (l.generic && cut) ? 1 : 0; phase <= ((l.generic && cut) ? 2 : 0); phase++) {
+            for (uint32_t first = 0; first < l.n_frames; first += 65535u) {
+                ReconLaunch part = l;
+                part.frames = l.frames + first;
+                part.n_frames = std::min<uint32_t>(65535u, l.n_frames - first);
+                part.generic_phase = phase;
+                int rc = launch_recon(part, stream, &launches);
+                if (rc != 0) return b->ctx->fail_cuda((cudaError_t)rc, "reconstruction kernel launch");
+                b->last_launches += launches;
+            }
         }
     }
     cudaEventRecord(b->ev_last, (cudaStream_t)stream);

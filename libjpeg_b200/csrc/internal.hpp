@@ -262,6 +262,7 @@ struct ReconLaunch {
     uint32_t ncomp, subx, suby;    // uniform over the group
     bool generic;                  // formats outside the tuned kernels: any component count / factors, per-frame parameters
     bool planes_out;               // B200JPG_FLAG_NO_UPSAMPLE: the components leave as planes at their own resolution
+    int generic_phase;             // generic groups: 0 = IDCT then reconstruction, 1 = IDCT only, 2 = reconstruction only
     const int16_t *coef;
     int16_t *samples16;            // chroma sample planes every frame goes through
     int32_t *samples32;            // the same planes for the exact pass over frames flagged `narrow`

@@ -1304,14 +1304,23 @@ static int launch_recon_generic(const ReconLaunch &l, cudaStream_t s, int *launc
     uint32_t mb = 0;
     mb = l.max_bwc * l.max_bhc;  // the largest component block grid of the group (set by the host for generic groups)
     const uint32_t cblocks = (mb + kThreadsB - 1) / kThreadsB;
-    idct_planes_kernel<int32_t, false><<<dim3(cblocks, l.n_frames, l.ncomp), kThreadsB, 0, s>>>(l.frames, l.coef, l.samples32, l.wide_flags, nullptr, 0);
+    int n = 0;
+    if (l.generic_phase != 2) {
+        idct_planes_kernel<int32_t, false><<<dim3(cblocks, l.n_frames, l.ncomp), kThreadsB, 0, s>>>(l.frames, l.coef, l.samples32, l.wide_flags, nullptr, 0);
+        n++;
+    }
+    if (l.generic_phase == 1) {
+        if (launches) *launches = n;
+        return (int)cudaGetLastError();
+    }
+    n++;
     if (l.planes_out) {
         const uint32_t gx = std::min<uint32_t>((l.max_bw0 * l.max_bh0 * 64u + 255u) / 256u, 4096u);
         planes_out_kernel<<<dim3(gx, l.n_frames, l.ncomp), 256, 0, s>>>(l.frames, l.samples32, l.out);
     } else {
         generic_reconstruct_kernel<<<dim3((l.max_bw0 + 63) / 64, l.max_bh0, l.n_frames), 64, 0, s>>>(l.frames, l.samples32, l.out);
     }
-    if (launches) *launches = 2;
+    if (launches) *launches = n;
     return (int)cudaGetLastError();
 }
 
