@@ -1413,4 +1413,61 @@ done:
     return rc;
 }
 
+int b200jpg_decode_to_device_ex(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, unsigned flags, uint8_t **out_dev,
+                                uint64_t *out_bytes) {
+    if (!ctx || !out_dev) return B200JPG_ERR_INVALID_PARAMETER;
+    *out_dev = nullptr;
+    b200jpg_batch *b = nullptr;
+    int rc = b200jpg_batch_create_ex(ctx, frames, lens, n, 0, flags, &b);
+    if (rc) return rc;
+    uint8_t *d_out = nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_out, b->out_total ? b->out_total : 1);
+    if (e != cudaSuccess) {
+        rc = ctx->fail(B200JPG_ERR_OUT_OF_MEMORY, "device allocation of the output failed");
+        goto done;
+    }
+    e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        rc = ctx->fail_cuda(e, "cudaStreamCreate");
+        goto done;
+    }
+    rc = b200jpg_batch_upload(b, s);
+    if (!rc) rc = b200jpg_batch_decode(b, d_out, s);
+    if (!rc) {
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = ctx->fail_cuda(e, "decode");
+    }
+    for (int i = 0; i < n && !rc; i++) {
+        int st = b200jpg_batch_frame_status(b, i);
+        if (st) rc = ctx->fail(st, "frame " + std::to_string(i) + ": invalid stream, found invalid huffman code in entropy coded segment");
+    }
+    if (!rc) {
+        if (out_bytes) *out_bytes = b->out_total;
+        *out_dev = d_out;
+        d_out = nullptr;
+    }
+done:
+    if (s) cudaStreamDestroy(s);
+    if (d_out) cudaFree(d_out);
+    b200jpg_batch_destroy(b);
+    return rc;
+}
+
+void b200jpg_device_free(b200jpg_ctx *ctx, uint8_t *p) {
+    if (!p) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(p);
+}
+
+int b200jpg_device_copy_rect(b200jpg_ctx *ctx, uint8_t *dst_dev, int64_t dst_pitch, const uint8_t *src_dev, int64_t src_pitch, uint64_t width_bytes,
+                             uint64_t rows) {
+    if (!ctx || !dst_dev || !src_dev || dst_pitch < 0 || src_pitch < 0) return B200JPG_ERR_INVALID_PARAMETER;
+    if (width_bytes == 0 || rows == 0) return B200JPG_OK;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMemcpy2D(dst_dev, (size_t)dst_pitch, src_dev, (size_t)src_pitch, (size_t)width_bytes, (size_t)rows, cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) return ctx->fail_cuda(e, "device rectangle copy");
+    return B200JPG_OK;
+}
+
 }  // extern "C"

@@ -178,10 +178,21 @@ struct JPEG::Impl {
     size_t pixel_bytes;
     bool decoded;
     unsigned decoded_flags;  // request flags the cached pixels were decoded with (colour transformation on / off)
+    // the same frame kept on the device for clients whose bitmaps are device memory (JPGTAG_B200_DEVICE_BITMAPS)
+    uint8_t *d_pixels;
+    b200jpg_ctx *d_ctx;
+    unsigned d_flags;
     JPG_LONG err_code;
     std::string err_msg;
 
-    Impl() : device(-1), have_image(false), pixel_bytes(0), decoded(false), decoded_flags(0), err_code(0) { memset(&info, 0, sizeof(info)); }
+    Impl() : device(-1), have_image(false), pixel_bytes(0), decoded(false), decoded_flags(0), d_pixels(0), d_ctx(0), d_flags(0), err_code(0) {
+        memset(&info, 0, sizeof(info));
+    }
+    ~Impl() { drop_device_frame(); }
+    void drop_device_frame() {
+        if (d_pixels) b200jpg_device_free(d_ctx, d_pixels);
+        d_pixels = 0;
+    }
     JPG_LONG fail(JPG_LONG code, const std::string &msg) {
         err_code = code;
         err_msg = msg;
@@ -282,7 +293,7 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
     // ---- rectangle request (rectanglerequest.cpp:62-165)
     JPG_LONG minx = 0, miny = 0, maxx = (JPG_LONG)s.info.width - 1, maxy = (JPG_LONG)s.info.height - 1;
     JPG_LONG firstc = 0, lastc = s.info.ncomp - 1;
-    bool upsample = true, colortrafo = true;
+    bool upsample = true, colortrafo = true, device_bitmaps = false;
     for (const struct JPG_TagItem *t = tags; t; t = t->NextTagItem()) {
         const JPG_LONG v = t->ti_Data.ti_lData;
         switch (t->ti_Tag) {
@@ -318,6 +329,7 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
             if (v < 0 || v > 65535) return s.fail(JPGERR_OVERFLOW_PARAMETER, "MaxComponent overflow, must be >= 0 && < 65536");
             if (v < lastc) lastc = v;
             break;
+        case JPGTAG_B200_DEVICE_BITMAPS: device_bitmaps = v != 0; break;
         case JPGTAG_DECODER_UPSAMPLE: upsample = v != 0; break;
         case JPGTAG_MATRIX_LTRAFO: colortrafo = v != JPGFLAG_MATRIX_COLORTRANSFORMATION_NONE; break;
         default: break;
@@ -354,7 +366,26 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
     // ---- decode on first use (CUDA; the whole frame, kept for later rectangles)
     const unsigned want_flags = !upsample ? (B200JPG_FLAG_NO_UPSAMPLE | B200JPG_FLAG_NO_COLOR_TRANSFORM)
                                           : ((!colortrafo && s.info.ycbcr) ? B200JPG_FLAG_NO_COLOR_TRANSFORM : 0u);
-    if (!s.decoded || s.decoded_flags != want_flags) {
+    if (device_bitmaps) {
+        if (!upsample) return s.fail(JPGERR_NOT_IMPLEMENTED, "device bitmaps are filled with upsampled, interleaved pixels only");
+        if (!s.d_pixels || s.d_flags != want_flags) {
+            b200jpg_ctx *ctx = 0;
+            std::string msg;
+            int rc = shared_context(s.device, &ctx, msg);
+            if (rc) return s.fail(rc, msg);
+            s.drop_device_frame();
+            const uint8_t *frames[1] = {s.stream.data()};
+            size_t lens[1] = {s.stream.size()};
+            rc = b200jpg_decode_to_device_ex(ctx, frames, lens, 1, want_flags, &s.d_pixels, 0);
+            if (rc) {
+                const char *m = 0;
+                b200jpg_last_error(0, &m);
+                return s.fail(rc, (m && *m) ? m : "decoding failed");
+            }
+            s.d_ctx = ctx;
+            s.d_flags = want_flags;
+        }
+    } else if (!s.decoded || s.decoded_flags != want_flags) {
         b200jpg_ctx *ctx = 0;
         std::string msg;
         int rc = shared_context(s.device, &ctx, msg);
@@ -447,6 +478,26 @@ JPG_LONG JPEG::DisplayRectangle(struct JPG_TagItem *tags) {
     // block rows up to min(MaxY >> 3, (smallest BIO_HEIGHT >> 3) - 1) are reconstructed (blockbitmaprequester.cpp:1166-1167)
     long long last_by = (long long)(cmaxy >> 3);
     if ((long long)max_block_row < last_by) last_by = (long long)max_block_row;
+    if (device_bitmaps) {
+        // the client's bitmaps are device memory: one rectangle copy on the device. Only the usual layout -- one interleaved
+        // canvas, component c at base + c -- is offered; whole blocks whose origin lies outside the bitmap stay unwritten
+        // (imagebitmap.cpp:78-110), like in the loop below
+        const BitmapLayout &l = lay[0];
+        if (!interleaved && !(nc == 1 && l.mem && l.pixel_type && l.bytes_per_pixel == sample_bytes && deep == wide_out && firstc == 0 && lastc == 0))
+            return s.fail(JPGERR_INVALID_PARAMETER, "device bitmaps must be one interleaved canvas of the frame's sample type");
+        JPG_LONG xlast = cmaxx, ylast = cmaxy;
+        if (last_by * 8 + 7 < ylast) ylast = (JPG_LONG)(last_by * 8 + 7);
+        if (l.width > 0 && (JPG_LONG)((((l.width - 1) >> 3) << 3) + 7) < xlast) xlast = (JPG_LONG)((((l.width - 1) >> 3) << 3) + 7);
+        if (l.height > 0 && (JPG_LONG)((((l.height - 1) >> 3) << 3) + 7) < ylast) ylast = (JPG_LONG)((((l.height - 1) >> 3) << 3) + 7);
+        if (l.width > 0 && l.height > 0 && l.width > (JPG_ULONG)cminx && l.height > (JPG_ULONG)cminy && xlast >= cminx && ylast >= cminy) {
+            const size_t px = (size_t)nc * sample_bytes;
+            int rc = b200jpg_device_copy_rect(s.d_ctx, l.mem + (ptrdiff_t)cminx * l.bytes_per_pixel + (ptrdiff_t)cminy * l.bytes_per_row, l.bytes_per_row,
+                                              s.d_pixels + ((size_t)cminy * W + (size_t)cminx) * px, (int64_t)((size_t)W * px),
+                                              (uint64_t)(xlast - cminx + 1) * px, (uint64_t)(ylast - cminy + 1));
+            if (rc) return s.fail(rc, "device rectangle copy failed");
+        }
+        last_by = -1;  // nothing left for the host loop
+    }
     for (long long by = (long long)(cminy >> 3); by <= last_by; by++) {
         const JPG_LONG y0 = (by == (cminy >> 3)) ? cminy : (JPG_LONG)(by << 3);
         const JPG_LONG y1 = ((JPG_LONG)(by << 3) + 7 < cmaxy) ? (JPG_LONG)(by << 3) + 7 : cmaxy;

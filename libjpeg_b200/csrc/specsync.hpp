@@ -109,7 +109,12 @@ B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_
     const uint32_t ac0 = sc.ac_tab[0], ac1 = sc.ac_tab[1], ac2 = sc.ac_tab[2], ac3 = sc.ac_tab[3];
     uint32_t bit = from.bit, blk = from.blk, k = 0, n = 0;
     // the stream words around `bit` in registers: a symbol has fewer than 32 bits, so at most one new word per step
-    uint32_t wi = bit >> 5, x0 = spec_word(w, nwords, wi), x1 = spec_word(w, nwords, wi + 1u);
+    // (x2 is a prefetch: the load of a new word has two words' worth of symbols to arrive before the window needs it)
+    uint32_t wi = bit >> 5, x0 = spec_word(w, nwords, wi), x1 = spec_word(w, nwords, wi + 1u), x2 = spec_word(w, nwords, wi + 2u);
+    // tables of the block the path is in: chosen when the block changes, not per symbol
+    uint32_t cur = (comp_bits >> (2u * blk)) & 3u;
+    uint32_t dct = cur == 0 ? dc0 : (cur == 1 ? dc1 : (cur == 2 ? dc2 : dc3));
+    uint32_t act = cur == 0 ? ac0 : (cur == 1 ? ac1 : (cur == 2 ? ac2 : ac3));
     int32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     int mark = 0, merge_at = -1;   // next mark to pass; the mark the path merged at
     uint32_t next_mark = first_mark_bit;
@@ -144,14 +149,12 @@ B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_
             }
             if (merge_at >= 0) break;
         }
-        const uint32_t c = (comp_bits >> (2u * blk)) & 3u;
+        const uint32_t c = cur;
 #if defined(__CUDA_ARCH__)
         const uint32_t hi = __funnelshift_l(x1, x0, bit);
 #else
         const uint32_t hi = (bit & 31u) ? ((x0 << (bit & 31u)) | (x1 >> (32u - (bit & 31u)))) : x0;
 #endif
-        const uint32_t dct = c == 0 ? dc0 : (c == 1 ? dc1 : (c == 2 ? dc2 : dc3));
-        const uint32_t act = c == 0 ? ac0 : (c == 1 ? ac1 : (c == 2 ? ac2 : ac3));
         const uint32_t e = spec_lookup(lut + (k == 0 ? dct : act), hi);
         if (k == 0) {
             if ((int32_t)e >= 0) {
@@ -171,11 +174,15 @@ B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_
             k = 0;
             n++;
             blk = blk + 1 == bpm ? 0 : blk + 1;
+            cur = (comp_bits >> (2u * blk)) & 3u;
+            dct = cur == 0 ? dc0 : (cur == 1 ? dc1 : (cur == 2 ? dc2 : dc3));
+            act = cur == 0 ? ac0 : (cur == 1 ? ac1 : (cur == 2 ? ac2 : ac3));
         }
         if ((bit >> 5) != wi) {  // the window moves up by one word
             wi = bit >> 5;
             x0 = x1;
-            x1 = spec_word(w, nwords, wi + 1u);
+            x1 = x2;
+            x2 = spec_word(w, nwords, wi + 2u);
         }
     }
     if (!counting) {  // the walk ended inside the run-up (end of the data): nothing of the subsequence is there

@@ -20,8 +20,11 @@ namespace b200jpg {
 namespace {
 
 constexpr int kSyncThreads = 512;
+#ifndef B200JPG_SPEC_MINCTAS
+#define B200JPG_SPEC_MINCTAS 2
+#endif
 
-__global__ void __launch_bounds__(kSyncThreads)
+__global__ void __launch_bounds__(kSyncThreads, B200JPG_SPEC_MINCTAS)
 spec_sync_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uint64_t *__restrict__ clean_off,
                  const uint32_t *__restrict__ interval_len, const uint8_t *__restrict__ tables, SpecSegment *__restrict__ segs,
                  unsigned long long *__restrict__ exits, unsigned long long *__restrict__ entries, uint32_t *__restrict__ counts,

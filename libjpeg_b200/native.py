@@ -69,6 +69,9 @@ def _load():
         "b200jpg_selftest_restartless": (i32, [vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
         "b200jpg_decode_to_host": (i32, [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t), i32, vp, u64]),
         "b200jpg_decode_to_host_ex": (i32, [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t), i32, vp, u64, ctypes.c_uint]),
+        "b200jpg_decode_to_device_ex": (i32, [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t), i32, ctypes.c_uint, ctypes.POINTER(vp), ctypes.POINTER(u64)]),
+        "b200jpg_device_free": (None, [vp, vp]),
+        "b200jpg_device_copy_rect": (i32, [vp, vp, ctypes.c_int64, vp, ctypes.c_int64, u64, u64]),
         "b200jpg_microbench_int32": (i32, [i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     }
     for name, (res, args) in sig.items():
@@ -85,7 +88,8 @@ ABI_SYMBOLS = [
     "b200jpg_batch_ecs_bytes", "b200jpg_batch_stored_blocks", "b200jpg_batch_h2d_bytes", "b200jpg_batch_export_tables",
     "b200jpg_batch_import_tables", "b200jpg_batch_upload", "b200jpg_batch_reindex", "b200jpg_batch_decode", "b200jpg_batch_decode_entropy",
     "b200jpg_batch_reconstruct", "b200jpg_batch_frame_status", "b200jpg_batch_read_coefficients",
-    "b200jpg_batch_last_launch_count", "b200jpg_batch_enable_timing", "b200jpg_batch_last_timing", "b200jpg_batch_last_unstuff_ms", "b200jpg_decode_to_host", "b200jpg_decode_to_host_ex", "b200jpg_selftest_restartless",
+    "b200jpg_batch_last_launch_count", "b200jpg_batch_enable_timing", "b200jpg_batch_last_timing", "b200jpg_batch_last_unstuff_ms", "b200jpg_decode_to_host", "b200jpg_decode_to_host_ex", "b200jpg_decode_to_device_ex",
+    "b200jpg_device_free", "b200jpg_device_copy_rect", "b200jpg_selftest_restartless",
     "b200jpg_microbench_int32",
 ]
 

@@ -211,3 +211,39 @@ def test_parser_reads_the_xt_boxes(built):
     with pytest.raises(NativeError) as e:
         built.parse(bytes(data))
     assert e.value.code == -1038
+
+
+def test_parser_survives_damaged_streams(built, oracle):
+    """Host parser (markers, tables, restart index, JPEG XT boxes) and the oracle's on truncated and bit-flipped streams of every
+    kind of fixture: an error code or a frame, never a crash, and sizes that stay inside the stream."""
+    import glob
+    import random
+    from libjpeg_b200 import NativeError
+    rng = random.Random(1234)
+    pool = sorted(glob.glob(os.path.join(GOLDEN, "*.jpg")))[:4] + sorted(glob.glob(os.path.join(GOLDEN, "xt", "*.jpg")))[:4] + \
+        sorted(glob.glob(os.path.join(GOLDEN, "progressive", "*.jpg")))[:2] + sorted(glob.glob(os.path.join(GOLDEN, "deep12", "*.jpg")))[:1]
+    outcomes = {"ok": 0, "error": 0}
+    for path in pool:
+        data = open(path, "rb").read()
+        for trial in range(60):
+            d = bytearray(data)
+            kind = trial % 3
+            if kind == 0:
+                d = d[:rng.randrange(2, len(d))]
+            elif kind == 1:
+                for _ in range(rng.randrange(1, 6)):
+                    d[rng.randrange(2, len(d))] = rng.randrange(256)
+            else:  # damage inside the marker segments in front of the first scan (where the boxes and tables live)
+                sos = d.find(b"\xff\xda")
+                for _ in range(rng.randrange(1, 4)):
+                    d[rng.randrange(2, max(3, sos))] ^= 1 << rng.randrange(8)
+            try:
+                fi = built.parse(bytes(d))
+                assert 0 < fi.width <= 65535 and 0 < fi.height <= 65535 and fi.ecs_bytes <= len(d)
+                outcomes["ok"] += 1
+            except NativeError as e:
+                assert e.code < 0
+                outcomes["error"] += 1
+            rc, _ = oracle.info(bytes(d))
+            assert rc <= 0
+    assert outcomes["ok"] > 50 and outcomes["error"] > 50
