@@ -18,7 +18,8 @@ from tools import bench_inputs
 
 def main():
     res = {}
-    ctx = libjpeg_b200.Context(-1)
+    from libjpeg_b200.decoder import Context
+    ctx = Context(-1)
     for wl in ("cfg3", "cfg3n", "cfg4", "cfg2"):
         data = bench_inputs.make_frames(wl, 1, 1)[0]
         fi = libjpeg_b200.parse(data)

@@ -28,7 +28,7 @@ frames += [open(p, "rb").read() for p in sorted(glob.glob("tests/golden/xt/*.jpg
 frames += [open(p, "rb").read() for p in sorted(glob.glob("tests/golden/deep12/*.jpg"))[:3]]
 frames += [open(p, "rb").read() for p in sorted(glob.glob("tests/golden/subsampling/*.jpg"))[:4]]
 frames.append(oracle_binding.with_fourth_component(synth.encode(synth.source_image(70, 50, 5), 80, (2, 2), 5, 1)))
-frames.append(oracle_binding.with_restart_damage(good, oracle_binding.RESTART_DAMAGES[0]))
+frames.append(oracle_binding.with_restart_damage(synth.encode(synth.source_image(320, 240, 5), 75, (2, 2), 5).tobytes(), oracle_binding.RESTART_DAMAGES[0]))
 dec = libjpeg_b200.BatchDecoder(frames, tolerate_bad=True)
 out = dec.new_output(); dec.upload(); dec.decode(out); torch.cuda.synchronize()
 print("statuses", [dec.status(i) for i in range(len(frames))])
