@@ -1167,12 +1167,17 @@ generic_reconstruct_kernel(const FrameRecon *__restrict__ frames, const int32_t 
     const uint32_t bx = blockIdx.x * 64 + threadIdx.x, by = blockIdx.y;
     if (bx >= (W + 7) / 8 || by >= (H + 7) / 8) return;
     const int X = 8 * (int)bx, Y = 8 * (int)by;
-    int buf[4][64];  // 64 upsampled samples per component (local memory: this path is not tuned)
+    // 64 upsampled samples per subsampled component (local memory: this path is not tuned); a component at full resolution is
+    // read where it lies -- inside the image its sample plane IS the upsampled image
+    int buf[4][64];
+    const int32_t *direct[4] = {nullptr, nullptr, nullptr, nullptr};
     for (uint32_t c = 0; c < nc; c++) {
         const int sx = f.csx[c], sy = f.csy[c];
         const int w = (int)((W + sx - 1) / sx), h = (int)((H + sy - 1) / sy);
-        generic_upsample_block(samples + f.sample_base[c], 8u * f.bw[c], w, h, sx, sy, X, Y, buf[c]);
+        if (sx == 1 && sy == 1) direct[c] = samples + f.sample_base[c] + (uint64_t)Y * (8u * f.bw[c]) + (uint64_t)X;
+        else generic_upsample_block(samples + f.sample_base[c], 8u * f.bw[c], w, h, sx, sy, X, Y, buf[c]);
     }
+    auto base_at = [&](uint32_t c, int x, int y) -> int { return direct[c] ? direct[c][(uint64_t)y * (8u * f.bw[c]) + (uint32_t)x] : buf[c][8 * y + x]; };
     const int xmax = (X + 7 < (int)W) ? 7 : (int)((W - 1) & 7), ymax = (Y + 7 < (int)H) ? 7 : (int)((H - 1) & 7);
     if (f.xt & 1u) {
         // ---- JPEG XT: base image + residual image, YCbCrTrafo<..., Residual | Extended | ClampFlag, ...>::YCbCr2RGB
@@ -1180,11 +1185,14 @@ generic_reconstruct_kernel(const FrameRecon *__restrict__ frames, const int32_t 
         // 425-520; ParametricToneMappingBox::ScaledTableOf boxes/parametrictonemappingbox.cpp:387-426): Q = identity over the
         // pre-shifted range 0..4095, R2 = floor(i / 16 + 0.5), L = identity over 0..255, C = identity; a lookup clamps its index
         int rbuf[3][64];
+        const int32_t *rdirect[3] = {nullptr, nullptr, nullptr};
         for (uint32_t c = 0; c < nc; c++) {
             const int sx = f.res_csx[c], sy = f.res_csy[c];
             const int w = (int)((W + sx - 1) / sx), h = (int)((H + sy - 1) / sy);
-            generic_upsample_block(samples + f.res_sample_base[c], 8u * f.res_bw[c], w, h, sx, sy, X, Y, rbuf[c]);
+            if (sx == 1 && sy == 1) rdirect[c] = samples + f.res_sample_base[c] + (uint64_t)Y * (8u * f.res_bw[c]) + (uint64_t)X;
+            else generic_upsample_block(samples + f.res_sample_base[c], 8u * f.res_bw[c], w, h, sx, sy, X, Y, rbuf[c]);
         }
+        auto res_at = [&](uint32_t c, int x, int y) -> int { return rdirect[c] ? rdirect[c][(uint64_t)y * (8u * f.res_bw[c]) + (uint32_t)x] : rbuf[c][8 * y + x]; };
         auto clamp_to = [](long long v, long long mx) { return v < 0 ? 0ll : (v > mx ? mx : v); };
         for (int y = 0; y <= ymax; y++) {
             uint8_t *o = out + f.out_base + ((uint64_t)(Y + y) * W + (uint64_t)X) * nc;
@@ -1192,20 +1200,20 @@ generic_reconstruct_kernel(const FrameRecon *__restrict__ frames, const int32_t 
                 const int i = 8 * y + x;
                 long long res[3] = {128, 128, 128}, v[3] = {0, 0, 0};
                 if (nc == 3 && (f.xt & 4u)) {  // the residual: Q table, R transformation (FIX_COLOR_TO_INTCOLOR), R2 table
-                    const long long yv = clamp_to(rbuf[0][i], 4095), cb = clamp_to(rbuf[1][i], 4095) - (128 << 4), cr = clamp_to(rbuf[2][i], 4095) - (128 << 4);
+                    const long long yv = clamp_to(res_at(0, x, y), 4095), cb = clamp_to(res_at(1, x, y), 4095) - (128 << 4), cr = clamp_to(res_at(2, x, y), 4095) - (128 << 4);
                     res[0] = (yv * 8192 + cr * 11485 + 4096) >> 13;
                     res[1] = (yv * 8192 - cb * 2819 - cr * 5850 + 4096) >> 13;
                     res[2] = (yv * 8192 + cb * 14516 + 4096) >> 13;
                 } else {
-                    for (uint32_t c = 0; c < nc; c++) res[c] = clamp_to(rbuf[c][i], 4095);
+                    for (uint32_t c = 0; c < nc; c++) res[c] = clamp_to(res_at(c, x, y), 4095);
                 }
                 if (nc == 3 && (f.xt & 2u)) {  // the base image: L transformation (FIX_COLOR_TO_INT), L table
-                    const long long yv = buf[0][i], cb = (long long)buf[1][i] - (128 << 4), cr = (long long)buf[2][i] - (128 << 4);
+                    const long long yv = base_at(0, x, y), cb = (long long)base_at(1, x, y) - (128 << 4), cr = (long long)base_at(2, x, y) - (128 << 4);
                     v[0] = (yv * 8192 + cr * 11485 + 65536) >> 17;
                     v[1] = (yv * 8192 - cb * 2819 - cr * 5850 + 65536) >> 17;
                     v[2] = (yv * 8192 + cb * 14516 + 65536) >> 17;
                 } else {
-                    for (uint32_t c = 0; c < nc; c++) v[c] = ((long long)buf[c][i] + 8) >> 4;
+                    for (uint32_t c = 0; c < nc; c++) v[c] = ((long long)base_at(c, x, y) + 8) >> 4;
                 }
                 for (uint32_t c = 0; c < nc; c++)  // merge and clamp (:863-878, :935-947)
                     o[nc * x + c] = (uint8_t)clamp_to(clamp_to(v[c], 255) + ((clamp_to(res[c], 4095) + 8) >> 4) - 128, 255);
@@ -1224,12 +1232,12 @@ generic_reconstruct_kernel(const FrameRecon *__restrict__ frames, const int32_t 
         for (int x = 0; x <= xmax; x++) {
             long long v[4];
             if (nc == 3 && f.ycbcr) {
-                const long long yv = buf[0][8 * y + x], cb = (long long)buf[1][8 * y + x] - coff, cr = (long long)buf[2][8 * y + x] - coff;
+                const long long yv = base_at(0, x, y), cb = (long long)base_at(1, x, y) - coff, cr = (long long)base_at(2, x, y) - coff;
                 v[0] = (yv * 8192 + cr * 11485 + 65536) >> 17;
                 v[1] = (yv * 8192 - cb * 2819 - cr * 5850 + 65536) >> 17;
                 v[2] = (yv * 8192 + cb * 14516 + 65536) >> 17;
             } else {
-                for (uint32_t c = 0; c < nc; c++) v[c] = ((long long)buf[c][8 * y + x] + 8) >> 4;
+                for (uint32_t c = 0; c < nc; c++) v[c] = ((long long)base_at(c, x, y) + 8) >> 4;
             }
             for (uint32_t c = 0; c < nc; c++) {
                 const long long w = v[c] < 0 ? 0 : (v[c] > maxval ? maxval : v[c]);
