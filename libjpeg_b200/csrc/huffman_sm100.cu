@@ -256,7 +256,10 @@ unstuff_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const ui
 // where two ranges meet in the middle of a word.
 constexpr int kLongThreads = 1024;
 
-__global__ void __launch_bounds__(kLongThreads)
+#ifndef B200JPG_LONG_MINCTAS
+#define B200JPG_LONG_MINCTAS 2
+#endif
+__global__ void __launch_bounds__(kLongThreads, B200JPG_LONG_MINCTAS)
 unstuff_long_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ interval_off,
                     const uint64_t *__restrict__ interval_end, const uint64_t *__restrict__ clean_off, uint8_t *__restrict__ clean,
                     uint32_t *__restrict__ interval_len) {
@@ -304,11 +307,19 @@ unstuff_long_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, con
         }
         return n;
     };
+    // steps that lie inside this warp's range with room to spare and hold no 0xFF at all (about 60 % of them) keep every byte
+    auto plain_step = [&](uint64_t base, uint64_t limit, uint32_t &cur) -> bool {
+        if (base < src0 + 4 || base + 132 > limit) return false;  // (warp-uniform)
+        cur = __ldg(reinterpret_cast<const uint32_t *>(bytes + base + 4ull * lane));
+        const uint32_t prv = (lane == 0) ? bytes[base - 1] : 0u;   // a 00 at the front of the step could follow an FF of the last one
+        return !__any_sync(kFull, __vcmpeq4(cur, 0xffffffffu) != 0u || prv == 0xffu);
+    };
     // ---- pass 1: count
     uint32_t mine = 0;
     for (uint64_t base = lo; base < hi; base += 128) {
         uint32_t cur, keep[4];
-        mine += classify(base, hi, cur, keep);
+        if (plain_step(base, hi, cur)) mine += 4;
+        else mine += classify(base, hi, cur, keep);
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(kFull, mine, d);
@@ -341,6 +352,17 @@ unstuff_long_kernel(uint32_t n_intervals, const uint8_t *__restrict__ bytes, con
     uint32_t out = before;
     for (uint64_t base = lo; base < hi; base += 128) {
         uint32_t cur, keep[4];
+        if (plain_step(base, hi, cur)) {  // 128 bytes move as they are: one word store per lane when the destination is aligned
+            const uint32_t o = out + 4u * lane;
+            if ((out & 3u) == 0u) {
+                *reinterpret_cast<uint32_t *>(dst + o) = __byte_perm(cur, 0, 0x0123);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) dst[(o + k) ^ 3u] = (uint8_t)(cur >> (8 * k));
+            }
+            out += 128;
+            continue;
+        }
         classify(base, hi, cur, keep);
         const uint32_t b0 = __ballot_sync(kFull, keep[0]), b1 = __ballot_sync(kFull, keep[1]);
         const uint32_t b2 = __ballot_sync(kFull, keep[2]), b3 = __ballot_sync(kFull, keep[3]);
