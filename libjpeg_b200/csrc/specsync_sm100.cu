@@ -20,11 +20,10 @@ namespace b200jpg {
 namespace {
 
 constexpr int kSyncThreads = 512;
-#ifndef B200JPG_SPEC_MINCTAS
-#define B200JPG_SPEC_MINCTAS 2
-#endif
-
-__global__ void __launch_bounds__(kSyncThreads, B200JPG_SPEC_MINCTAS)
+// kMinCtas = CTAs per SM the register allocation aims at: 3 (40 registers, a few spills) wins when many scans are in flight,
+// 2 (64 registers) is the shorter way through one scan
+template <int kMinCtas>
+__global__ void __launch_bounds__(kSyncThreads, kMinCtas)
 spec_sync_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uint64_t *__restrict__ clean_off,
                  const uint32_t *__restrict__ interval_len, const uint8_t *__restrict__ tables, SpecSegment *__restrict__ segs,
                  unsigned long long *__restrict__ exits, unsigned long long *__restrict__ entries, uint32_t *__restrict__ counts,
@@ -126,12 +125,16 @@ spec_sync_kernel(ScanClassParams p, const uint8_t *__restrict__ clean, const uin
 int launch_spec_sync(const EntropyLaunch &l, void *stream) {
     if (l.p.n_scans == 0) return 0;
     const size_t smem = (size_t)l.p.lut_words * 4;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool many = l.p.n_scans >= 2u * (uint32_t)sms;  // more CTAs than two per SM: occupancy counts more than the single path
+    auto kernel = many ? spec_sync_kernel<3> : spec_sync_kernel<2>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(spec_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    spec_sync_kernel<<<l.p.n_scans, kSyncThreads, smem, (cudaStream_t)stream>>>(l.p, l.clean, l.clean_off, l.interval_len, l.tables, l.spec_segments,
-                                                                                 l.spec_exits, l.spec_entries, l.spec_counts, l.spec_dc_sums, l.spec_logs);
+    kernel<<<l.p.n_scans, kSyncThreads, smem, (cudaStream_t)stream>>>(l.p, l.clean, l.clean_off, l.interval_len, l.tables, l.spec_segments, l.spec_exits,
+                                                                      l.spec_entries, l.spec_counts, l.spec_dc_sums, l.spec_logs);
     return (int)cudaGetLastError();
 }
 
