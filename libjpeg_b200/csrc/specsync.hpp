@@ -156,15 +156,19 @@ B200JPG_HD SpecResult spec_decode(const SpecScan &sc, const uint32_t *w, uint32_
         const uint32_t hi = (bit & 31u) ? ((x0 << (bit & 31u)) | (x1 >> (32u - (bit & 31u)))) : x0;
 #endif
         const uint32_t e = spec_lookup(lut + (k == 0 ? dct : act), hi);
-        // ONE straight line for the DC symbol of a block and for its AC symbols: with 32 lanes somewhere in their blocks a branch
-        // between the two is taken both ways in nearly every iteration. An entry that must not be decoded (bit 31) ends the block
-        // -- after one bit for a DC symbol, after its own length for an AC one: any rule does for a path that is wrong anyway.
-        {
-            const bool dc = k == 0, bad = (int32_t)e < 0;
-            const int32_t v = (dc && !bad) ? spec_value(e, hi) : 0;
-            s0 += c == 0 ? v : 0, s1 += c == 1 ? v : 0, s2 += c == 2 ? v : 0, s3 += c == 3 ? v : 0;
-            bit += (dc && bad) ? 1u : ((e >> 26) & 31u);
-            k = dc ? (bad ? 64u : 1u) : k + ((e >> 19) & 127u);  // AC: run + 1, 16 for ZRL, kQzBlockEnds for EOB and error entries
+        if (k == 0) {
+            if ((int32_t)e >= 0) {
+                const int32_t v = spec_value(e, hi);
+                s0 += c == 0 ? v : 0, s1 += c == 1 ? v : 0, s2 += c == 2 ? v : 0, s3 += c == 3 ? v : 0;
+                bit += e >> 26;
+                k = 1;
+            } else {  // an entry that must not be decoded ends the block here: any rule does for a path that is wrong anyway
+                bit += 1;
+                k = 64;
+            }
+        } else {
+            bit += (e >> 26) & 31u;
+            k += (e >> 19) & 127u;  // run + 1, 16 for ZRL, kQzBlockEnds for EOB and error entries
         }
         if (k > 63) {
             k = 0;
