@@ -33,7 +33,10 @@ namespace b200jpg {
 #endif
 constexpr uint32_t kSpecSeqBits = B200JPG_SPEC_SEQ_BITS;  // bits per subsequence (256 words; measured: 4096 -> 8192 bits takes 15 % off the batch AND off a single 4K frame, 16384 nothing more)
 constexpr int kSpecMaxBlocksPerMcu = 10;
-constexpr uint32_t kSpecRunUpBits = 2048;   // the first round starts this far in front of a subsequence (see spec_decode)
+#ifndef B200JPG_SPEC_RUNUP_BITS
+#define B200JPG_SPEC_RUNUP_BITS 2048
+#endif
+constexpr uint32_t kSpecRunUpBits = B200JPG_SPEC_RUNUP_BITS;   // the first round starts this far in front of a subsequence (see spec_decode)
 constexpr size_t kSpecMinBytes = 4096;    // shorter restart-less scans stay one work item (eight subsequences are not worth the rounds)
 
 struct SpecScan {               // what the length-only decoder needs to know about the scan
