@@ -33,6 +33,9 @@ CASES = [
     ("xt_420r_96x80_q75_Q80", 96, 80, False, ["-r", "-q", "75", "-Q", "80", "-h", "-s", "1x1,2x2,2x2", "-sr", "1x1,2x2,2x2"]),
     ("xt_p444_64x48_q75_Q90", 64, 48, False, ["-r", "-q", "75", "-Q", "90", "-v"]),
     ("xt_444_256x192_z8_q75_Q90", 256, 192, False, ["-r", "-q", "75", "-Q", "90", "-h", "-z", "8"]),
+    ("xt_c444_80x56_q75_Q90", 80, 56, False, ["-r", "-q", "75", "-Q", "90", "-c"]),  # no decorrelation: L and R transformation = identity
+    ("xt_rv444_80x56_q75_Q90", 80, 56, False, ["-r", "-q", "75", "-Q", "90", "-rv"]),  # progressive residual codestream
+    ("xt_420_sr422_80x56_q60_Q85", 80, 56, False, ["-r", "-q", "60", "-Q", "85", "-qt", "3", "-s", "1x1,2x2,2x2", "-sr", "1x1,2x1,2x1"]),
 ]
 OUTSIDE = [  # accepted by the reference, outside the covered profile
     ("xt_lossless_33x17__nimpl", 33, 17, False, ["-r", "-q", "50", "-Q", "100", "-h"]),  # residual after an RCT, int-to-int DCT
