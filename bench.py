@@ -270,8 +270,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=0, help="distinct frames cycled through the batch (default 64; cfg5: 2)")
     ap.add_argument("--e2e-chunk", type=int, default=32)
     ap.add_argument("--e2e-producers", type=int, default=0,
-                    help="host threads that prepare chunks (b200jpg_batch_create) ahead of the device; 0 = 1 on one GPU (the link is the limit and the "
-                         "1-GPU box grants few CPUs), 2 on several (measured on 4 GPUs: 4.85 k -> 5.73 k frames/s)")
+                    help="host threads that prepare chunks (b200jpg_batch_create) ahead of the device; 0 = 2 on two to four GPUs, else 1 (measured, see the e2e section)")
     ap.add_argument("--p2d-chunks", type=int, default=2, help="pinned_to_device_rgb: chunks per step (each: H2D + index + kernels on its own stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -518,7 +517,9 @@ def main():
                   "host": torch.empty(ob, dtype=torch.uint8).pin_memory()} for _ in range(nslots)]
         counters = {"h2d": 0, "d2h": 0}
 
-        nprod = args.e2e_producers if args.e2e_producers > 0 else (1 if world == 1 else 2)
+        # measured (profiles/README.md): one GPU 2.13 k frames/s with one thread, 2.05 k with two; four GPUs 4.85 k / 5.73 k; eight GPUs
+        # 9.66 k / 9.35 k (eight ranks x two threads x 16 parsing threads oversubscribe the host)
+        nprod = args.e2e_producers if args.e2e_producers > 0 else (2 if 2 <= world <= 4 else 1)
 
         def e2e_step(keep_last=False):
             # host preparation (b200jpg_batch_create: parse + pack into pinned memory) runs ahead of the device in `nprod` threads,
