@@ -167,6 +167,11 @@ B200JPG_API int b200jpg_microbench_int32(int device, float *imad_gops, float *al
  * device kernel for scan 0 of one codestream on the host and checks the resulting work items against a front-to-back walk.
  * Returns B200JPG_OK, a parser error, or -1..-4 for an inconsistent partition. */
 B200JPG_API int b200jpg_selftest_restartless(const uint8_t *data, size_t len, uint32_t *rounds, uint32_t *n_segments);
+/* Host-only self-test of the decoder-table cache of b200jpg_batch_create (frames of one source share their tables; the tables of a
+ * scan are built once per distinct set of Huffman specifications, quantisation tables and scan parameters): every scan of the
+ * given codestreams through the cache, twice, against a fresh HuffmanTemplate::BuildDecoder-equivalent build
+ * (coding/huffmantemplate.cpp:802-874).  Returns the number of scans compared, or a negative value on a mismatch. */
+B200JPG_API int b200jpg_selftest_table_cache(const uint8_t *const *frames, const size_t *lens, int n);
 
 /* One-call convenience used by the C++ JPEG shim: host codestreams in, HOST pixels out (upload, decode,
  * download, synchronise).  `out_host` receives b200jpg_batch_out_bytes(batch,-1) bytes. */

@@ -219,6 +219,51 @@ struct b200jpg_batch {
 
 extern "C" {
 
+// Frames of one source share their tables: the decoder tables of a scan are built once per distinct set of inputs of
+// build_table_set -- the scan's Huffman specifications, quantisation tables, point transform and spectral selection -- and copied
+// for the other scans that have the same (b200jpg_selftest_table_cache checks the cache against fresh builds on the host).
+struct TableCache {
+    std::map<std::string, TableSet> built;
+};
+
+static std::string table_inputs_key(const ScanInfo &sc) {
+    std::string k;
+    k.reserve(2048);
+    auto put = [&](const void *p, size_t n) { k.append(reinterpret_cast<const char *>(p), n); };
+    const int head[6] = {sc.progressive ? 1 : 0, sc.ss, sc.se, sc.ah, sc.lowbit, sc.ns};
+    put(head, sizeof(head));
+    put(sc.td, sizeof(sc.td));
+    put(sc.ta, sizeof(sc.ta));
+    for (int pass = 0; pass < 2; pass++)
+        for (int t = 0; t < 4; t++) {
+            const HuffSpec &h = pass ? sc.ac[t] : sc.dc[t];
+            const uint8_t d = h.defined ? 1 : 0;
+            put(&d, 1);
+            if (!h.defined) continue;
+            put(h.bits, 16);
+            put(&h.nvals, sizeof(h.nvals));
+            put(h.vals, (size_t)std::min(std::max(h.nvals, 0), 256));
+        }
+    for (int t = 0; t < 4; t++) {
+        const uint8_t d = sc.quant_defined[t] ? 1 : 0;
+        put(&d, 1);
+        if (d) put(sc.quant[t], sizeof(sc.quant[t]));
+    }
+    return k;
+}
+
+static int build_table_set_cached(const ScanInfo &sc, TableSet &out, std::string &err, TableCache &cache) {
+    std::string key = table_inputs_key(sc);
+    auto it = cache.built.find(key);
+    if (it != cache.built.end()) {
+        out = it->second;
+        return B200JPG_OK;
+    }
+    const int rc = build_table_set(sc, out, err);
+    if (rc == B200JPG_OK) cache.built.emplace(std::move(key), out);
+    return rc;
+}
+
 // JPEG XT: the residual codestream of `base` (its RESI box) as a frame of its own; what of it the path covers
 static int parse_residual(const ParsedFrame &base, ParsedFrame &rf, std::string &err, bool device_index) {
     int rst;
@@ -455,6 +500,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
     for (int i = 0; i < n_user; i++)
         if (b->xt_child[i] >= 0) b->xt_parent[b->xt_child[i]] = i;
     std::vector<std::vector<TableSet>> frame_tables(n);
+    TableCache table_cache;
     for (int i = 0; i < n; i++) {
         ParsedFrame &pf = b->frames[i];
         int &st = b->parse_status[i];
@@ -487,7 +533,7 @@ static int batch_create_impl(b200jpg_ctx *ctx, const uint8_t *const *frames, con
             frame_tables[i].resize(pf.scans.size());
             for (size_t si = 0; si < pf.scans.size() && st == 0; si++) {
                 try {
-                    st = build_table_set(pf.scans[si], frame_tables[i][si], errs[i]);
+                    st = build_table_set_cached(pf.scans[si], frame_tables[i][si], errs[i], table_cache);
                 } catch (const std::bad_alloc &) {
                     st = B200JPG_ERR_OUT_OF_MEMORY;
                     errs[i] = "out of memory while building the decoder tables";
@@ -1363,6 +1409,27 @@ int b200jpg_selftest_restartless(const uint8_t *data, size_t len, uint32_t *roun
     }
     if (covered != total_blocks) return -4;
     return B200JPG_OK;
+}
+
+int b200jpg_selftest_table_cache(const uint8_t *const *frames, const size_t *lens, int n) {
+    if (!frames || !lens || n <= 0) return B200JPG_ERR_INVALID_PARAMETER;
+    TableCache cache;
+    int scans_checked = 0;
+    for (int pass = 0; pass < 2; pass++)  // twice: the second time every scan comes out of the cache
+        for (int i = 0; i < n; i++) {
+            ParsedFrame pf;
+            std::string err;
+            if (parse_codestream(frames[i], lens[i], pf, err) != 0) continue;
+            for (const ScanInfo &sc : pf.scans) {
+                TableSet cached, fresh;
+                std::string e1, e2;
+                const int r1 = build_table_set_cached(sc, cached, e1, cache), r2 = build_table_set(sc, fresh, e2);
+                if (r1 != r2) return -1;
+                if (r1 == 0 && cached.blob != fresh.blob) return -2;
+                scans_checked++;
+            }
+        }
+    return scans_checked;
 }
 
 int b200jpg_decode_to_host(b200jpg_ctx *ctx, const uint8_t *const *frames, const size_t *lens, int n, uint8_t *out_host,

@@ -247,3 +247,21 @@ def test_parser_survives_damaged_streams(built, oracle):
             rc, _ = oracle.info(bytes(d))
             assert rc <= 0
     assert outcomes["ok"] > 50 and outcomes["error"] > 50
+
+
+def test_decoder_table_cache_equals_fresh_builds(built):
+    """b200jpg_batch_create builds the decoder tables of a scan once per distinct set of inputs and copies them for the other scans
+    that share them: every scan of every fixture (baseline, optimised tables, progressive scripts, 12 bit, unusual samplings, JPEG XT)
+    through the cache, in one mixed sequence and twice, equals a fresh build byte for byte (host only)."""
+    import glob
+    import random
+    from libjpeg_b200 import native
+    paths = sorted(glob.glob(os.path.join(GOLDEN, "*.jpg")) + glob.glob(os.path.join(GOLDEN, "*", "*.jpg")))
+    assert len(paths) > 60
+    random.Random(5).shuffle(paths)
+    datas = [open(p, "rb").read() for p in paths]
+    bufs = [(ctypes.c_char * len(d)).from_buffer_copy(d) for d in datas]
+    ptrs = (ctypes.c_void_p * len(bufs))(*[ctypes.addressof(b) for b in bufs])
+    lens = (ctypes.c_size_t * len(bufs))(*[len(d) for d in datas])
+    n = native.lib.b200jpg_selftest_table_cache(ptrs, lens, len(bufs))
+    assert n >= 2 * len(paths) * 0.8, n  # (a few fixtures are deliberately unparsable)
